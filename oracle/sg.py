@@ -1,0 +1,343 @@
+"""Oracle: the stochastic-Galerkin data model, operator application and PCG.
+
+Restates
+  * ``MultiVector``                 reference src/spuq/application/egsz/multi_vector.py:29-166
+  * ``ListCoefficientField``        reference src/spuq/application/egsz/coefficient_field.py:55-104
+  * ``MultiOperator.apply``         reference src/spuq/application/egsz/multi_operator2.py:38-84
+  * ``PreconditioningOperator``     reference src/spuq/application/egsz/multi_operator2.py:139-165
+  * ``pcg``                         reference src/spuq/application/egsz/pcg.py:15-53
+  * ``ForgetfulVector``             reference src/spuq/utils/forgetful_vector.py:46-66
+  * batched form / Delta matrices   reference src/spuq/linalg/tensor_operator.py:65-79,
+                                    src/spuq/polyquad/structure_coefficients.py:11-41
+Test infrastructure only (see oracle/__init__.py).
+"""
+import logging
+
+import numpy as np
+import scipy.sparse as sps
+
+from .linalg import Operator, Scalar, Vector, inner
+from .multiindex import Multiindex
+
+logger = logging.getLogger(__name__)
+
+
+class MultiVector(Vector):
+    """dict {Multiindex -> Vector}; multi_vector.py:29-166."""
+
+    def __init__(self, on_modify=lambda: None, multivector=None):
+        self.mi2vec = dict()
+        self.on_modify = on_modify
+        if multivector is not None:
+            for mu, vec in multivector.items():
+                self[mu] = vec
+
+    @property
+    def max_order(self):
+        return max(len(mu) for mu in self.keys())
+
+    def __getitem__(self, mi):
+        return self.mi2vec[mi]
+
+    def __setitem__(self, mi, val):
+        self.on_modify()
+        self.mi2vec[mi] = val
+
+    def __len__(self):
+        return len(self.mi2vec)
+
+    def keys(self):
+        return self.mi2vec.keys()
+
+    def values(self):
+        return self.mi2vec.values()
+
+    def items(self):
+        return self.mi2vec.items()
+
+    iteritems = items
+
+    def active_indices(self):
+        return sorted(self.keys())
+
+    def copy(self):
+        mv = type(self)()
+        for mi in self.keys():
+            mv[mi] = self[mi].copy()
+        return mv
+
+    def set_defaults(self, multiindex_set, init_vector):
+        self.on_modify()
+        for mi in multiindex_set:
+            self[Multiindex(mi)] = init_vector.copy()
+
+    def set_zero(self):
+        for mu in self.active_indices():
+            self[mu].set_zero()
+
+    def __eq__(self, other):
+        return type(self) == type(other) and self.mi2vec == other.mi2vec
+
+    __hash__ = None
+
+    def __neg__(self):
+        new = self.copy()
+        for mi in self.active_indices():
+            new[mi] = -self[mi]
+        return new
+
+    def __iadd__(self, other):
+        assert self.active_indices() == other.active_indices()
+        self.on_modify()
+        for mi in self.active_indices():
+            self[mi] += other[mi]
+        return self
+
+    def __isub__(self, other):
+        assert self.active_indices() == other.active_indices()
+        self.on_modify()
+        for mi in self.active_indices():
+            self[mi] -= other[mi]
+        return self
+
+    def __imul__(self, other):
+        assert isinstance(other, Scalar)
+        self.on_modify()
+        for mi in self.keys():
+            self[mi] *= other
+        return self
+
+    def __inner__(self, other):
+        assert isinstance(other, MultiVector)
+        s = 0.0
+        for mi in self.keys():
+            s += inner(self[mi], other[mi])
+        return s
+
+    def __repr__(self):
+        return "<%s keys=%s>" % (type(self).__name__, list(self.mi2vec.keys()))
+
+    # slab view used by the tests: columns in active_indices() order (multi_vector.py:388-403)
+    def to_slab(self):
+        return np.stack([self[mu].coeffs for mu in self.active_indices()], axis=1)
+
+
+class ListCoefficientField:
+    """(mean_func, [(a_m, rv_m)]); coefficient_field.py:55-104."""
+
+    def __init__(self, mean_func, funcs, rvs):
+        assert len(funcs) == len(rvs)
+        self._mean_func, self._funcs, self._rvs = mean_func, list(funcs), list(rvs)
+
+    @classmethod
+    def create_with_iid_rvs(cls, mean_func, funcs, rv):
+        return cls(mean_func, funcs, [rv] * len(funcs))
+
+    mean_func = property(lambda self: self._mean_func)
+    funcs = property(lambda self: self._funcs)
+    rvs = property(lambda self: self._rvs)
+
+    def __len__(self):
+        return len(self._funcs)
+
+    def __getitem__(self, i):
+        assert i < len(self._funcs), "invalid index"
+        return self._funcs[i], self._rvs[i]
+
+
+class MultiOperator(Operator):
+    """The SG operator on one shared spatial basis; multi_operator2.py:26-84."""
+
+    def __init__(self, coeff_field, assemble_0, assemble_m=None, domain=None, codomain=None):
+        if not (isinstance(coeff_field, ListCoefficientField) or hasattr(coeff_field, "mean_func")):
+            raise TypeError("coeff_field")
+        if not callable(assemble_0) or not (assemble_m is None or callable(assemble_m)):
+            raise TypeError("assemble callback")
+        self._assemble_0 = assemble_0
+        self._assemble_m = assemble_m or assemble_0
+        self._coeff_field = coeff_field
+        self._domain, self._codomain = domain, codomain
+
+    domain = property(lambda self: self._domain)
+    codomain = property(lambda self: self._codomain)
+
+    def apply(self, w):
+        if not isinstance(w, MultiVector):
+            raise TypeError("MultiOperator.apply needs a MultiVector")
+        v = 0 * w                                                     # :42
+        Lambda = w.active_indices()                                   # :43
+        maxm = w.max_order                                            # :44
+        if len(self._coeff_field) < maxm:                             # :45-48
+            logger.warning("insufficient length of coefficient field for MultiVector "
+                           "(%i instead of %i", len(self._coeff_field), maxm)
+            maxm = len(self._coeff_field)
+        basis = w[Lambda[0]].basis                                    # :51 (shared basis)
+        for mu in Lambda:                                             # :52
+            A0 = self._assemble_0(basis, self._coeff_field.mean_func)
+            cur_v = A0 * w[mu]                                        # :56
+            for m in range(maxm):                                     # :59
+                am_f, am_rv = self._coeff_field[m]
+                Am = self._assemble_m(basis, am_f)
+                beta = am_rv.orth_polys.get_beta(mu[m])               # :66
+                cur_w = -beta[0] * w[mu]                              # :69
+                mu1 = mu.inc(m)
+                if mu1 in Lambda:                                     # :72-74
+                    cur_w += beta[1] * w[mu1]
+                mu2 = mu.dec(m)
+                if mu2 in Lambda:                                     # :77-79
+                    cur_w += beta[-1] * w[mu2]
+                cur_v += Am * cur_w                                   # :82
+            v[mu] = cur_v
+        return v
+
+
+class PreconditioningOperator(Operator):
+    """Mean-based block-diagonal preconditioner; multi_operator2.py:139-165."""
+
+    def __init__(self, mean_func, assemble_solver, domain=None, codomain=None):
+        self._assemble_solver = assemble_solver
+        self._mean_func = mean_func
+        self._domain, self._codomain = domain, codomain
+
+    domain = property(lambda self: self._domain)
+    codomain = property(lambda self: self._codomain)
+
+    def apply(self, w):
+        v = 0 * w
+        for mu in w.active_indices():
+            A0 = self._assemble_solver(w[mu].basis, self._mean_func)
+            v[mu] = A0 * w[mu]
+        return v
+
+
+class ForgetfulVector:
+    """Ring buffer remembering the last ``remember`` entries; forgetful_vector.py:46-66."""
+
+    def __init__(self, remember, start=0):
+        self.rem, self.curr = remember, start
+        self.items = remember * [None]
+
+    def __getitem__(self, k):
+        if not self.curr - self.rem < k <= self.curr:
+            raise IndexError("index out of range: %d not in [%d, %d]"
+                             % (k, self.curr - self.rem + 1, self.curr))
+        return self.items[self.curr - k]
+
+    def __setitem__(self, k, item):
+        if not self.curr - self.rem < k <= self.curr + 1:
+            raise IndexError("index out of range: %d not in [%d, %d]"
+                             % (k, self.curr - self.rem + 1, self.curr + 1))
+        if k == self.curr + 1:
+            self.items = [item] + self.items[:-1]
+            self.curr += 1
+        else:
+            self.items[self.curr - k] = item
+
+
+def pcg(A, f, P, w0, eps=1e-4, maxiter=100, history=None):
+    """Preconditioned CG; pcg.py:15-53.  Returns (w, zeta, i).
+
+    ``history`` (a list, optional, not in the reference) receives zeta of every pass so tests can
+    compare trajectories at a fixed iteration index.
+    """
+    w, rho, s, v, z, alpha = (ForgetfulVector(1) for _ in range(6))
+    zeta = ForgetfulVector(2)
+    w[0] = w0
+    rho[0] = f - A * w[0]
+    s[0] = P * rho[0]
+    v[0] = s[0]
+    zeta[0] = inner(rho[0], s[0])
+    for i in range(1, maxiter):
+        if history is not None:
+            history.append(float(zeta[i - 1]))
+        if logger.isEnabledFor(logging.INFO):
+            logger.info("pcg iter: %s -> zeta=%s, rho^2=%s", i, zeta[i - 1],
+                        inner(rho[i - 1], rho[i - 1]))
+        if zeta[i - 1] < 0:
+            raise Exception("Preconditioner for PCG is not positive definite (%s)" % zeta[i - 1])
+        if zeta[i - 1] <= eps ** 2:
+            return (w[i - 1], zeta[i - 1], i)
+        z[i - 1] = A * v[i - 1]
+        alpha[i - 1] = inner(z[i - 1], v[i - 1])
+        if alpha[i - 1] == 0:
+            raise Exception("Matrix for PCG is singular (%s)" % alpha[i - 1])
+        elif alpha[i - 1] < 0:
+            raise Exception("Matrix for PCG is not positive definite (%s)" % alpha[i - 1])
+        w[i] = w[i - 1] + zeta[i - 1] / alpha[i - 1] * v[i - 1]
+        rho[i] = rho[i - 1] - zeta[i - 1] / alpha[i - 1] * z[i - 1]
+        s[i] = P * rho[i]
+        zeta[i] = inner(rho[i], s[i])
+        v[i] = s[i] + zeta[i] / zeta[i - 1] * v[i - 1]
+    raise Exception("PCG did not converge")
+
+
+# ---- structural helpers used by the parity tests -----------------------------------------------
+def neighbour_tables(Lambda, maxm):
+    """Positions of mu+e_m / mu-e_m inside the sorted list ``Lambda`` (-1 when absent), found the
+    way the reference finds them: ``mu.inc(m) in Lambda`` / ``mu.dec(m) in Lambda``
+    (multi_operator2.py:72-79), i.e. by Multiindex equality, not by any array trick."""
+    pos = {mu: k for k, mu in enumerate(Lambda)}
+    up = -np.ones((maxm, len(Lambda)), dtype=np.int32)
+    dn = -np.ones((maxm, len(Lambda)), dtype=np.int32)
+    for k, mu in enumerate(Lambda):
+        for m in range(maxm):
+            mu1 = mu.inc(m)
+            if mu1 in pos:
+                up[m, k] = pos[mu1]
+            mu2 = mu.dec(m)
+            if mu2 is not None and mu2 in pos:
+                dn[m, k] = pos[mu2]
+    return up, dn
+
+
+def stochastic_matrices(Lambda, rvs, maxm):
+    """K_m (L x L, CSR) with the row-degree convention of MultiOperator.apply:
+    K_m[mu, mu] = -beta0(mu_m), K_m[mu, mu+e_m] = beta1(mu_m), K_m[mu, mu-e_m] = beta_{-1}(mu_m)."""
+    L = len(Lambda)
+    up, dn = neighbour_tables(Lambda, maxm)
+    mats = []
+    for m in range(maxm):
+        polys = rvs[m].orth_polys
+        K = sps.lil_matrix((L, L))
+        for k, mu in enumerate(Lambda):
+            b = polys.get_beta(mu[m])
+            if b[0] != 0.0:
+                K[k, k] = -b[0]
+            if up[m, k] >= 0:
+                K[k, up[m, k]] = b[1]
+            if dn[m, k] >= 0:
+                K[k, dn[m, k]] = b[-1]
+        mats.append(K.tocsr())
+    return mats
+
+
+def apply_batched(A0, Ams, Ks, W):
+    """Batched CPU form  Y = A0 W + sum_m A_m (W K_m^T)  on the N x L slab W (columns in sorted
+    Lambda order).  This is the reference's TensorOperator formulation (tensor_operator.py:65-79,
+    tensor_vector.py:50-56) with the MultiOperator sign / degree conventions; it is the form the GPU
+    implements and the 'best effort' CPU baseline of BASELINE.md."""
+    Y = A0 @ W
+    for Am, K in zip(Ams, Ks):
+        if K.nnz:
+            Y += Am @ (K @ W.T).T
+    return Y
+
+
+def evaluate_triples(polysys, I_a, I_b):
+    """structure_coefficients.py:11-41: L[0] = identity pattern, L[k+1][i,j] = beta_k(mu_j[k])[d]
+    with d = mu_i[k]-mu_j[k] in {-1,0,1} when mu_i and mu_j agree off component k."""
+    Mi, Nj, K = I_a.shape[0], I_b.shape[0], I_a.shape[1]
+    if not isinstance(polysys, (list, tuple)):
+        polysys = [polysys] * K
+    out = [sps.dok_matrix((Mi, Nj)) for _ in range(-1, K)]
+    for k in range(-1, K):
+        for i, mui in enumerate(I_a):
+            for j, muj in enumerate(I_b):
+                same = mui == muj
+                if np.all(same[:k]) and np.all(same[k + 1:]):
+                    delta = int(mui[k]) - int(muj[k])
+                    if -1 <= delta <= 1:
+                        val = polysys[k].get_beta(int(muj[k]))[delta] if k != -1 else 1
+                        if val != 0.0:
+                            out[k + 1][i, j] = val
+    return [m.asformat("csr") for m in out]

@@ -1,0 +1,20 @@
+"""spuq_b200 -- B200-native stochastic-Galerkin operator application and PCG for spuq.
+
+Drop-in surface (same names as the reference):
+    Multiindex, MultiindexSet, MultiVector, MultiVectorSharedBasis, SlabMultiVector,
+    MultiOperator, PreconditioningOperator, pcg, inner, FlatVector, the leaf operators,
+    ListCoefficientField, NormalRV, UniformRV.
+"""
+from .multiindex import Multiindex, MultiindexSet
+from .polyquad import (LegendrePolynomials, StochasticHermitePolynomials, JacobiPolynomials,
+                       ChebyshevT, ChebyshevU)
+from .random_variable import NormalRV, UniformRV, RandomVariable
+from .coefficient_field import CoefficientField, ListCoefficientField, ParametricCoefficientField
+from .linalg import (Basis, CanonicalBasis, BasisMismatchError, Vector, FlatVector, inner, Operator,
+                     MatrixOperator, DiagonalMatrixOperator, MatrixSolveOperator,
+                     MultiplicationOperator, ScipyOperator, ScipySolveOperator)
+from .multi_vector import MultiVector, MultiVectorSharedBasis, SlabMultiVector
+from .multi_operator import MultiOperator, PreconditioningOperator, DeviceBlocks
+from .pcg import pcg
+
+__version__ = "0.1.0"

@@ -1,0 +1,142 @@
+// common.h -- shared declarations of libspuq_sg (error handling, launch macro, plan layout).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include <vector>
+
+#ifdef SPUQ_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define SPUQ_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#include "../../include/spuq_sg.h"
+
+namespace spuq {
+
+void set_error(const char* fmt, ...);
+
+#define SPUQ_CUDA_TRY(expr)                                                               \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            spuq::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),      \
+                            __FILE__, __LINE__);                                          \
+            return SPUQ_E_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+#define SPUQ_REQUIRE(cond, ...)                                                           \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            spuq::set_error(__VA_ARGS__);                                                 \
+            return SPUQ_E_INVALID;                                                        \
+        }                                                                                 \
+    } while (0)
+
+int sm_count(int device);
+
+// ---- device-side views handed to the kernels (plain structs, passed by value) ---------------
+
+// Per-column term lists: column mu of Y is  sum_t coef[t] * A_{mat[t]} * W[:, col[t]]
+// for t in [ptr[mu], ptr[mu+1]).  mat = 0 is the mean block, 1+m the m-th expansion block.
+struct TermView {
+    const int32_t* ptr;    // L+1
+    const int32_t* mat;    // T
+    const int32_t* col;    // T
+    const double* coef;    // T
+};
+
+// Diagonal storage of a 9-point-window pattern: offsets off[d] = dx + s*dy with dx,dy in {-1,0,1};
+// values of block b on diagonal d for row i at vals[(b*D + d)*N + i] (0 where the CSR pattern has
+// no entry).  Block slots b index the blocks this shard owns (slot_of_mat maps mat -> slot).
+struct StencilView {
+    int32_t D;
+    int32_t s;             // row stride of the grid (nx)
+    int64_t N;
+    int32_t off[9];
+    int32_t dx[9], dy[9];
+    const double* vals;
+};
+
+// Column blocks for the register-tiled stencil kernel: block k owns columns
+// bcol[k*C + c], c < C (-1 = padding), and its work is a list of groups; group g applies ONE
+// block matrix (gmat[g], already a slot index) to gcnt[g] terms starting at gterm[g]; term t
+// reads column tcol[t] and accumulates coef tcoef[t] times the stencil result into accumulator
+// tacc[t] (< C).
+struct BlockView {
+    int32_t C;
+    int32_t nblk;
+    const int32_t* bcol;    // nblk*C
+    const int32_t* bgrp;    // nblk+1  (group range of each block)
+    const int32_t* gmat;    // G
+    const int32_t* gterm;   // G+1
+    const int32_t* tcol;    // T
+    const int32_t* tacc;    // T
+    const double* tcoef;    // T
+};
+
+}  // namespace spuq
+
+struct spuq_sg_plan;
+namespace spuq {
+// apply with an optional PCG gate word (see kernels_apply.cuh); the C ABI passes gate = null
+int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t ldy,
+               cudaStream_t stream, const double* gate);
+}
+
+struct spuq_sg_plan {
+    int device = 0;
+    int64_t n_rows = 0, n_cols = 0, nnz = 0;
+    int32_t L = 0, M = 0, m_begin = 0, m_end = 0;
+    int include_mean = 1;
+    int32_t path = SPUQ_PATH_CSR;
+    int32_t max_row_nnz = 0;
+    int n_sm = 148;
+
+    // borrowed CSR (device) + device array of the M+1 value pointers
+    const int32_t* rowptr = nullptr;
+    const int32_t* colidx = nullptr;
+    const double** vals_ptrs_dev = nullptr;
+    std::vector<const double*> vals_host;
+    std::vector<int32_t> slot_of_mat;     // mat -> compact slot among owned blocks (-1 = not owned)
+    int32_t* slot_dev = nullptr;          // device copy of slot_of_mat
+    int32_t n_slots = 0;
+
+    // per-column term lists
+    int64_t n_terms = 0;
+    int32_t* term_ptr = nullptr;
+    int32_t* term_mat = nullptr;
+    int32_t* term_col = nullptr;
+    double* term_coef = nullptr;
+    std::vector<int32_t> h_term_ptr, h_term_mat, h_term_col;
+    std::vector<double> h_term_coef;
+
+    // ELL copy
+    int32_t ell_K = 0;
+    int32_t* ell_cols = nullptr;      // K * n_rows
+    double* ell_vals = nullptr;       // n_slots * K * n_rows
+
+    // stencil copy
+    spuq::StencilView st{};
+    double* dia_vals = nullptr;       // n_slots * D * N
+
+    // column blocks for the tiled stencil kernel (built lazily for the C in use)
+    spuq::BlockView bv{};
+    int32_t ny = 0;                   // grid rows of the stencil path (N = s * ny)
+    bool nine = false;
+    std::vector<void*> block_dev;     // device arrays of the current BlockView
+    std::vector<void*> owned_dev;     // everything cudaMalloc'ed by the plan
+
+    // tunables
+    int32_t variant = 0, cols_per_block = 0, rows_per_thread = 0, ctas_per_sm = 0;
+
+    // reporting
+    int last_launches = 0;
+    std::string kernel_name;
+    int64_t alg_bytes = 0, alg_flops = 0;
+};

@@ -1,0 +1,193 @@
+// kernels_blas.cuh -- K2/K3: slab dot products and fused vector updates with device scalars.
+//
+// Replace MultiVector.__inner__ (application/egsz/multi_vector.py:147-152, per-mu np.dot summed
+// in dict order) and the copy-then-in-place vector arithmetic of linalg/vector.py:103-133 that
+// application/egsz/pcg.py:26-51 executes.  Scalars (zeta, alpha) never leave the device.
+//
+// Reductions are deterministic: a fixed grid of REDUCE_BLOCKS blocks writes one partial each;
+// the last block to finish (atomic ticket) adds the partials in index order with one warp.
+#pragma once
+#include "common.h"
+
+namespace spuq {
+
+constexpr int REDUCE_THREADS = 256;
+constexpr int REDUCE_MAX_BLOCKS = 1024;
+// scratch layout: [0, 2*REDUCE_MAX_BLOCKS) doubles of partials, then one uint32 ticket
+constexpr int64_t REDUCE_SCRATCH_BYTES = 2 * REDUCE_MAX_BLOCKS * 8 + 64;
+
+#ifndef SPUQ_EMU
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// NOUT = 1: out[0] = <x,y>;  NOUT = 2: out[0] = <x,y>, out[1] = <x,x>
+template <int NOUT>
+__global__ void __launch_bounds__(REDUCE_THREADS)
+k_dot(int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+      double* __restrict__ out, double* __restrict__ partials, unsigned int* ticket,
+      const double* gate) {
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+    double sxy = 0.0, sxx = 0.0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0;
+    if (vec) {
+        const int64_t n2 = n >> 1;
+        const double2* x2 = reinterpret_cast<const double2*>(x);
+        const double2* y2 = reinterpret_cast<const double2*>(y);
+        for (int64_t i = tid; i < n2; i += nthr) {
+            const double2 a = x2[i], b = y2[i];
+            sxy += a.x * b.x;
+            sxy += a.y * b.y;
+            if (NOUT == 2) { sxx += a.x * a.x; sxx += a.y * a.y; }
+        }
+        if ((n & 1) && tid == 0) {
+            sxy += x[n - 1] * y[n - 1];
+            if (NOUT == 2) sxx += x[n - 1] * x[n - 1];
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += nthr) {
+            sxy += x[i] * y[i];
+            if (NOUT == 2) sxx += x[i] * x[i];
+        }
+    }
+    __shared__ double sh[2][REDUCE_THREADS / 32];
+    __shared__ bool is_last;
+    sxy = warp_sum(sxy);
+    if (NOUT == 2) sxx = warp_sum(sxx);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][wid] = sxy; sh[1][wid] = sxx; }
+    __syncthreads();
+    if (wid == 0) {
+        double a = lane < REDUCE_THREADS / 32 ? sh[0][lane] : 0.0;
+        double b = lane < REDUCE_THREADS / 32 ? sh[1][lane] : 0.0;
+        a = warp_sum(a);
+        if (NOUT == 2) b = warp_sum(b);
+        if (lane == 0) {
+            partials[blockIdx.x] = a;
+            if (NOUT == 2) partials[REDUCE_MAX_BLOCKS + blockIdx.x] = b;
+            __threadfence();
+            const unsigned int done = atomicAdd(ticket, 1u);
+            is_last = (done == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (is_last && wid == 0) {
+        __threadfence();
+        double a = 0.0, b = 0.0;
+        for (int i = lane; i < (int)gridDim.x; i += 32) {
+            a += partials[i];
+            if (NOUT == 2) b += partials[REDUCE_MAX_BLOCKS + i];
+        }
+        a = warp_sum(a);
+        if (NOUT == 2) b = warp_sum(b);
+        if (lane == 0) {
+            out[0] = a;
+            if (NOUT == 2) out[1] = b;
+            *ticket = 0u;   // ready for the next reduction on this stream
+        }
+    }
+}
+#else
+template <int NOUT>
+void k_dot(int64_t n, const double* x, const double* y, double* out, double*, unsigned int*,
+           const double* gate) {
+    if (gate != nullptr && *gate != (double)SPUQ_PCG_RUNNING) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double sxy = 0.0, sxx = 0.0;
+    for (int64_t i = 0; i < n; ++i) { sxy += x[i] * y[i]; sxx += x[i] * x[i]; }
+    out[0] = sxy;
+    if (NOUT == 2) out[1] = sxx;
+}
+#endif
+
+__device__ __forceinline__ double ratio_of(double alpha, const double* num, const double* den) {
+    double a = alpha;
+    if (num) a *= __ldg(num);
+    if (den) a /= __ldg(den);
+    return a;
+}
+
+// y += a*x
+__global__ void __launch_bounds__(256)
+k_axpy(int64_t n, double alpha, const double* num, const double* den,
+       const double* __restrict__ x, double* __restrict__ y, const double* gate) {
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+    const double a = ratio_of(alpha, num, den);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n; i += nthr) y[i] += a * x[i];
+}
+
+// w += a*v ; rho -= a*z        (pcg.py:47-48, a = zeta/alpha)
+__global__ void __launch_bounds__(256)
+k_axpy2(int64_t n, const double* num, const double* den, const double* __restrict__ v,
+        double* __restrict__ w, const double* __restrict__ z, double* __restrict__ rho,
+        const double* gate) {
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+    const double a = ratio_of(1.0, num, den);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n; i += nthr) {
+        w[i] += a * v[i];
+        rho[i] -= a * z[i];
+    }
+}
+
+// v = s + b*v                  (pcg.py:51, b = zeta_new/zeta_old)
+__global__ void __launch_bounds__(256)
+k_xpay(int64_t n, const double* num, const double* den, const double* __restrict__ s,
+       double* __restrict__ v, const double* gate) {
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+    const double b = ratio_of(1.0, num, den);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n; i += nthr) v[i] = s[i] + b * v[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_scal(int64_t n, double alpha, double* __restrict__ x) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n; i += nthr) x[i] *= alpha;
+}
+
+// out = a - b   (residual rho = f - A w, pcg.py:27)
+__global__ void __launch_bounds__(256)
+k_sub(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+      double* __restrict__ out) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n; i += nthr) out[i] = a[i] - b[i];
+}
+
+// ---- PCG branch conditions evaluated on the device (one thread) --------------------------------
+// state: [0] zeta  [1] alpha  [2] zeta_new  [3] <rho,rho>  [4] status  [5] numit  [6] eps^2
+__global__ void k_pcg_check_zeta(double* st, int32_t pass, double* hist) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st[4] != (double)SPUQ_PCG_RUNNING) return;
+    const double zeta = st[0];
+    if (hist) hist[pass - 1] = zeta;
+    st[5] = (double)pass;
+    if (zeta < 0.0) st[4] = (double)SPUQ_PCG_PRECOND_NOT_PD;       // pcg.py:33-36
+    else if (zeta <= st[6]) st[4] = (double)SPUQ_PCG_CONVERGED;   // pcg.py:37-38
+}
+
+__global__ void k_pcg_check_alpha(double* st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st[4] != (double)SPUQ_PCG_RUNNING) return;
+    const double alpha = st[1];
+    if (alpha == 0.0) st[4] = (double)SPUQ_PCG_SINGULAR;          // pcg.py:42-43
+    else if (alpha < 0.0) st[4] = (double)SPUQ_PCG_NOT_PD;        // pcg.py:44-45
+}
+
+__global__ void k_pcg_rotate(double* st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st[4] != (double)SPUQ_PCG_RUNNING) return;
+    st[0] = st[2];
+}
+
+}  // namespace spuq

@@ -1,0 +1,27 @@
+// precond.h -- preconditioner handle of libspuq_sg (K4).
+#pragma once
+#include "common.h"
+
+struct spuq_sg_precond {
+    enum Kind { IDENTITY = 0, PLAN = 1, MEAN_FD = 2 } kind = IDENTITY;
+    double scale = 1.0;              // IDENTITY
+    spuq_sg_plan* plan = nullptr;    // PLAN (borrowed)
+    // MEAN_FD: A_0 = tridiag_x(ox, dxx, ox) (+) tridiag_y(oy, dyy, oy) on an nx x ny grid
+    int device = 0;
+    int32_t nx = 0, ny = 0;
+    double d = 0.0, ox = 0.0, oy = 0.0;
+    double* q_dev = nullptr;         // nx x nx sine-transform matrix (symmetric, orthogonal)
+    double* lam_dev = nullptr;       // nx eigenvalues of the x part
+    double* piv_dev = nullptr;       // nx x ny Thomas pivots of (T_y + lam_k I)
+};
+
+namespace spuq {
+int mean_fd_destroy(spuq_sg_precond* p);
+int64_t mean_fd_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L);
+int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
+                  cudaStream_t stream, const double* gate);
+int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S,
+                       void* work, cudaStream_t stream, const double* gate);
+int dot_impl(int nout, int64_t n, const double* x, const double* y, double* out, void* scratch,
+             cudaStream_t stream, const double* gate);
+}

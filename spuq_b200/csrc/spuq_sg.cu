@@ -1,0 +1,484 @@
+// spuq_sg.cu -- plan construction and launch of the SG operator application (K1) behind the C ABI
+// of include/spuq_sg.h.  Reference interface replaced: MultiOperator.__init__/apply,
+// application/egsz/multi_operator2.py:30-84.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <set>
+
+#include "common.h"
+#include "kernels_apply.cuh"
+#include "kernels_tiled.cuh"
+
+#ifdef SPUQ_EMU
+thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
+#endif
+
+namespace spuq {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count(int device) {
+#ifdef SPUQ_EMU
+    (void)device;
+    return emu_sm_count();
+#else
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+    return n;
+#endif
+}
+
+template <typename T>
+static int dev_upload(spuq_sg_plan* p, const std::vector<T>& h, T** out) {
+    *out = nullptr;
+    void* d = nullptr;
+    SPUQ_CUDA_TRY(cudaMalloc(&d, std::max<size_t>(h.size() * sizeof(T), 16)));
+    p->owned_dev.push_back(d);
+    if (!h.empty()) SPUQ_CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<T*>(d);
+    return SPUQ_OK;
+}
+
+static int dev_alloc(spuq_sg_plan* p, size_t bytes, void** out) {
+    *out = nullptr;
+    cudaError_t e = cudaMalloc(out, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return SPUQ_E_NOMEM;
+    }
+    p->owned_dev.push_back(*out);
+    return SPUQ_OK;
+}
+
+// ---- pattern analysis: is the shared CSR pattern a 3x3-window stencil on an s x ny grid? -------
+struct StencilShape {
+    bool ok = false;
+    int32_t s = 0, ny = 0;
+    bool nine = false;
+};
+
+static bool check_grid(const std::vector<int32_t>& rowptr, const std::vector<int32_t>& colidx,
+                       int64_t N, int64_t s, bool* nine) {
+    if (s < 3 || N % s != 0) return false;
+    *nine = false;
+    for (int64_t i = 0; i < N; ++i) {
+        const int64_t ix = i % s, iy = i / s;
+        for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int64_t j = colidx[k];
+            const int64_t dx = j % s - ix, dy = j / s - iy;
+            if (dx < -1 || dx > 1 || dy < -1 || dy > 1) return false;
+            if (dx != 0 && dy != 0) *nine = true;
+        }
+    }
+    return true;
+}
+
+static StencilShape analyse_pattern(const std::vector<int32_t>& rowptr,
+                                    const std::vector<int32_t>& colidx, int64_t n_rows,
+                                    int64_t n_cols) {
+    StencilShape sh;
+    if (n_rows != n_cols || n_rows < 3 || n_rows > 0x7fffffffLL) return sh;
+    const int64_t N = n_rows;
+    int64_t big = 0;   // smallest offset magnitude > 1
+    bool any_far = false;
+    for (int64_t i = 0; i < N; ++i)
+        for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            int64_t o = (int64_t)colidx[k] - i;
+            if (o < 0) o = -o;
+            if (o > 1 && (!any_far || o < big)) { big = o; any_far = true; }
+        }
+    std::vector<int64_t> cand;
+    if (!any_far) cand = {N};                   // tridiagonal: one grid row
+    else cand = {big, big + 1, big - 1};
+    for (int64_t s : cand) {
+        bool nine = false;
+        if (check_grid(rowptr, colidx, N, s, &nine)) {
+            sh.ok = true; sh.s = (int32_t)s; sh.ny = (int32_t)(N / s); sh.nine = nine;
+            return sh;
+        }
+    }
+    return sh;
+}
+
+// ---- term lists -----------------------------------------------------------------------------------
+static void build_terms(spuq_sg_plan* p, const int32_t* nbr_up, const int32_t* nbr_dn,
+                        const double* beta_up, const double* beta_dn, const double* beta_0) {
+    const int32_t L = p->L;
+    p->h_term_ptr.assign(L + 1, 0);
+    for (int32_t mu = 0; mu < L; ++mu) {
+        if (p->include_mean) {
+            p->h_term_mat.push_back(0); p->h_term_col.push_back(mu); p->h_term_coef.push_back(1.0);
+        }
+        for (int32_t m = p->m_begin; m < p->m_end; ++m) {
+            const int64_t q = (int64_t)m * L + mu;
+            // same order as the reference builds cur_w (multi_operator2.py:69-79)
+            if (beta_0 && beta_0[q] != 0.0) {
+                p->h_term_mat.push_back(1 + m); p->h_term_col.push_back(mu);
+                p->h_term_coef.push_back(-beta_0[q]);
+            }
+            if (nbr_up[q] >= 0) {
+                p->h_term_mat.push_back(1 + m); p->h_term_col.push_back(nbr_up[q]);
+                p->h_term_coef.push_back(beta_up[q]);
+            }
+            if (nbr_dn[q] >= 0) {
+                p->h_term_mat.push_back(1 + m); p->h_term_col.push_back(nbr_dn[q]);
+                p->h_term_coef.push_back(beta_dn[q]);
+            }
+        }
+        p->h_term_ptr[mu + 1] = (int32_t)p->h_term_mat.size();
+    }
+    p->n_terms = (int64_t)p->h_term_mat.size();
+}
+
+// ---- column blocks of the tiled kernel: C consecutive columns (sorted-Lambda order keeps
+// indices with a common leading part adjacent, which is what makes groups share a block matrix)
+static int build_blocks(spuq_sg_plan* p, int32_t C) {
+    const int32_t L = p->L;
+    const int32_t nblk = (L + C - 1) / C;
+    std::vector<int32_t> bcol((size_t)nblk * C, -1), bgrp(nblk + 1, 0), gmat, gterm, tcol, tacc;
+    std::vector<double> tcoef;
+    struct T { int32_t slot, col, acc; double coef; };
+    std::vector<T> ts;
+    for (int32_t b = 0; b < nblk; ++b) {
+        ts.clear();
+        for (int32_t c = 0; c < C; ++c) {
+            const int32_t mu = b * C + c;
+            if (mu >= L) break;
+            bcol[(size_t)b * C + c] = mu;
+            for (int32_t t = p->h_term_ptr[mu]; t < p->h_term_ptr[mu + 1]; ++t)
+                ts.push_back({p->slot_of_mat[p->h_term_mat[t]], p->h_term_col[t], c, p->h_term_coef[t]});
+        }
+        std::stable_sort(ts.begin(), ts.end(), [](const T& a, const T& b2) {
+            if (a.slot != b2.slot) return a.slot < b2.slot;
+            return a.col < b2.col;
+        });
+        for (size_t i = 0; i < ts.size(); ++i) {
+            if (i == 0 || ts[i].slot != ts[i - 1].slot) {
+                gmat.push_back(ts[i].slot);
+                gterm.push_back((int32_t)tcol.size());
+            }
+            tcol.push_back(ts[i].col); tacc.push_back(ts[i].acc); tcoef.push_back(ts[i].coef);
+        }
+        bgrp[b + 1] = (int32_t)gmat.size();
+    }
+    gterm.push_back((int32_t)tcol.size());
+    for (void* d : p->block_dev) cudaFree(d);
+    p->block_dev.clear();
+    p->bv = BlockView{};
+    int rc;
+    int32_t *d_bcol, *d_bgrp, *d_gmat, *d_gterm, *d_tcol, *d_tacc; double* d_tcoef;
+    const size_t first = p->owned_dev.size();
+    if ((rc = dev_upload(p, bcol, &d_bcol))) return rc;
+    if ((rc = dev_upload(p, bgrp, &d_bgrp))) return rc;
+    if ((rc = dev_upload(p, gmat, &d_gmat))) return rc;
+    if ((rc = dev_upload(p, gterm, &d_gterm))) return rc;
+    if ((rc = dev_upload(p, tcol, &d_tcol))) return rc;
+    if ((rc = dev_upload(p, tacc, &d_tacc))) return rc;
+    if ((rc = dev_upload(p, tcoef, &d_tcoef))) return rc;
+    p->block_dev.assign(p->owned_dev.begin() + first, p->owned_dev.end());
+    p->owned_dev.resize(first);
+    p->bv.C = C; p->bv.nblk = nblk;
+    p->bv.bcol = d_bcol; p->bv.bgrp = d_bgrp; p->bv.gmat = d_gmat; p->bv.gterm = d_gterm;
+    p->bv.tcol = d_tcol; p->bv.tacc = d_tacc; p->bv.tcoef = d_tcoef;
+    return SPUQ_OK;
+}
+
+
+}  // namespace spuq
+
+using namespace spuq;
+
+extern "C" const char* spuq_sg_last_error(void) { return g_err; }
+extern "C" int spuq_sg_abi_version(void) { return SPUQ_SG_ABI_VERSION; }
+
+extern "C" int spuq_sg_plan_create(spuq_sg_plan** plan_out, int device, int64_t n_rows,
+                                   int64_t n_cols, int32_t L, int32_t M,
+                                   const int32_t* rowptr_dev, const int32_t* colidx_dev,
+                                   const double* const* vals_host, const int32_t* nbr_up,
+                                   const int32_t* nbr_dn, const double* beta_up,
+                                   const double* beta_dn, const double* beta_0, int32_t m_begin,
+                                   int32_t m_end, int include_mean, int32_t flags) {
+    SPUQ_REQUIRE(plan_out != nullptr, "plan_create: plan_out is null");
+    *plan_out = nullptr;
+    SPUQ_REQUIRE(n_rows > 0 && n_cols > 0 && n_rows < 0x7fffffffLL && n_cols < 0x7fffffffLL,
+                 "plan_create: bad block shape %lld x %lld", (long long)n_rows, (long long)n_cols);
+    SPUQ_REQUIRE(L > 0 && M >= 0, "plan_create: need L > 0 and M >= 0 (got L=%d M=%d)", L, M);
+    SPUQ_REQUIRE(M == 0 || n_rows == n_cols, "plan_create: SG operator blocks must be square");
+    SPUQ_REQUIRE(rowptr_dev && colidx_dev && vals_host, "plan_create: null CSR pointer");
+    SPUQ_REQUIRE(0 <= m_begin && m_begin <= m_end && m_end <= M,
+                 "plan_create: bad shard range [%d, %d) for M=%d", m_begin, m_end, M);
+    SPUQ_REQUIRE(M == 0 || (nbr_up && nbr_dn && beta_up && beta_dn),
+                 "plan_create: neighbour / beta tables missing");
+    SPUQ_REQUIRE(!include_mean || vals_host[0], "plan_create: mean block values missing");
+    for (int32_t m = m_begin; m < m_end; ++m)
+        SPUQ_REQUIRE(vals_host[1 + m], "plan_create: values of block m=%d missing", m);
+    for (int64_t q = 0; q < (int64_t)M * L; ++q) {
+        SPUQ_REQUIRE(nbr_up[q] >= -1 && nbr_up[q] < L && nbr_dn[q] >= -1 && nbr_dn[q] < L,
+                     "plan_create: neighbour table entry %lld out of range", (long long)q);
+    }
+
+    SPUQ_CUDA_TRY(cudaSetDevice(device));
+    spuq_sg_plan* p = new spuq_sg_plan();
+    struct Guard { spuq_sg_plan* p; ~Guard() { if (p) spuq_sg_plan_destroy(p); } } guard{p};
+    p->device = device; p->n_rows = n_rows; p->n_cols = n_cols; p->L = L; p->M = M;
+    p->m_begin = m_begin; p->m_end = m_end; p->include_mean = include_mean ? 1 : 0;
+    p->rowptr = rowptr_dev; p->colidx = colidx_dev;
+    p->vals_host.assign(vals_host, vals_host + M + 1);
+    p->n_sm = sm_count(device);
+
+    // pattern to the host for analysis
+    std::vector<int32_t> h_rowptr(n_rows + 1);
+    SPUQ_CUDA_TRY(cudaMemcpy(h_rowptr.data(), rowptr_dev, sizeof(int32_t) * (n_rows + 1), cudaMemcpyDeviceToHost));
+    SPUQ_REQUIRE(h_rowptr[0] == 0, "plan_create: rowptr[0] must be 0");
+    p->nnz = h_rowptr[n_rows];
+    for (int64_t i = 0; i < n_rows; ++i) {
+        SPUQ_REQUIRE(h_rowptr[i + 1] >= h_rowptr[i], "plan_create: rowptr not monotone at row %lld", (long long)i);
+        p->max_row_nnz = std::max(p->max_row_nnz, h_rowptr[i + 1] - h_rowptr[i]);
+    }
+    std::vector<int32_t> h_colidx((size_t)p->nnz);
+    if (p->nnz) SPUQ_CUDA_TRY(cudaMemcpy(h_colidx.data(), colidx_dev, sizeof(int32_t) * p->nnz, cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < p->nnz; ++k)
+        SPUQ_REQUIRE(h_colidx[k] >= 0 && h_colidx[k] < n_cols, "plan_create: column index out of range at %lld", (long long)k);
+
+    // owned blocks -> compact slots
+    p->slot_of_mat.assign(M + 1, -1);
+    if (p->include_mean) p->slot_of_mat[0] = p->n_slots++;
+    for (int32_t m = m_begin; m < m_end; ++m) p->slot_of_mat[1 + m] = p->n_slots++;
+
+    build_terms(p, nbr_up, nbr_dn, beta_up, beta_dn, beta_0);
+    int rc;
+    if ((rc = dev_upload(p, p->h_term_ptr, &p->term_ptr))) return rc;
+    if ((rc = dev_upload(p, p->h_term_mat, &p->term_mat))) return rc;
+    if ((rc = dev_upload(p, p->h_term_col, &p->term_col))) return rc;
+    if ((rc = dev_upload(p, p->h_term_coef, &p->term_coef))) return rc;
+    {
+        std::vector<const double*> ptrs(p->vals_host);
+        const double** d = nullptr;
+        if ((rc = dev_upload(p, ptrs, const_cast<const double***>(&d)))) return rc;
+        p->vals_ptrs_dev = d;
+    }
+    int32_t* d_slot = nullptr;
+    if ((rc = dev_upload(p, p->slot_of_mat, &d_slot))) return rc;
+
+    // reporting numbers: compulsory bytes, non-trivial flops
+    {
+        std::set<int32_t> active;
+        for (int32_t mat : p->h_term_mat) active.insert(mat);
+        p->alg_bytes = 8 * (n_cols + n_rows) * (int64_t)L + 8 * p->nnz * (int64_t)active.size()
+                       + 4 * p->nnz + 4 * (n_rows + 1) + (int64_t)(m_end - m_begin) * L * (2 * 4 + 3 * 8);
+        p->alg_flops = 2 * p->nnz * p->n_terms;
+    }
+
+    // ---- choose the path -----------------------------------------------------------------------
+    const int32_t want = flags & SPUQ_PATH_MASK;
+    StencilShape sh;
+    if (want == SPUQ_PATH_AUTO || want == SPUQ_PATH_STENCIL) sh = analyse_pattern(h_rowptr, h_colidx, n_rows, n_cols);
+    if (want == SPUQ_PATH_STENCIL && !sh.ok) {
+        set_error("plan_create: pattern is not a 3x3-window grid stencil; stencil path unavailable");
+        return SPUQ_E_UNSUPPORTED;
+    }
+    const bool ell_ok = p->max_row_nnz <= 64 &&
+                        ((int64_t)p->max_row_nnz * n_rows <= 3 * p->nnz || (int64_t)p->max_row_nnz * n_rows <= (1 << 20));
+    if (want == SPUQ_PATH_ELL && !ell_ok) {
+        set_error("plan_create: ELL padding too large (max row nnz %d)", p->max_row_nnz);
+        return SPUQ_E_UNSUPPORTED;
+    }
+    if (want == SPUQ_PATH_CSR) p->path = SPUQ_PATH_CSR;
+    else if (want == SPUQ_PATH_ELL) p->path = SPUQ_PATH_ELL;
+    else if (sh.ok) p->path = SPUQ_PATH_STENCIL;
+    else p->path = ell_ok ? SPUQ_PATH_ELL : SPUQ_PATH_CSR;
+
+    const int threads = 128;
+    const unsigned row_blocks = (unsigned)((n_rows + threads - 1) / threads);
+    if (p->path == SPUQ_PATH_ELL) {
+        const int32_t K = std::max(p->max_row_nnz, 1);
+        p->ell_K = K;
+        void* d;
+        if ((rc = dev_alloc(p, sizeof(int32_t) * (size_t)K * n_rows, &d))) return rc;
+        p->ell_cols = static_cast<int32_t*>(d);
+        if ((rc = dev_alloc(p, sizeof(double) * (size_t)p->n_slots * K * n_rows, &d))) return rc;
+        p->ell_vals = static_cast<double*>(d);
+        bool cols_done = false;
+        for (int32_t mat = 0; mat <= M; ++mat) {
+            if (p->slot_of_mat[mat] < 0) continue;
+            double* dst = p->ell_vals + (size_t)p->slot_of_mat[mat] * K * n_rows;
+            SPUQ_LAUNCH(k_csr_to_ell, dim3(row_blocks), dim3(threads), 0, 0, n_rows, K, rowptr_dev, colidx_dev,
+                        p->vals_host[mat], cols_done ? (int32_t*)nullptr : p->ell_cols, dst);
+            cols_done = true;
+        }
+        if (!cols_done)
+            SPUQ_LAUNCH(k_csr_to_ell, dim3(row_blocks), dim3(threads), 0, 0, n_rows, K, rowptr_dev, colidx_dev,
+                        (const double*)nullptr, p->ell_cols, (double*)nullptr);
+        SPUQ_CUDA_TRY(cudaGetLastError());
+        SPUQ_CUDA_TRY(cudaDeviceSynchronize());
+    } else if (p->path == SPUQ_PATH_STENCIL) {
+        StencilView& st = p->st;
+        st.s = sh.s; st.N = n_rows;
+        st.D = sh.nine ? 9 : 5;
+        int d = 0;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (!sh.nine && dx != 0 && dy != 0) continue;
+                st.dx[d] = dx; st.dy[d] = dy; st.off[d] = dx + sh.s * dy;
+                ++d;
+            }
+        void* dv;
+        if ((rc = dev_alloc(p, sizeof(double) * (size_t)p->n_slots * st.D * n_rows, &dv))) return rc;
+        p->dia_vals = static_cast<double*>(dv);
+        st.vals = p->dia_vals;
+        for (int32_t mat = 0; mat <= M; ++mat) {
+            if (p->slot_of_mat[mat] < 0) continue;
+            double* dst = p->dia_vals + (size_t)p->slot_of_mat[mat] * st.D * n_rows;
+            SPUQ_LAUNCH(k_csr_to_dia, dim3(row_blocks), dim3(threads), 0, 0, st, rowptr_dev, colidx_dev,
+                        p->vals_host[mat], dst);
+        }
+        SPUQ_CUDA_TRY(cudaGetLastError());
+        SPUQ_CUDA_TRY(cudaDeviceSynchronize());
+    }
+    p->slot_dev = d_slot;
+    p->ny = sh.ok ? sh.ny : 0;
+    p->nine = sh.nine;
+    guard.p = nullptr;
+    *plan_out = p;
+    return SPUQ_OK;
+}
+
+extern "C" int spuq_sg_plan_destroy(spuq_sg_plan* p) {
+    if (!p) return SPUQ_OK;
+    cudaSetDevice(p->device);
+    for (void* d : p->block_dev) cudaFree(d);
+    for (void* d : p->owned_dev) cudaFree(d);
+    delete p;
+    return SPUQ_OK;
+}
+
+extern "C" int spuq_sg_plan_info(const spuq_sg_plan* p, int32_t* path, int64_t* n_terms,
+                                 int64_t* nnz, int64_t* alg_bytes, int64_t* alg_flops) {
+    SPUQ_REQUIRE(p != nullptr, "plan_info: null plan");
+    if (path) *path = p->path;
+    if (n_terms) *n_terms = p->n_terms;
+    if (nnz) *nnz = p->nnz;
+    if (alg_bytes) *alg_bytes = p->alg_bytes;
+    if (alg_flops) *alg_flops = p->alg_flops;
+    return SPUQ_OK;
+}
+
+extern "C" int spuq_sg_plan_tune(spuq_sg_plan* p, int32_t variant, int32_t cols_per_block,
+                                 int32_t rows_per_thread, int32_t ctas_per_sm) {
+    SPUQ_REQUIRE(p != nullptr, "plan_tune: null plan");
+    SPUQ_REQUIRE(variant >= 0 && variant <= 2, "plan_tune: variant must be 0 (auto), 1 (simple) or 2 (tiled)");
+    p->variant = variant; p->cols_per_block = cols_per_block;
+    p->rows_per_thread = rows_per_thread; p->ctas_per_sm = ctas_per_sm;
+    return SPUQ_OK;
+}
+
+extern "C" int spuq_sg_plan_last_launches(const spuq_sg_plan* p) { return p ? p->last_launches : 0; }
+extern "C" const char* spuq_sg_plan_kernel_name(const spuq_sg_plan* p) { return p ? p->kernel_name.c_str() : ""; }
+
+namespace spuq {
+
+static int32_t pick_cols_per_cta(const spuq_sg_plan* p, int64_t row_blocks) {
+    const int64_t target = 16LL * p->n_sm;
+    int64_t cpc = row_blocks * p->L / target;
+    if (cpc < 1) cpc = 1;
+    if (cpc > 16) cpc = 16;
+    return (int32_t)cpc;
+}
+
+template <int RY, int C, bool NINE>
+static void launch_tiled(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t ldy,
+                         cudaStream_t stream, const double* gate) {
+    using Cfg = TiledCfg<RY, C, NINE>;
+    const int32_t ntx = (p->st.s + Cfg::TILE_X - 1) / Cfg::TILE_X;
+    const int32_t nty = (p->ny + Cfg::TILE_Y - 1) / Cfg::TILE_Y;
+    const int64_t items = (int64_t)ntx * nty * p->bv.nblk;
+    SPUQ_LAUNCH((k_apply_tiled<RY, C, NINE>), dim3((unsigned)items), dim3(Cfg::THREADS), 0, stream,
+                p->st, p->bv, p->ny, ntx, nty, W, ldw, Y, ldy, gate);
+    char name[64];
+    snprintf(name, sizeof(name), "k_apply_tiled<RY=%d,C=%d,%s>", RY, C, NINE ? "9pt" : "5pt");
+    p->kernel_name = name;
+}
+
+int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t ldy,
+               cudaStream_t stream, const double* gate) {
+    SPUQ_REQUIRE(p && W && Y, "apply: null argument");
+    SPUQ_REQUIRE(ldw >= p->n_cols && ldy >= p->n_rows, "apply: leading dimension too small");
+    SPUQ_REQUIRE(W != Y, "apply: input and output slab must not alias");
+    p->last_launches = 0;
+    const TermView tv{p->term_ptr, p->term_mat, p->term_col, p->term_coef};
+    const int threads = 128;
+    if (p->path == SPUQ_PATH_CSR || p->path == SPUQ_PATH_ELL) {
+        const int64_t row_blocks = (p->n_rows + threads - 1) / threads;
+        const int32_t cpc = p->cols_per_block > 0 ? p->cols_per_block : pick_cols_per_cta(p, row_blocks);
+        const dim3 grid((unsigned)row_blocks, (unsigned)((p->L + cpc - 1) / cpc));
+        SPUQ_REQUIRE(grid.y <= 65535u, "apply: too many column chunks (%u); raise cols_per_block", grid.y);
+        if (p->path == SPUQ_PATH_CSR) {
+            SPUQ_LAUNCH(k_apply_csr, grid, dim3(threads), 0, stream, p->n_rows, p->L, p->rowptr, p->colidx,
+                        p->vals_ptrs_dev, tv, W, ldw, Y, ldy, cpc, gate);
+            p->kernel_name = "k_apply_csr";
+        } else if (p->ell_K <= 8) {
+            SPUQ_LAUNCH((k_apply_ell<8>), grid, dim3(threads), 0, stream, p->n_rows, p->L, p->ell_K, p->ell_cols,
+                        p->ell_vals, p->slot_dev, tv, W, ldw, Y, ldy, cpc, gate);
+            p->kernel_name = "k_apply_ell<8>";
+        } else {
+            SPUQ_LAUNCH((k_apply_ell<0>), grid, dim3(threads), 0, stream, p->n_rows, p->L, p->ell_K, p->ell_cols,
+                        p->ell_vals, p->slot_dev, tv, W, ldw, Y, ldy, cpc, gate);
+            p->kernel_name = "k_apply_ell<0>";
+        }
+    } else {
+        const bool aligned = (p->st.s % 2 == 0) && (ldw % 2 == 0) && (ldy % 2 == 0) &&
+                             (((uintptr_t)W | (uintptr_t)Y) & 15) == 0;
+        SPUQ_REQUIRE(p->variant != 2 || aligned,
+                     "apply: tiled stencil kernel needs an even grid width, even leading dimensions and 16-byte aligned slabs");
+        const bool tiled = p->variant == 2 || (p->variant == 0 && aligned);
+        if (!tiled) {
+            const int64_t pair_blocks = ((p->n_rows + 1) / 2 + threads - 1) / threads;
+            const int32_t cpc = p->cols_per_block > 0 ? p->cols_per_block : pick_cols_per_cta(p, pair_blocks);
+            const dim3 grid((unsigned)pair_blocks, (unsigned)((p->L + cpc - 1) / cpc));
+            SPUQ_REQUIRE(grid.y <= 65535u, "apply: too many column chunks (%u); raise cols_per_block", grid.y);
+            SPUQ_LAUNCH(k_apply_stencil_simple, grid, dim3(threads), 0, stream, p->L, p->st, p->slot_dev, tv,
+                        W, ldw, Y, ldy, cpc, gate);
+            p->kernel_name = "k_apply_stencil_simple";
+        } else {
+            int32_t RY = p->rows_per_thread > 0 ? p->rows_per_thread : 2;
+            int32_t C = p->cols_per_block > 0 ? p->cols_per_block : (RY == 4 ? 4 : 8);
+            if (p->bv.bcol == nullptr || p->bv.C != C) {
+                int rc = build_blocks(p, C);
+                if (rc) return rc;
+            }
+            const bool nine = p->nine;
+#define SPUQ_TILED(ry, c)                                                                  \
+    if (RY == ry && C == c) {                                                              \
+        if (nine) launch_tiled<ry, c, true>(p, W, ldw, Y, ldy, stream, gate);              \
+        else launch_tiled<ry, c, false>(p, W, ldw, Y, ldy, stream, gate);                  \
+    } else
+            SPUQ_TILED(1, 8) SPUQ_TILED(1, 16) SPUQ_TILED(2, 4) SPUQ_TILED(2, 8) SPUQ_TILED(2, 16)
+            SPUQ_TILED(4, 4) SPUQ_TILED(4, 8)
+            {
+                set_error("apply: no tiled kernel instantiated for rows_per_thread=%d cols_per_block=%d", RY, C);
+                return SPUQ_E_UNSUPPORTED;
+            }
+#undef SPUQ_TILED
+        }
+    }
+    p->last_launches = 1;
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+
+}  // namespace spuq
+
+extern "C" int spuq_sg_apply(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t ldy,
+                             void* stream) {
+    SPUQ_REQUIRE(p != nullptr, "apply: null plan");
+    SPUQ_CUDA_TRY(cudaSetDevice(p->device));
+    return apply_impl(p, W, ldw, Y, ldy, static_cast<cudaStream_t>(stream), nullptr);
+}

@@ -1,0 +1,154 @@
+"""Deterministic synthetic inputs for the SG operator.
+
+The reference assembles its spatial blocks with FEniCS, which is not available; what it needs from
+an assembly is only a callback ``(basis, coeff) -> Operator``.  This module supplies such blocks for
+the model problem of the reference's sample set-ups (spuq/application/egsz/sample_problems2.py):
+
+  * domain: unit square, homogeneous Dirichlet boundary, uniform n x n grid of interior unknowns,
+    rows ordered i = iy*n + ix;
+  * discretisation: 5-point finite-difference / lumped-P1 stiffness with face-averaged coefficient,
+    all blocks on ONE shared CSR pattern;
+  * coefficient: mean a_0 = 1 and  a_m(x) = A_m cos(pi k1 x1) cos(pi k2 x2)
+    (sample_problems2.py:36), (k1, k2) the (m+1)-th pair of the 2-D complete-order generator
+    (freqskip = 0, :201-203), amplitude A_m = amp / (m + start)^decay with decay = 2, gamma = 0.9
+    and start / amp from the zeta rule (:164-169, :184-187), which keeps the operator SPD.
+
+Everything is written with torch so the same code builds small cases on the host (for the oracle
+and the parity tests) and the benchmark-size cases directly in HBM.
+"""
+import math
+from itertools import islice
+
+import numpy as np
+import scipy.sparse as sps
+import torch
+from scipy.special import zeta as _hurwitz_zeta
+
+from .multiindex import MultiindexSet
+from .lambda_tables import sort_permutation
+from .random_variable import NormalRV, UniformRV
+
+__all__ = ["kl_frequencies", "kl_amplitudes", "fd_pattern", "fd_values", "fd_blocks",
+           "complete_order_indices", "anisotropic_indices", "truncated_complete_indices",
+           "make_rvs", "blocks_to_scipy"]
+
+
+def kl_frequencies(M):
+    """(k1, k2) of terms 0..M-1: the 2-D complete-order sequence without its first element (0,0)."""
+    gen = MultiindexSet.createCompleteOrderSet(2)
+    next(gen)
+    return [(int(mu[0]), int(mu[1])) for mu in islice(gen, M)]
+
+
+def kl_amplitudes(M, gamma=0.9, decay=2.0):
+    """A_m = amp / (m + start)^decay, with start the smallest integer such that
+    zeta(decay, start) < gamma and amp = gamma / zeta(decay, start)."""
+    start = 1
+    while _hurwitz_zeta(decay, start) >= gamma:
+        start += 1
+    amp = gamma / _hurwitz_zeta(decay, start)
+    return [float(amp / (float(m) + start) ** decay) for m in range(M)]
+
+
+def fd_pattern(n, device="cpu"):
+    """Shared CSR pattern of the 5-point stencil on an n x n grid (columns ascending in a row).
+    Returns (rowptr int32 [N+1], colidx int32 [nnz], valid mask [N, 5])."""
+    N = n * n
+    i = torch.arange(N, device=device, dtype=torch.int64)
+    ix, iy = i % n, i // n
+    cols = torch.stack([i - n, i - 1, i, i + 1, i + n], dim=1)
+    valid = torch.stack([iy > 0, ix > 0, torch.ones_like(ix, dtype=torch.bool), ix < n - 1, iy < n - 1], dim=1)
+    counts = valid.sum(dim=1)
+    rowptr = torch.zeros(N + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(counts, 0)
+    colidx = cols[valid]
+    return rowptr.to(torch.int32), colidx.to(torch.int32), valid
+
+
+def fd_values(a_nodal, valid):
+    """Stencil values on the shared pattern for a coefficient given at the (n+2) x (n+2) grid nodes
+    (boundary ring included): off-diagonals are minus the face average, the diagonal is the sum of
+    the four face coefficients (Dirichlet neighbours eliminated)."""
+    c = a_nodal[1:-1, 1:-1]
+    cs = 0.5 * (c + a_nodal[:-2, 1:-1])     # face towards iy-1
+    cn = 0.5 * (c + a_nodal[2:, 1:-1])      # face towards iy+1
+    cw = 0.5 * (c + a_nodal[1:-1, :-2])     # face towards ix-1
+    ce = 0.5 * (c + a_nodal[1:-1, 2:])      # face towards ix+1
+    vals = torch.stack([-cs, -cw, cs + cw + ce + cn, -ce, -cn], dim=2).reshape(-1, 5)
+    return vals[valid]
+
+
+def _coefficient(n, k1, k2, amp, device, dtype=torch.float64):
+    x = torch.linspace(0.0, 1.0, n + 2, device=device, dtype=dtype)
+    cx = torch.cos(math.pi * k1 * x)
+    cy = torch.cos(math.pi * k2 * x)
+    return amp * cy[:, None] * cx[None, :]          # [iy, ix]: x1 runs along ix
+
+
+def fd_blocks(n, M, device="cpu", gamma=0.9, decay=2.0, mean=1.0):
+    """rowptr, colidx, vals[(M+1), nnz]: block 0 is the mean block, block 1+m the m-th term."""
+    rowptr, colidx, valid = fd_pattern(n, device)
+    vals = torch.empty((M + 1, colidx.numel()), dtype=torch.float64, device=device)
+    vals[0] = fd_values(torch.full((n + 2, n + 2), float(mean), dtype=torch.float64, device=device), valid)
+    amps = kl_amplitudes(M, gamma, decay)
+    for m, (k1, k2) in enumerate(kl_frequencies(M)):
+        vals[1 + m] = fd_values(_coefficient(n, k1, k2, amps[m], device), valid)
+    return rowptr, colidx, vals
+
+
+def blocks_to_scipy(rowptr, colidx, vals, n_rows):
+    """Host scipy CSR matrices of the blocks (for the oracle and for assemble callbacks)."""
+    rp = rowptr.cpu().numpy().astype(np.int32)
+    ci = colidx.cpu().numpy().astype(np.int32)
+    v = vals.cpu().numpy()
+    return [sps.csr_matrix((v[k].copy(), ci, rp), shape=(n_rows, n_rows)) for k in range(v.shape[0])]
+
+
+# ---- index sets -----------------------------------------------------------------------------------
+def _sorted(arr):
+    arr = np.ascontiguousarray(arr, dtype=np.int32)
+    return np.ascontiguousarray(arr[sort_permutation(arr)])
+
+
+def complete_order_indices(M, p):
+    """All mu in N^M with |mu| <= p, in active_indices() order."""
+    return _sorted(MultiindexSet.createCompleteOrderSet(M, p).arr)
+
+
+def truncated_complete_indices(M, p, L):
+    """First L indices of the sorted complete-order set (a prefix of a graded order is
+    downward closed)."""
+    arr = complete_order_indices(M, p)
+    assert L <= arr.shape[0]
+    return np.ascontiguousarray(arr[:L])
+
+
+def anisotropic_indices(M, T):
+    """Downward-closed anisotropic set {mu : sum_m mu_m * 2 ln(m+2) <= T}."""
+    w = [2.0 * math.log(m + 2.0) for m in range(M)]
+    out = []
+    cur = [0] * M
+
+    def rec(m, budget):
+        if m == M:
+            out.append(list(cur))
+            return
+        k = 0
+        while k * w[m] <= budget + 1e-12:
+            cur[m] = k
+            rec(m + 1, budget - k * w[m])
+            k += 1
+        cur[m] = 0
+
+    rec(0, float(T))
+    return _sorted(np.array(out, dtype=np.int32))
+
+
+def make_rvs(kind, M, mu=0.0):
+    if kind == "legendre":
+        rv = UniformRV(-1, 1)
+    elif kind == "hermite":
+        rv = NormalRV(mu, 1)
+    else:
+        raise ValueError("unknown polynomial family %r" % kind)
+    return [rv] * M
