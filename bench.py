@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- SG operator apply throughput (GDoF/s = N*|Lambda| per apply) on 1..8 B200.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line on rank 0.  A step is one application y = A w of the stochastic-Galerkin operator to one slab.
+
+  value      whole-job GDoF/s with the input slab already resident in HBM (CUDA events, max over
+             ranks, barrier + synchronize on both sides)
+  e2e        same metric through the public API with HOST buffers: pinned host slab -> H2D ->
+             MultiOperator kernel -> D2H of the result, every step
+  roofline   algorithmic (compulsory) bytes of one apply / kernel time vs the measured HBM peak
+  cpu_baseline  the oracle port of the reference's CPU path (dict of vectors, one scipy SpMV per
+             (mu, m)) timed on a bounded sample of output columns of the same workload
+  --impl reference   times that CPU path as the main line (the reference itself is Python 2 and
+             cannot be imported here)
+
+Workloads (BASELINE.json configs, synthetic inputs of SURVEY.md 8d):
+  c3  (default) 1000 x 1000 grid (N = 10^6), M = 50, anisotropic Lambda with 988 indices, Hermite
+      chaos -- the configuration the headline target (N = 1M x |Lambda| = 1000) is quoted on
+  c2  512 x 512 grid, M = 20, total degree 3 (1771 indices), Legendre
+  c4  500 x 500 grid, M = 30, first 5000 indices of the degree-3 set, Legendre
+  c1  32 x 32 grid, M = 5, total degree 2 (21 indices): the reference's CPU-runnable case
+Multi-GPU (N > 1): the M expansion terms are sharded over the ranks (balanced by term count), every
+rank applies its terms to a full replica of w and the partial results are combined with an NCCL
+reduce-scatter along the Lambda (column) axis; total work is fixed => "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "c1": dict(n=32, M=5, lam=("td", 5, 2), kind="legendre", mu=0.0),
+    "c2": dict(n=512, M=20, lam=("td", 20, 3), kind="legendre", mu=0.0),
+    "c3": dict(n=1000, M=50, lam=("aniso", 50, 11.3), kind="hermite", mu=0.0),
+    "c4": dict(n=500, M=30, lam=("prefix", 30, 3, 5000), kind="legendre", mu=0.0),
+}
+
+
+def workload_name(key):
+    c = CONFIGS[key]
+    lam = c["lam"]
+    if lam[0] == "td":
+        ls = "total-degree-%d Lambda" % lam[2]
+    elif lam[0] == "aniso":
+        ls = "anisotropic downward-closed Lambda (T=%s)" % lam[2]
+    else:
+        ls = "first %d indices of the degree-%d set" % (lam[3], lam[2])
+    return "%s: 2D diffusion %dx%d FD grid (N=%d), M=%d, %s, %s chaos" % (
+        key, c["n"], c["n"], c["n"] ** 2, c["M"], ls, c["kind"])
+
+
+def index_set(cfg):
+    from spuq_b200 import synthetic
+    lam = cfg["lam"]
+    if lam[0] == "td":
+        return synthetic.complete_order_indices(lam[1], lam[2])
+    if lam[0] == "aniso":
+        return synthetic.anisotropic_indices(lam[1], lam[2])
+    return synthetic.truncated_complete_indices(lam[1], lam[2], lam[3])
+
+
+# ---- clocks ----------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---- CPU path (oracle port of the reference) ------------------------------------------------------
+class CpuReference:
+    """The reference-faithful CPU path on a sample of output columns.
+
+    The reference's apply is a loop over mu (multi_operator2.py:52-83); output column mu costs one
+    leaf apply of A_0 plus, for every m < maxm, the vector combination and one leaf apply of A_m,
+    independently of all other columns, so the time of a sample of columns extrapolates linearly
+    to |Lambda|.  The timed loop is oracle.sg.MultiOperator.apply restricted to the sampled
+    columns (``only=``): dict-of-vectors MultiVector, Multiindex `in Lambda` scans, one scipy SpMV
+    per (mu, m), cached CSR leaves -- single-threaded, as the reference is."""
+
+    def __init__(self, cfg, n_cols, seed=1234):
+        import numpy as np
+        from oracle import linalg as olin, multiindex as omi, polys as opolys, sg as osg
+        from spuq_b200 import synthetic, lambda_tables
+        n, M = cfg["n"], cfg["M"]
+        self.N = N = n * n
+        idx = index_set(cfg)
+        self.L = L = idx.shape[0]
+        rowptr, colidx, vals = synthetic.fd_blocks(n, M)
+        mats = synthetic.blocks_to_scipy(rowptr, colidx, vals, N)
+        rv = opolys.UniformRV(-1, 1) if cfg["kind"] == "legendre" else opolys.NormalRV(cfg["mu"], 1)
+        cf = osg.ListCoefficientField("mean", list(range(M)), [rv] * M)
+        basis = olin.CanonicalBasis(N)
+        leaves = {}
+
+        def assemble(b, f):
+            k = 0 if f == "mean" else 1 + f
+            if k not in leaves:
+                leaves[k] = olin.ScipyOperator(mats[k], b, b)
+            return leaves[k]
+
+        self.A = osg.MultiOperator(cf, assemble)
+        pick = np.unique(np.linspace(0, L - 1, min(n_cols, L)).astype(int))
+        up, dn = lambda_tables.neighbour_tables(idx)
+        touched = set(int(k) for k in pick)
+        for k in pick:
+            touched.update(int(v) for v in up[:, k] if v >= 0)
+            touched.update(int(v) for v in dn[:, k] if v >= 0)
+        rng = np.random.RandomState(seed)
+        shared = olin.FlatVector(np.zeros(N), basis)     # untouched columns share one zero vector
+        keys = [omi.Multiindex(r.astype(np.int64)) for r in idx]
+        self.w = osg.MultiVector()
+        for k, mu in enumerate(keys):
+            self.w[mu] = olin.FlatVector(rng.random_sample(N), basis) if k in touched else shared
+        Lambda = self.w.active_indices()
+        self.only = [Lambda[k] for k in pick]
+        self.n_cols = len(pick)
+
+    def run(self):
+        """(GDoF/s, seconds) for one pass over the sampled columns."""
+        t0 = time.perf_counter()
+        self.A.apply(self.w, only=self.only)
+        dt = time.perf_counter() - t0
+        return self.N * self.n_cols / dt / 1e9, dt
+
+
+# ---- GPU arm ----------------------------------------------------------------------------------------
+def shard_ranges(tables, M, G):
+    """Contiguous m-ranges per rank balanced by term count (the mean block's L terms go to rank 0)."""
+    import numpy as np
+    w = np.array([(tables.nbr_up[m] >= 0).sum() + (tables.nbr_dn[m] >= 0).sum()
+                  + (tables.beta_0[m] != 0).sum() for m in range(M)], dtype=np.float64)
+    total = w.sum() + tables.L
+    target = total / G
+    ranges, lo, acc = [], 0, float(tables.L)
+    for g in range(G):
+        hi = lo
+        if g == G - 1:
+            hi = M
+        else:
+            while hi < M and acc + w[hi] / 2 <= target * (g + 1):
+                acc += w[hi]; hi += 1
+        ranges.append((lo, hi))
+        lo = hi
+    return ranges
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import spuq_b200 as sp
+    from spuq_b200 import _abi, synthetic, lambda_tables
+    from spuq_b200.multi_operator import DeviceBlocks
+    dev = _abi.device()
+    cfg = CONFIGS[args.config]
+    n, M = cfg["n"], cfg["M"]
+    N = n * n
+    idx = index_set(cfg)
+    L = idx.shape[0]
+    rvs = synthetic.make_rvs(cfg["kind"], M, cfg["mu"])
+    tables = lambda_tables.LambdaTables(idx, rvs)
+
+    rowptr, colidx, vals = synthetic.fd_blocks(n, M, device=dev)
+    blocks = DeviceBlocks(rowptr, colidx, vals, (N, N))
+    if world > 1:
+        ranges = shard_ranges(tables, M, world)
+        A = sp.MultiOperator.from_blocks(blocks, rvs, m_range=ranges[rank], include_mean=(rank == 0))
+    else:
+        A = sp.MultiOperator.from_blocks(blocks, rvs)
+    Lp = ((L + world - 1) // world) * world                 # pad columns for equal reduce-scatter shares
+    g = torch.Generator(device=dev); g.manual_seed(1234)
+    Wt = torch.rand((L, N), dtype=torch.float64, device=dev, generator=g)
+    w = sp.SlabMultiVector(idx, slab=Wt, _sorted=True)
+    plan = A.plan_for(w)
+    if args.variant or args.cols or args.rows:
+        plan.tune(args.variant, args.cols, args.rows, 0)
+    Yfull = torch.zeros((Lp, N), dtype=torch.float64, device=dev)
+    Yown = torch.empty((Lp // world, N), dtype=torch.float64, device=dev) if world > 1 else None
+    info = plan.info()
+
+    def step():
+        plan.apply(Wt, Yfull[:L])
+        if world > 1:
+            dist.reduce_scatter_tensor(Yown, Yfull, op=dist.ReduceOp.SUM)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record()
+    for k in range(args.steps):
+        kev[k][0].record()
+        plan.apply(Wt, Yfull[:L])
+        kev[k][1].record()
+        if world > 1:
+            dist.reduce_scatter_tensor(Yown, Yfull, op=dist.ReduceOp.SUM)
+    ev1.record()
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    launches = args.steps * plan.last_launches
+
+    # ---- e2e: host buffers through the public operator API, H2D + kernel + D2H every step -------
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        h_in = torch.empty((L, N), dtype=torch.float64, pin_memory=True)
+        h_out = torch.empty((Lp // world if world > 1 else L, N), dtype=torch.float64, pin_memory=True)
+        h_in.copy_(Wt)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            Wt.copy_(h_in, non_blocking=True)                     # H2D of this step's input slab
+            y = A.apply(w)                                        # public API: MultiOperator.apply
+            if world > 1:
+                Yfull[:L].copy_(y.slab)
+                dist.reduce_scatter_tensor(Yown, Yfull, op=dist.ReduceOp.SUM)
+                h_out.copy_(Yown, non_blocking=True)
+            else:
+                h_out.copy_(y.slab, non_blocking=True)            # D2H of the result
+            return y
+
+        e2e_step(); barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te[0]) / e2e_steps
+        e2e = {"value": N * L / (e2e_ms * 1e-3) / 1e9, "unit": "GDoF/s", "steps": e2e_steps,
+               "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h_in.numel() * 8),
+               "d2h_bytes_per_step": int(h_out.numel() * 8)}
+        launches += e2e_steps * plan.last_launches
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    achieved = info["algorithmic_bytes"] / (kernel_ms * 1e-3) / 1e9
+    out = {
+        "metric": "SG operator apply throughput (N*|Lambda| per apply)",
+        "value": N * L / (ms_per_step * 1e-3) / 1e9, "unit": "GDoF/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config), "N": N, "L": L, "M": M,
+                   "n_terms": info["n_terms"], "nnz_per_block": info["nnz"],
+                   "parallelism": ("M-sharded x%d + NCCL reduce-scatter over Lambda" % world) if world > 1 else "1 GPU",
+                   "l2_note": "input slab %.1f GB >> 126 MB L2, no flush needed" % (N * L * 8 / 1e9),
+                   "kernel": plan.kernel_name, "path": info["path"]},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": info["algorithmic_bytes"], "kernel_ms": kernel_ms,
+                     "fp64_gflops": info["algorithmic_flops"] / (kernel_ms * 1e-3) / 1e9},
+        "clocks": clocks, "gpu_launches": launches,
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        ref = CpuReference(cfg, args.cpu_cols)
+        v, secs = ref.run()
+        ncols = ref.n_cols
+        out["cpu_baseline"] = {"value": v, "unit": "GDoF/s", "cores": 1, "kind": "port",
+                               "sample": "%d of %d output columns of the same workload through the oracle port of "
+                                         "MultiOperator.apply (cached scipy CSR leaves, one SpMV per (mu, m)); "
+                                         "%.1f s; per-column cost is independent of the other columns" % (ncols, L, secs),
+                               "host_cpus": os.cpu_count()}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]
+    ref = CpuReference(cfg, args.ref_cols)
+    N, L, ncols = ref.N, ref.L, ref.n_cols
+    secs = []
+    for k in range(args.warmup + args.steps):
+        _, s = ref.run()
+        if k >= args.warmup:
+            secs.append(s)
+    ms = statistics.mean(secs) * 1e3 * (L / ncols)          # one full apply, extrapolated linearly in L
+    value = N * L / (ms * 1e-3) / 1e9
+    out = {"impl": "reference", "metric": "SG operator apply throughput (N*|Lambda| per apply)",
+           "value": value, "unit": "GDoF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(args.config), "N": N, "L": L, "M": cfg["M"]},
+           "cpu_baseline": {"value": value, "unit": "GDoF/s", "cores": 1, "kind": "port",
+                            "sample": "each step = %d of %d output columns through the oracle port of the reference's "
+                                      "MultiOperator.apply (single-threaded Python + scipy SpMV, as the reference); "
+                                      "ms_per_step extrapolated linearly to all columns" % (ncols, L),
+                            "host_cpus": os.cpu_count()},
+           "e2e": {"value": value, "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--cols", type=int, default=0)
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-cols", type=int, default=24)
+    ap.add_argument("--ref-cols", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -161,10 +161,12 @@ class MultiOperator(Operator):
     domain = property(lambda self: self._domain)
     codomain = property(lambda self: self._codomain)
 
-    def apply(self, w):
+    def apply(self, w, only=None):
+        """``only`` (not in the reference): restrict the outer loop to these output indices; the
+        loop body is unchanged.  Used to time / check a sample of columns of a large problem."""
         if not isinstance(w, MultiVector):
             raise TypeError("MultiOperator.apply needs a MultiVector")
-        v = 0 * w                                                     # :42
+        v = 0 * w if only is None else MultiVector()                  # :42
         Lambda = w.active_indices()                                   # :43
         maxm = w.max_order                                            # :44
         if len(self._coeff_field) < maxm:                             # :45-48
@@ -172,7 +174,7 @@ class MultiOperator(Operator):
                            "(%i instead of %i", len(self._coeff_field), maxm)
             maxm = len(self._coeff_field)
         basis = w[Lambda[0]].basis                                    # :51 (shared basis)
-        for mu in Lambda:                                             # :52
+        for mu in (Lambda if only is None else only):                 # :52
             A0 = self._assemble_0(basis, self._coeff_field.mean_func)
             cur_v = A0 * w[mu]                                        # :56
             for m in range(maxm):                                     # :59

@@ -212,14 +212,11 @@ extern "C" int spuq_sg_plan_create(spuq_sg_plan** plan_out, int device, int64_t 
                  "plan_create: bad block shape %lld x %lld", (long long)n_rows, (long long)n_cols);
     SPUQ_REQUIRE(L > 0 && M >= 0, "plan_create: need L > 0 and M >= 0 (got L=%d M=%d)", L, M);
     SPUQ_REQUIRE(M == 0 || n_rows == n_cols, "plan_create: SG operator blocks must be square");
-    SPUQ_REQUIRE(rowptr_dev && colidx_dev && vals_host, "plan_create: null CSR pointer");
+    SPUQ_REQUIRE(rowptr_dev && vals_host, "plan_create: null CSR pointer");
     SPUQ_REQUIRE(0 <= m_begin && m_begin <= m_end && m_end <= M,
                  "plan_create: bad shard range [%d, %d) for M=%d", m_begin, m_end, M);
     SPUQ_REQUIRE(M == 0 || (nbr_up && nbr_dn && beta_up && beta_dn),
                  "plan_create: neighbour / beta tables missing");
-    SPUQ_REQUIRE(!include_mean || vals_host[0], "plan_create: mean block values missing");
-    for (int32_t m = m_begin; m < m_end; ++m)
-        SPUQ_REQUIRE(vals_host[1 + m], "plan_create: values of block m=%d missing", m);
     for (int64_t q = 0; q < (int64_t)M * L; ++q) {
         SPUQ_REQUIRE(nbr_up[q] >= -1 && nbr_up[q] < L && nbr_dn[q] >= -1 && nbr_dn[q] < L,
                      "plan_create: neighbour table entry %lld out of range", (long long)q);
@@ -239,6 +236,10 @@ extern "C" int spuq_sg_plan_create(spuq_sg_plan** plan_out, int device, int64_t 
     SPUQ_CUDA_TRY(cudaMemcpy(h_rowptr.data(), rowptr_dev, sizeof(int32_t) * (n_rows + 1), cudaMemcpyDeviceToHost));
     SPUQ_REQUIRE(h_rowptr[0] == 0, "plan_create: rowptr[0] must be 0");
     p->nnz = h_rowptr[n_rows];
+    SPUQ_REQUIRE(p->nnz == 0 || colidx_dev, "plan_create: null column index array");
+    SPUQ_REQUIRE(p->nnz == 0 || !include_mean || vals_host[0], "plan_create: mean block values missing");
+    for (int32_t m = m_begin; m < m_end; ++m)
+        SPUQ_REQUIRE(p->nnz == 0 || vals_host[1 + m], "plan_create: values of block m=%d missing", m);
     for (int64_t i = 0; i < n_rows; ++i) {
         SPUQ_REQUIRE(h_rowptr[i + 1] >= h_rowptr[i], "plan_create: rowptr not monotone at row %lld", (long long)i);
         p->max_row_nnz = std::max(p->max_row_nnz, h_rowptr[i + 1] - h_rowptr[i]);

@@ -1,0 +1,415 @@
+"""Parity checks of the product path against the oracle.  The SAME functions run on the host-
+emulated build of the CUDA sources (tests/test_emu_parity.py, no GPU) and on the real library on a
+B200 (tests/test_gpu_parity.py, -m gpu); which one is decided by the fixture that selected the
+backend before the call.  Tolerance: 1e-12 relative in fp64 (BASELINE.json north_star)."""
+import logging
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import torch
+
+import spuq_b200 as sp
+from oracle import linalg as olin
+from oracle import multiindex as omi
+from oracle import polys as opolys
+from oracle import sg as osg
+from spuq_b200 import _abi, synthetic
+from spuq_b200.multi_operator import DeviceBlocks, SGPlan
+from tests.cases import fd_case, oracle_multivector, oracle_operator, random_sparse_case, relerr
+
+TOL = 1e-12
+
+
+def _dev(t):
+    return t.to(_abi.device())
+
+
+def device_blocks(c):
+    if hasattr(c, "rowptr"):
+        return DeviceBlocks(_dev(c.rowptr), _dev(c.colidx), _dev(c.vals), (c.N, c.N))
+    return DeviceBlocks.from_scipy(c.mats)
+
+
+def product_apply(c, path=_abi.PATH_AUTO, tune=None, m_range=None, include_mean=True):
+    A = sp.MultiOperator.from_blocks(device_blocks(c), c.rvs, path=path, m_range=m_range,
+                                     include_mean=include_mean)
+    w = sp.SlabMultiVector.from_array(c.idx, c.W)
+    before = w.slab.clone()
+    if tune:
+        A.plan_for(w).tune(*tune)
+    y = A.apply(w)
+    assert torch.equal(before, w.slab), "apply modified its argument"
+    assert y is not w and y.slab.data_ptr() != w.slab.data_ptr()
+    return y.to_array(), A.plan_for(w)
+
+
+# ---- apply -------------------------------------------------------------------------------------
+def check_apply_paths(n=12, M=4, p=2, kind="legendre", mu=0.0):
+    idx = synthetic.complete_order_indices(M, p)
+    c = fd_case(n, M, idx, kind, mu)
+    seen = set()
+    for path in (_abi.PATH_CSR, _abi.PATH_ELL, _abi.PATH_STENCIL, _abi.PATH_AUTO):
+        Y, plan = product_apply(c, path)
+        assert relerr(Y, c.Y) <= TOL, (path, relerr(Y, c.Y))
+        seen.add(plan.kernel_name)
+    assert {"k_apply_csr", "k_apply_ell<8>"} <= seen
+    for tune in [(1, 0, 0, 0), (2, 8, 2, 0), (2, 4, 2, 0), (2, 16, 2, 0), (2, 8, 1, 0), (2, 16, 1, 0), (2, 4, 4, 0)]:
+        Y, plan = product_apply(c, _abi.PATH_STENCIL, tune)
+        assert relerr(Y, c.Y) <= TOL, (tune, plan.kernel_name, relerr(Y, c.Y))
+    info = plan.info()
+    L, N, nnz = idx.shape[0], c.N, c.colidx.numel()
+    assert info["nnz"] == nnz and info["path"] == "stencil"
+    up, dn = sp.lambda_tables.neighbour_tables(idx)
+    E2 = int((up >= 0).sum() + (dn >= 0).sum())
+    D = L * M if (kind == "hermite" and mu != 0.0) else 0
+    assert info["n_terms"] == L + E2 + D
+    assert info["algorithmic_flops"] == 2 * nnz * (L + E2 + D)
+    assert info["algorithmic_bytes"] == 16 * N * L + 8 * nnz * (M + 1) + 4 * nnz + 4 * (N + 1) + M * L * 32
+
+
+def check_apply_c1_dense_callbacks():
+    """Config C1: 32x32 grid, M=5, TD-2 (21 indices), blocks handed over as dense MatrixOperators
+    through the reference constructor MultiOperator(coeff_field, assemble_0, assemble_m)."""
+    n, M = 32, 5
+    idx = synthetic.complete_order_indices(M, 2)
+    c = fd_case(n, M, idx, "legendre", dense=True)
+    basis = sp.CanonicalBasis(c.N)
+    calls = []
+
+    def assemble(b, f):
+        calls.append(f)
+        k = 0 if f == "mean" else 1 + f
+        return sp.MatrixOperator(c.mats[k].toarray(), b, b)
+
+    cf = sp.ListCoefficientField("mean", list(range(M)), [sp.UniformRV(-1, 1)] * M)
+    A = sp.MultiOperator(cf, assemble)
+    w = sp.MultiVector()
+    for k, row in enumerate(idx):
+        w[sp.Multiindex(row)] = sp.FlatVector(c.W[:, k].copy(), basis)
+    y = A * w                                           # host container in -> host container out
+    assert type(y) is sp.MultiVector and len(calls) == M + 1      # one assembly per block
+    Y = np.stack([y[mu].coeffs for mu in y.active_indices()], axis=1)
+    assert relerr(Y, c.Y) <= TOL
+    y2 = A(sp.SlabMultiVector.from_multivector(w))      # slab in -> slab out, call syntax
+    assert isinstance(y2, sp.SlabMultiVector) and relerr(y2.to_array(), c.Y) <= TOL
+    assert len(calls) == M + 1                          # blocks and plan were cached
+    with pytest.raises(TypeError):
+        A.apply(sp.FlatVector(np.zeros(3)))
+    with pytest.raises(TypeError):
+        sp.MultiOperator(3, assemble)
+    with pytest.raises(TypeError):
+        sp.MultiOperator(cf, 7)
+
+
+def check_apply_reference_known_answer():
+    """application/egsz/tests/test_multi_operator.py:57-90 through the product path."""
+    N = 4
+    consts = {"mean": 2.0, 0: 3.0, 1: 4.0}
+    cf = sp.ListCoefficientField("mean", [0, 1], [sp.UniformRV(), sp.NormalRV(mu=0.5)])
+
+    def diag_assemble(basis, func):
+        return sp.DiagonalMatrixOperator(np.full(basis.dim, abs(consts[func])), basis, basis)
+
+    A = sp.MultiOperator(cf, diag_assemble)
+    mis = [sp.Multiindex([0]), sp.Multiindex([1]), sp.Multiindex([0, 1]), sp.Multiindex([0, 2])]
+    rng = np.random.RandomState(5)
+    basis = sp.CanonicalBasis(N)
+    vecs = [sp.FlatVector(rng.random_sample(N), basis) for _ in mis]
+    w = sp.MultiVector()
+    for mi, v in zip(mis, vecs):
+        w[mi] = v
+    v = A * w
+    L = opolys.LegendrePolynomials(normalised=True)
+    H = opolys.StochasticHermitePolynomials(mu=0.5, normalised=True)
+    c = [x.coeffs for x in vecs]
+    v0 = 2 * c[0] + 3 * (L.get_beta(0)[1] * c[1] - L.get_beta(0)[0] * c[0]) + 4 * (H.get_beta(0)[1] * c[2] - H.get_beta(0)[0] * c[0])
+    v2 = 2 * c[2] + 4 * (H.get_beta(1)[1] * c[3] - H.get_beta(1)[0] * c[2] + H.get_beta(1)[-1] * c[0])
+    assert np.allclose(v[mis[0]].coeffs, v0, rtol=1e-14, atol=0)
+    assert np.allclose(v[mis[2]].coeffs, v2, rtol=1e-14, atol=0)
+
+
+def check_apply_unstructured():
+    idx = synthetic.anisotropic_indices(4, 6.0)
+    c = random_sparse_case(57, 4, idx)                 # different pattern per block, beta0 != 0
+    for path in (_abi.PATH_CSR, _abi.PATH_ELL, _abi.PATH_AUTO):
+        Y, plan = product_apply(c, path)
+        assert relerr(Y, c.Y) <= TOL, (path, relerr(Y, c.Y))
+    assert plan.info()["path"] == "ell"
+    with pytest.raises(_abi.SpuqError, match="not a 3x3-window grid stencil"):
+        product_apply(c, _abi.PATH_STENCIL)
+
+
+def nine_point_case(nx, ny, M, idx, seed=3):
+    """Random 9-point-window blocks on an nx x ny grid (non-square grid, full 3x3 coupling)."""
+    rng = np.random.RandomState(seed)
+    N = nx * ny
+    rows, cols = [], []
+    for iy in range(ny):
+        for ix in range(nx):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    if 0 <= ix + dx < nx and 0 <= iy + dy < ny:
+                        rows.append(iy * nx + ix); cols.append((iy + dy) * nx + ix + dx)
+    mats = [sps.csr_matrix((rng.standard_normal(len(rows)), (rows, cols)), shape=(N, N)) for _ in range(M + 1)]
+    from tests.cases import Case
+    c = Case()
+    c.N, c.M, c.idx, c.mats = N, M, idx, mats
+    c.W = rng.random_sample((N, idx.shape[0]))
+    c.rvs = synthetic.make_rvs("hermite", M, 0.5)
+    c.orvs = [opolys.NormalRV(0.5, 1)] * M
+    c.A, c.cf = oracle_operator(mats, c.orvs)
+    c.w = oracle_multivector(idx, c.W)
+    c.Y = (c.A * c.w).to_slab()
+    return c
+
+
+def check_apply_nine_point_and_odd_shapes():
+    idx = synthetic.complete_order_indices(3, 2)
+    c = nine_point_case(10, 7, 3, idx)
+    for tune in [None, (1, 0, 0, 0), (2, 8, 2, 0), (2, 4, 2, 0), (2, 8, 1, 0)]:
+        Y, plan = product_apply(c, _abi.PATH_STENCIL, tune)
+        assert relerr(Y, c.Y) <= TOL, (tune, plan.kernel_name)
+    assert "9pt" in product_apply(c)[1].kernel_name
+    # odd grid width: vector loads impossible -> the simple stencil kernel is chosen
+    c = nine_point_case(7, 5, 2, synthetic.complete_order_indices(2, 2))
+    Y, plan = product_apply(c)
+    assert plan.kernel_name == "k_apply_stencil_simple" and relerr(Y, c.Y) <= TOL
+    with pytest.raises(_abi.SpuqError, match="even grid width"):
+        product_apply(c, _abi.PATH_STENCIL, (2, 8, 2, 0))
+    # 1-D problem (tridiagonal blocks): one grid row
+    N, M = 40, 2
+    idx = synthetic.complete_order_indices(M, 3)
+    rng = np.random.RandomState(9)
+    mats = [sps.diags([rng.standard_normal(N - 1), rng.standard_normal(N), rng.standard_normal(N - 1)],
+                      [-1, 0, 1], format="csr") for _ in range(M + 1)]
+    from tests.cases import Case
+    c = Case(); c.N, c.M, c.idx, c.mats = N, M, idx, mats
+    c.W = rng.random_sample((N, idx.shape[0]))
+    c.rvs = synthetic.make_rvs("legendre", M); c.orvs = [opolys.UniformRV(-1, 1)] * M
+    c.A, _ = oracle_operator(mats, c.orvs); c.w = oracle_multivector(idx, c.W); c.Y = (c.A * c.w).to_slab()
+    for tune in [None, (1, 0, 0, 0), (2, 8, 2, 0)]:
+        Y, plan = product_apply(c, _abi.PATH_AUTO, tune)
+        assert plan.info()["path"] == "stencil" and relerr(Y, c.Y) <= TOL
+
+
+def check_apply_edge_cases():
+    # |Lambda| = 1 (mean only), tiny grid, L not a multiple of the column block
+    c = fd_case(4, 0, np.zeros((1, 1), dtype=np.int32), "legendre")
+    c.rvs = []
+    Y, plan = product_apply(c)
+    assert relerr(Y, c.Y) <= TOL and plan.info()["n_terms"] == 1
+    idx = synthetic.complete_order_indices(2, 3)          # L = 10
+    c = fd_case(6, 2, idx, "hermite", 0.5)
+    for tune in [(2, 4, 2, 0), (2, 8, 2, 0), (2, 16, 1, 0)]:
+        assert relerr(product_apply(c, _abi.PATH_STENCIL, tune)[0], c.Y) <= TOL
+    # a set with missing neighbours (not downward closed) and unsorted input order
+    idx = np.array([[0, 2], [0, 0], [1, 0], [0, 1], [3, 1]], dtype=np.int32)
+    W = np.random.RandomState(2).random_sample((36, 5))
+    c = fd_case(6, 2, idx, "hermite", 0.5, with_oracle=False)
+    c.W = W
+    c.orvs = [opolys.NormalRV(0.5, 1)] * 2
+    c.A, _ = oracle_operator(c.mats, c.orvs)
+    c.w = oracle_multivector(idx, W)
+    c.Y = (c.A * c.w).to_slab()
+    assert relerr(product_apply(c)[0], c.Y) <= TOL
+    # coefficient field shorter than the longest index: maxm is capped (multi_operator2.py:45-48)
+    idx = synthetic.complete_order_indices(3, 2)
+    c = fd_case(5, 3, idx, "legendre", with_oracle=False)
+    c.orvs = [opolys.UniformRV(-1, 1)] * 2
+    c.A, _ = oracle_operator(c.mats[:3], c.orvs)
+    c.w = oracle_multivector(idx, c.W)
+    c.Y = (c.A * c.w).to_slab()
+    blocks = device_blocks(c)
+    short = DeviceBlocks(blocks.rowptr, blocks.colidx, blocks.vals[:3].contiguous(), blocks.shape)
+    A = sp.MultiOperator.from_blocks(short, c.rvs[:2])
+    y = A.apply(sp.SlabMultiVector.from_array(idx, c.W))
+    assert relerr(y.to_array(), c.Y) <= TOL
+
+
+def check_apply_m_shards():
+    """M-sharded plans (one per rank in the multi-GPU path) sum to the full operator."""
+    idx = synthetic.complete_order_indices(5, 2)
+    c = fd_case(8, 5, idx, "hermite", 0.5)
+    total = np.zeros_like(c.Y)
+    for g, (lo, hi) in enumerate([(0, 2), (2, 3), (3, 5)]):
+        Y, _ = product_apply(c, m_range=(lo, hi), include_mean=(g == 0))
+        total += Y
+    assert relerr(total, c.Y) <= TOL
+
+
+# ---- vectors ------------------------------------------------------------------------------------
+def check_slab_multivector_api():
+    FV = sp.FlatVector
+    mis = sp.MultiindexSet.createCompleteOrderSet(3, 4)
+    a, b, c3 = sp.SlabMultiVector(), sp.SlabMultiVector(), sp.SlabMultiVector()
+    a.set_defaults(mis, FV([3, 4, 5])); b.set_defaults(mis, FV([6, 8, 12])); c3.set_defaults(mis, FV([9, 12, 17]))
+    assert a + b == c3 and len(a) == 35
+    assert a[sp.Multiindex([1, 2, 1])] == FV([3, 4, 5]) and a[sp.Multiindex()] == FV([3, 4, 5])
+    with pytest.raises(KeyError):
+        a[sp.Multiindex([1, 2, 2])]
+    d = sp.SlabMultiVector(); d.set_defaults(mis, FV([6, 8, 10]))
+    assert 2 * a == d and a * 2.0 == d and (d - a) == a
+    assert (-a)[sp.Multiindex(mis[-1])] == FV([-3, -4, -5])
+    keys = a.active_indices()
+    assert keys == sorted(keys) and a.max_order == 3
+    a2 = a.copy()
+    a[sp.Multiindex([1, 2, 1])] = FV([7, 7, 7])
+    assert a2[sp.Multiindex([1, 2, 1])] == FV([3, 4, 5]) and a[sp.Multiindex([1, 2, 1])] == FV([7, 7, 7])
+    # trailing zeros collide; new keys grow Lambda (zero-initialised column, sorted re-layout)
+    mv = sp.SlabMultiVector()
+    mv[sp.Multiindex([1, 2, 3])] = FV([3, 4, 5])
+    mv[sp.Multiindex([0, 1, 2, 3])] = FV([3, 4, 6])
+    mv[sp.Multiindex([1, 2, 3, 0])] = FV([3, 4, 7])
+    assert len(mv) == 2 and mv[sp.Multiindex([1, 2, 3])] == FV([3, 4, 7])
+    assert [list(k.as_array) for k in mv.active_indices()] == [[0, 1, 2, 3], [1, 2, 3]]
+    assert str(mv) == "<SlabMultiVector keys=[<Multiindex inds=[0 1 2 3]>, <Multiindex inds=[1 2 3]>]>"
+    # inner product, dict round trip, flatten layout, pickling
+    rng = np.random.RandomState(4)
+    idx = synthetic.complete_order_indices(3, 2)
+    X, Y = rng.random_sample((17, 10)), rng.random_sample((17, 10))
+    x, y = sp.SlabMultiVector.from_array(idx, X), sp.SlabMultiVector.from_array(idx, Y)
+    assert abs(sp.inner(x, y) - float((X * Y).sum())) <= 1e-13 * abs((X * Y).sum())
+    host = x.to_multivector()
+    assert type(host) is sp.MultiVector and sp.SlabMultiVector.from_multivector(host) == x
+    assert abs(sp.inner(host, y.to_multivector()) - sp.inner(x, y)) < 1e-12
+    assert np.array_equal(x.flatten().coeffs, X.T.reshape(-1))         # column-major N x L slab
+    import pickle
+    assert pickle.loads(pickle.dumps(x)) == x
+    with pytest.raises(AssertionError):
+        x += sp.SlabMultiVector.from_array(idx[:5], X[:, :5])
+
+
+def check_blas():
+    lib = _abi.lib()
+    rng = np.random.RandomState(8)
+    for n in (1, 7, 1000, 100003):
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        tx, ty = _dev(torch.from_numpy(x)), _dev(torch.from_numpy(y))
+        scratch = torch.zeros(int(lib.spuq_sg_reduce_scratch_bytes()) // 8 + 1, dtype=torch.float64, device=tx.device)
+        out = torch.zeros(2, dtype=torch.float64, device=tx.device)
+        _abi.check(lib.spuq_sg_dot2(n, _abi.ptr(tx), _abi.ptr(ty), _abi.ptr(out), _abi.ptr(scratch), _abi.stream_ptr()))
+        got = out.cpu().numpy()
+        assert abs(got[0] - x @ y) <= 1e-12 * max(1.0, np.abs(x * y).sum())
+        assert abs(got[1] - x @ x) <= 1e-12 * (x @ x)
+        r1 = got.copy()
+        _abi.check(lib.spuq_sg_dot2(n, _abi.ptr(tx), _abi.ptr(ty), _abi.ptr(out), _abi.ptr(scratch), _abi.stream_ptr()))
+        assert np.array_equal(out.cpu().numpy(), r1)            # deterministic
+        num = _dev(torch.tensor([3.0], dtype=torch.float64)); den = _dev(torch.tensor([4.0], dtype=torch.float64))
+        w, rho = tx.clone(), ty.clone()
+        _abi.check(lib.spuq_sg_axpy2(n, _abi.ptr(num), _abi.ptr(den), _abi.ptr(ty), _abi.ptr(w), _abi.ptr(tx),
+                                     _abi.ptr(rho), _abi.stream_ptr()))
+        assert np.allclose(w.cpu().numpy(), x + 0.75 * y, rtol=1e-15) and np.allclose(rho.cpu().numpy(), y - 0.75 * x, rtol=1e-15)
+        v = tx.clone()
+        _abi.check(lib.spuq_sg_xpay(n, _abi.ptr(num), _abi.ptr(den), _abi.ptr(ty), _abi.ptr(v), _abi.stream_ptr()))
+        assert np.allclose(v.cpu().numpy(), y + 0.75 * x, rtol=1e-15)
+
+
+# ---- pcg ------------------------------------------------------------------------------------------
+def check_pcg_reference_test():
+    """application/egsz/tests/test_pcg.py:12-44 against the product classes."""
+    rand = np.random.mtrand.RandomState(1234).random_sample
+    N = 7
+    M = rand((N, N))
+    A = sp.MatrixOperator(np.dot(M, M.T))
+    P = sp.MultiplicationOperator(1, sp.CanonicalBasis(N))
+    x = sp.FlatVector(rand((N,)))
+    b = A * x
+    assert np.allclose(b.coeffs, np.dot(M, M.T) @ x.coeffs, rtol=1e-14)
+    x_ap, zeta, it = sp.pcg(A, b, P, 0 * x, eps=0.00001)
+    np.testing.assert_array_almost_equal(x.coeffs, x_ap.coeffs)
+    assert it <= N + 3
+    # oracle on the same numbers: same iteration count, same zeta trajectory
+    oh, ph = [], []
+    oA = olin.MatrixOperator(np.dot(M, M.T))
+    ox, _, oit = osg.pcg(oA, oA * olin.FlatVector(x.coeffs.copy()), olin.MultiplicationOperator(1, olin.CanonicalBasis(N)),
+                         olin.FlatVector(np.zeros(N)), eps=0.00001, history=oh)
+    sp.pcg(A, b, P, 0 * x, eps=0.00001, history=ph)
+    assert abs(it - oit) <= 1 and np.allclose(ph[:4], oh[:4], rtol=1e-9)
+    P = sp.MatrixSolveOperator(np.dot(M, M.T))
+    x_ap, zeta, it = sp.pcg(A, b, P, 0 * x, eps=0.00001)
+    np.testing.assert_array_almost_equal(x.coeffs, x_ap.coeffs)
+    assert it <= 2
+    P = sp.MatrixOperator(np.asarray(P.as_matrix()))
+    x_ap, zeta, it = sp.pcg(A, b, P, 0 * x, eps=0.00001)
+    np.testing.assert_array_almost_equal(x.coeffs, x_ap.coeffs)
+    P = sp.DiagonalMatrixOperator(np.diag(A.as_matrix())).inverse()
+    x_ap, zeta, it = sp.pcg(A, b, P, 0 * x, eps=0.00001)
+    np.testing.assert_array_almost_equal(x.coeffs, x_ap.coeffs)
+    # leaf known answers, linalg/tests/test_operator.py:44-49,112-117
+    assert sp.MatrixOperator(np.array([[1, 2, 4], [3, 4, 5]], dtype=float)) * sp.FlatVector([2, 3, 4]) == sp.FlatVector([24, 38])
+    assert sp.DiagonalMatrixOperator(np.array([1, 2, 3])) * sp.FlatVector([3, 4, 5]) == sp.FlatVector([3, 8, 15])
+    with pytest.raises(TypeError):
+        sp.pcg(A, b, 3, 0 * x)
+
+
+def check_pcg_failures():
+    N = 4
+    basis = sp.CanonicalBasis(N)
+    I = sp.MultiplicationOperator(1, basis)
+    x = sp.FlatVector(np.ones(N))
+    with pytest.raises(Exception, match="Matrix for PCG is not positive definite"):
+        sp.pcg(sp.MatrixOperator(-np.eye(N)), x, I, 0 * x)
+    with pytest.raises(Exception, match="Matrix for PCG is singular"):
+        sp.pcg(sp.MatrixOperator(np.zeros((N, N))), x, I, 0 * x)
+    with pytest.raises(Exception, match="Preconditioner for PCG is not positive definite"):
+        sp.pcg(sp.MatrixOperator(np.eye(N)), x, sp.MultiplicationOperator(-1, basis), 0 * x)
+    with pytest.raises(Exception, match="PCG did not converge"):
+        sp.pcg(sp.MatrixOperator(np.diag([1.0, 10.0, 100.0, 1000.0])), x, I, 0 * x, eps=1e-14, maxiter=3)
+
+
+def check_pcg_sg(n=8, M=3, p=2, kind="legendre", precond="jacobi", eps=1e-8, poll_every=3):
+    """PCG on the SG system against the oracle's PCG on the same numbers: same status, iteration
+    count within one, zeta trajectory to 1e-9 at fixed iteration index, same solution."""
+    idx = synthetic.complete_order_indices(M, p)
+    c = fd_case(n, M, idx, kind)
+    basis_o = olin.CanonicalBasis(c.N)
+    f_o = c.A * c.w                                     # right-hand side f = A x*, x* ~ U(0,1)
+    w0_o = 0 * c.w
+    d = c.mats[0].diagonal()
+    if precond == "jacobi":
+        Pleaf_o = olin.DiagonalMatrixOperator(1.0 / d, basis_o, basis_o)
+        Pleaf_p = lambda b: sp.DiagonalMatrixOperator(1.0 / d, b, b)            # noqa: E731
+    else:
+        Pleaf_o = olin.MultiplicationOperator(1.0, basis_o)
+        Pleaf_p = None
+    P_o = osg.PreconditioningOperator("mean", lambda b, f: Pleaf_o) if precond == "jacobi" else Pleaf_o
+    oh = []
+    if precond == "jacobi":
+        x_o, zeta_o, it_o = osg.pcg(c.A, f_o, P_o, w0_o, eps=eps, maxiter=200, history=oh)
+    else:
+        class _Id(olin.Operator):
+            def apply(self, v):
+                return v.copy()
+        x_o, zeta_o, it_o = osg.pcg(c.A, f_o, _Id(), w0_o, eps=eps, maxiter=200, history=oh)
+
+    A = sp.MultiOperator.from_blocks(device_blocks(c), c.rvs)
+    f = A.apply(sp.SlabMultiVector.from_array(idx, c.W))
+    w0 = 0 * f
+    if precond == "jacobi":
+        class _JacobiSolver:                                      # explicit-matrix mean preconditioner
+            def __init__(self, b):
+                self._d = sp.DiagonalMatrixOperator(1.0 / d, b, b)
+
+            def as_matrix(self):
+                return self._d.as_matrix()
+        P = sp.PreconditioningOperator("mean", lambda b, f_: _JacobiSolver(b))
+    else:
+        P = sp.MultiplicationOperator(1.0, sp.CanonicalBasis(c.N))
+    ph = []
+    x, zeta, it = sp.pcg(A, f, P, w0, eps=eps, maxiter=200, poll_every=poll_every, history=ph)
+    assert isinstance(x, sp.SlabMultiVector)
+    assert abs(it - it_o) <= 1, (it, it_o)
+    k = min(len(ph), len(oh)) - 1
+    assert np.allclose(ph[:k], oh[:k], rtol=1e-9), (ph[:k], oh[:k])
+    assert len(ph) == it and zeta == ph[-1] and zeta <= eps ** 2
+    X = x.to_array()
+    assert np.max(np.abs(X - x_o.to_slab())) <= 1e-6 * np.max(np.abs(c.W))
+    assert np.max(np.abs(X - c.W)) <= 1e-5
+    # host containers in -> host container out
+    xh, _, ith = sp.pcg(A, f.to_multivector(), P, w0.to_multivector(), eps=eps, maxiter=200)
+    assert type(xh) is sp.MultiVector and ith == it
+    # the mean preconditioner as an operator on its own
+    s = P * f if precond == "jacobi" else None
+    if s is not None:
+        assert relerr(s.to_array(), f.to_array() / d[:, None]) <= 1e-14

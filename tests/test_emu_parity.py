@@ -1,0 +1,64 @@
+"""Parity suite on the HOST-EMULATED build of the CUDA sources (no GPU needed): exercises the plan
+builder, the term/block tables, the kernels' index arithmetic and the Python drop-in layer.  The
+same checks run on the real library in tests/test_gpu_parity.py."""
+import pytest
+
+from tests import parity_suite as ps
+
+
+@pytest.fixture(autouse=True)
+def _backend(emu):
+    yield
+
+
+def test_apply_paths_legendre():
+    ps.check_apply_paths(12, 4, 2, "legendre")
+
+
+def test_apply_paths_hermite_shifted():
+    ps.check_apply_paths(10, 3, 3, "hermite", 0.5)
+
+
+def test_apply_c1_dense_callbacks():
+    ps.check_apply_c1_dense_callbacks()
+
+
+def test_apply_reference_known_answer():
+    ps.check_apply_reference_known_answer()
+
+
+def test_apply_unstructured():
+    ps.check_apply_unstructured()
+
+
+def test_apply_nine_point_and_odd_shapes():
+    ps.check_apply_nine_point_and_odd_shapes()
+
+
+def test_apply_edge_cases():
+    ps.check_apply_edge_cases()
+
+
+def test_apply_m_shards():
+    ps.check_apply_m_shards()
+
+
+def test_slab_multivector_api():
+    ps.check_slab_multivector_api()
+
+
+def test_blas():
+    ps.check_blas()
+
+
+def test_pcg_reference_test():
+    ps.check_pcg_reference_test()
+
+
+def test_pcg_failures():
+    ps.check_pcg_failures()
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "identity"])
+def test_pcg_sg(precond):
+    ps.check_pcg_sg(precond=precond)

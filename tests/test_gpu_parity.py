@@ -1,0 +1,178 @@
+"""Parity tests proper: the CUDA path on a B200, called through the C ABI, against the oracle.
+
+Small cases: the whole parity suite (same checks the emulated build passes on the CPU).
+Full-size cases (BASELINE.json configs 2 and 3): the oracle cannot run L*(M+1) SpMVs of 10^6 rows in
+seconds, so they are checked (i) against the oracle on a SAMPLE of output columns -- y[mu] only
+needs w[mu] and its 2M neighbours, which scipy does in milliseconds -- and (ii) through
+size-independent properties: linearity, symmetry of the SG operator, agreement of every kernel
+path, and the M-shard sum."""
+import numpy as np
+import pytest
+import torch
+
+from tests import parity_suite as ps
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _backend(gpu):
+    yield
+
+
+def test_library_is_the_cuda_build(gpu):
+    assert gpu.library_path().endswith("spuq_b200/libspuq_sg.so") and not gpu.is_emulated()
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+def test_apply_paths_legendre():
+    ps.check_apply_paths(12, 4, 2, "legendre")
+
+
+def test_apply_paths_hermite_shifted():
+    ps.check_apply_paths(10, 3, 3, "hermite", 0.5)
+
+
+def test_apply_paths_wide_grid():
+    ps.check_apply_paths(70, 3, 2, "hermite", 0.5)        # x-tiles with a ragged tail, several y-tiles
+
+
+def test_apply_c1_dense_callbacks():
+    ps.check_apply_c1_dense_callbacks()
+
+
+def test_apply_reference_known_answer():
+    ps.check_apply_reference_known_answer()
+
+
+def test_apply_unstructured():
+    ps.check_apply_unstructured()
+
+
+def test_apply_nine_point_and_odd_shapes():
+    ps.check_apply_nine_point_and_odd_shapes()
+
+
+def test_apply_edge_cases():
+    ps.check_apply_edge_cases()
+
+
+def test_apply_m_shards():
+    ps.check_apply_m_shards()
+
+
+def test_slab_multivector_api():
+    ps.check_slab_multivector_api()
+
+
+def test_blas():
+    ps.check_blas()
+
+
+def test_pcg_reference_test():
+    ps.check_pcg_reference_test()
+
+
+def test_pcg_failures():
+    ps.check_pcg_failures()
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "identity"])
+def test_pcg_sg(precond):
+    ps.check_pcg_sg(precond=precond)
+
+
+def test_pcg_sg_bigger():
+    ps.check_pcg_sg(n=24, M=4, p=3, kind="hermite", precond="jacobi", eps=1e-7, poll_every=8)
+
+
+# ---- full-size configurations ---------------------------------------------------------------------
+def _oracle_columns(mats_vals, rowptr, colidx, N, tables, W, cols):
+    """Oracle y[mu] for a few columns: the per-mu body of MultiOperator.apply
+    (multi_operator2.py:52-83) with scipy CSR leaves."""
+    import scipy.sparse as sps
+    rp, ci = rowptr.cpu().numpy(), colidx.cpu().numpy()
+    mats = {}
+
+    def mat(k):
+        if k not in mats:
+            mats[k] = sps.csr_matrix((mats_vals[k].cpu().numpy(), ci, rp), shape=(N, N))
+        return mats[k]
+    out = {}
+    for mu in cols:
+        w_mu = W[mu].cpu().numpy()
+        cur_v = mat(0) @ w_mu
+        for m in range(tables.maxm):
+            cur_w = -tables.beta_0[m, mu] * w_mu
+            if tables.nbr_up[m, mu] >= 0:
+                cur_w = cur_w + tables.beta_up[m, mu] * W[int(tables.nbr_up[m, mu])].cpu().numpy()
+            if tables.nbr_dn[m, mu] >= 0:
+                cur_w = cur_w + tables.beta_dn[m, mu] * W[int(tables.nbr_dn[m, mu])].cpu().numpy()
+            if np.any(cur_w):
+                cur_v = cur_v + mat(1 + m) @ cur_w
+        out[mu] = cur_v
+    return out
+
+
+def _full_size(n, M, idx, kind, mu, sample_cols, variants):
+    import spuq_b200 as sp
+    from spuq_b200 import _abi, synthetic
+    from spuq_b200.multi_operator import DeviceBlocks
+    dev = _abi.device()
+    N, L = n * n, idx.shape[0]
+    rowptr, colidx, vals = synthetic.fd_blocks(n, M, device=dev)
+    blocks = DeviceBlocks(rowptr, colidx, vals, (N, N))
+    rvs = synthetic.make_rvs(kind, M, mu)
+    A = sp.MultiOperator.from_blocks(blocks, rvs)
+    g = torch.Generator(device=dev); g.manual_seed(1234)
+    W = torch.rand((L, N), dtype=torch.float64, device=dev, generator=g)
+    w = sp.SlabMultiVector(idx, slab=W, _sorted=True)
+    plan = A.plan_for(w)
+    y = A.apply(w)
+    # (i) sampled columns against the oracle formula
+    ref = _oracle_columns(vals, rowptr, colidx, N, plan.tables, W, sample_cols)
+    ynorm = float(torch.linalg.norm(y.slab))
+    for mu_, r in ref.items():
+        err = np.linalg.norm(y.slab[mu_].cpu().numpy() - r) / np.linalg.norm(r)
+        assert err <= 1e-12, (mu_, err)
+    # (ii) every kernel variant produces the same slab (to reassociation)
+    for tune in variants:
+        plan.tune(*tune)
+        y2 = A.apply(w)
+        d = float(torch.linalg.norm(y2.slab - y.slab)) / ynorm
+        assert d <= 1e-13, (tune, plan.kernel_name, d)
+    plan.tune(0, 0, 0, 0)
+    # (iii) linearity and symmetry
+    X = torch.rand((L, N), dtype=torch.float64, device=dev, generator=g)
+    x = w.like(X)
+    ax = A.apply(x)
+    comb = A.apply(w.like(2.5 * W - 0.75 * X))
+    lin = float(torch.linalg.norm(comb.slab - (2.5 * y.slab - 0.75 * ax.slab))) / ynorm
+    assert lin <= 1e-13, lin
+    s1, s2 = sp.inner(y, x), sp.inner(w, ax)
+    assert abs(s1 - s2) <= 1e-12 * abs(s1), (s1, s2)
+    del comb, ax, x, X
+    # (iv) M-shard sum
+    half = M // 2
+    A1 = sp.MultiOperator.from_blocks(blocks, rvs, m_range=(0, half), include_mean=True)
+    A2 = sp.MultiOperator.from_blocks(blocks, rvs, m_range=(half, M), include_mean=False)
+    ysum = A1.apply(w)
+    ysum += A2.apply(w)
+    d = float(torch.linalg.norm(ysum.slab - y.slab)) / ynorm
+    assert d <= 1e-13, d
+
+
+def test_full_size_config2():
+    """512 x 512 grid, M = 20, total degree 3 (1771 indices), Legendre: 3.7 GB per slab."""
+    from spuq_b200 import synthetic
+    idx = synthetic.complete_order_indices(20, 3)
+    _full_size(512, 20, idx, "legendre", 0.0, [0, 1, 7, 230, 231, 1000, 1770],
+               [(1, 0, 0, 0), (2, 4, 2, 0), (2, 16, 1, 0)])
+
+
+def test_full_size_config3_hermite_shifted():
+    """1000 x 1000 grid, M = 50, anisotropic Lambda (988 indices), Hermite chaos with the
+    reference's default NormalRV(mu=0.5) (beta0 != 0): 8 GB per slab."""
+    from spuq_b200 import synthetic
+    idx = synthetic.anisotropic_indices(50, 11.3)
+    _full_size(1000, 50, idx, "hermite", 0.5, [0, 3, 50, 500, 987], [(2, 4, 2, 0)])
