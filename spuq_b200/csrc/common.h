@@ -132,6 +132,13 @@ struct spuq_sg_plan {
     std::vector<void*> block_dev;     // device arrays of the current BlockView
     std::vector<void*> owned_dev;     // everything cudaMalloc'ed by the plan
 
+    // TMA descriptors of the pipelined kernel (opaque 128-byte CUtensorMap blobs)
+    alignas(64) unsigned char tmap_w[128];
+    alignas(64) unsigned char tmap_a[128];
+    const void* tmap_w_ptr = nullptr;     // slab / ld / box the W map was encoded for
+    int64_t tmap_w_ld = 0;
+    int32_t tmap_w_rows = 0, tmap_a_rows = 0;
+
     // tunables
     int32_t variant = 0, cols_per_block = 0, rows_per_thread = 0, ctas_per_sm = 0;
 

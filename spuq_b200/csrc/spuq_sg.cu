@@ -9,6 +9,7 @@
 #include "common.h"
 #include "kernels_apply.cuh"
 #include "kernels_tiled.cuh"
+#include "kernels_tma.cuh"
 
 #ifdef SPUQ_EMU
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -375,7 +376,7 @@ extern "C" int spuq_sg_plan_info(const spuq_sg_plan* p, int32_t* path, int64_t* 
 extern "C" int spuq_sg_plan_tune(spuq_sg_plan* p, int32_t variant, int32_t cols_per_block,
                                  int32_t rows_per_thread, int32_t ctas_per_sm) {
     SPUQ_REQUIRE(p != nullptr, "plan_tune: null plan");
-    SPUQ_REQUIRE(variant >= 0 && variant <= 2, "plan_tune: variant must be 0 (auto), 1 (simple) or 2 (tiled)");
+    SPUQ_REQUIRE(variant >= 0 && variant <= 3, "plan_tune: variant must be 0 (auto), 1 (simple), 2 (tiled) or 3 (tma)");
     p->variant = variant; p->cols_per_block = cols_per_block;
     p->rows_per_thread = rows_per_thread; p->ctas_per_sm = ctas_per_sm;
     return SPUQ_OK;
@@ -393,6 +394,80 @@ static int32_t pick_cols_per_cta(const spuq_sg_plan* p, int64_t row_blocks) {
     if (cpc > 16) cpc = 16;
     return (int32_t)cpc;
 }
+
+#ifndef SPUQ_EMU
+// ---- TMA descriptors ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 3-D fp64 tensor (x fastest): dims {nx, ny, nz}, strides in elements {1, sy, sz}, box {bx, by, bz}
+static int encode_3d(void* out, const void* base, int64_t nx, int64_t ny, int64_t nz, int64_t sy, int64_t sz,
+                     int bx, int by, int bz) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return SPUQ_E_CUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
+    cuuint64_t strides[2] = {(cuuint64_t)sy * 8, (cuuint64_t)sz * 8};
+    cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base),
+                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SPUQ_E_CUDA; }
+    return SPUQ_OK;
+}
+
+template <int RY, int WY, int C, bool NINE>
+static int launch_tma(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t ldy,
+                      cudaStream_t stream, const double* gate) {
+    using Cfg = TmaCfg<RY, WY, NINE>;
+    int rc;
+    if (p->tmap_a_rows != Cfg::TILE_Y) {
+        if ((rc = encode_3d(p->tmap_a, p->dia_vals, p->st.s, p->ny, (int64_t)p->n_slots * Cfg::D, p->st.s, p->st.N,
+                            Cfg::TILE_X, Cfg::TILE_Y, Cfg::D))) return rc;
+        p->tmap_a_rows = Cfg::TILE_Y;
+    }
+    if (p->tmap_w_ptr != W || p->tmap_w_ld != ldw || p->tmap_w_rows != Cfg::WIN_ROWS) {
+        if ((rc = encode_3d(p->tmap_w, W, p->st.s, p->ny, p->L, p->st.s, ldw, Cfg::BOX_W, Cfg::WIN_ROWS, 1))) return rc;
+        p->tmap_w_ptr = W; p->tmap_w_ld = ldw; p->tmap_w_rows = Cfg::WIN_ROWS;
+    }
+    auto kern = k_apply_tma<RY, WY, C, NINE>;
+    static bool attr_done = false;
+    static int ctas_per_sm = 1;
+    if (!attr_done) {
+        SPUQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SPUQ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        attr_done = true;
+    }
+    const int32_t ntx = (p->st.s + Cfg::TILE_X - 1) / Cfg::TILE_X;
+    const int32_t nty = (p->ny + Cfg::TILE_Y - 1) / Cfg::TILE_Y;
+    const int64_t items = (int64_t)ntx * nty * p->bv.nblk;
+    const int per_sm = p->ctas_per_sm > 0 ? std::min(p->ctas_per_sm, ctas_per_sm) : ctas_per_sm;
+    const int64_t grid = std::min<int64_t>(items, (int64_t)p->n_sm * per_sm);
+    CUtensorMap mw, ma;
+    std::memcpy(&mw, p->tmap_w, sizeof(mw));
+    std::memcpy(&ma, p->tmap_a, sizeof(ma));
+    kern<<<dim3((unsigned)grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream>>>(mw, ma, p->bv, p->st.s, p->ny, ntx, nty,
+                                                                                items, Y, ldy, gate);
+    char name[80];
+    snprintf(name, sizeof(name), "k_apply_tma<RY=%d,WY=%d,C=%d,%s>x%d", RY, WY, C, NINE ? "9pt" : "5pt", per_sm);
+    p->kernel_name = name;
+    return SPUQ_OK;
+}
+#endif  // !SPUQ_EMU
 
 template <int RY, int C, bool NINE>
 static void launch_tiled(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t ldy,
@@ -439,8 +514,17 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
                              (((uintptr_t)W | (uintptr_t)Y) & 15) == 0;
         SPUQ_REQUIRE(p->variant != 2 || aligned,
                      "apply: tiled stencil kernel needs an even grid width, even leading dimensions and 16-byte aligned slabs");
-        const bool tiled = p->variant == 2 || (p->variant == 0 && aligned);
-        if (!tiled) {
+        SPUQ_REQUIRE(p->variant != 3 || aligned,
+                     "apply: TMA stencil kernel needs an even grid width, even leading dimensions and 16-byte aligned slabs");
+#ifdef SPUQ_EMU
+        const bool can_tma = false;
+#else
+        const bool can_tma = aligned && ldw % 2 == 0;
+#endif
+        // automatic choice: TMA pipeline on grids at least one box wide/tall, else loads through registers
+        const bool use_tma = can_tma && (p->variant == 3 || (p->variant == 0 && p->st.s >= 66 && p->ny >= 18));
+        const bool tiled = !use_tma && (p->variant == 2 || p->variant == 3 || (p->variant == 0 && aligned));
+        if (!tiled && !use_tma) {
             const int64_t pair_blocks = ((p->n_rows + 1) / 2 + threads - 1) / threads;
             const int32_t cpc = p->cols_per_block > 0 ? p->cols_per_block : pick_cols_per_cta(p, pair_blocks);
             const dim3 grid((unsigned)pair_blocks, (unsigned)((p->L + cpc - 1) / cpc));
@@ -456,18 +540,38 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
                 if (rc) return rc;
             }
             const bool nine = p->nine;
+            bool launched = false;
+#ifndef SPUQ_EMU
+            if (use_tma) {
+                int rc = SPUQ_OK;
+#define SPUQ_TMA(ry, wy, c)                                                                       \
+    if (!launched && RY == ry && C == c) {                                                        \
+        rc = nine ? launch_tma<ry, wy, c, true>(p, W, ldw, Y, ldy, stream, gate)                  \
+                  : launch_tma<ry, wy, c, false>(p, W, ldw, Y, ldy, stream, gate);                \
+        launched = true;                                                                          \
+    }
+                SPUQ_TMA(2, 4, 4) SPUQ_TMA(2, 4, 8) SPUQ_TMA(2, 4, 12) SPUQ_TMA(2, 4, 16)
+                SPUQ_TMA(4, 2, 4) SPUQ_TMA(1, 8, 8) SPUQ_TMA(1, 8, 16)
+#undef SPUQ_TMA
+                if (rc) return rc;
+                SPUQ_REQUIRE(launched || p->variant != 3,
+                             "apply: no TMA kernel instantiated for rows_per_thread=%d cols_per_block=%d", RY, C);
+            }
+#endif
+            if (!launched) {
 #define SPUQ_TILED(ry, c)                                                                  \
     if (RY == ry && C == c) {                                                              \
         if (nine) launch_tiled<ry, c, true>(p, W, ldw, Y, ldy, stream, gate);              \
         else launch_tiled<ry, c, false>(p, W, ldw, Y, ldy, stream, gate);                  \
     } else
-            SPUQ_TILED(1, 8) SPUQ_TILED(1, 16) SPUQ_TILED(2, 4) SPUQ_TILED(2, 8) SPUQ_TILED(2, 16)
-            SPUQ_TILED(4, 4) SPUQ_TILED(4, 8)
-            {
-                set_error("apply: no tiled kernel instantiated for rows_per_thread=%d cols_per_block=%d", RY, C);
-                return SPUQ_E_UNSUPPORTED;
-            }
+                SPUQ_TILED(1, 8) SPUQ_TILED(1, 16) SPUQ_TILED(2, 4) SPUQ_TILED(2, 8) SPUQ_TILED(2, 16)
+                SPUQ_TILED(4, 4)
+                {
+                    set_error("apply: no tiled kernel instantiated for rows_per_thread=%d cols_per_block=%d", RY, C);
+                    return SPUQ_E_UNSUPPORTED;
+                }
 #undef SPUQ_TILED
+            }
         }
     }
     p->last_launches = 1;

@@ -413,3 +413,63 @@ def check_pcg_sg(n=8, M=3, p=2, kind="legendre", precond="jacobi", eps=1e-8, pol
     s = P * f if precond == "jacobi" else None
     if s is not None:
         assert relerr(s.to_array(), f.to_array() / d[:, None]) <= 1e-14
+
+
+# ---- K4: exact mean preconditioner ------------------------------------------------------------------
+def check_mean_preconditioner():
+    """S = A_0^{-1} R column by column against scipy's sparse direct solve (what the reference's
+    ScipySolveOperator.apply calls, linalg/scipy_operator.py:45-49)."""
+    import scipy.sparse.linalg as spla
+    from spuq_b200.multi_operator import MeanSolveSlabOperator
+    rng = np.random.RandomState(21)
+    for nx, ny, L in [(12, 12, 5), (70, 9, 3), (9, 33, 4), (130, 2, 2), (17, 1, 3)]:
+        T = lambda n, o, dd: sps.diags([o, dd, o], [-1, 0, 1], shape=(n, n))      # noqa: E731
+        if ny > 1:
+            A0 = sps.kron(sps.identity(ny), T(nx, -1.0, 2.0)) + sps.kron(T(ny, -1.0, 2.0), sps.identity(nx))
+        else:
+            A0 = T(nx, -1.0, 4.0)
+        A0 = sps.csr_matrix(A0)
+        N = nx * ny
+        R = rng.random_sample((L, N))
+        solver = MeanSolveSlabOperator(A0, L)
+        Rt = _dev(torch.from_numpy(R.copy()))
+        St = torch.empty_like(Rt)
+        solver.apply_slab(Rt, St)
+        lu = spla.splu(A0.tocsc())
+        ref = np.stack([lu.solve(R[k]) for k in range(L)])
+        err = np.max(np.linalg.norm(St.cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1))
+        assert err <= 1e-12, (nx, ny, err)
+        assert torch.equal(Rt.cpu(), torch.from_numpy(R))
+    with pytest.raises(_abi.SpuqError, match="constant-coefficient"):
+        MeanSolveSlabOperator(sps.csr_matrix(sps.diags([np.arange(1.0, 10.0)], [0])), 1)
+
+
+def check_pcg_sg_mean(n=12, M=3, p=2, eps=1e-10):
+    """Config-4 style solve: PCG with the exact mean-based preconditioner against the oracle's PCG
+    with a sparse direct solve per column."""
+    idx = synthetic.complete_order_indices(M, p)
+    c = fd_case(n, M, idx, "legendre")
+    basis_o = olin.CanonicalBasis(c.N)
+    solve_o = olin.ScipySolveOperator(c.mats[0], basis_o, basis_o, factor=True)
+    P_o = osg.PreconditioningOperator("mean", lambda b, f: solve_o)
+    f_o = c.A * c.w
+    oh = []
+    x_o, zeta_o, it_o = osg.pcg(c.A, f_o, P_o, 0 * c.w, eps=eps, maxiter=100, history=oh)
+
+    A = sp.MultiOperator.from_blocks(device_blocks(c), c.rvs)
+    f = A.apply(sp.SlabMultiVector.from_array(idx, c.W))
+    P = sp.PreconditioningOperator("mean", lambda b, f_: sp.ScipySolveOperator(c.mats[0], b, b))
+    ph = []
+    x, zeta, it = sp.pcg(A, f, P, 0 * f, eps=eps, maxiter=100, history=ph)
+    assert abs(it - it_o) <= 1, (it, it_o)
+    k = min(len(ph), len(oh)) - 1
+    assert np.allclose(ph[:k], oh[:k], rtol=1e-9), (ph, oh)
+    assert np.max(np.abs(x.to_array() - x_o.to_slab())) <= 1e-8
+    assert np.max(np.abs(x.to_array() - c.W)) <= 1e-7
+    assert it <= 30                                       # mean-based preconditioning: few iterations
+    # the preconditioner as a stand-alone operator: P * f, host containers too
+    s = P * f
+    lu_ref = (P_o * f_o).to_slab()
+    assert relerr(s.to_array(), lu_ref) <= 1e-12
+    sh = P * f.to_multivector()
+    assert type(sh) is sp.MultiVector

@@ -62,3 +62,11 @@ def test_pcg_failures():
 @pytest.mark.parametrize("precond", ["jacobi", "identity"])
 def test_pcg_sg(precond):
     ps.check_pcg_sg(precond=precond)
+
+
+def test_mean_preconditioner():
+    ps.check_mean_preconditioner()
+
+
+def test_pcg_sg_mean():
+    ps.check_pcg_sg_mean()
