@@ -5,11 +5,13 @@
 // longer travel through per-thread global loads.  A persistent CTA walks its (spatial tile, column
 // block) work items; one producer thread runs AHEAD of four consumer warps and fetches, with TMA
 // (cp.async.bulk.tensor, completion on mbarriers),
-//   * the W window of every term:  box {66, TILE_Y+2, 1} of the slab viewed as the 3-D tensor
-//     (x, y, column), origin (x_tile-1, y_tile-1, nu).  Out-of-range coordinates are zero-filled by
+//   * the W window of every term:  box {68, TILE_Y+2, 1} of the slab viewed as the 3-D tensor
+//     (x, y, column), origin (x_tile-2, y_tile-1, nu).  Out-of-range coordinates are zero-filled by
 //     the TMA unit, which is exactly the homogeneous-boundary behaviour the stencil needs, so the
-//     kernel has no boundary branches.  The odd x origin makes every thread's four window values
-//     x0-1..x0+2 one 32-byte, 16-byte-aligned run: two conflict-free LDS.128;
+//     kernel has no boundary branches.  (The innermost box coordinate must be 16-byte aligned --
+//     an odd fp64 start raises "illegal instruction", measured with tools/tma_probe.cu -- hence
+//     x_tile-2 and not x_tile-1.)  A thread reads its centre pair with one LDS.128 and the two
+//     x-halo values with LDS.64;
 //   * the A tile of every group:   box {64, TILE_Y, D} of the diagonal storage viewed as
 //     (x, y, slot*D + d).
 // Rings of W_STAGES windows and A_STAGES tiles decouple the ~1 us L2/HBM latency from the FP64 pipe:
@@ -62,7 +64,7 @@ struct TmaCfg {
     static constexpr int CONSUMERS = 32 * WARPS_Y;
     static constexpr int THREADS = CONSUMERS + 32;          // + one producer warp
     static constexpr int TILE_X = 64, TILE_Y = WARPS_Y * RY;
-    static constexpr int BOX_W = 66;                        // x_tile-1 .. x_tile+64
+    static constexpr int BOX_W = 68;                        // x_tile-2 .. x_tile+65
     static constexpr int WIN_ROWS = TILE_Y + 2;
     static constexpr int WIN_BYTES = BOX_W * WIN_ROWS * 8;
     static constexpr int WIN_STRIDE = (WIN_BYTES + 127) / 128 * 128;
@@ -119,7 +121,7 @@ k_apply_tma(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CU
                 for (int32_t t = t0; t < t1; ++t) {
                     mbar_wait(emptyW(sw), pw ^ 1u);
                     mbar_expect_tx(fullW(sw), Cfg::WIN_BYTES);
-                    tma_load_3d(smem_u32(wring + sw * Cfg::WIN_STRIDE), &mapW, xt - 1, yt - 1, __ldg(bv.tcol + t), fullW(sw));
+                    tma_load_3d(smem_u32(wring + sw * Cfg::WIN_STRIDE), &mapW, xt - 2, yt - 1, __ldg(bv.tcol + t), fullW(sw));
                     if (++sw == Cfg::W_STAGES) { sw = 0; pw ^= 1u; }
                 }
             }
@@ -175,9 +177,15 @@ k_apply_tma(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CU
                                        + (warp * RY) * Cfg::BOX_W + 2 * lane;
 #pragma unroll
                     for (int rr = 0; rr < RY + 2; ++rr) {
-                        const double2 lo = *reinterpret_cast<const double2*>(wt + rr * Cfg::BOX_W);
-                        const double2 hi = *reinterpret_cast<const double2*>(wt + rr * Cfg::BOX_W + 2);
-                        win[rr][0] = lo.x; win[rr][1] = lo.y; win[rr][2] = hi.x; win[rr][3] = hi.y;
+                        // box element e <-> x = x_tile - 2 + e; this thread's x0 = x_tile + 2*lane
+                        const double2 ctr = *reinterpret_cast<const double2*>(wt + rr * Cfg::BOX_W + 2);
+                        win[rr][1] = ctr.x; win[rr][2] = ctr.y;
+                        if (NINE || (rr >= 1 && rr <= RY)) {
+                            win[rr][0] = wt[rr * Cfg::BOX_W + 1];
+                            win[rr][3] = wt[rr * Cfg::BOX_W + 4];
+                        } else {
+                            win[rr][0] = win[rr][3] = 0.0;
+                        }
                     }
                 }
                 __syncwarp();
