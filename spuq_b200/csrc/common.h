@@ -139,6 +139,16 @@ struct spuq_sg_plan {
     int64_t tmap_w_ld = 0;
     int32_t tmap_w_rows = 0, tmap_a_rows = 0;
 
+    // TMEM-accumulator kernel: schedule tables (host copy + device arrays) and the work counter
+    std::vector<int32_t> h_nbr_up, h_nbr_dn;          // M x L, kept for the column order
+    void* sched_host = nullptr;                        // spuq::Schedule*
+    int32_t sched_K = 0;
+    const void* d_recs = nullptr;
+    const int32_t* d_pcmd = nullptr;
+    const int32_t* d_blk_pcmd = nullptr;
+    unsigned long long* d_work_counter = nullptr;
+    std::vector<void*> sched_dev;                      // device arrays of the current schedule
+
     // tunables
     int32_t variant = 0, cols_per_block = 0, rows_per_thread = 0, ctas_per_sm = 0;
 

@@ -1,0 +1,388 @@
+// kernels_tmem.cuh -- K1, the production apply kernel: warp-specialised, TMA-fed, accumulators in
+// tensor memory.
+//
+// Why this shape (rates measured with tools/microbench.cu on a B200):
+//   * an SM issues 64 DFMA/clk but its shared-memory pipe moves 128 B/clk (16 doubles) and a
+//     conflict-free LDS of the 5-point window costs 4 doubles per grid point, so a kernel that reads
+//     one operand per term from shared memory is bound by LDS at < 40 % of the FP64 rate;
+//   * tensor memory is a second, private, 256 KB on-chip store with its own datapath (measured
+//     385 B/clk/SM load, 650 B/clk/SM store) -- the tcgen05 accumulator file.  This kernel uses it
+//     the way a tcgen05 GEMM does, as the accumulator home, but fills it from the FP64 CUDA cores
+//     (tcgen05.ld / DFMA / tcgen05.st): 64 output columns x 4 grid points per thread.  That frees the
+//     register file to hold K block-matrix tiles at once, so ONE window read from shared memory
+//     serves every (matrix, output column) pair of the block that needs that input column.
+//
+// A CTA is 4 consumer warps (2 x 2 grid points per thread, lanes along x: a 64 x 8 tile) and one
+// producer warp.  The producer pulls work items (tile, column block) from a global counter and
+// walks the block's command list (schedule.h), issuing with cp.async.bulk[.tensor] and mbarriers
+//     - the W window of every job   (box 68 x 10 of the slab seen as (x, y, column); zero fill
+//                                    outside the grid = the homogeneous boundary),
+//     - the A tile of every matrix  (box 64 x 8 x D of the diagonal storage),
+//     - the 512-byte chunks of the block's record stream,
+// into three shared-memory rings.  The consumers interpret the records: ASET loads an A tile into
+// register set k, JOB switches to the next window (already prefetched into registers), ENTRY
+// evaluates the stencil (20 DFMA) if the matrix changed and accumulates coef * S into the TMEM
+// accumulator of the output column, STORE writes two finished columns of Y.  Control flow is
+// warp-uniform throughout.
+//
+// Reference semantics: MultiOperator.apply, application/egsz/multi_operator2.py:38-84; only the
+// order in which the terms of a column are summed differs (grouped by register set and input).
+#pragma once
+#include "common.h"
+#include "schedule.h"
+
+#ifndef SPUQ_EMU
+#include <cuda.h>
+#include "kernels_tma.cuh"   // mbarrier / TMA helpers
+
+namespace spuq {
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t (&r)[8], uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+// the wait names the registers so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t (&r)[16], uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int K_, bool NINE_>
+struct TmemCfg {
+    static constexpr int K = K_;
+    static constexpr bool NINE = NINE_;
+    static constexpr int D = NINE ? 9 : 5;
+    static constexpr int TILE_X = 64, TILE_Y = 8;
+    static constexpr int CONSUMER_WARPS = 4;
+    static constexpr int CONSUMERS = 32 * CONSUMER_WARPS;
+    static constexpr int THREADS = CONSUMERS + 32;
+    static constexpr int BOX_W = 68, WIN_ROWS = TILE_Y + 2;
+    static constexpr int WIN_BYTES = BOX_W * WIN_ROWS * 8;
+    static constexpr int WIN_STRIDE = (WIN_BYTES + 127) / 128 * 128;
+    static constexpr int A_BYTES = TILE_X * TILE_Y * D * 8;
+    static constexpr int META_BYTES = SCHED_CHUNK_RECS * 16;
+    static constexpr int W_STAGES = 16, A_STAGES = NINE ? 2 : 4, M_STAGES = 8, I_STAGES = 4;
+    static constexpr int OFF_A = W_STAGES * WIN_STRIDE;
+    static constexpr int OFF_M = OFF_A + A_STAGES * A_BYTES;
+    static constexpr int OFF_I = OFF_M + M_STAGES * META_BYTES;
+    static constexpr int OFF_BAR = OFF_I + I_STAGES * 16;
+    static constexpr int N_BARS = 2 * (W_STAGES + A_STAGES + M_STAGES + I_STAGES);
+    static constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
+    static constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;       // + alignment slack
+};
+
+template <int K, bool NINE>
+__global__ void __launch_bounds__(160, 1)
+k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapA,
+             const SchedRec* __restrict__ recs, const int32_t* __restrict__ pcmd,
+             const int32_t* __restrict__ blk_pcmd, int32_t nblk, int32_t s, int32_t ny, int32_t nty,
+             int64_t n_items, unsigned long long* __restrict__ work_counter,
+             double* __restrict__ Y, int64_t ldy, const double* gate) {
+    using Cfg = TmemCfg<K, NINE>;
+    constexpr int D = Cfg::D;
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* wring = smem;
+    uint8_t* aring = smem + Cfg::OFF_A;
+    uint8_t* mring = smem + Cfg::OFF_M;
+    int4* iring = reinterpret_cast<int4*>(smem + Cfg::OFF_I);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_TMEM);
+    const uint32_t bar0 = smem_u32(smem + Cfg::OFF_BAR);
+    // barrier slots: full/empty pairs of the W, A, metadata and item rings
+    auto fullW = [&](int i) { return bar0 + 8u * i; };
+    auto emptyW = [&](int i) { return bar0 + 8u * (Cfg::W_STAGES + i); };
+    constexpr int BA = 2 * Cfg::W_STAGES;
+    auto fullA = [&](int i) { return bar0 + 8u * (BA + i); };
+    auto emptyA = [&](int i) { return bar0 + 8u * (BA + Cfg::A_STAGES + i); };
+    constexpr int BM = BA + 2 * Cfg::A_STAGES;
+    auto fullM = [&](int i) { return bar0 + 8u * (BM + i); };
+    auto emptyM = [&](int i) { return bar0 + 8u * (BM + Cfg::M_STAGES + i); };
+    constexpr int BI = BM + 2 * Cfg::M_STAGES;
+    auto fullI = [&](int i) { return bar0 + 8u * (BI + i); };
+    auto emptyI = [&](int i) { return bar0 + 8u * (BI + Cfg::I_STAGES + i); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::W_STAGES; ++i) { mbar_init(fullW(i), 1); mbar_init(emptyW(i), Cfg::CONSUMER_WARPS); }
+        for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(fullA(i), 1); mbar_init(emptyA(i), Cfg::CONSUMER_WARPS); }
+        for (int i = 0; i < Cfg::M_STAGES; ++i) { mbar_init(fullM(i), 1); mbar_init(emptyM(i), Cfg::CONSUMER_WARPS); }
+        for (int i = 0; i < Cfg::I_STAGES; ++i) { mbar_init(fullI(i), 1); mbar_init(emptyI(i), Cfg::CONSUMER_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    if (warp == Cfg::CONSUMER_WARPS) {
+        // ================================ producer warp ============================================
+        int sw = 0, sa = 0, sm = 0, si = 0;
+        uint32_t pw = 0, pa = 0, pm = 0, pi = 0;
+        for (;;) {
+            unsigned long long item = 0;
+            if (lane == 0) item = atomicAdd(work_counter, 1ull);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            const bool valid = item < (unsigned long long)n_items;
+            int32_t xt = -1, yt = -1, blk = 0;
+            if (valid) {
+                blk = (int32_t)(item % (unsigned long long)nblk);
+                const int64_t tile = (int64_t)(item / (unsigned long long)nblk);
+                yt = (int32_t)(tile % nty) * Cfg::TILE_Y;
+                xt = (int32_t)(tile / nty) * Cfg::TILE_X;
+            }
+            if (lane == 0) {
+                mbar_wait(emptyI(si), pi ^ 1u);
+                iring[si] = make_int4(xt, yt, 0, 0);
+                mbar_arrive(fullI(si));
+            }
+            if (++si == Cfg::I_STAGES) { si = 0; pi ^= 1u; }
+            if (!valid) break;
+            const int32_t c0 = __ldg(blk_pcmd + blk), c1 = __ldg(blk_pcmd + blk + 1);
+            int32_t next = (c0 + lane < c1) ? __ldg(pcmd + c0 + lane) : 0;
+            for (int32_t base = c0; base < c1; base += 32) {
+                const int32_t mine = next;
+                if (base + 32 + lane < c1) next = __ldg(pcmd + base + 32 + lane);
+                const int n = min(32, c1 - base);
+                for (int i = 0; i < n; ++i) {
+                    const int32_t cmd = __shfl_sync(0xffffffffu, mine, i);
+                    if (lane == 0) {
+                        const int32_t kind = cmd & PCMD_KIND_MASK, val = cmd & PCMD_VAL_MASK;
+                        if (kind == PCMD_WINDOW) {
+                            mbar_wait(emptyW(sw), pw ^ 1u);
+                            mbar_expect_tx(fullW(sw), Cfg::WIN_BYTES);
+                            tma_load_3d(smem_u32(wring + sw * Cfg::WIN_STRIDE), &mapW, xt - 2, yt - 1, val, fullW(sw));
+                            if (++sw == Cfg::W_STAGES) { sw = 0; pw ^= 1u; }
+                        } else if (kind == PCMD_ATILE) {
+                            mbar_wait(emptyA(sa), pa ^ 1u);
+                            mbar_expect_tx(fullA(sa), Cfg::A_BYTES);
+                            tma_load_3d(smem_u32(aring + sa * Cfg::A_BYTES), &mapA, xt, yt, val * D, fullA(sa));
+                            if (++sa == Cfg::A_STAGES) { sa = 0; pa ^= 1u; }
+                        } else {
+                            mbar_wait(emptyM(sm), pm ^ 1u);
+                            mbar_expect_tx(fullM(sm), Cfg::META_BYTES);
+                            bulk_load(smem_u32(mring + sm * Cfg::META_BYTES), recs + (size_t)val * SCHED_CHUNK_RECS,
+                                      Cfg::META_BYTES, fullM(sm));
+                            if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        return;
+    }
+
+    // ==================================== consumer warps ===========================================
+    const uint32_t tmem_warp = *tmem_slot + ((uint32_t)(warp * 32) << 16);
+    int sw = 0, sa = 0, sm = 0, si = 0;
+    uint32_t pw = 0, pa = 0, pm = 0, pi = 0;
+
+    double A[K][D][2][2];
+    double win[4][4], nwin[4][4];
+    double S[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int d = 0; d < D; ++d) A[k][d][0][0] = A[k][d][0][1] = A[k][d][1][0] = A[k][d][1][1] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) win[r][0] = win[r][1] = win[r][2] = win[r][3] = nwin[r][0] = nwin[r][1] = nwin[r][2] = nwin[r][3] = 0.0;
+
+    // window at the head of the W ring -> nwin, slot released right away
+    auto fetch_window = [&]() {
+        mbar_wait(fullW(sw), pw);
+        const double* wt = reinterpret_cast<const double*>(wring + sw * Cfg::WIN_STRIDE) + (2 * warp) * Cfg::BOX_W + 2 * lane;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            // box element e <-> x = x_tile - 2 + e; this thread's x0 = x_tile + 2*lane
+            const double2 c = *reinterpret_cast<const double2*>(wt + rr * Cfg::BOX_W + 2);
+            nwin[rr][1] = c.x; nwin[rr][2] = c.y;
+            if (NINE || rr == 1 || rr == 2) {
+                nwin[rr][0] = wt[rr * Cfg::BOX_W + 1];
+                nwin[rr][3] = wt[rr * Cfg::BOX_W + 4];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(emptyW(sw));
+        if (++sw == Cfg::W_STAGES) { sw = 0; pw ^= 1u; }
+    };
+    auto pop_item = [&](int32_t& xt, int32_t& yt) {
+        mbar_wait(fullI(si), pi);
+        const int4 it = iring[si];
+        xt = it.x; yt = it.y;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(emptyI(si));
+        if (++si == Cfg::I_STAGES) { si = 0; pi ^= 1u; }
+    };
+
+    int32_t xt, yt;
+    pop_item(xt, yt);
+    if (xt >= 0) fetch_window();
+    while (xt >= 0) {
+        int32_t nxt_xt = -1, nxt_yt = -1;
+        const int32_t x0 = xt + 2 * lane, y0 = yt + 2 * warp;
+
+        mbar_wait(fullM(sm), pm);
+        const int4* chunk = reinterpret_cast<const int4*>(mring + sm * Cfg::META_BYTES);
+        int ri = 0;
+        int4 cur = chunk[0];
+        for (;;) {
+            const int type = cur.x & REC_TYPE_MASK;
+            if (type == REC_END_ITEM) break;
+            // step to (and prefetch) the next record before working on this one
+            if (++ri == SCHED_CHUNK_RECS) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(emptyM(sm));
+                if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
+                mbar_wait(fullM(sm), pm);
+                chunk = reinterpret_cast<const int4*>(mring + sm * Cfg::META_BYTES);
+                ri = 0;
+            }
+            const int4 nxt = chunk[ri];
+            const int k = (cur.x >> REC_K_SHIFT) & 0xF;
+
+            if (type == REC_ENTRY) {
+                const uint32_t taddr = tmem_warp + (uint32_t)cur.y;
+                const double coef = __hiloint2double(cur.w, cur.z);
+                const bool init = (cur.x & REC_F_INIT) != 0;
+                uint32_t ar[8];
+                if (!init) tmem_ld8(ar, taddr);
+                if (cur.x & REC_F_FIRST) {
+#pragma unroll
+                    for (int kk = 0; kk < K; ++kk) {
+                        if (k == kk) {
+#pragma unroll
+                            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                                for (int p = 0; p < 2; ++p) {
+                                    double v;
+                                    if (NINE) {
+                                        v = A[kk][0][r][p] * win[r][p];
+                                        v = fma(A[kk][1][r][p], win[r][p + 1], v);
+                                        v = fma(A[kk][2][r][p], win[r][p + 2], v);
+                                        v = fma(A[kk][3][r][p], win[r + 1][p], v);
+                                        v = fma(A[kk][4][r][p], win[r + 1][p + 1], v);
+                                        v = fma(A[kk][5][r][p], win[r + 1][p + 2], v);
+                                        v = fma(A[kk][6][r][p], win[r + 2][p], v);
+                                        v = fma(A[kk][7][r][p], win[r + 2][p + 1], v);
+                                        v = fma(A[kk][8][r][p], win[r + 2][p + 2], v);
+                                    } else {
+                                        v = A[kk][0][r][p] * win[r][p + 1];
+                                        v = fma(A[kk][1][r][p], win[r + 1][p], v);
+                                        v = fma(A[kk][2][r][p], win[r + 1][p + 1], v);
+                                        v = fma(A[kk][3][r][p], win[r + 1][p + 2], v);
+                                        v = fma(A[kk][4][r][p], win[r + 2][p + 1], v);
+                                    }
+                                    S[r * 2 + p] = v;
+                                }
+                        }
+                    }
+                }
+                if (!init) {
+                    tmem_wait_ld8(ar);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double v = fma(coef, S[q], __hiloint2double((int)ar[2 * q + 1], (int)ar[2 * q]));
+                        ar[2 * q] = (uint32_t)__double2loint(v); ar[2 * q + 1] = (uint32_t)__double2hiint(v);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double v = coef * S[q];
+                        ar[2 * q] = (uint32_t)__double2loint(v); ar[2 * q + 1] = (uint32_t)__double2hiint(v);
+                    }
+                }
+                tmem_st8(taddr, ar);
+            } else if (type == REC_JOB) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) { win[rr][0] = nwin[rr][0]; win[rr][1] = nwin[rr][1]; win[rr][2] = nwin[rr][2]; win[rr][3] = nwin[rr][3]; }
+                if (cur.x & REC_F_LAST) {
+                    // the next window in the ring belongs to the next item (if there is one)
+                    pop_item(nxt_xt, nxt_yt);
+                    if (nxt_xt >= 0) fetch_window();
+                } else {
+                    fetch_window();
+                }
+            } else if (type == REC_ASET) {
+                mbar_wait(fullA(sa), pa);
+                const double* at = reinterpret_cast<const double*>(aring + sa * Cfg::A_BYTES) + (2 * warp) * Cfg::TILE_X + 2 * lane;
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk) {
+                    if (k == kk) {
+#pragma unroll
+                        for (int d = 0; d < D; ++d)
+#pragma unroll
+                            for (int r = 0; r < 2; ++r) {
+                                const double2 v = *reinterpret_cast<const double2*>(at + (d * Cfg::TILE_Y + r) * Cfg::TILE_X);
+                                A[kk][d][r][0] = v.x; A[kk][d][r][1] = v.y;
+                            }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(emptyA(sa));
+                if (++sa == Cfg::A_STAGES) { sa = 0; pa ^= 1u; }
+            } else if (type == REC_STORE) {
+                tmem_wait_st();
+                uint32_t r16[16];
+                tmem_ld16(r16, tmem_warp + (uint32_t)cur.y);
+                tmem_wait_ld16(r16);
+                const int32_t cols[2] = {cur.z, cur.w};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (cols[q] >= 0 && x0 < s) {
+                        double* yp = Y + (int64_t)cols[q] * ldy + (int64_t)y0 * s + x0;
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+                            if (y0 + r < ny)
+                                *reinterpret_cast<double2*>(yp + (int64_t)r * s) =
+                                    make_double2(__hiloint2double((int)r16[8 * q + 4 * r + 1], (int)r16[8 * q + 4 * r]),
+                                                 __hiloint2double((int)r16[8 * q + 4 * r + 3], (int)r16[8 * q + 4 * r + 2]));
+                    }
+                }
+            }
+            cur = nxt;
+        }
+        // END_ITEM: the rest of the chunk is padding
+        __syncwarp();
+        if (lane == 0) mbar_arrive(emptyM(sm));
+        if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
+        xt = nxt_xt; yt = nxt_yt;
+    }
+
+    // all TMEM traffic of the CTA is complete (every load was waited for): release the columns
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    asm volatile("bar.sync 1, 128;");
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(512));
+}
+
+}  // namespace spuq
+#endif  // !SPUQ_EMU

@@ -10,6 +10,8 @@
 #include "kernels_apply.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_tma.cuh"
+#include "kernels_tmem.cuh"
+#include "schedule.h"
 
 #ifdef SPUQ_EMU
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -193,6 +195,40 @@ static int build_blocks(spuq_sg_plan* p, int32_t C) {
 }
 
 
+
+// ---- schedule of the TMEM-accumulator kernel (schedule.h), rebuilt when K changes ----------------
+static int build_schedule(spuq_sg_plan* p, int32_t K) {
+    std::vector<int32_t> slot(p->h_term_mat.size());
+    for (size_t t = 0; t < slot.size(); ++t) slot[t] = p->slot_of_mat[p->h_term_mat[t]];
+    TermLists tl;
+    tl.L = p->L; tl.ptr = p->h_term_ptr.data(); tl.slot = slot.data();
+    tl.col = p->h_term_col.data(); tl.coef = p->h_term_coef.data();
+    std::vector<int32_t> order;
+    schedule_column_order(p->L, p->M, p->h_nbr_up.empty() ? nullptr : p->h_nbr_up.data(),
+                          p->h_nbr_dn.empty() ? nullptr : p->h_nbr_dn.data(), &order);
+    Schedule* sc = static_cast<Schedule*>(p->sched_host);
+    if (!sc) { sc = new Schedule(); p->sched_host = sc; }
+    schedule_build(tl, order, K, p->n_slots, sc);
+    for (void* d : p->sched_dev) cudaFree(d);
+    p->sched_dev.clear();
+    p->d_recs = nullptr; p->d_pcmd = nullptr; p->d_blk_pcmd = nullptr; p->d_work_counter = nullptr;
+    p->sched_K = 0;
+    int rc;
+    SchedRec* d_recs; int32_t *d_pcmd, *d_blk; 
+    const size_t first = p->owned_dev.size();
+    std::vector<unsigned long long> zero(2, 0ull);
+    unsigned long long* d_cnt;
+    if ((rc = dev_upload(p, sc->recs, &d_recs))) return rc;
+    if ((rc = dev_upload(p, sc->pcmd, &d_pcmd))) return rc;
+    if ((rc = dev_upload(p, sc->blk_pcmd, &d_blk))) return rc;
+    if ((rc = dev_upload(p, zero, &d_cnt))) return rc;
+    p->sched_dev.assign(p->owned_dev.begin() + first, p->owned_dev.end());
+    p->owned_dev.resize(first);
+    p->d_recs = d_recs; p->d_pcmd = d_pcmd; p->d_blk_pcmd = d_blk; p->d_work_counter = d_cnt;
+    p->sched_K = K;
+    return SPUQ_OK;
+}
+
 }  // namespace spuq
 
 using namespace spuq;
@@ -256,6 +292,10 @@ extern "C" int spuq_sg_plan_create(spuq_sg_plan** plan_out, int device, int64_t 
     for (int32_t m = m_begin; m < m_end; ++m) p->slot_of_mat[1 + m] = p->n_slots++;
 
     build_terms(p, nbr_up, nbr_dn, beta_up, beta_dn, beta_0);
+    if (M > 0) {
+        p->h_nbr_up.assign(nbr_up, nbr_up + (size_t)M * L);
+        p->h_nbr_dn.assign(nbr_dn, nbr_dn + (size_t)M * L);
+    }
     int rc;
     if ((rc = dev_upload(p, p->h_term_ptr, &p->term_ptr))) return rc;
     if ((rc = dev_upload(p, p->h_term_mat, &p->term_mat))) return rc;
@@ -357,7 +397,9 @@ extern "C" int spuq_sg_plan_destroy(spuq_sg_plan* p) {
     if (!p) return SPUQ_OK;
     cudaSetDevice(p->device);
     for (void* d : p->block_dev) cudaFree(d);
+    for (void* d : p->sched_dev) cudaFree(d);
     for (void* d : p->owned_dev) cudaFree(d);
+    delete static_cast<spuq::Schedule*>(p->sched_host);
     delete p;
     return SPUQ_OK;
 }
@@ -376,7 +418,8 @@ extern "C" int spuq_sg_plan_info(const spuq_sg_plan* p, int32_t* path, int64_t* 
 extern "C" int spuq_sg_plan_tune(spuq_sg_plan* p, int32_t variant, int32_t cols_per_block,
                                  int32_t rows_per_thread, int32_t ctas_per_sm) {
     SPUQ_REQUIRE(p != nullptr, "plan_tune: null plan");
-    SPUQ_REQUIRE(variant >= 0 && variant <= 3, "plan_tune: variant must be 0 (auto), 1 (simple), 2 (tiled) or 3 (tma)");
+    SPUQ_REQUIRE(variant >= 0 && variant <= 4,
+                 "plan_tune: variant must be 0 (auto), 1 (simple), 2 (tiled), 3 (tma) or 4 (tmem)");
     p->variant = variant; p->cols_per_block = cols_per_block;
     p->rows_per_thread = rows_per_thread; p->ctas_per_sm = ctas_per_sm;
     return SPUQ_OK;
@@ -467,6 +510,44 @@ static int launch_tma(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, 
     p->kernel_name = name;
     return SPUQ_OK;
 }
+
+template <int K, bool NINE>
+static int launch_tmem(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t ldy,
+                       cudaStream_t stream, const double* gate) {
+    using Cfg = TmemCfg<K, NINE>;
+    int rc;
+    if (p->tmap_a_rows != Cfg::TILE_Y) {
+        if ((rc = encode_3d(p->tmap_a, p->dia_vals, p->st.s, p->ny, (int64_t)p->n_slots * Cfg::D, p->st.s, p->st.N,
+                            Cfg::TILE_X, Cfg::TILE_Y, Cfg::D))) return rc;
+        p->tmap_a_rows = Cfg::TILE_Y;
+    }
+    if (p->tmap_w_ptr != W || p->tmap_w_ld != ldw || p->tmap_w_rows != Cfg::WIN_ROWS) {
+        if ((rc = encode_3d(p->tmap_w, W, p->st.s, p->ny, p->L, p->st.s, ldw, Cfg::BOX_W, Cfg::WIN_ROWS, 1))) return rc;
+        p->tmap_w_ptr = W; p->tmap_w_ld = ldw; p->tmap_w_rows = Cfg::WIN_ROWS;
+    }
+    auto kern = k_apply_tmem<K, NINE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SPUQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    const Schedule* sc = static_cast<const Schedule*>(p->sched_host);
+    const int32_t ntx = (p->st.s + Cfg::TILE_X - 1) / Cfg::TILE_X;
+    const int32_t nty = (p->ny + Cfg::TILE_Y - 1) / Cfg::TILE_Y;
+    const int64_t items = (int64_t)ntx * nty * sc->nblk;
+    const int64_t grid = std::min<int64_t>(items, (int64_t)p->n_sm);
+    SPUQ_CUDA_TRY(cudaMemsetAsync(p->d_work_counter, 0, sizeof(unsigned long long), stream));
+    CUtensorMap mw, ma;
+    std::memcpy(&mw, p->tmap_w, sizeof(mw));
+    std::memcpy(&ma, p->tmap_a, sizeof(ma));
+    kern<<<dim3((unsigned)grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream>>>(
+        mw, ma, static_cast<const SchedRec*>(p->d_recs), p->d_pcmd, p->d_blk_pcmd, sc->nblk, p->st.s, p->ny, nty,
+        items, p->d_work_counter, Y, ldy, gate);
+    char name[80];
+    snprintf(name, sizeof(name), "k_apply_tmem<K=%d,%s>", K, NINE ? "9pt" : "5pt");
+    p->kernel_name = name;
+    return SPUQ_OK;
+}
 #endif  // !SPUQ_EMU
 
 template <int RY, int C, bool NINE>
@@ -521,8 +602,50 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
 #else
         const bool can_tma = aligned && ldw % 2 == 0;
 #endif
-        // automatic choice: TMA pipeline on grids at least one box wide/tall, else loads through registers
-        const bool use_tma = can_tma && (p->variant == 3 || (p->variant == 0 && p->st.s >= 66 && p->ny >= 18));
+        SPUQ_REQUIRE(p->variant != 4 || (aligned && p->n_slots > 0),
+                     "apply: TMEM stencil kernel needs an even grid width, even leading dimensions, 16-byte aligned slabs "
+                     "and at least one block matrix");
+        // automatic choice: the TMEM-accumulator kernel whenever its alignment conditions hold
+        const bool use_tmem = aligned && p->n_slots > 0 && (p->variant == 4 || p->variant == 0);
+        if (use_tmem) {
+            const int32_t Kdef = p->nine ? 2 : 4;
+            const int32_t K = p->cols_per_block > 0 ? p->cols_per_block : Kdef;
+            SPUQ_REQUIRE(K >= 1 && K <= (p->nine ? 2 : 4), "apply: TMEM kernel supports 1..%d register sets (got %d)",
+                         p->nine ? 2 : 4, K);
+            if (p->sched_K != K) {
+                int rc = build_schedule(p, K);
+                if (rc) return rc;
+            }
+#ifdef SPUQ_EMU
+            // no TMA / TMEM on the host: interpret the same schedule tables with plain loops
+            schedule_run_host(*static_cast<const Schedule*>(p->sched_host), p->st.D, p->st.dx, p->st.dy, p->st.s, p->ny,
+                              p->dia_vals, W, ldw, Y, ldy);
+            {
+                char name[64];
+                snprintf(name, sizeof(name), "schedule_run_host<K=%d,%s>", K, p->nine ? "9pt" : "5pt");
+                p->kernel_name = name;
+            }
+#else
+            int rc = SPUQ_OK;
+            bool launched = false;
+#define SPUQ_TMEM(k)                                                                              \
+    if (!launched && K == k) {                                                                    \
+        rc = p->nine ? (k <= 2 ? launch_tmem<(k <= 2 ? k : 2), true>(p, W, ldw, Y, ldy, stream, gate) : SPUQ_E_UNSUPPORTED) \
+                     : launch_tmem<k, false>(p, W, ldw, Y, ldy, stream, gate);                    \
+        launched = true;                                                                          \
+    }
+            SPUQ_TMEM(1) SPUQ_TMEM(2) SPUQ_TMEM(3) SPUQ_TMEM(4)
+#undef SPUQ_TMEM
+            if (rc) return rc;
+            p->last_launches = 2;      // counter reset + kernel
+            SPUQ_CUDA_TRY(cudaGetLastError());
+            return SPUQ_OK;
+#endif
+            p->last_launches = 1;
+            return SPUQ_OK;
+        }
+        // TMA pipeline on grids at least one box wide/tall, else loads through registers
+        const bool use_tma = can_tma && p->variant == 3;
         const bool tiled = !use_tma && (p->variant == 2 || p->variant == 3 || (p->variant == 0 && aligned));
         if (!tiled && !use_tma) {
             const int64_t pair_blocks = ((p->n_rows + 1) / 2 + threads - 1) / threads;

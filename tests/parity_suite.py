@@ -54,7 +54,8 @@ def check_apply_paths(n=12, M=4, p=2, kind="legendre", mu=0.0):
         assert relerr(Y, c.Y) <= TOL, (path, relerr(Y, c.Y))
         seen.add(plan.kernel_name)
     assert {"k_apply_csr", "k_apply_ell<8>"} <= seen
-    for tune in [(1, 0, 0, 0), (2, 8, 2, 0), (2, 4, 2, 0), (2, 16, 2, 0), (2, 8, 1, 0), (2, 16, 1, 0), (2, 4, 4, 0)]:
+    for tune in [(1, 0, 0, 0), (2, 8, 2, 0), (2, 4, 2, 0), (2, 16, 2, 0), (2, 8, 1, 0), (2, 16, 1, 0), (2, 4, 4, 0),
+                 (4, 1, 0, 0), (4, 2, 0, 0), (4, 3, 0, 0), (4, 4, 0, 0)]:
         Y, plan = product_apply(c, _abi.PATH_STENCIL, tune)
         assert relerr(Y, c.Y) <= TOL, (tune, plan.kernel_name, relerr(Y, c.Y))
     info = plan.info()
@@ -167,7 +168,7 @@ def nine_point_case(nx, ny, M, idx, seed=3):
 def check_apply_nine_point_and_odd_shapes():
     idx = synthetic.complete_order_indices(3, 2)
     c = nine_point_case(10, 7, 3, idx)
-    for tune in [None, (1, 0, 0, 0), (2, 8, 2, 0), (2, 4, 2, 0), (2, 8, 1, 0)]:
+    for tune in [None, (1, 0, 0, 0), (2, 8, 2, 0), (2, 4, 2, 0), (2, 8, 1, 0), (4, 1, 0, 0), (4, 2, 0, 0)]:
         Y, plan = product_apply(c, _abi.PATH_STENCIL, tune)
         assert relerr(Y, c.Y) <= TOL, (tune, plan.kernel_name)
     assert "9pt" in product_apply(c)[1].kernel_name
@@ -236,6 +237,27 @@ def check_apply_m_shards():
         Y, _ = product_apply(c, m_range=(lo, hi), include_mean=(g == 0))
         total += Y
     assert relerr(total, c.Y) <= TOL
+
+
+def check_apply_multiblock():
+    """More than one 64-column block: the TMEM-kernel schedule reorders Lambda (reconstructed from
+    the neighbour tables), cuts it into blocks and register sets; anisotropic and isotropic sets,
+    beta0 != 0, and M-shards that leave some output columns without any term."""
+    cases = [(8, synthetic.complete_order_indices(6, 3), 6, "legendre", 0.0),          # L = 84
+             (6, synthetic.anisotropic_indices(8, 9.0), 8, "hermite", 0.5),
+             (6, synthetic.truncated_complete_indices(7, 3, 100), 7, "hermite", 0.0)]
+    for n, idx, M, kind, mu in cases:
+        assert idx.shape[0] > 64
+        c = fd_case(n, M, idx, kind, mu)
+        for tune in [(4, 1, 0, 0), (4, 3, 0, 0), (4, 4, 0, 0), None]:
+            Y, plan = product_apply(c, _abi.PATH_STENCIL, tune)
+            assert relerr(Y, c.Y) <= TOL, (tune, plan.kernel_name, relerr(Y, c.Y))
+        total = np.zeros_like(c.Y)
+        shards = [(0, 1), (1, 3), (3, M)]
+        for g, (lo, hi) in enumerate(shards):
+            Y, _ = product_apply(c, _abi.PATH_STENCIL, (4, 2, 0, 0), m_range=(lo, hi), include_mean=(g == 1))
+            total += Y
+        assert relerr(total, c.Y) <= TOL
 
 
 # ---- vectors ------------------------------------------------------------------------------------

@@ -43,6 +43,10 @@ def test_apply_m_shards():
     ps.check_apply_m_shards()
 
 
+def test_apply_multiblock():
+    ps.check_apply_multiblock()
+
+
 def test_slab_multivector_api():
     ps.check_slab_multivector_api()
 

@@ -194,6 +194,56 @@ __global__ void k_tmem(double* out, int iters, long long* clk) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512));
 }
 
+// single-warp dependent chains: MODE 0 = ld,wait (latency of a load), 1 = ld,wait,fma,st,wait::st (full RMW round trip),
+// 2 = ld,wait,fma,st without wait::st (same address every iteration)
+template <int MODE>
+__global__ void k_tmem_lat(double* out, int iters, long long* clk) {
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t base = tmem_base_s;
+    const uint32_t a = base + (((uint32_t)(warp & 3) * 32u) << 16);
+    uint32_t r[8];
+    for (int i = 0; i < 8; ++i) r[i] = 0;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a + (r[0] & 0)) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (MODE >= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double d = __hiloint2double(r[2 * i + 1], r[2 * i]);
+                d = fma(d, 1.0, 1.0);
+                r[2 * i] = __double2loint(d); r[2 * i + 1] = __double2hiint(d);
+            }
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                         ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+            if (MODE == 1) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    long long t1 = clock64();
+    // read back: with MODE 1/2 every iteration added 1.0 -> value must equal iters if ld-after-st is ordered
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (threadIdx.x == 0 && blockIdx.x == 0) { clk[0] = t1 - t0; out[0] = __hiloint2double(r[1], r[0]); }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512));
+}
+
 static float timeit(void (*launch)(void*), void* arg, int reps = 3) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     launch(arg); CK(cudaDeviceSynchronize());
@@ -223,6 +273,20 @@ int main(int argc, char** argv) {
         CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1);
         double fl = 2.0 * 8 * iters * warps * 32.0 * nsm;
         printf("DFMA  ILP8  %2d warps/SM: %.2f TFLOP/s (%.3f ms)\n", warps, fl / ms * 1e-9, ms);
+    }
+    {
+        auto runilp = [&](auto kern, int ilp, int warps) {
+            const int iters = 20000;
+            kern<<<nsm, warps * 32>>>(dout, 100, 1.0000001, 0.5); CK(cudaDeviceSynchronize());
+            cudaEventRecord(e0); kern<<<nsm, warps * 32>>>(dout, iters, 1.0000001, 0.5); cudaEventRecord(e1);
+            CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1);
+            double fl = 2.0 * ilp * iters * warps * 32.0 * nsm;
+            printf("DFMA  ILP%d  %2d warps/SM: %.2f TFLOP/s\n", ilp, warps, fl / ms * 1e-9);
+        };
+        for (int warps : {4, 8}) {
+            runilp(k_dfma<1>, 1, warps); runilp(k_dfma<2>, 2, warps); runilp(k_dfma<3>, 3, warps);
+            runilp(k_dfma<4>, 4, warps); runilp(k_dfma<6>, 6, warps); runilp(k_dfma<12>, 12, warps);
+        }
     }
     // ---- LDS / SHFL
     {
@@ -306,6 +370,19 @@ int main(int argc, char** argv) {
             run(k_tmem<1>, "TMEM st x16", 64, warps);
             run(k_tmem<2>, "TMEM ld+8DFMA+st", 64, warps);
         }
+    }
+    {
+        const int iters = 10000;
+        auto run = [&](auto kern, const char* name, int warps) {
+            kern<<<1, warps * 32>>>(dout, iters, dclk); CK(cudaDeviceSynchronize());
+            long long clk; double v; CK(cudaMemcpy(&clk, dclk, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&v, dout, 8, cudaMemcpyDeviceToHost));
+            printf("%-40s %d warps: %.1f clk/iter, final value %.1f (expect %d when ordered)\n", name, warps, (double)clk / iters, v, iters);
+        };
+        run(k_tmem_lat<0>, "TMEM ld.x8 + wait (latency)", 1);
+        run(k_tmem_lat<1>, "TMEM ld,wait,fma,st,wait::st", 1);
+        run(k_tmem_lat<2>, "TMEM ld,wait,fma,st (no wait::st)", 1);
+        run(k_tmem_lat<1>, "TMEM ld,wait,fma,st,wait::st", 4);
+        run(k_tmem_lat<2>, "TMEM ld,wait,fma,st (no wait::st)", 4);
     }
     printf("done\n");
     return 0;
