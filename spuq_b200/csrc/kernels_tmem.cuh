@@ -71,6 +71,88 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+
+// ---- explicit shared-space loads (32-bit shared addresses; the ring buffers are written by TMA) ----
+__device__ __forceinline__ void lds_f64x2(uint32_t addr, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double x;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(addr) : "memory");
+    return x;
+}
+__device__ __forceinline__ int4 lds_i32x4(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// S = A_k * window on the thread's 2 x 2 patch; a[d][r*2+p], w rows y0-1..y0+2 / x0-1..x0+2
+template <bool NINE>
+__device__ __forceinline__ void stencil1(const double (&a)[NINE ? 9 : 5][4], const double (&w)[4][4], double (&S)[4]) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int q = r * 2 + p;
+            double v;
+            if (NINE) {
+                v = a[0][q] * w[r][p];
+                v = fma(a[1][q], w[r][p + 1], v);
+                v = fma(a[2][q], w[r][p + 2], v);
+                v = fma(a[3][q], w[r + 1][p], v);
+                v = fma(a[4][q], w[r + 1][p + 1], v);
+                v = fma(a[5][q], w[r + 1][p + 2], v);
+                v = fma(a[6][q], w[r + 2][p], v);
+                v = fma(a[7][q], w[r + 2][p + 1], v);
+                v = fma(a[8][q], w[r + 2][p + 2], v);
+            } else {
+                v = a[0][q] * w[r][p + 1];
+                v = fma(a[1][q], w[r + 1][p], v);
+                v = fma(a[2][q], w[r + 1][p + 1], v);
+                v = fma(a[3][q], w[r + 1][p + 2], v);
+                v = fma(a[4][q], w[r + 2][p + 1], v);
+            }
+            S[q] = v;
+        }
+}
+// both window buffers with the same matrix: eight independent DFMA chains in one basic block
+template <bool NINE>
+__device__ __forceinline__ void stencil2(const double (&a)[NINE ? 9 : 5][4], const double (&wa)[4][4],
+                                         const double (&wb)[4][4], double (&SA)[4], double (&SB)[4]) {
+    stencil1<NINE>(a, wa, SA);
+    stencil1<NINE>(a, wb, SB);
+}
+// acc[taddr] (+)= coef * S through tensor memory
+__device__ __forceinline__ void accumulate(uint32_t (&ar)[8], uint32_t taddr, double coef, const double (&S)[4], bool loaded) {
+    if (loaded) {
+        tmem_wait_ld8(ar);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double v = fma(coef, S[q], __hiloint2double((int)ar[2 * q + 1], (int)ar[2 * q]));
+            ar[2 * q] = (uint32_t)__double2loint(v); ar[2 * q + 1] = (uint32_t)__double2hiint(v);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double v = coef * S[q];
+            ar[2 * q] = (uint32_t)__double2loint(v); ar[2 * q + 1] = (uint32_t)__double2hiint(v);
+        }
+    }
+    tmem_st8(taddr, ar);
+}
+
 template <int K_, bool NINE_>
 struct TmemCfg {
     static constexpr int K = K_;
@@ -205,150 +287,107 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     const uint32_t tmem_warp = *tmem_slot + ((uint32_t)(warp * 32) << 16);
     int sw = 0, sa = 0, sm = 0, si = 0;
     uint32_t pw = 0, pa = 0, pm = 0, pi = 0;
+    const uint32_t wring_s = smem_u32(wring), aring_s = smem_u32(aring), mring_s = smem_u32(mring);
+    // this thread's corner inside a staged window / A tile (bytes)
+    const uint32_t win_off = (uint32_t)(((2 * warp) * Cfg::BOX_W + 2 * lane) * 8);
+    const uint32_t a_off = (uint32_t)(((2 * warp) * Cfg::TILE_X + 2 * lane) * 8);
 
-    double A[K][D][2][2];
-    double win[4][4], nwin[4][4];
-    double S[4] = {0.0, 0.0, 0.0, 0.0};
+    double A[K][D][4];                    // [register set][diagonal][point r*2+p]
+    double wa[4][4], wb[4][4];            // window buffers A and B: rows y0-1..y0+2, x0-1..x0+2
+    double SA[4] = {0.0, 0.0, 0.0, 0.0}, SB[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
-        for (int d = 0; d < D; ++d) A[k][d][0][0] = A[k][d][0][1] = A[k][d][1][0] = A[k][d][1][1] = 0.0;
+        for (int d = 0; d < D; ++d) A[k][d][0] = A[k][d][1] = A[k][d][2] = A[k][d][3] = 0.0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) win[r][0] = win[r][1] = win[r][2] = win[r][3] = nwin[r][0] = nwin[r][1] = nwin[r][2] = nwin[r][3] = 0.0;
+    for (int r = 0; r < 4; ++r) wa[r][0] = wa[r][1] = wa[r][2] = wa[r][3] = wb[r][0] = wb[r][1] = wb[r][2] = wb[r][3] = 0.0;
 
-    // window at the head of the W ring -> nwin, slot released right away
-    auto fetch_window = [&]() {
-        mbar_wait(fullW(sw), pw);
-        const double* wt = reinterpret_cast<const double*>(wring + sw * Cfg::WIN_STRIDE) + (2 * warp) * Cfg::BOX_W + 2 * lane;
+    bool w_ready = false;                 // result of an early probe of the next W-ring slot
+    // window at the head of the W ring -> registers; the slot is released right away and the
+    // following slot probed, so that the next call rarely has to wait
+    auto load_window = [&](double (&w)[4][4]) {
+        if (!w_ready) mbar_wait(fullW(sw), pw);
+        const uint32_t base = wring_s + (uint32_t)sw * Cfg::WIN_STRIDE + win_off;
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             // box element e <-> x = x_tile - 2 + e; this thread's x0 = x_tile + 2*lane
-            const double2 c = *reinterpret_cast<const double2*>(wt + rr * Cfg::BOX_W + 2);
-            nwin[rr][1] = c.x; nwin[rr][2] = c.y;
+            lds_f64x2(base + (rr * Cfg::BOX_W + 2) * 8, w[rr][1], w[rr][2]);
             if (NINE || rr == 1 || rr == 2) {
-                nwin[rr][0] = wt[rr * Cfg::BOX_W + 1];
-                nwin[rr][3] = wt[rr * Cfg::BOX_W + 4];
+                w[rr][0] = lds_f64(base + (rr * Cfg::BOX_W + 1) * 8);
+                w[rr][3] = lds_f64(base + (rr * Cfg::BOX_W + 4) * 8);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(emptyW(sw));
         if (++sw == Cfg::W_STAGES) { sw = 0; pw ^= 1u; }
+        w_ready = mbar_test(fullW(sw), pw);
     };
-    auto pop_item = [&](int32_t& xt, int32_t& yt) {
+
+    for (;;) {
+        // ---- next work item -----------------------------------------------------------------------
         mbar_wait(fullI(si), pi);
-        const int4 it = iring[si];
-        xt = it.x; yt = it.y;
+        const int4 it = lds_i32x4(smem_u32(iring + si));
         __syncwarp();
         if (lane == 0) mbar_arrive(emptyI(si));
         if (++si == Cfg::I_STAGES) { si = 0; pi ^= 1u; }
-    };
-
-    int32_t xt, yt;
-    pop_item(xt, yt);
-    if (xt >= 0) fetch_window();
-    while (xt >= 0) {
-        int32_t nxt_xt = -1, nxt_yt = -1;
-        const int32_t x0 = xt + 2 * lane, y0 = yt + 2 * warp;
+        if (it.x < 0) break;
+        const int32_t x0 = it.x + 2 * lane, y0 = it.y + 2 * warp;
 
         mbar_wait(fullM(sm), pm);
-        const int4* chunk = reinterpret_cast<const int4*>(mring + sm * Cfg::META_BYTES);
-        int ri = 0;
-        int4 cur = chunk[0];
+        uint32_t rptr = mring_s + (uint32_t)sm * Cfg::META_BYTES;
+        int4 cur = lds_i32x4(rptr);
         for (;;) {
-            const int type = cur.x & REC_TYPE_MASK;
-            if (type == REC_END_ITEM) break;
-            // step to (and prefetch) the next record before working on this one
-            if (++ri == SCHED_CHUNK_RECS) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(emptyM(sm));
-                if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
-                mbar_wait(fullM(sm), pm);
-                chunk = reinterpret_cast<const int4*>(mring + sm * Cfg::META_BYTES);
-                ri = 0;
-            }
-            const int4 nxt = chunk[ri];
-            const int k = (cur.x >> REC_K_SHIFT) & 0xF;
+            // the record after this one is fetched before this one is worked on
+            rptr += 16;
+            const int4 nxt = lds_i32x4(rptr);
+            const int a = cur.x;
+            const int type = a & REC_TYPE_MASK;
 
-            if (type == REC_ENTRY) {
+            if (type == REC_OP) {
                 const uint32_t taddr = tmem_warp + (uint32_t)cur.y;
                 const double coef = __hiloint2double(cur.w, cur.z);
-                const bool init = (cur.x & REC_F_INIT) != 0;
+                const bool load_acc = (a & (REC_F_INIT | REC_F_NOACC)) == 0;
                 uint32_t ar[8];
-                if (!init) tmem_ld8(ar, taddr);
-                if (cur.x & REC_F_FIRST) {
+                if (load_acc) tmem_ld8(ar, taddr);
+                if (a & (REC_F_STA | REC_F_STB)) {
+                    const int k = (a >> REC_K_SHIFT) & 3;
 #pragma unroll
                     for (int kk = 0; kk < K; ++kk) {
                         if (k == kk) {
-#pragma unroll
-                            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                                for (int p = 0; p < 2; ++p) {
-                                    double v;
-                                    if (NINE) {
-                                        v = A[kk][0][r][p] * win[r][p];
-                                        v = fma(A[kk][1][r][p], win[r][p + 1], v);
-                                        v = fma(A[kk][2][r][p], win[r][p + 2], v);
-                                        v = fma(A[kk][3][r][p], win[r + 1][p], v);
-                                        v = fma(A[kk][4][r][p], win[r + 1][p + 1], v);
-                                        v = fma(A[kk][5][r][p], win[r + 1][p + 2], v);
-                                        v = fma(A[kk][6][r][p], win[r + 2][p], v);
-                                        v = fma(A[kk][7][r][p], win[r + 2][p + 1], v);
-                                        v = fma(A[kk][8][r][p], win[r + 2][p + 2], v);
-                                    } else {
-                                        v = A[kk][0][r][p] * win[r][p + 1];
-                                        v = fma(A[kk][1][r][p], win[r + 1][p], v);
-                                        v = fma(A[kk][2][r][p], win[r + 1][p + 1], v);
-                                        v = fma(A[kk][3][r][p], win[r + 1][p + 2], v);
-                                        v = fma(A[kk][4][r][p], win[r + 2][p + 1], v);
-                                    }
-                                    S[r * 2 + p] = v;
-                                }
+                            if ((a & (REC_F_STA | REC_F_STB)) == (REC_F_STA | REC_F_STB)) {
+                                stencil2<NINE>(A[kk], wa, wb, SA, SB);
+                            } else if (a & REC_F_STA) {
+                                stencil1<NINE>(A[kk], wa, SA);
+                            } else {
+                                stencil1<NINE>(A[kk], wb, SB);
+                            }
                         }
                     }
                 }
-                if (!init) {
-                    tmem_wait_ld8(ar);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const double v = fma(coef, S[q], __hiloint2double((int)ar[2 * q + 1], (int)ar[2 * q]));
-                        ar[2 * q] = (uint32_t)__double2loint(v); ar[2 * q + 1] = (uint32_t)__double2hiint(v);
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const double v = coef * S[q];
-                        ar[2 * q] = (uint32_t)__double2loint(v); ar[2 * q + 1] = (uint32_t)__double2hiint(v);
-                    }
+                if (!(a & REC_F_NOACC)) {
+                    if (a & REC_F_SRCB) accumulate(ar, taddr, coef, SB, load_acc);
+                    else accumulate(ar, taddr, coef, SA, load_acc);
                 }
-                tmem_st8(taddr, ar);
-            } else if (type == REC_JOB) {
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) { win[rr][0] = nwin[rr][0]; win[rr][1] = nwin[rr][1]; win[rr][2] = nwin[rr][2]; win[rr][3] = nwin[rr][3]; }
-                if (cur.x & REC_F_LAST) {
-                    // the next window in the ring belongs to the next item (if there is one)
-                    pop_item(nxt_xt, nxt_yt);
-                    if (nxt_xt >= 0) fetch_window();
-                } else {
-                    fetch_window();
-                }
+            } else if (type == REC_RELOAD) {
+                if (a & REC_F_BUFA) load_window(wa);
+                if (a & REC_F_BUFB) load_window(wb);
             } else if (type == REC_ASET) {
-                mbar_wait(fullA(sa), pa);
-                const double* at = reinterpret_cast<const double*>(aring + sa * Cfg::A_BYTES) + (2 * warp) * Cfg::TILE_X + 2 * lane;
+                const int cnt = (a >> REC_CNT_SHIFT) & 0xF;
 #pragma unroll
                 for (int kk = 0; kk < K; ++kk) {
-                    if (k == kk) {
+                    if (kk < cnt) {
+                        mbar_wait(fullA(sa), pa);
+                        const uint32_t base = aring_s + (uint32_t)sa * Cfg::A_BYTES + a_off;
 #pragma unroll
                         for (int d = 0; d < D; ++d)
 #pragma unroll
-                            for (int r = 0; r < 2; ++r) {
-                                const double2 v = *reinterpret_cast<const double2*>(at + (d * Cfg::TILE_Y + r) * Cfg::TILE_X);
-                                A[kk][d][r][0] = v.x; A[kk][d][r][1] = v.y;
-                            }
+                            for (int r = 0; r < 2; ++r)
+                                lds_f64x2(base + ((d * Cfg::TILE_Y + r) * Cfg::TILE_X) * 8, A[kk][d][2 * r], A[kk][d][2 * r + 1]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(emptyA(sa));
+                        if (++sa == Cfg::A_STAGES) { sa = 0; pa ^= 1u; }
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(emptyA(sa));
-                if (++sa == Cfg::A_STAGES) { sa = 0; pa ^= 1u; }
             } else if (type == REC_STORE) {
                 tmem_wait_st();
                 uint32_t r16[16];
@@ -367,6 +406,16 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                                                  __hiloint2double((int)r16[8 * q + 4 * r + 3], (int)r16[8 * q + 4 * r + 2]));
                     }
                 }
+            } else if (type == REC_NEXT_CHUNK) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(emptyM(sm));
+                if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
+                mbar_wait(fullM(sm), pm);
+                rptr = mring_s + (uint32_t)sm * Cfg::META_BYTES;
+                cur = lds_i32x4(rptr);
+                continue;
+            } else {
+                break;      // REC_END_ITEM
             }
             cur = nxt;
         }
@@ -374,7 +423,6 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         __syncwarp();
         if (lane == 0) mbar_arrive(emptyM(sm));
         if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
-        xt = nxt_xt; yt = nxt_yt;
     }
 
     // all TMEM traffic of the CTA is complete (every load was waited for): release the columns

@@ -55,6 +55,8 @@ void schedule_column_order(int32_t L, int32_t M, const int32_t* nbr_up, const in
 
 namespace {
 struct Term { int32_t slot, in_col, out; double coef; };
+struct Entry { int32_t k, out; double coef; };
+struct Job { int32_t in_col; uint32_t kmask; std::vector<Entry> es; };
 
 struct Emitter {
     Schedule* s;
@@ -65,12 +67,15 @@ struct Emitter {
         chunk0 = (int32_t)(s->recs.size() / SCHED_CHUNK_RECS);
         chunk_cmds.clear();
     }
-    void rec(int32_t a, int32_t b, double c, int32_t cmd = -1) {
+    // append a record (the last slot of every chunk is the link to the next chunk); returns the chunk
+    int32_t rec(int32_t a, int32_t b, double c) {
+        if (s->recs.size() % SCHED_CHUNK_RECS == SCHED_CHUNK_RECS - 1) s->recs.push_back(SchedRec{REC_NEXT_CHUNK, 0, 0.0});
         const int32_t chunk = (int32_t)(s->recs.size() / SCHED_CHUNK_RECS) - chunk0;
         if ((int32_t)chunk_cmds.size() <= chunk) chunk_cmds.resize(chunk + 1);
-        if (cmd != -1) chunk_cmds[chunk].push_back(cmd);
         s->recs.push_back(SchedRec{a, b, c});
+        return chunk;
     }
+    void cmd(int32_t chunk, int32_t c) { chunk_cmds[chunk].push_back(c); }
     void end_block() {
         rec(REC_END_ITEM, 0, 0.0);
         while (s->recs.size() % SCHED_CHUNK_RECS) s->recs.push_back(SchedRec{REC_END_ITEM, 0, 0.0});
@@ -78,7 +83,7 @@ struct Emitter {
         // producer stream: metadata chunks run two ahead of the fetches they describe
         for (int32_t c = 0; c < std::min(nch, 2); ++c) s->pcmd.push_back(PCMD_META | (chunk0 + c));
         for (int32_t c = 0; c < nch; ++c) {
-            for (int32_t cmd : chunk_cmds[c]) s->pcmd.push_back(cmd);
+            for (int32_t x : chunk_cmds[c]) s->pcmd.push_back(x);
             if (c + 2 < nch) s->pcmd.push_back(PCMD_META | (chunk0 + c + 2));
         }
         s->blk_pcmd.push_back((int32_t)s->pcmd.size());
@@ -114,12 +119,11 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
             }
         }
         // a block without any term still has to write zeros: one null term on its first column
-        if (ts.empty()) ts.push_back(Term{0, order[(size_t)b * C], 0, 0.0});
+        if (ts.empty()) { ts.push_back(Term{0, order[(size_t)b * C], 0, 0.0}); slot_count[0] = 1; }
         // matrices of this block, busiest first; K at a time form a register set
         std::vector<int32_t> slots;
         for (int32_t sl = 0; sl < (int32_t)slot_count.size(); ++sl)
             if (slot_count[sl] > 0) slots.push_back(sl);
-        if (slots.empty()) slots.push_back(ts[0].slot);
         std::stable_sort(slots.begin(), slots.end(), [&](int32_t a, int32_t c2) { return slot_count[a] > slot_count[c2]; });
         std::vector<int32_t> k_of_slot(slot_count.size(), -1), set_of_slot(slot_count.size(), -1);
         for (size_t i = 0; i < slots.size(); ++i) {
@@ -127,50 +131,81 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
             k_of_slot[slots[i]] = (int32_t)(i % K);
         }
         const int32_t nsets = (int32_t)((slots.size() + K - 1) / K);
-        std::stable_sort(ts.begin(), ts.end(), [&](const Term& x, const Term& y) {
-            if (set_of_slot[x.slot] != set_of_slot[y.slot]) return set_of_slot[x.slot] < set_of_slot[y.slot];
-            if (x.in_col != y.in_col) return x.in_col < y.in_col;
-            if (k_of_slot[x.slot] != k_of_slot[y.slot]) return k_of_slot[x.slot] < k_of_slot[y.slot];
-            return x.out < y.out;
-        });
         std::vector<char> touched(ncols, 0);
         int32_t n_touched = 0;
-        size_t i = 0;
+
         for (int32_t set = 0; set < nsets; ++set) {
-            for (int32_t k = 0; k < K && (size_t)(set * K + k) < slots.size(); ++k) {
-                const int32_t sl = slots[(size_t)set * K + k];
-                em.rec(REC_ASET | (k << REC_K_SHIFT), sl, 0.0, PCMD_ATILE | sl);
-                s.n_asets += 1;
+            // ---- A tiles of the set
+            const int32_t cnt = std::min<int32_t>(K, (int32_t)slots.size() - set * K);
+            {
+                const int32_t ch = em.rec(REC_ASET | (cnt << REC_CNT_SHIFT), 0, 0.0);
+                for (int32_t k = 0; k < cnt; ++k) em.cmd(ch, PCMD_ATILE | slots[(size_t)set * K + k]);
+                s.n_asets += cnt;
             }
-            while (i < ts.size() && set_of_slot[ts[i].slot] == set) {
-                const int32_t in_col = ts[i].in_col;
-                size_t j = i;
-                while (j < ts.size() && set_of_slot[ts[j].slot] == set && ts[j].in_col == in_col) ++j;
-                const bool last_job = (j == ts.size());
-                em.rec(REC_JOB | (last_job ? REC_F_LAST : 0), in_col, 0.0, PCMD_WINDOW | in_col);
-                s.n_jobs += 1;
-                int32_t prev_k = -1;
-                for (size_t e = i; e < j; ++e) {
-                    const int32_t k = k_of_slot[ts[e].slot];
-                    int32_t a = REC_ENTRY | (k << REC_K_SHIFT);
-                    if (k != prev_k) { a |= REC_F_FIRST; s.n_stencils += 1; }
-                    prev_k = k;
-                    if (!touched[ts[e].out]) { a |= REC_F_INIT; touched[ts[e].out] = 1; ++n_touched; }
-                    em.rec(a, ts[e].out * SCHED_ACC_STRIDE, ts[e].coef);
-                    s.n_entries += 1;
+            // ---- jobs of the set: one per input column, entries ordered by register set k
+            std::map<int32_t, Job> by_col;
+            for (const Term& t : ts) {
+                if (set_of_slot[t.slot] != set) continue;
+                Job& j = by_col[t.in_col];
+                j.in_col = t.in_col;
+                j.kmask |= 1u << k_of_slot[t.slot];
+                j.es.push_back(Entry{k_of_slot[t.slot], t.out, t.coef});
+            }
+            std::vector<Job> jobs;
+            for (auto& kv : by_col) {
+                std::stable_sort(kv.second.es.begin(), kv.second.es.end(), [](const Entry& x, const Entry& y) {
+                    if (x.k != y.k) return x.k < y.k;
+                    return x.out < y.out;
+                });
+                jobs.push_back(std::move(kv.second));
+            }
+            // jobs that use the same matrices next to each other, so that pairs share their stencils
+            std::stable_sort(jobs.begin(), jobs.end(), [](const Job& x, const Job& y) { return x.kmask > y.kmask; });
+            s.n_jobs += (int64_t)jobs.size();
+
+            auto emit_reload = [&](size_t first_job) {
+                const bool two = first_job + 1 < jobs.size();
+                const int32_t ch = em.rec(REC_RELOAD | REC_F_BUFA | (two ? REC_F_BUFB : 0), 0, 0.0);
+                em.cmd(ch, PCMD_WINDOW | jobs[first_job].in_col);
+                if (two) em.cmd(ch, PCMD_WINDOW | jobs[first_job + 1].in_col);
+            };
+            if (!jobs.empty()) emit_reload(0);
+            for (size_t j0 = 0; j0 < jobs.size(); j0 += 2) {
+                const Job& ja = jobs[j0];
+                const Job* jb = (j0 + 1 < jobs.size()) ? &jobs[j0 + 1] : nullptr;
+                const uint32_t kunion = ja.kmask | (jb ? jb->kmask : 0u);
+                int32_t last_k = -1;
+                for (int32_t k = 0; k < K; ++k) if (kunion >> k & 1u) last_k = k;
+                for (int32_t k = 0; k < K; ++k) {
+                    if (!(kunion >> k & 1u)) continue;
+                    // accumulations of this matrix: (source buffer, entry)
+                    std::vector<std::pair<int, const Entry*>> acc;
+                    for (const Entry& e : ja.es) if (e.k == k) acc.push_back({0, &e});
+                    if (jb) for (const Entry& e : jb->es) if (e.k == k) acc.push_back({1, &e});
+                    int32_t st = 0;
+                    if (ja.kmask >> k & 1u) st |= REC_F_STA;
+                    if (jb && (jb->kmask >> k & 1u)) st |= REC_F_STB;
+                    s.n_stencils += (st & REC_F_STA ? 1 : 0) + (st & REC_F_STB ? 1 : 0);
+                    for (size_t q = 0; q < acc.size(); ++q) {
+                        const Entry& e = *acc[q].second;
+                        int32_t a = REC_OP | (k << REC_K_SHIFT) | (q == 0 ? st : 0);
+                        if (acc[q].first) a |= REC_F_SRCB;
+                        if (!touched[e.out]) { a |= REC_F_INIT; touched[e.out] = 1; ++n_touched; }
+                        em.rec(a, e.out * SCHED_ACC_STRIDE, e.coef);
+                        s.n_entries += 1;
+                        // the windows are dead once the last stencil of the pair has been issued:
+                        // fetch the next pair's while the remaining accumulations run
+                        if (q == 0 && k == last_k && j0 + 2 < jobs.size()) emit_reload(j0 + 2);
+                    }
                 }
-                if (last_job && n_touched < ncols) {
-                    // output columns without any term (possible for an M-shard): zero them with a
-                    // null entry that reuses the last stencil value
-                    for (int32_t o = 0; o < ncols; ++o)
-                        if (!touched[o]) {
-                            em.rec(REC_ENTRY | (prev_k << REC_K_SHIFT) | REC_F_INIT, o * SCHED_ACC_STRIDE, 0.0);
-                            touched[o] = 1; ++n_touched; s.n_entries += 1;
-                        }
-                }
-                i = j;
             }
         }
+        // output columns without any term (possible for an M-shard): zero them (0 * last S_A)
+        for (int32_t o = 0; o < ncols; ++o)
+            if (!touched[o]) {
+                em.rec(REC_OP | REC_F_INIT, o * SCHED_ACC_STRIDE, 0.0);
+                touched[o] = 1; ++n_touched; s.n_entries += 1;
+            }
         for (int32_t o = 0; o < ncols; o += 2) {
             const int32_t c0 = s.blk_cols[(size_t)b * C + o];
             const int32_t c1 = (o + 1 < ncols) ? s.blk_cols[(size_t)b * C + o + 1] : -1;
@@ -187,43 +222,53 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                        const double* dia, const double* W, int64_t ldw, double* Y, int64_t ldy) {
     const int64_t N = (int64_t)nx * ny;
     const int32_t C = SCHED_BLOCK_COLS;
-    std::vector<double> acc((size_t)C * N), S(N);
+    std::vector<double> acc((size_t)C * N), S[2];
+    S[0].assign(N, 0.0); S[1].assign(N, 0.0);
     std::vector<int32_t> set_slot(std::max(s.K, 1), -1);
-    // the producer command list must name exactly the fetches the records imply, in order
+    auto fail = [&]() { Y[0] = 0.0 / 0.0; };
     for (int32_t b = 0; b < s.nblk; ++b) {
-        size_t r = 0;
-        // first chunk of the block = value of the first META command
-        int32_t pc = s.blk_pcmd[b];
-        const int32_t pc_end = s.blk_pcmd[b + 1];
+        // what the producer would fetch, in order, and the first chunk of the block
         int32_t chunk0 = -1;
-        std::vector<int32_t> fetches;
-        for (int32_t p = pc; p < pc_end; ++p) {
+        std::vector<int32_t> fetches, metas;
+        for (int32_t p = s.blk_pcmd[b]; p < s.blk_pcmd[b + 1]; ++p) {
             const int32_t cmd = s.pcmd[p];
-            if ((cmd & PCMD_KIND_MASK) == PCMD_META) { if (chunk0 < 0) chunk0 = cmd & PCMD_VAL_MASK; }
+            if ((cmd & PCMD_KIND_MASK) == PCMD_META) { if (chunk0 < 0) chunk0 = cmd & PCMD_VAL_MASK; metas.push_back(cmd & PCMD_VAL_MASK); }
             else fetches.push_back(cmd);
         }
-        r = (size_t)chunk0 * SCHED_CHUNK_RECS;
-        size_t f = 0;
-        int32_t cur_col = -1;
+        if (chunk0 < 0) { fail(); return; }
+        size_t r = (size_t)chunk0 * SCHED_CHUNK_RECS, f = 0, chunks_seen = 1;
+        int32_t win_col[2] = {-1, -1};
         bool running = true;
         while (running) {
             const SchedRec& rec = s.recs[r++];
             const int32_t type = rec.a & REC_TYPE_MASK;
-            const int32_t k = (rec.a >> REC_K_SHIFT) & 0xF;
             switch (type) {
             case REC_END_ITEM: running = false; break;
-            case REC_ASET:
-                set_slot[k] = rec.b;
-                if (f >= fetches.size() || fetches[f++] != (PCMD_ATILE | rec.b)) { Y[0] = 0.0 / 0.0; return; }
+            case REC_NEXT_CHUNK:
+                if (r % SCHED_CHUNK_RECS != 0) { fail(); return; }       // must be the last slot of its chunk
+                ++chunks_seen;
                 break;
-            case REC_JOB:
-                cur_col = rec.b;
-                if (f >= fetches.size() || fetches[f++] != (PCMD_WINDOW | rec.b)) { Y[0] = 0.0 / 0.0; return; }
+            case REC_ASET: {
+                const int32_t cnt = (rec.a >> REC_CNT_SHIFT) & 0xF;
+                for (int32_t k = 0; k < cnt; ++k) {
+                    if (f >= fetches.size() || (fetches[f] & PCMD_KIND_MASK) != PCMD_ATILE) { fail(); return; }
+                    set_slot[k] = fetches[f++] & PCMD_VAL_MASK;
+                }
                 break;
-            case REC_ENTRY: {
-                if (rec.a & REC_F_FIRST) {
+            }
+            case REC_RELOAD:
+                for (int q = 0; q < 2; ++q) {
+                    if (!(rec.a & (q ? REC_F_BUFB : REC_F_BUFA))) continue;
+                    if (f >= fetches.size() || (fetches[f] & PCMD_KIND_MASK) != PCMD_WINDOW) { fail(); return; }
+                    win_col[q] = fetches[f++] & PCMD_VAL_MASK;
+                }
+                break;
+            case REC_OP: {
+                const int32_t k = (rec.a >> REC_K_SHIFT) & 3;
+                for (int q = 0; q < 2; ++q) {
+                    if (!(rec.a & (q ? REC_F_STB : REC_F_STA))) continue;
                     const double* a = dia + (size_t)set_slot[k] * D * N;
-                    const double* w = W + (int64_t)cur_col * ldw;
+                    const double* w = W + (int64_t)win_col[q] * ldw;
                     for (int32_t iy = 0; iy < ny; ++iy)
                         for (int32_t ix = 0; ix < nx; ++ix) {
                             const int64_t i = (int64_t)iy * nx + ix;
@@ -233,12 +278,14 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                                 const double wv = (jx >= 0 && jx < nx && jy >= 0 && jy < ny) ? w[(int64_t)jy * nx + jx] : 0.0;
                                 v += a[(size_t)d * N + i] * wv;
                             }
-                            S[i] = v;
+                            S[q][i] = v;
                         }
                 }
+                if (rec.a & REC_F_NOACC) break;
+                const std::vector<double>& src = S[(rec.a & REC_F_SRCB) ? 1 : 0];
                 double* ac = &acc[(size_t)(rec.b / SCHED_ACC_STRIDE) * N];
-                if (rec.a & REC_F_INIT) for (int64_t i = 0; i < N; ++i) ac[i] = rec.c * S[i];
-                else for (int64_t i = 0; i < N; ++i) ac[i] += rec.c * S[i];
+                if (rec.a & REC_F_INIT) for (int64_t i = 0; i < N; ++i) ac[i] = rec.c * src[i];
+                else for (int64_t i = 0; i < N; ++i) ac[i] += rec.c * src[i];
                 break;
             }
             case REC_STORE: {
@@ -250,10 +297,10 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                         std::memcpy(Y + (int64_t)cols[q] * ldy, &acc[(size_t)(rec.b / SCHED_ACC_STRIDE + q) * N], sizeof(double) * N);
                 break;
             }
-            default: break;
+            default: fail(); return;
             }
         }
-        if (f != fetches.size()) { Y[0] = 0.0 / 0.0; return; }
+        if (f != fetches.size() || chunks_seen != metas.size()) { fail(); return; }
     }
 }
 

@@ -9,8 +9,9 @@
 //             512 TMEM columns of a CTA;
 //   A-set   = up to K block matrices of that block whose tiles sit in registers at the same time;
 //   job     = one input column: its window is read from shared memory ONCE and used by every
-//             (matrix of the set, output column of the block) pair that needs it;
-//   entry   = one term: optional stencil evaluation S = A_k * window, then acc[out] += coef * S.
+//             (matrix of the set, output column of the block) pair that needs it; jobs are processed
+//             two at a time (window buffers A and B);
+//   op      = one term: optional stencil evaluation S = A_k * window, then acc[out] += coef * S.
 //
 // The host flattens this into a stream of 16-byte records per block, cut into 512-byte chunks that
 // the producer thread copies into a shared-memory ring ahead of the consumers, plus a compact
@@ -22,23 +23,34 @@
 namespace spuq {
 
 struct SchedRec {
-    int32_t a;      // type | k << 4 | flags << 8
-    int32_t b;      // ENTRY/STORE: TMEM column offset; JOB: input column; ASET: block-matrix slot
-    double c;       // ENTRY: coefficient; STORE: two int32 output columns (bit pattern)
+    int32_t a;      // type | flags (see below)
+    int32_t b;      // OP/STORE: TMEM column offset of the accumulator
+    double c;       // OP: coefficient; STORE: two int32 output columns (bit pattern)
 };
 static_assert(sizeof(SchedRec) == 16, "record must be 16 bytes");
 
+// The consumer warps hold TWO windows (buffers A and B) and K block-matrix tiles in registers.  An
+// OP record optionally evaluates the stencil of matrix k on buffer A and/or B in one basic block
+// (8 independent DFMA chains: a single warp per SM sub-partition needs that much instruction-level
+// parallelism to keep the FP64 pipe busy, DFMA latency being 8 clk at 2 clk issue), then adds
+// coef * S_A or coef * S_B to one TMEM accumulator.
 enum : int32_t {
-    REC_END_ITEM = 0,   // end of the block's stream
-    REC_ASET = 1,       // load the A tile at the head of the A ring into register set k
-    REC_JOB = 2,        // switch to the next window of the W ring
-    REC_ENTRY = 3,      // one term
-    REC_STORE = 4,      // write two accumulators to Y
+    REC_END_ITEM = 0,     // end of the block's stream
+    REC_OP = 1,           // [stencil(s)] + one accumulation
+    REC_ASET = 2,         // load the next `count` A tiles of the A ring into register sets 0..count-1
+    REC_RELOAD = 3,       // load the next window(s) of the W ring into buffer A and/or B
+    REC_STORE = 4,        // write two accumulators to Y
+    REC_NEXT_CHUNK = 5,   // last record of a 512-byte chunk: continue in the next ring stage
     REC_TYPE_MASK = 0xF,
-    REC_K_SHIFT = 4,
-    REC_F_FIRST = 1 << 8,   // ENTRY: evaluate the stencil with matrix k first
-    REC_F_INIT = 1 << 9,    // ENTRY: first touch of the accumulator (store, do not load)
-    REC_F_LAST = 1 << 8,    // JOB: last job of the block
+    REC_F_STA = 1 << 4,       // OP: S_A = A_k * window A first
+    REC_F_STB = 1 << 5,       // OP: S_B = A_k * window B first
+    REC_K_SHIFT = 6,          // OP: k in bits 6..7
+    REC_F_SRCB = 1 << 8,      // OP: accumulate S_B (else S_A)
+    REC_F_INIT = 1 << 9,      // OP: first touch of the accumulator (store, do not load)
+    REC_F_NOACC = 1 << 10,    // OP: stencil only
+    REC_CNT_SHIFT = 4,        // ASET: count in bits 4..7
+    REC_F_BUFA = 1 << 4,      // RELOAD: buffer A
+    REC_F_BUFB = 1 << 5,      // RELOAD: buffer B
 };
 
 constexpr int SCHED_CHUNK_RECS = 32;             // 512 bytes
