@@ -33,6 +33,7 @@
 
 #ifndef SPUQ_EMU
 #include <cuda.h>
+#include <type_traits>
 #include "kernels_tma.cuh"   // mbarrier / TMA helpers
 
 namespace spuq {
@@ -127,30 +128,46 @@ __device__ __forceinline__ void stencil1(const double (&a)[NINE ? 9 : 5][4], con
             S[q] = v;
         }
 }
-// both window buffers with the same matrix: eight independent DFMA chains in one basic block
-template <bool NINE>
-__device__ __forceinline__ void stencil2(const double (&a)[NINE ? 9 : 5][4], const double (&wa)[4][4],
-                                         const double (&wb)[4][4], double (&SA)[4], double (&SB)[4]) {
-    stencil1<NINE>(a, wa, SA);
-    stencil1<NINE>(a, wb, SB);
-}
-// acc[taddr] (+)= coef * S through tensor memory
-__device__ __forceinline__ void accumulate(uint32_t (&ar)[8], uint32_t taddr, double coef, const double (&S)[4], bool loaded) {
-    if (loaded) {
-        tmem_wait_ld8(ar);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const double v = fma(coef, S[q], __hiloint2double((int)ar[2 * q + 1], (int)ar[2 * q]));
-            ar[2 * q] = (uint32_t)__double2loint(v); ar[2 * q + 1] = (uint32_t)__double2hiint(v);
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const double v = coef * S[q];
-            ar[2 * q] = (uint32_t)__double2loint(v); ar[2 * q + 1] = (uint32_t)__double2hiint(v);
-        }
+// wait for all outstanding tcgen05.ld; names the destination registers so that no use of them can be
+// scheduled above the wait
+template <int NREG> struct TmemWait;
+template <> struct TmemWait<8> {
+    __device__ static __forceinline__ void run(uint32_t* r) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
     }
-    tmem_st8(taddr, ar);
+};
+template <> struct TmemWait<16> {
+    __device__ static __forceinline__ void run(uint32_t* r) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                       "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
+    }
+};
+template <> struct TmemWait<24> {
+    __device__ static __forceinline__ void run(uint32_t* r) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                       "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                       "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]) :: "memory");
+    }
+};
+__device__ __forceinline__ void tmem_ld8p(uint32_t* r, uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8p(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// 32 TMEM columns of this warp's lanes <- 0
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+                 ::"r"(taddr), "r"(z) : "memory");
 }
 
 template <int K_, bool NINE_>
@@ -225,10 +242,16 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
+    const uint32_t wring_s0 = smem_u32(wring), aring_s0 = smem_u32(aring), mring_s0 = smem_u32(mring);
     if (warp == Cfg::CONSUMER_WARPS) {
         // ================================ producer warp ============================================
-        int sw = 0, sa = 0, sm = 0, si = 0;
-        uint32_t pw = 0, pa = 0, pm = 0, pi = 0;
+        // Every lane owns one command of a batch of 32: it computes its own ring stage from a ballot
+        // prefix, waits for that stage to be free and issues its own copy, so the ~500 clk round trip
+        // of (barrier probe, expect_tx, TMA issue) is paid 32-fold in parallel, not per command.
+        uint32_t n_w = 0, n_a = 0, n_m = 0;               // fetches issued so far, per ring
+        int si = 0;
+        uint32_t pi = 0;
+        const uint32_t lt = (1u << lane) - 1u;
         for (;;) {
             unsigned long long item = 0;
             if (lane == 0) item = atomicAdd(work_counter, 1ull);
@@ -249,35 +272,45 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             if (++si == Cfg::I_STAGES) { si = 0; pi ^= 1u; }
             if (!valid) break;
             const int32_t c0 = __ldg(blk_pcmd + blk), c1 = __ldg(blk_pcmd + blk + 1);
-            int32_t next = (c0 + lane < c1) ? __ldg(pcmd + c0 + lane) : 0;
             for (int32_t base = c0; base < c1; base += 32) {
-                const int32_t mine = next;
-                if (base + 32 + lane < c1) next = __ldg(pcmd + base + 32 + lane);
-                const int n = min(32, c1 - base);
-                for (int i = 0; i < n; ++i) {
-                    const int32_t cmd = __shfl_sync(0xffffffffu, mine, i);
-                    if (lane == 0) {
-                        const int32_t kind = cmd & PCMD_KIND_MASK, val = cmd & PCMD_VAL_MASK;
-                        if (kind == PCMD_WINDOW) {
-                            mbar_wait(emptyW(sw), pw ^ 1u);
-                            mbar_expect_tx(fullW(sw), Cfg::WIN_BYTES);
-                            tma_load_3d(smem_u32(wring + sw * Cfg::WIN_STRIDE), &mapW, xt - 2, yt - 1, val, fullW(sw));
-                            if (++sw == Cfg::W_STAGES) { sw = 0; pw ^= 1u; }
-                        } else if (kind == PCMD_ATILE) {
-                            mbar_wait(emptyA(sa), pa ^ 1u);
-                            mbar_expect_tx(fullA(sa), Cfg::A_BYTES);
-                            tma_load_3d(smem_u32(aring + sa * Cfg::A_BYTES), &mapA, xt, yt, val * D, fullA(sa));
-                            if (++sa == Cfg::A_STAGES) { sa = 0; pa ^= 1u; }
-                        } else {
-                            mbar_wait(emptyM(sm), pm ^ 1u);
-                            mbar_expect_tx(fullM(sm), Cfg::META_BYTES);
-                            bulk_load(smem_u32(mring + sm * Cfg::META_BYTES), recs + (size_t)val * SCHED_CHUNK_RECS,
-                                      Cfg::META_BYTES, fullM(sm));
-                            if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
+                const bool have = base + lane < c1;
+                const int32_t cmd = have ? __ldg(pcmd + base + lane) : 0;
+                const int32_t kind = cmd & PCMD_KIND_MASK, val = cmd & PCMD_VAL_MASK;
+                const bool is_w = have && kind == PCMD_WINDOW, is_a = have && kind == PCMD_ATILE,
+                           is_m = have && kind == PCMD_META;
+                const uint32_t mw = __ballot_sync(0xffffffffu, is_w), ma = __ballot_sync(0xffffffffu, is_a),
+                               mm = __ballot_sync(0xffffffffu, is_m);
+                // Two fetches of one batch that map to the same ring stage must not probe its barrier
+                // concurrently (a parity wait cannot tell "two phases behind" from "done"): a batch is
+                // issued in rounds of at most STAGES fetches per ring.
+                const uint32_t rw = __popc(mw & lt), ra = __popc(ma & lt), rm = __popc(mm & lt);
+                const uint32_t my_round = is_w ? rw / Cfg::W_STAGES : (is_a ? ra / Cfg::A_STAGES : rm / Cfg::M_STAGES);
+                const uint32_t rounds = max(max((__popc(mw) + Cfg::W_STAGES - 1) / Cfg::W_STAGES,
+                                                (__popc(ma) + Cfg::A_STAGES - 1) / Cfg::A_STAGES),
+                                            (__popc(mm) + Cfg::M_STAGES - 1) / Cfg::M_STAGES);
+                for (uint32_t round = 0; round < rounds; ++round) {
+                    if (my_round == round) {
+                        if (is_w) {
+                            const uint32_t n = n_w + rw, st = n % Cfg::W_STAGES, par = (n / Cfg::W_STAGES) & 1u;
+                            mbar_wait(emptyW(st), par ^ 1u);
+                            mbar_expect_tx(fullW(st), Cfg::WIN_BYTES);
+                            tma_load_3d(wring_s0 + st * Cfg::WIN_STRIDE, &mapW, xt - 2, yt - 1, val, fullW(st));
+                        } else if (is_a) {
+                            const uint32_t n = n_a + ra, st = n % Cfg::A_STAGES, par = (n / Cfg::A_STAGES) & 1u;
+                            mbar_wait(emptyA(st), par ^ 1u);
+                            mbar_expect_tx(fullA(st), Cfg::A_BYTES);
+                            tma_load_3d(aring_s0 + st * Cfg::A_BYTES, &mapA, xt, yt, val * D, fullA(st));
+                        } else if (is_m) {
+                            const uint32_t n = n_m + rm, st = n % Cfg::M_STAGES, par = (n / Cfg::M_STAGES) & 1u;
+                            mbar_wait(emptyM(st), par ^ 1u);
+                            mbar_expect_tx(fullM(st), Cfg::META_BYTES);
+                            bulk_load(mring_s0 + st * Cfg::META_BYTES, recs + (size_t)val * SCHED_CHUNK_RECS, Cfg::META_BYTES, fullM(st));
                         }
                     }
                     __syncwarp();
                 }
+                n_w += __popc(mw); n_a += __popc(ma); n_m += __popc(mm);
+                __syncwarp();
             }
         }
         return;
@@ -287,40 +320,91 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     const uint32_t tmem_warp = *tmem_slot + ((uint32_t)(warp * 32) << 16);
     int sw = 0, sa = 0, sm = 0, si = 0;
     uint32_t pw = 0, pa = 0, pm = 0, pi = 0;
-    const uint32_t wring_s = smem_u32(wring), aring_s = smem_u32(aring), mring_s = smem_u32(mring);
+    const uint32_t wring_s = wring_s0, aring_s = aring_s0, mring_s = mring_s0;
     // this thread's corner inside a staged window / A tile (bytes)
     const uint32_t win_off = (uint32_t)(((2 * warp) * Cfg::BOX_W + 2 * lane) * 8);
     const uint32_t a_off = (uint32_t)(((2 * warp) * Cfg::TILE_X + 2 * lane) * 8);
 
     double A[K][D][4];                    // [register set][diagonal][point r*2+p]
-    double wa[4][4], wb[4][4];            // window buffers A and B: rows y0-1..y0+2, x0-1..x0+2
-    double SA[4] = {0.0, 0.0, 0.0, 0.0}, SB[4] = {0.0, 0.0, 0.0, 0.0};
+    double w[4][4], wn[4][4];             // window of the current job and of the next one
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
         for (int d = 0; d < D; ++d) A[k][d][0] = A[k][d][1] = A[k][d][2] = A[k][d][3] = 0.0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) wa[r][0] = wa[r][1] = wa[r][2] = wa[r][3] = wb[r][0] = wb[r][1] = wb[r][2] = wb[r][3] = 0.0;
+    for (int r = 0; r < 4; ++r) w[r][0] = w[r][1] = w[r][2] = w[r][3] = wn[r][0] = wn[r][1] = wn[r][2] = wn[r][3] = 0.0;
 
-    bool w_ready = false;                 // result of an early probe of the next W-ring slot
-    // window at the head of the W ring -> registers; the slot is released right away and the
-    // following slot probed, so that the next call rarely has to wait
-    auto load_window = [&](double (&w)[4][4]) {
-        if (!w_ready) mbar_wait(fullW(sw), pw);
+    // window at the head of the W ring -> wn; the slot is released right away
+    auto load_window = [&]() {
+        mbar_wait(fullW(sw), pw);
         const uint32_t base = wring_s + (uint32_t)sw * Cfg::WIN_STRIDE + win_off;
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             // box element e <-> x = x_tile - 2 + e; this thread's x0 = x_tile + 2*lane
-            lds_f64x2(base + (rr * Cfg::BOX_W + 2) * 8, w[rr][1], w[rr][2]);
+            lds_f64x2(base + (rr * Cfg::BOX_W + 2) * 8, wn[rr][1], wn[rr][2]);
             if (NINE || rr == 1 || rr == 2) {
-                w[rr][0] = lds_f64(base + (rr * Cfg::BOX_W + 1) * 8);
-                w[rr][3] = lds_f64(base + (rr * Cfg::BOX_W + 4) * 8);
+                wn[rr][0] = lds_f64(base + (rr * Cfg::BOX_W + 1) * 8);
+                wn[rr][3] = lds_f64(base + (rr * Cfg::BOX_W + 4) * 8);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(emptyW(sw));
         if (++sw == Cfg::W_STAGES) { sw = 0; pw ^= 1u; }
-        w_ready = mbar_test(fullW(sw), pw);
+    };
+    uint32_t rptr = 0;                    // shared address of the next unit of the record stream
+    auto next_chunk = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(emptyM(sm));
+        if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
+        mbar_wait(fullM(sm), pm);
+        rptr = mring_s + (uint32_t)sm * Cfg::META_BYTES;
+    };
+    bool have_next = false;               // wn already holds the window of the next job
+
+    // one RUN: n jobs with the same matrices (kmask) and S accumulation slots per matrix
+    auto run_jobs = [&](auto s_tag, const uint32_t kmask, const int n, const bool more) {
+        constexpr int S = decltype(s_tag)::value;
+        constexpr int CU = (S + 1) / 2, JU = 1 + K * CU;
+        if (!have_next) load_window();
+        for (int j = 0; j < n; ++j) {
+            int4 d = lds_i32x4(rptr);
+            if ((d.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); d = lds_i32x4(rptr); }
+            double cf[K][2 * CU];
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk)
+#pragma unroll
+                for (int u = 0; u < CU; ++u) lds_f64x2(rptr + 16 * (1 + kk * CU + u), cf[kk][2 * u], cf[kk][2 * u + 1]);
+            rptr += 16 * JU;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) { w[rr][0] = wn[rr][0]; w[rr][1] = wn[rr][1]; w[rr][2] = wn[rr][2]; w[rr][3] = wn[rr][3]; }
+            have_next = (j + 1 < n) || more;
+            if (have_next) load_window();
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) {
+                if (kmask >> kk & 1u) {
+                    const uint32_t pack = (uint32_t)(kk == 0 ? d.y : (kk == 1 ? d.z : d.w));
+                    uint32_t ar[S * 8];
+                    uint32_t ta[S];
+#pragma unroll
+                    for (int sl = 0; sl < S; ++sl) {
+                        ta[sl] = tmem_warp + ((pack >> (9 * sl)) & 511u) * SCHED_ACC_STRIDE;
+                        tmem_ld8p(ar + 8 * sl, ta[sl]);
+                    }
+                    double Sv[4];
+                    stencil1<NINE>(A[kk], w, Sv);
+                    TmemWait<S * 8>::run(ar);
+#pragma unroll
+                    for (int sl = 0; sl < S; ++sl) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double v = fma(cf[kk][sl], Sv[q], __hiloint2double((int)ar[8 * sl + 2 * q + 1], (int)ar[8 * sl + 2 * q]));
+                            ar[8 * sl + 2 * q] = (uint32_t)__double2loint(v); ar[8 * sl + 2 * q + 1] = (uint32_t)__double2hiint(v);
+                        }
+                        tmem_st8p(ta[sl], ar + 8 * sl);
+                    }
+                }
+            }
+        }
     };
 
     for (;;) {
@@ -333,46 +417,27 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         if (it.x < 0) break;
         const int32_t x0 = it.x + 2 * lane, y0 = it.y + 2 * warp;
 
-        mbar_wait(fullM(sm), pm);
-        uint32_t rptr = mring_s + (uint32_t)sm * Cfg::META_BYTES;
-        int4 cur = lds_i32x4(rptr);
-        for (;;) {
-            // the record after this one is fetched before this one is worked on
-            rptr += 16;
-            const int4 nxt = lds_i32x4(rptr);
-            const int a = cur.x;
-            const int type = a & REC_TYPE_MASK;
-
-            if (type == REC_OP) {
-                const uint32_t taddr = tmem_warp + (uint32_t)cur.y;
-                const double coef = __hiloint2double(cur.w, cur.z);
-                const bool load_acc = (a & (REC_F_INIT | REC_F_NOACC)) == 0;
-                uint32_t ar[8];
-                if (load_acc) tmem_ld8(ar, taddr);
-                if (a & (REC_F_STA | REC_F_STB)) {
-                    const int k = (a >> REC_K_SHIFT) & 3;
+        // accumulators <- 0 (tcgen05 operations of a warp complete in order)
 #pragma unroll
-                    for (int kk = 0; kk < K; ++kk) {
-                        if (k == kk) {
-                            if ((a & (REC_F_STA | REC_F_STB)) == (REC_F_STA | REC_F_STB)) {
-                                stencil2<NINE>(A[kk], wa, wb, SA, SB);
-                            } else if (a & REC_F_STA) {
-                                stencil1<NINE>(A[kk], wa, SA);
-                            } else {
-                                stencil1<NINE>(A[kk], wb, SB);
-                            }
-                        }
-                    }
-                }
-                if (!(a & REC_F_NOACC)) {
-                    if (a & REC_F_SRCB) accumulate(ar, taddr, coef, SB, load_acc);
-                    else accumulate(ar, taddr, coef, SA, load_acc);
-                }
-            } else if (type == REC_RELOAD) {
-                if (a & REC_F_BUFA) load_window(wa);
-                if (a & REC_F_BUFB) load_window(wb);
+        for (int c = 0; c < 512; c += 32) tmem_zero32(tmem_warp + c);
+        have_next = false;
+
+        mbar_wait(fullM(sm), pm);
+        rptr = mring_s + (uint32_t)sm * Cfg::META_BYTES;
+        for (;;) {
+            const int4 u = lds_i32x4(rptr);
+            const int type = u.x & REC_TYPE_MASK;
+            if (type == REC_NEXT_CHUNK) { next_chunk(); continue; }
+            rptr += 16;
+            if (type == REC_RUN) {
+                const uint32_t kmask = (uint32_t)(u.x >> REC_RUN_KMASK_SHIFT) & 0xFu;
+                const int S = (u.x >> REC_RUN_S_SHIFT) & 3;
+                const bool more = (u.x & REC_RUN_MORE) != 0;
+                if (S == 1) run_jobs(std::integral_constant<int, 1>{}, kmask, u.y, more);
+                else if (S == 2) run_jobs(std::integral_constant<int, 2>{}, kmask, u.y, more);
+                else run_jobs(std::integral_constant<int, 3>{}, kmask, u.y, more);
             } else if (type == REC_ASET) {
-                const int cnt = (a >> REC_CNT_SHIFT) & 0xF;
+                const int cnt = (u.x >> REC_CNT_SHIFT) & 0xF;
 #pragma unroll
                 for (int kk = 0; kk < K; ++kk) {
                     if (kk < cnt) {
@@ -391,9 +456,9 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             } else if (type == REC_STORE) {
                 tmem_wait_st();
                 uint32_t r16[16];
-                tmem_ld16(r16, tmem_warp + (uint32_t)cur.y);
+                tmem_ld16(r16, tmem_warp + (uint32_t)u.y);
                 tmem_wait_ld16(r16);
-                const int32_t cols[2] = {cur.z, cur.w};
+                const int32_t cols[2] = {u.z, u.w};
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     if (cols[q] >= 0 && x0 < s) {
@@ -406,18 +471,9 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                                                  __hiloint2double((int)r16[8 * q + 4 * r + 3], (int)r16[8 * q + 4 * r + 2]));
                     }
                 }
-            } else if (type == REC_NEXT_CHUNK) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(emptyM(sm));
-                if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
-                mbar_wait(fullM(sm), pm);
-                rptr = mring_s + (uint32_t)sm * Cfg::META_BYTES;
-                cur = lds_i32x4(rptr);
-                continue;
             } else {
                 break;      // REC_END_ITEM
             }
-            cur = nxt;
         }
         // END_ITEM: the rest of the chunk is padding
         __syncwarp();

@@ -55,8 +55,13 @@ void schedule_column_order(int32_t L, int32_t M, const int32_t* nbr_up, const in
 
 namespace {
 struct Term { int32_t slot, in_col, out; double coef; };
-struct Entry { int32_t k, out; double coef; };
-struct Job { int32_t in_col; uint32_t kmask; std::vector<Entry> es; };
+struct Entry { int32_t out; double coef; };
+struct Job {
+    int32_t in_col = -1;
+    uint32_t kmask = 0;
+    int32_t S = 0;
+    std::vector<Entry> es[SCHED_MAX_K];
+};
 
 struct Emitter {
     Schedule* s;
@@ -67,18 +72,30 @@ struct Emitter {
         chunk0 = (int32_t)(s->recs.size() / SCHED_CHUNK_RECS);
         chunk_cmds.clear();
     }
-    // append a record (the last slot of every chunk is the link to the next chunk); returns the chunk
-    int32_t rec(int32_t a, int32_t b, double c) {
-        if (s->recs.size() % SCHED_CHUNK_RECS == SCHED_CHUNK_RECS - 1) s->recs.push_back(SchedRec{REC_NEXT_CHUNK, 0, 0.0});
+    int32_t pos() const { return (int32_t)(s->recs.size() % SCHED_CHUNK_RECS); }
+    // make room for n contiguous units in the current chunk (else link to a fresh chunk)
+    void ensure(int32_t n) {
+        if (pos() + n <= SCHED_CHUNK_USABLE) return;
+        s->recs.push_back(SchedRec{REC_NEXT_CHUNK, 0, 0.0});
+        while (pos() != 0) s->recs.push_back(SchedRec{REC_NEXT_CHUNK, 0, 0.0});
+    }
+    int32_t unit(int32_t a, int32_t b, double c) {
         const int32_t chunk = (int32_t)(s->recs.size() / SCHED_CHUNK_RECS) - chunk0;
         if ((int32_t)chunk_cmds.size() <= chunk) chunk_cmds.resize(chunk + 1);
         s->recs.push_back(SchedRec{a, b, c});
         return chunk;
     }
+    int32_t unit_words(int32_t w0, int32_t w1, int32_t w2, int32_t w3) {
+        const uint64_t bits = (uint64_t)(uint32_t)w2 | ((uint64_t)(uint32_t)w3 << 32);
+        double c;
+        std::memcpy(&c, &bits, 8);
+        return unit(w0, w1, c);
+    }
     void cmd(int32_t chunk, int32_t c) { chunk_cmds[chunk].push_back(c); }
     void end_block() {
-        rec(REC_END_ITEM, 0, 0.0);
-        while (s->recs.size() % SCHED_CHUNK_RECS) s->recs.push_back(SchedRec{REC_END_ITEM, 0, 0.0});
+        ensure(1);
+        unit(REC_END_ITEM, 0, 0.0);
+        while (pos() != 0) s->recs.push_back(SchedRec{REC_END_ITEM, 0, 0.0});
         const int32_t nch = (int32_t)chunk_cmds.size();
         // producer stream: metadata chunks run two ahead of the fetches they describe
         for (int32_t c = 0; c < std::min(nch, 2); ++c) s->pcmd.push_back(PCMD_META | (chunk0 + c));
@@ -95,6 +112,7 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                     Schedule* out) {
     Schedule& s = *out;
     s = Schedule{};
+    if (K > SCHED_MAX_K) K = SCHED_MAX_K;
     s.K = K;
     const int32_t L = terms.L;
     const int32_t C = SCHED_BLOCK_COLS;
@@ -118,8 +136,6 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                 slot_count[terms.slot[t]] += 1;
             }
         }
-        // a block without any term still has to write zeros: one null term on its first column
-        if (ts.empty()) { ts.push_back(Term{0, order[(size_t)b * C], 0, 0.0}); slot_count[0] = 1; }
         // matrices of this block, busiest first; K at a time form a register set
         std::vector<int32_t> slots;
         for (int32_t sl = 0; sl < (int32_t)slot_count.size(); ++sl)
@@ -131,88 +147,102 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
             k_of_slot[slots[i]] = (int32_t)(i % K);
         }
         const int32_t nsets = (int32_t)((slots.size() + K - 1) / K);
-        std::vector<char> touched(ncols, 0);
-        int32_t n_touched = 0;
 
+        // ---- all runs of the block first (the RUN header needs to know whether another follows)
+        struct Run { int32_t set; uint32_t kmask; int32_t S; std::vector<Job> jobs; };
+        std::vector<Run> runs;
         for (int32_t set = 0; set < nsets; ++set) {
-            // ---- A tiles of the set
-            const int32_t cnt = std::min<int32_t>(K, (int32_t)slots.size() - set * K);
-            {
-                const int32_t ch = em.rec(REC_ASET | (cnt << REC_CNT_SHIFT), 0, 0.0);
-                for (int32_t k = 0; k < cnt; ++k) em.cmd(ch, PCMD_ATILE | slots[(size_t)set * K + k]);
-                s.n_asets += cnt;
-            }
-            // ---- jobs of the set: one per input column, entries ordered by register set k
             std::map<int32_t, Job> by_col;
             for (const Term& t : ts) {
                 if (set_of_slot[t.slot] != set) continue;
                 Job& j = by_col[t.in_col];
                 j.in_col = t.in_col;
-                j.kmask |= 1u << k_of_slot[t.slot];
-                j.es.push_back(Entry{k_of_slot[t.slot], t.out, t.coef});
+                j.es[k_of_slot[t.slot]].push_back(Entry{t.out, t.coef});
             }
+            // a (column, matrix) pair with more than SCHED_MAX_S outputs is served in several rounds
             std::vector<Job> jobs;
             for (auto& kv : by_col) {
-                std::stable_sort(kv.second.es.begin(), kv.second.es.end(), [](const Entry& x, const Entry& y) {
-                    if (x.k != y.k) return x.k < y.k;
-                    return x.out < y.out;
-                });
-                jobs.push_back(std::move(kv.second));
+                Job& full = kv.second;
+                for (size_t round = 0;; ++round) {
+                    Job j;
+                    j.in_col = full.in_col;
+                    for (int32_t k = 0; k < K; ++k) {
+                        const size_t lo = round * SCHED_MAX_S;
+                        if (full.es[k].size() <= lo) continue;
+                        const size_t hi = std::min(full.es[k].size(), lo + SCHED_MAX_S);
+                        j.es[k].assign(full.es[k].begin() + lo, full.es[k].begin() + hi);
+                        j.kmask |= 1u << k;
+                        j.S = std::max<int32_t>(j.S, (int32_t)(hi - lo));
+                    }
+                    if (!j.kmask) break;
+                    jobs.push_back(std::move(j));
+                }
             }
-            // jobs that use the same matrices next to each other, so that pairs share their stencils
-            std::stable_sort(jobs.begin(), jobs.end(), [](const Job& x, const Job& y) { return x.kmask > y.kmask; });
-            s.n_jobs += (int64_t)jobs.size();
+            std::stable_sort(jobs.begin(), jobs.end(), [](const Job& x, const Job& y) {
+                if (x.kmask != y.kmask) return x.kmask > y.kmask;
+                return x.S > y.S;
+            });
+            for (size_t i = 0; i < jobs.size();) {
+                size_t j = i;
+                while (j < jobs.size() && jobs[j].kmask == jobs[i].kmask && jobs[j].S == jobs[i].S) ++j;
+                Run r;
+                r.set = set; r.kmask = jobs[i].kmask; r.S = jobs[i].S;
+                r.jobs.assign(std::make_move_iterator(jobs.begin() + i), std::make_move_iterator(jobs.begin() + j));
+                runs.push_back(std::move(r));
+                i = j;
+            }
+        }
 
-            auto emit_reload = [&](size_t first_job) {
-                const bool two = first_job + 1 < jobs.size();
-                const int32_t ch = em.rec(REC_RELOAD | REC_F_BUFA | (two ? REC_F_BUFB : 0), 0, 0.0);
-                em.cmd(ch, PCMD_WINDOW | jobs[first_job].in_col);
-                if (two) em.cmd(ch, PCMD_WINDOW | jobs[first_job + 1].in_col);
-            };
-            if (!jobs.empty()) emit_reload(0);
-            for (size_t j0 = 0; j0 < jobs.size(); j0 += 2) {
-                const Job& ja = jobs[j0];
-                const Job* jb = (j0 + 1 < jobs.size()) ? &jobs[j0 + 1] : nullptr;
-                const uint32_t kunion = ja.kmask | (jb ? jb->kmask : 0u);
-                int32_t last_k = -1;
-                for (int32_t k = 0; k < K; ++k) if (kunion >> k & 1u) last_k = k;
+        // ---- emit
+        int32_t cur_set = -1;
+        for (size_t ri = 0; ri < runs.size(); ++ri) {
+            const Run& r = runs[ri];
+            if (r.set != cur_set) {
+                cur_set = r.set;
+                const int32_t cnt = std::min<int32_t>(K, (int32_t)slots.size() - cur_set * K);
+                em.ensure(1);
+                const int32_t ch = em.unit(REC_ASET | (cnt << REC_CNT_SHIFT), 0, 0.0);
+                for (int32_t k = 0; k < cnt; ++k) em.cmd(ch, PCMD_ATILE | slots[(size_t)cur_set * K + k]);
+                s.n_asets += cnt;
+            }
+            const int32_t cu = (r.S + 1) / 2;               // coefficient units per register set
+            const int32_t job_units = 1 + K * cu;
+            em.ensure(1 + job_units);                        // header and first job in one chunk
+            em.unit(REC_RUN | ((int32_t)r.kmask << REC_RUN_KMASK_SHIFT) | (r.S << REC_RUN_S_SHIFT) |
+                        (ri + 1 < runs.size() ? REC_RUN_MORE : 0),
+                    (int32_t)r.jobs.size(), 0.0);
+            s.n_jobs += (int64_t)r.jobs.size();
+            for (const Job& j : r.jobs) {
+                em.ensure(job_units);
+                int32_t packs[SCHED_MAX_K] = {0, 0, 0};
+                for (int32_t k = 0; k < K; ++k)
+                    for (int32_t sl = 0; sl < SCHED_MAX_S; ++sl) {
+                        const int32_t o = (sl < (int32_t)j.es[k].size()) ? j.es[k][sl].out : SCHED_TRASH_ACC;
+                        packs[k] |= o << (9 * sl);
+                    }
+                const int32_t ch = em.unit_words(REC_JOB, packs[0], packs[1], packs[2]);
+                em.cmd(ch, PCMD_WINDOW | j.in_col);
                 for (int32_t k = 0; k < K; ++k) {
-                    if (!(kunion >> k & 1u)) continue;
-                    // accumulations of this matrix: (source buffer, entry)
-                    std::vector<std::pair<int, const Entry*>> acc;
-                    for (const Entry& e : ja.es) if (e.k == k) acc.push_back({0, &e});
-                    if (jb) for (const Entry& e : jb->es) if (e.k == k) acc.push_back({1, &e});
-                    int32_t st = 0;
-                    if (ja.kmask >> k & 1u) st |= REC_F_STA;
-                    if (jb && (jb->kmask >> k & 1u)) st |= REC_F_STB;
-                    s.n_stencils += (st & REC_F_STA ? 1 : 0) + (st & REC_F_STB ? 1 : 0);
-                    for (size_t q = 0; q < acc.size(); ++q) {
-                        const Entry& e = *acc[q].second;
-                        int32_t a = REC_OP | (k << REC_K_SHIFT) | (q == 0 ? st : 0);
-                        if (acc[q].first) a |= REC_F_SRCB;
-                        if (!touched[e.out]) { a |= REC_F_INIT; touched[e.out] = 1; ++n_touched; }
-                        em.rec(a, e.out * SCHED_ACC_STRIDE, e.coef);
-                        s.n_entries += 1;
-                        // the windows are dead once the last stencil of the pair has been issued:
-                        // fetch the next pair's while the remaining accumulations run
-                        if (q == 0 && k == last_k && j0 + 2 < jobs.size()) emit_reload(j0 + 2);
+                    if (r.kmask >> k & 1u) { s.n_stencils += 1; s.n_entries += (int64_t)j.es[k].size(); }
+                    for (int32_t u = 0; u < cu; ++u) {
+                        double c2[2] = {0.0, 0.0};
+                        for (int q = 0; q < 2; ++q)
+                            if (2 * u + q < (int32_t)j.es[k].size()) c2[q] = j.es[k][2 * u + q].coef;
+                        SchedRec rec;
+                        std::memcpy(&rec.a, &c2[0], 8);       // a,b = first coefficient, c = second
+                        rec.c = c2[1];
+                        const int32_t chunk = (int32_t)(s.recs.size() / SCHED_CHUNK_RECS) - em.chunk0;
+                        (void)chunk;
+                        s.recs.push_back(rec);
                     }
                 }
             }
         }
-        // output columns without any term (possible for an M-shard): zero them (0 * last S_A)
-        for (int32_t o = 0; o < ncols; ++o)
-            if (!touched[o]) {
-                em.rec(REC_OP | REC_F_INIT, o * SCHED_ACC_STRIDE, 0.0);
-                touched[o] = 1; ++n_touched; s.n_entries += 1;
-            }
         for (int32_t o = 0; o < ncols; o += 2) {
             const int32_t c0 = s.blk_cols[(size_t)b * C + o];
             const int32_t c1 = (o + 1 < ncols) ? s.blk_cols[(size_t)b * C + o + 1] : -1;
-            const uint64_t bits = (uint64_t)(uint32_t)c0 | ((uint64_t)(uint32_t)c1 << 32);
-            double c;
-            std::memcpy(&c, &bits, 8);
-            em.rec(REC_STORE, o * SCHED_ACC_STRIDE, c);
+            em.ensure(1);
+            em.unit_words(REC_STORE, o * SCHED_ACC_STRIDE, c0, c1);
         }
         em.end_block();
     }
@@ -221,13 +251,17 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
 void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const int32_t* dy, int32_t nx, int32_t ny,
                        const double* dia, const double* W, int64_t ldw, double* Y, int64_t ldy) {
     const int64_t N = (int64_t)nx * ny;
-    const int32_t C = SCHED_BLOCK_COLS;
-    std::vector<double> acc((size_t)C * N), S[2];
-    S[0].assign(N, 0.0); S[1].assign(N, 0.0);
-    std::vector<int32_t> set_slot(std::max(s.K, 1), -1);
+    const int32_t K = s.K;
+    std::vector<double> acc((size_t)(SCHED_TRASH_ACC + 1) * N), S(N);
+    std::vector<int32_t> set_slot(std::max(K, 1), -1);
     auto fail = [&]() { Y[0] = 0.0 / 0.0; };
+    auto words = [](const SchedRec& r, int32_t (&w)[4]) {
+        uint64_t bits;
+        std::memcpy(&bits, &r.c, 8);
+        w[0] = r.a; w[1] = r.b; w[2] = (int32_t)(uint32_t)(bits & 0xffffffffu); w[3] = (int32_t)(uint32_t)(bits >> 32);
+    };
     for (int32_t b = 0; b < s.nblk; ++b) {
-        // what the producer would fetch, in order, and the first chunk of the block
+        // what the producer would fetch, in order, and the chunks of the block
         int32_t chunk0 = -1;
         std::vector<int32_t> fetches, metas;
         for (int32_t p = s.blk_pcmd[b]; p < s.blk_pcmd[b + 1]; ++p) {
@@ -236,18 +270,16 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
             else fetches.push_back(cmd);
         }
         if (chunk0 < 0) { fail(); return; }
+        for (size_t i = 0; i < metas.size(); ++i) if (metas[i] != chunk0 + (int32_t)i) { fail(); return; }
+        std::fill(acc.begin(), acc.end(), 0.0);
         size_t r = (size_t)chunk0 * SCHED_CHUNK_RECS, f = 0, chunks_seen = 1;
-        int32_t win_col[2] = {-1, -1};
+        auto next_chunk = [&]() { r = (r / SCHED_CHUNK_RECS + 1) * SCHED_CHUNK_RECS; ++chunks_seen; };
         bool running = true;
         while (running) {
+            if ((s.recs[r].a & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); continue; }
             const SchedRec& rec = s.recs[r++];
-            const int32_t type = rec.a & REC_TYPE_MASK;
-            switch (type) {
+            switch (rec.a & REC_TYPE_MASK) {
             case REC_END_ITEM: running = false; break;
-            case REC_NEXT_CHUNK:
-                if (r % SCHED_CHUNK_RECS != 0) { fail(); return; }       // must be the last slot of its chunk
-                ++chunks_seen;
-                break;
             case REC_ASET: {
                 const int32_t cnt = (rec.a >> REC_CNT_SHIFT) & 0xF;
                 for (int32_t k = 0; k < cnt; ++k) {
@@ -256,45 +288,52 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                 }
                 break;
             }
-            case REC_RELOAD:
-                for (int q = 0; q < 2; ++q) {
-                    if (!(rec.a & (q ? REC_F_BUFB : REC_F_BUFA))) continue;
+            case REC_RUN: {
+                const uint32_t kmask = (uint32_t)(rec.a >> REC_RUN_KMASK_SHIFT) & 0xFu;
+                const int32_t Sn = (rec.a >> REC_RUN_S_SHIFT) & 3, n = rec.b;
+                const int32_t cu = (Sn + 1) / 2, job_units = 1 + K * cu;
+                for (int32_t j = 0; j < n; ++j) {
+                    if ((s.recs[r].a & REC_TYPE_MASK) == REC_NEXT_CHUNK) next_chunk();
+                    if (r % SCHED_CHUNK_RECS + job_units > SCHED_CHUNK_USABLE) { fail(); return; }
+                    int32_t w[4];
+                    words(s.recs[r], w);
+                    if (w[0] != REC_JOB) { fail(); return; }
                     if (f >= fetches.size() || (fetches[f] & PCMD_KIND_MASK) != PCMD_WINDOW) { fail(); return; }
-                    win_col[q] = fetches[f++] & PCMD_VAL_MASK;
-                }
-                break;
-            case REC_OP: {
-                const int32_t k = (rec.a >> REC_K_SHIFT) & 3;
-                for (int q = 0; q < 2; ++q) {
-                    if (!(rec.a & (q ? REC_F_STB : REC_F_STA))) continue;
-                    const double* a = dia + (size_t)set_slot[k] * D * N;
-                    const double* w = W + (int64_t)win_col[q] * ldw;
-                    for (int32_t iy = 0; iy < ny; ++iy)
-                        for (int32_t ix = 0; ix < nx; ++ix) {
-                            const int64_t i = (int64_t)iy * nx + ix;
-                            double v = 0.0;
-                            for (int32_t d = 0; d < D; ++d) {
-                                const int32_t jx = ix + dx[d], jy = iy + dy[d];
-                                const double wv = (jx >= 0 && jx < nx && jy >= 0 && jy < ny) ? w[(int64_t)jy * nx + jx] : 0.0;
-                                v += a[(size_t)d * N + i] * wv;
+                    const int32_t in_col = fetches[f++] & PCMD_VAL_MASK;
+                    const double* wv = W + (int64_t)in_col * ldw;
+                    for (int32_t k = 0; k < K; ++k) {
+                        if (!(kmask >> k & 1u)) continue;
+                        const double* a = dia + (size_t)set_slot[k] * D * N;
+                        for (int32_t iy = 0; iy < ny; ++iy)
+                            for (int32_t ix = 0; ix < nx; ++ix) {
+                                const int64_t i = (int64_t)iy * nx + ix;
+                                double v = 0.0;
+                                for (int32_t d = 0; d < D; ++d) {
+                                    const int32_t jx = ix + dx[d], jy = iy + dy[d];
+                                    const double x = (jx >= 0 && jx < nx && jy >= 0 && jy < ny) ? wv[(int64_t)jy * nx + jx] : 0.0;
+                                    v += a[(size_t)d * N + i] * x;
+                                }
+                                S[i] = v;
                             }
-                            S[q][i] = v;
+                        for (int32_t sl = 0; sl < Sn; ++sl) {
+                            const int32_t o = (w[1 + k] >> (9 * sl)) & 511;
+                            const SchedRec& cr = s.recs[r + 1 + k * cu + sl / 2];
+                            double coef;
+                            if (sl % 2 == 0) std::memcpy(&coef, &cr.a, 8); else coef = cr.c;
+                            double* ac = &acc[(size_t)o * N];
+                            for (int64_t i = 0; i < N; ++i) ac[i] += coef * S[i];
                         }
+                    }
+                    r += job_units;
                 }
-                if (rec.a & REC_F_NOACC) break;
-                const std::vector<double>& src = S[(rec.a & REC_F_SRCB) ? 1 : 0];
-                double* ac = &acc[(size_t)(rec.b / SCHED_ACC_STRIDE) * N];
-                if (rec.a & REC_F_INIT) for (int64_t i = 0; i < N; ++i) ac[i] = rec.c * src[i];
-                else for (int64_t i = 0; i < N; ++i) ac[i] += rec.c * src[i];
                 break;
             }
             case REC_STORE: {
-                uint64_t bits;
-                std::memcpy(&bits, &rec.c, 8);
-                const int32_t cols[2] = {(int32_t)(uint32_t)(bits & 0xffffffffu), (int32_t)(uint32_t)(bits >> 32)};
+                int32_t w[4];
+                words(rec, w);
                 for (int q = 0; q < 2; ++q)
-                    if (cols[q] >= 0)
-                        std::memcpy(Y + (int64_t)cols[q] * ldy, &acc[(size_t)(rec.b / SCHED_ACC_STRIDE + q) * N], sizeof(double) * N);
+                    if (w[2 + q] >= 0)
+                        std::memcpy(Y + (int64_t)w[2 + q] * ldy, &acc[(size_t)(w[1] / SCHED_ACC_STRIDE + q) * N], sizeof(double) * N);
                 break;
             }
             default: fail(); return;

@@ -22,40 +22,56 @@
 
 namespace spuq {
 
-struct SchedRec {
-    int32_t a;      // type | flags (see below)
-    int32_t b;      // OP/STORE: TMEM column offset of the accumulator
-    double c;       // OP: coefficient; STORE: two int32 output columns (bit pattern)
+struct SchedRec {           // one 16-byte unit of the record stream
+    int32_t a, b;
+    double c;
 };
-static_assert(sizeof(SchedRec) == 16, "record must be 16 bytes");
+static_assert(sizeof(SchedRec) == 16, "unit must be 16 bytes");
 
-// The consumer warps hold TWO windows (buffers A and B) and K block-matrix tiles in registers.  An
-// OP record optionally evaluates the stencil of matrix k on buffer A and/or B in one basic block
-// (8 independent DFMA chains: a single warp per SM sub-partition needs that much instruction-level
-// parallelism to keep the FP64 pipe busy, DFMA latency being 8 clk at 2 clk issue), then adds
-// coef * S_A or coef * S_B to one TMEM accumulator.
+// Stream of a block (all units 16 bytes, read by the consumer warps from the metadata ring):
+//
+//   ASET  cnt                    load the next cnt A tiles of the A ring into register sets 0..cnt-1
+//   RUN   kmask S n more         n jobs follow that all use the matrices in kmask with S accumulation
+//                                slots per matrix.  Every job is 1 + K*ceil(S/2) units:
+//                                  unit 0     a = REC_JOB, words 1..3: for register set kk the
+//                                             accumulator numbers of its S slots, 9 bits each
+//                                  unit 1+..  for every kk (used or not) ceil(S/2) units holding the
+//                                             slot coefficients (two doubles per unit)
+//                                A slot that is not needed points at the scratch accumulator
+//                                (SCHED_TRASH_ACC) with coefficient 0, so the loop over a run is
+//                                branch-free in the data: window -> registers, then for every matrix
+//                                of kmask the stencil (20 DFMA) and S read-modify-writes of TMEM.
+//                                A job never straddles a chunk; `more` = another RUN follows in this
+//                                block (its first window is prefetched by the last job of this one).
+//   STORE taddr col0 col1        write two accumulators to Y
+//   NEXT_CHUNK                   continue in the next ring stage (rest of this chunk is unused)
+//   END_ITEM
+//
+// The consumer warps are ONE warp per SM sub-partition (TMEM lane ownership: 4 points x 64 columns
+// per thread), which exposes every branch (~10 clk) and every barrier round trip (30-50 clk);
+// hence the regular, padded run format instead of one record per term.
 enum : int32_t {
-    REC_END_ITEM = 0,     // end of the block's stream
-    REC_OP = 1,           // [stencil(s)] + one accumulation
-    REC_ASET = 2,         // load the next `count` A tiles of the A ring into register sets 0..count-1
-    REC_RELOAD = 3,       // load the next window(s) of the W ring into buffer A and/or B
-    REC_STORE = 4,        // write two accumulators to Y
-    REC_NEXT_CHUNK = 5,   // last record of a 512-byte chunk: continue in the next ring stage
+    REC_END_ITEM = 0,
+    REC_ASET = 2,
+    REC_STORE = 4,
+    REC_NEXT_CHUNK = 5,
+    REC_RUN = 6,
+    REC_JOB = 7,
     REC_TYPE_MASK = 0xF,
-    REC_F_STA = 1 << 4,       // OP: S_A = A_k * window A first
-    REC_F_STB = 1 << 5,       // OP: S_B = A_k * window B first
-    REC_K_SHIFT = 6,          // OP: k in bits 6..7
-    REC_F_SRCB = 1 << 8,      // OP: accumulate S_B (else S_A)
-    REC_F_INIT = 1 << 9,      // OP: first touch of the accumulator (store, do not load)
-    REC_F_NOACC = 1 << 10,    // OP: stencil only
     REC_CNT_SHIFT = 4,        // ASET: count in bits 4..7
-    REC_F_BUFA = 1 << 4,      // RELOAD: buffer A
-    REC_F_BUFB = 1 << 5,      // RELOAD: buffer B
+    REC_RUN_KMASK_SHIFT = 4,  // RUN: kmask in bits 4..7
+    REC_RUN_S_SHIFT = 8,      // RUN: S in bits 8..9
+    REC_RUN_MORE = 1 << 10,   // RUN: another RUN follows in this block
+                              // RUN: b = number of jobs
 };
 
 constexpr int SCHED_CHUNK_RECS = 32;             // 512 bytes
-constexpr int SCHED_BLOCK_COLS = 64;             // output columns per block
+constexpr int SCHED_CHUNK_USABLE = 31;           // the last unit of a chunk is always NEXT_CHUNK / END
+constexpr int SCHED_BLOCK_COLS = 63;             // output columns per block (64 accumulators - scratch)
+constexpr int SCHED_TRASH_ACC = 63;              // scratch accumulator for padded slots
 constexpr int SCHED_ACC_STRIDE = 8;              // TMEM columns per accumulator (4 doubles)
+constexpr int SCHED_MAX_K = 3;                   // register sets (limited by the job unit layout)
+constexpr int SCHED_MAX_S = 3;
 
 enum : int32_t {                                  // producer commands
     PCMD_WINDOW = 0,        // low bits: input column

@@ -608,10 +608,10 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
         // automatic choice: the TMEM-accumulator kernel whenever its alignment conditions hold
         const bool use_tmem = aligned && p->n_slots > 0 && (p->variant == 4 || p->variant == 0);
         if (use_tmem) {
-            const int32_t Kdef = p->nine ? 2 : 4;
+            const int32_t Kdef = p->nine ? 2 : 3;
             const int32_t K = p->cols_per_block > 0 ? p->cols_per_block : Kdef;
-            SPUQ_REQUIRE(K >= 1 && K <= (p->nine ? 2 : 4), "apply: TMEM kernel supports 1..%d register sets (got %d)",
-                         p->nine ? 2 : 4, K);
+            SPUQ_REQUIRE(K >= 1 && K <= (p->nine ? 2 : 3), "apply: TMEM kernel supports 1..%d register sets (got %d)",
+                         p->nine ? 2 : 3, K);
             if (p->sched_K != K) {
                 int rc = build_schedule(p, K);
                 if (rc) return rc;
@@ -634,7 +634,7 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
                      : launch_tmem<k, false>(p, W, ldw, Y, ldy, stream, gate);                    \
         launched = true;                                                                          \
     }
-            SPUQ_TMEM(1) SPUQ_TMEM(2) SPUQ_TMEM(3) SPUQ_TMEM(4)
+            SPUQ_TMEM(1) SPUQ_TMEM(2) SPUQ_TMEM(3)
 #undef SPUQ_TMEM
             if (rc) return rc;
             p->last_launches = 2;      // counter reset + kernel
