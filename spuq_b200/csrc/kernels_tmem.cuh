@@ -184,8 +184,11 @@ struct TmemCfg {
     static constexpr int WIN_STRIDE = (WIN_BYTES + 127) / 128 * 128;
     static constexpr int A_BYTES = TILE_X * TILE_Y * D * 8;
     static constexpr int META_BYTES = SCHED_CHUNK_RECS * 16;
-    static constexpr int W_STAGES = 16, A_STAGES = NINE ? 2 : 4, M_STAGES = 8, I_STAGES = 4;
-    static constexpr int OFF_A = W_STAGES * WIN_STRIDE;
+    // W ring: stages of W_GROUP windows under ONE full/empty barrier pair (a barrier round trip costs the
+    // single consumer warp of a sub-partition 60-140 clk, so it is paid once per group, not per window)
+    static constexpr int W_GROUP = 4, W_STAGES = 4, W_SLOTS = W_GROUP * W_STAGES;
+    static constexpr int A_STAGES = NINE ? 2 : 4, M_STAGES = 4, I_STAGES = 4;
+    static constexpr int OFF_A = W_SLOTS * WIN_STRIDE;
     static constexpr int OFF_M = OFF_A + A_STAGES * A_BYTES;
     static constexpr int OFF_I = OFF_M + M_STAGES * META_BYTES;
     static constexpr int OFF_BAR = OFF_I + I_STAGES * 16;
@@ -228,7 +231,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < Cfg::W_STAGES; ++i) { mbar_init(fullW(i), 1); mbar_init(emptyW(i), Cfg::CONSUMER_WARPS); }
+        for (int i = 0; i < Cfg::W_STAGES; ++i) { mbar_init(fullW(i), Cfg::W_GROUP); mbar_init(emptyW(i), Cfg::CONSUMER_WARPS); }
         for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(fullA(i), 1); mbar_init(emptyA(i), Cfg::CONSUMER_WARPS); }
         for (int i = 0; i < Cfg::M_STAGES; ++i) { mbar_init(fullM(i), 1); mbar_init(emptyM(i), Cfg::CONSUMER_WARPS); }
         for (int i = 0; i < Cfg::I_STAGES; ++i) { mbar_init(fullI(i), 1); mbar_init(emptyI(i), Cfg::CONSUMER_WARPS); }
@@ -270,7 +273,12 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                 mbar_arrive(fullI(si));
             }
             if (++si == Cfg::I_STAGES) { si = 0; pi ^= 1u; }
-            if (!valid) break;
+            if (!valid) {
+                // complete the last, partly filled window group so that its consumers are released
+                if (lane == 0)
+                    for (uint32_t n = n_w; n % Cfg::W_GROUP != 0; ++n) mbar_arrive(fullW((n % Cfg::W_SLOTS) / Cfg::W_GROUP));
+                break;
+            }
             const int32_t c0 = __ldg(blk_pcmd + blk), c1 = __ldg(blk_pcmd + blk + 1);
             for (int32_t base = c0; base < c1; base += 32) {
                 const bool have = base + lane < c1;
@@ -284,17 +292,18 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                 // concurrently (a parity wait cannot tell "two phases behind" from "done"): a batch is
                 // issued in rounds of at most STAGES fetches per ring.
                 const uint32_t rw = __popc(mw & lt), ra = __popc(ma & lt), rm = __popc(mm & lt);
-                const uint32_t my_round = is_w ? rw / Cfg::W_STAGES : (is_a ? ra / Cfg::A_STAGES : rm / Cfg::M_STAGES);
-                const uint32_t rounds = max(max((__popc(mw) + Cfg::W_STAGES - 1) / Cfg::W_STAGES,
+                const uint32_t my_round = is_w ? rw / Cfg::W_SLOTS : (is_a ? ra / Cfg::A_STAGES : rm / Cfg::M_STAGES);
+                const uint32_t rounds = max(max((__popc(mw) + Cfg::W_SLOTS - 1) / Cfg::W_SLOTS,
                                                 (__popc(ma) + Cfg::A_STAGES - 1) / Cfg::A_STAGES),
                                             (__popc(mm) + Cfg::M_STAGES - 1) / Cfg::M_STAGES);
                 for (uint32_t round = 0; round < rounds; ++round) {
                     if (my_round == round) {
                         if (is_w) {
-                            const uint32_t n = n_w + rw, st = n % Cfg::W_STAGES, par = (n / Cfg::W_STAGES) & 1u;
+                            const uint32_t n = n_w + rw, slot = n % Cfg::W_SLOTS, st = slot / Cfg::W_GROUP,
+                                           par = (n / Cfg::W_SLOTS) & 1u;
                             mbar_wait(emptyW(st), par ^ 1u);
-                            mbar_expect_tx(fullW(st), Cfg::WIN_BYTES);
-                            tma_load_3d(wring_s0 + st * Cfg::WIN_STRIDE, &mapW, xt - 2, yt - 1, val, fullW(st));
+                            mbar_expect_tx(fullW(st), Cfg::WIN_BYTES);       // one arrival of W_GROUP + the bytes
+                            tma_load_3d(wring_s0 + slot * Cfg::WIN_STRIDE, &mapW, xt - 2, yt - 1, val, fullW(st));
                         } else if (is_a) {
                             const uint32_t n = n_a + ra, st = n % Cfg::A_STAGES, par = (n / Cfg::A_STAGES) & 1u;
                             mbar_wait(emptyA(st), par ^ 1u);
@@ -326,30 +335,34 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     const uint32_t a_off = (uint32_t)(((2 * warp) * Cfg::TILE_X + 2 * lane) * 8);
 
     double A[K][D][4];                    // [register set][diagonal][point r*2+p]
-    double w[4][4], wn[4][4];             // window of the current job and of the next one
+    double w0[4][4], w1[4][4];            // two window buffers: jobs alternate between them
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
         for (int d = 0; d < D; ++d) A[k][d][0] = A[k][d][1] = A[k][d][2] = A[k][d][3] = 0.0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) w[r][0] = w[r][1] = w[r][2] = w[r][3] = wn[r][0] = wn[r][1] = wn[r][2] = wn[r][3] = 0.0;
+    for (int r = 0; r < 4; ++r) w0[r][0] = w0[r][1] = w0[r][2] = w0[r][3] = w1[r][0] = w1[r][1] = w1[r][2] = w1[r][3] = 0.0;
 
-    // window at the head of the W ring -> wn; the slot is released right away
-    auto load_window = [&]() {
-        mbar_wait(fullW(sw), pw);
-        const uint32_t base = wring_s + (uint32_t)sw * Cfg::WIN_STRIDE + win_off;
+    uint32_t nw = 0;                      // windows taken from the W ring so far
+    // next window of the W ring -> buf; a group of W_GROUP windows shares one barrier pair
+    auto load_window = [&](double (&buf)[4][4]) {
+        const uint32_t slot = nw % Cfg::W_SLOTS, st = slot / Cfg::W_GROUP, sub = slot % Cfg::W_GROUP;
+        if (sub == 0) mbar_wait(fullW(st), (nw / Cfg::W_SLOTS) & 1u);
+        const uint32_t base = wring_s + slot * Cfg::WIN_STRIDE + win_off;
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             // box element e <-> x = x_tile - 2 + e; this thread's x0 = x_tile + 2*lane
-            lds_f64x2(base + (rr * Cfg::BOX_W + 2) * 8, wn[rr][1], wn[rr][2]);
+            lds_f64x2(base + (rr * Cfg::BOX_W + 2) * 8, buf[rr][1], buf[rr][2]);
             if (NINE || rr == 1 || rr == 2) {
-                wn[rr][0] = lds_f64(base + (rr * Cfg::BOX_W + 1) * 8);
-                wn[rr][3] = lds_f64(base + (rr * Cfg::BOX_W + 4) * 8);
+                buf[rr][0] = lds_f64(base + (rr * Cfg::BOX_W + 1) * 8);
+                buf[rr][3] = lds_f64(base + (rr * Cfg::BOX_W + 4) * 8);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(emptyW(sw));
-        if (++sw == Cfg::W_STAGES) { sw = 0; pw ^= 1u; }
+        if (sub == Cfg::W_GROUP - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(emptyW(st));
+        }
+        ++nw;
     };
     uint32_t rptr = 0;                    // shared address of the next unit of the record stream
     auto next_chunk = [&]() {
@@ -359,14 +372,15 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         mbar_wait(fullM(sm), pm);
         rptr = mring_s + (uint32_t)sm * Cfg::META_BYTES;
     };
-    bool have_next = false;               // wn already holds the window of the next job
+    bool have_next = false;               // the buffer `cur` already holds the window of the next job
+    int cur = 0;                          // buffer of the next job: 0 = w0, 1 = w1
 
     // one RUN: n jobs with the same matrices (kmask) and S accumulation slots per matrix
     auto run_jobs = [&](auto s_tag, const uint32_t kmask, const int n, const bool more) {
         constexpr int S = decltype(s_tag)::value;
         constexpr int CU = (S + 1) / 2, JU = 1 + K * CU;
-        if (!have_next) load_window();
-        for (int j = 0; j < n; ++j) {
+        // one job: window in wc (already loaded); the window after it is fetched into wp
+        auto job = [&](double (&wc)[4][4], double (&wp)[4][4], const bool prefetch) {
             int4 d = lds_i32x4(rptr);
             if ((d.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); d = lds_i32x4(rptr); }
             double cf[K][2 * CU];
@@ -375,10 +389,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
 #pragma unroll
                 for (int u = 0; u < CU; ++u) lds_f64x2(rptr + 16 * (1 + kk * CU + u), cf[kk][2 * u], cf[kk][2 * u + 1]);
             rptr += 16 * JU;
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) { w[rr][0] = wn[rr][0]; w[rr][1] = wn[rr][1]; w[rr][2] = wn[rr][2]; w[rr][3] = wn[rr][3]; }
-            have_next = (j + 1 < n) || more;
-            if (have_next) load_window();
+            if (prefetch) load_window(wp);
 #pragma unroll
             for (int kk = 0; kk < K; ++kk) {
                 if (kmask >> kk & 1u) {
@@ -391,7 +402,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                         tmem_ld8p(ar + 8 * sl, ta[sl]);
                     }
                     double Sv[4];
-                    stencil1<NINE>(A[kk], w, Sv);
+                    stencil1<NINE>(A[kk], wc, Sv);
                     TmemWait<S * 8>::run(ar);
 #pragma unroll
                     for (int sl = 0; sl < S; ++sl) {
@@ -404,7 +415,17 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                     }
                 }
             }
+        };
+        if (n <= 0) return;
+        if (!have_next) { if (cur == 0) load_window(w0); else load_window(w1); }
+        int j = 0;
+        if (cur == 1) { job(w1, w0, n > 1 || more); cur = 0; j = 1; }
+        for (; j + 1 < n; j += 2) {
+            job(w0, w1, true);
+            job(w1, w0, (j + 2 < n) || more);
         }
+        if (j < n) { job(w0, w1, more); cur = 1; }
+        have_next = more;
     };
 
     for (;;) {

@@ -13,7 +13,7 @@
 //             two at a time (window buffers A and B);
 //   op      = one term: optional stencil evaluation S = A_k * window, then acc[out] += coef * S.
 //
-// The host flattens this into a stream of 16-byte records per block, cut into 512-byte chunks that
+// The host flattens this into a stream of 16-byte records per block, cut into 2 KB chunks that
 // the producer thread copies into a shared-memory ring ahead of the consumers, plus a compact
 // command list for the producer itself (which window / A tile / chunk to fetch next).
 #pragma once
@@ -65,8 +65,8 @@ enum : int32_t {
                               // RUN: b = number of jobs
 };
 
-constexpr int SCHED_CHUNK_RECS = 32;             // 512 bytes
-constexpr int SCHED_CHUNK_USABLE = 31;           // the last unit of a chunk is always NEXT_CHUNK / END
+constexpr int SCHED_CHUNK_RECS = 128;            // 2 KB
+constexpr int SCHED_CHUNK_USABLE = 127;          // the last unit of a chunk is always NEXT_CHUNK / END
 constexpr int SCHED_BLOCK_COLS = 63;             // output columns per block (64 accumulators - scratch)
 constexpr int SCHED_TRASH_ACC = 63;              // scratch accumulator for padded slots
 constexpr int SCHED_ACC_STRIDE = 8;              // TMEM columns per accumulator (4 doubles)
