@@ -152,6 +152,15 @@ template <> struct TmemWait<24> {
                        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]) :: "memory");
     }
 };
+template <> struct TmemWait<32> {
+    __device__ static __forceinline__ void run(uint32_t* r) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                       "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                       "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                       "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) :: "memory");
+    }
+};
 __device__ __forceinline__ void tmem_ld8p(uint32_t* r, uint32_t taddr) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -428,6 +437,59 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         have_next = more;
     };
 
+    // one RUN2: n pairs of jobs (disjoint output columns) with the same matrices and S <= 2 slots; both
+    // windows of a pair go through the stencil in one basic block
+    auto run_pairs = [&](auto s_tag, const uint32_t kmask, const int n) {
+        constexpr int S = decltype(s_tag)::value;
+        constexpr int CU = (S + 1) / 2, JU = 1 + K * CU;
+        for (int j = 0; j < n; ++j) {
+            int4 da = lds_i32x4(rptr);
+            if ((da.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); da = lds_i32x4(rptr); }
+            const int4 db = lds_i32x4(rptr + 16);
+            load_window(w0);
+            load_window(w1);
+            const uint32_t cbase = rptr + 32;
+            rptr += 16 * 2 * JU;
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) {
+                if (kmask >> kk & 1u) {
+                    double cf[2][2 * CU];
+#pragma unroll
+                    for (int u = 0; u < CU; ++u) {
+                        lds_f64x2(cbase + 16 * (kk * CU + u), cf[0][2 * u], cf[0][2 * u + 1]);
+                        lds_f64x2(cbase + 16 * (K * CU + kk * CU + u), cf[1][2 * u], cf[1][2 * u + 1]);
+                    }
+                    const uint32_t pa2 = (uint32_t)(kk == 0 ? da.y : (kk == 1 ? da.z : da.w));
+                    const uint32_t pb2 = (uint32_t)(kk == 0 ? db.y : (kk == 1 ? db.z : db.w));
+                    uint32_t ar[2 * S * 8];
+                    uint32_t ta[2 * S];
+#pragma unroll
+                    for (int sl = 0; sl < S; ++sl) {
+                        ta[sl] = tmem_warp + ((pa2 >> (9 * sl)) & 511u) * SCHED_ACC_STRIDE;
+                        ta[S + sl] = tmem_warp + ((pb2 >> (9 * sl)) & 511u) * SCHED_ACC_STRIDE;
+                    }
+#pragma unroll
+                    for (int sl = 0; sl < 2 * S; ++sl) tmem_ld8p(ar + 8 * sl, ta[sl]);
+                    double Sv[2][4];
+                    stencil1<NINE>(A[kk], w0, Sv[0]);
+                    stencil1<NINE>(A[kk], w1, Sv[1]);
+                    TmemWait<2 * S * 8>::run(ar);
+#pragma unroll
+                    for (int sl = 0; sl < 2 * S; ++sl) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double v = fma(cf[sl / S][sl % S], Sv[sl / S][q],
+                                                 __hiloint2double((int)ar[8 * sl + 2 * q + 1], (int)ar[8 * sl + 2 * q]));
+                            ar[8 * sl + 2 * q] = (uint32_t)__double2loint(v); ar[8 * sl + 2 * q + 1] = (uint32_t)__double2hiint(v);
+                        }
+                        tmem_st8p(ta[sl], ar + 8 * sl);
+                    }
+                }
+            }
+        }
+        have_next = false;
+    };
+
     for (;;) {
         // ---- next work item -----------------------------------------------------------------------
         mbar_wait(fullI(si), pi);
@@ -457,6 +519,11 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                 if (S == 1) run_jobs(std::integral_constant<int, 1>{}, kmask, u.y, more);
                 else if (S == 2) run_jobs(std::integral_constant<int, 2>{}, kmask, u.y, more);
                 else run_jobs(std::integral_constant<int, 3>{}, kmask, u.y, more);
+            } else if (type == REC_RUN2) {
+                const uint32_t kmask = (uint32_t)(u.x >> REC_RUN_KMASK_SHIFT) & 0xFu;
+                const int S = (u.x >> REC_RUN_S_SHIFT) & 3;
+                if (S == 1) run_pairs(std::integral_constant<int, 1>{}, kmask, u.y);
+                else run_pairs(std::integral_constant<int, 2>{}, kmask, u.y);
             } else if (type == REC_ASET) {
                 const int cnt = (u.x >> REC_CNT_SHIFT) & 0xF;
 #pragma unroll

@@ -207,13 +207,26 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
             }
             const int32_t cu = (r.S + 1) / 2;               // coefficient units per register set
             const int32_t job_units = 1 + K * cu;
-            em.ensure(1 + job_units);                        // header and first job in one chunk
-            em.unit(REC_RUN | ((int32_t)r.kmask << REC_RUN_KMASK_SHIFT) | (r.S << REC_RUN_S_SHIFT) |
-                        (ri + 1 < runs.size() ? REC_RUN_MORE : 0),
-                    (int32_t)r.jobs.size(), 0.0);
-            s.n_jobs += (int64_t)r.jobs.size();
-            for (const Job& j : r.jobs) {
-                em.ensure(job_units);
+            // ---- pair up jobs whose output columns are disjoint (both windows in one basic block)
+            std::vector<std::pair<int32_t, int32_t>> pairs;
+            std::vector<int32_t> singles;
+            {
+                std::vector<uint64_t> outs(r.jobs.size(), 0);
+                for (size_t i = 0; i < r.jobs.size(); ++i)
+                    for (int32_t k = 0; k < K; ++k)
+                        for (const Entry& e : r.jobs[i].es[k]) outs[i] |= 1ull << e.out;
+                std::vector<char> used(r.jobs.size(), 0);
+                for (size_t i = 0; i < r.jobs.size(); ++i) {
+                    if (used[i]) continue;
+                    used[i] = 1;
+                    size_t partner = r.jobs.size();
+                    for (size_t j = i + 1; r.S <= 2 && j < r.jobs.size() && j < i + 64; ++j)
+                        if (!used[j] && !(outs[i] & outs[j])) { partner = j; break; }
+                    if (partner < r.jobs.size()) { used[partner] = 1; pairs.push_back({(int32_t)i, (int32_t)partner}); }
+                    else singles.push_back((int32_t)i);
+                }
+            }
+            auto unit0 = [&](const Job& j) {
                 int32_t packs[SCHED_MAX_K] = {0, 0, 0};
                 for (int32_t k = 0; k < K; ++k)
                     for (int32_t sl = 0; sl < SCHED_MAX_S; ++sl) {
@@ -222,6 +235,8 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                     }
                 const int32_t ch = em.unit_words(REC_JOB, packs[0], packs[1], packs[2]);
                 em.cmd(ch, PCMD_WINDOW | j.in_col);
+            };
+            auto coef_units = [&](const Job& j) {
                 for (int32_t k = 0; k < K; ++k) {
                     if (r.kmask >> k & 1u) { s.n_stencils += 1; s.n_entries += (int64_t)j.es[k].size(); }
                     for (int32_t u = 0; u < cu; ++u) {
@@ -231,10 +246,40 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                         SchedRec rec;
                         std::memcpy(&rec.a, &c2[0], 8);       // a,b = first coefficient, c = second
                         rec.c = c2[1];
-                        const int32_t chunk = (int32_t)(s.recs.size() / SCHED_CHUNK_RECS) - em.chunk0;
-                        (void)chunk;
                         s.recs.push_back(rec);
                     }
+                }
+            };
+            s.n_jobs += (int64_t)r.jobs.size();
+            const bool more_after = ri + 1 < runs.size();
+            if (!pairs.empty()) {
+                em.ensure(1 + 2 * job_units);
+                em.unit(REC_RUN2 | ((int32_t)r.kmask << REC_RUN_KMASK_SHIFT) | (r.S << REC_RUN_S_SHIFT), (int32_t)pairs.size(), 0.0);
+                for (const auto& pr : pairs) {
+                    em.ensure(2 * job_units);
+                    unit0(r.jobs[pr.first]);
+                    unit0(r.jobs[pr.second]);
+                    coef_units(r.jobs[pr.first]);
+                    coef_units(r.jobs[pr.second]);
+                }
+                s.n_pairs += (int64_t)pairs.size();
+            }
+            if (!singles.empty()) {
+                em.ensure(1 + job_units);                    // header and first job in one chunk
+                // `more`: the next run's first window may be prefetched by this run's last job -- only
+                // when that run is a RUN of single jobs too (pair runs load their windows themselves)
+                bool more = false;
+                if (more_after) {
+                    // conservative: look ahead is resolved after emission; pairs of the next run are not
+                    // known yet, so prefetch across runs is disabled
+                    more = false;
+                }
+                em.unit(REC_RUN | ((int32_t)r.kmask << REC_RUN_KMASK_SHIFT) | (r.S << REC_RUN_S_SHIFT) | (more ? REC_RUN_MORE : 0),
+                        (int32_t)singles.size(), 0.0);
+                for (int32_t i : singles) {
+                    em.ensure(job_units);
+                    unit0(r.jobs[i]);
+                    coef_units(r.jobs[i]);
                 }
             }
         }
@@ -288,43 +333,55 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                 }
                 break;
             }
-            case REC_RUN: {
+            case REC_RUN:
+            case REC_RUN2: {
+                const bool two = (rec.a & REC_TYPE_MASK) == REC_RUN2;
                 const uint32_t kmask = (uint32_t)(rec.a >> REC_RUN_KMASK_SHIFT) & 0xFu;
                 const int32_t Sn = (rec.a >> REC_RUN_S_SHIFT) & 3, n = rec.b;
                 const int32_t cu = (Sn + 1) / 2, job_units = 1 + K * cu;
+                const int32_t group_units = two ? 2 * job_units : job_units, per = two ? 2 : 1;
                 for (int32_t j = 0; j < n; ++j) {
                     if ((s.recs[r].a & REC_TYPE_MASK) == REC_NEXT_CHUNK) next_chunk();
-                    if (r % SCHED_CHUNK_RECS + job_units > SCHED_CHUNK_USABLE) { fail(); return; }
-                    int32_t w[4];
-                    words(s.recs[r], w);
-                    if (w[0] != REC_JOB) { fail(); return; }
-                    if (f >= fetches.size() || (fetches[f] & PCMD_KIND_MASK) != PCMD_WINDOW) { fail(); return; }
-                    const int32_t in_col = fetches[f++] & PCMD_VAL_MASK;
-                    const double* wv = W + (int64_t)in_col * ldw;
-                    for (int32_t k = 0; k < K; ++k) {
-                        if (!(kmask >> k & 1u)) continue;
-                        const double* a = dia + (size_t)set_slot[k] * D * N;
-                        for (int32_t iy = 0; iy < ny; ++iy)
-                            for (int32_t ix = 0; ix < nx; ++ix) {
-                                const int64_t i = (int64_t)iy * nx + ix;
-                                double v = 0.0;
-                                for (int32_t d = 0; d < D; ++d) {
-                                    const int32_t jx = ix + dx[d], jy = iy + dy[d];
-                                    const double x = (jx >= 0 && jx < nx && jy >= 0 && jy < ny) ? wv[(int64_t)jy * nx + jx] : 0.0;
-                                    v += a[(size_t)d * N + i] * x;
+                    if (r % SCHED_CHUNK_RECS + group_units > SCHED_CHUNK_USABLE) { fail(); return; }
+                    uint64_t seen_out = 0;
+                    for (int32_t q = 0; q < per; ++q) {
+                        int32_t w[4];
+                        words(s.recs[r + q], w);
+                        if (w[0] != REC_JOB) { fail(); return; }
+                        if (f >= fetches.size() || (fetches[f] & PCMD_KIND_MASK) != PCMD_WINDOW) { fail(); return; }
+                        const int32_t in_col = fetches[f++] & PCMD_VAL_MASK;
+                        const double* wv = W + (int64_t)in_col * ldw;
+                        const size_t cbase = r + per + (size_t)q * K * cu;
+                        uint64_t my_out = 0;
+                        for (int32_t k = 0; k < K; ++k) {
+                            if (!(kmask >> k & 1u)) continue;
+                            const double* a = dia + (size_t)set_slot[k] * D * N;
+                            for (int32_t iy = 0; iy < ny; ++iy)
+                                for (int32_t ix = 0; ix < nx; ++ix) {
+                                    const int64_t i = (int64_t)iy * nx + ix;
+                                    double v = 0.0;
+                                    for (int32_t d = 0; d < D; ++d) {
+                                        const int32_t jx = ix + dx[d], jy = iy + dy[d];
+                                        const double x = (jx >= 0 && jx < nx && jy >= 0 && jy < ny) ? wv[(int64_t)jy * nx + jx] : 0.0;
+                                        v += a[(size_t)d * N + i] * x;
+                                    }
+                                    S[i] = v;
                                 }
-                                S[i] = v;
+                            for (int32_t sl = 0; sl < Sn; ++sl) {
+                                const int32_t o = (w[1 + k] >> (9 * sl)) & 511;
+                                if (o != SCHED_TRASH_ACC) my_out |= 1ull << o;
+                                const SchedRec& cr = s.recs[cbase + (size_t)k * cu + sl / 2];
+                                double coef;
+                                if (sl % 2 == 0) std::memcpy(&coef, &cr.a, 8); else coef = cr.c;
+                                double* ac = &acc[(size_t)o * N];
+                                for (int64_t i = 0; i < N; ++i) ac[i] += coef * S[i];
                             }
-                        for (int32_t sl = 0; sl < Sn; ++sl) {
-                            const int32_t o = (w[1 + k] >> (9 * sl)) & 511;
-                            const SchedRec& cr = s.recs[r + 1 + k * cu + sl / 2];
-                            double coef;
-                            if (sl % 2 == 0) std::memcpy(&coef, &cr.a, 8); else coef = cr.c;
-                            double* ac = &acc[(size_t)o * N];
-                            for (int64_t i = 0; i < N; ++i) ac[i] += coef * S[i];
                         }
+                        // the two jobs of a pair run concurrently on the device: their outputs must differ
+                        if (seen_out & my_out) { fail(); return; }
+                        seen_out |= my_out;
                     }
-                    r += job_units;
+                    r += group_units;
                 }
                 break;
             }

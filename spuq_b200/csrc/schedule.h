@@ -43,6 +43,10 @@ static_assert(sizeof(SchedRec) == 16, "unit must be 16 bytes");
 //                                of kmask the stencil (20 DFMA) and S read-modify-writes of TMEM.
 //                                A job never straddles a chunk; `more` = another RUN follows in this
 //                                block (its first window is prefetched by the last job of this one).
+//   RUN2  kmask S n              n PAIRS of jobs with disjoint output columns: the consumer evaluates
+//                                both windows in one basic block (eight independent DFMA chains and
+//                                2S TMEM read-modify-writes in flight).  A pair is
+//                                  [unit 0 of job a][unit 0 of job b][coef units of a][coef units of b]
 //   STORE taddr col0 col1        write two accumulators to Y
 //   NEXT_CHUNK                   continue in the next ring stage (rest of this chunk is unused)
 //   END_ITEM
@@ -57,6 +61,7 @@ enum : int32_t {
     REC_NEXT_CHUNK = 5,
     REC_RUN = 6,
     REC_JOB = 7,
+    REC_RUN2 = 8,             // like RUN, but b = number of job PAIRS (see below)
     REC_TYPE_MASK = 0xF,
     REC_CNT_SHIFT = 4,        // ASET: count in bits 4..7
     REC_RUN_KMASK_SHIFT = 4,  // RUN: kmask in bits 4..7
@@ -89,7 +94,7 @@ struct Schedule {
     std::vector<int32_t> blk_pcmd;         // nblk+1: command range of each block
     std::vector<int32_t> blk_cols;         // nblk*64 output columns (-1 = padding), for reporting
     // statistics (reported through plan_info / used by DESIGN.md numbers)
-    int64_t n_jobs = 0, n_asets = 0, n_entries = 0, n_stencils = 0;
+    int64_t n_jobs = 0, n_pairs = 0, n_asets = 0, n_entries = 0, n_stencils = 0;
 };
 
 // Terms of the operator in per-output-column lists (slot = compact index of an owned block matrix).

@@ -2,6 +2,7 @@
 // of include/spuq_sg.h.  Reference interface replaced: MultiOperator.__init__/apply,
 // application/egsz/multi_operator2.py:30-84.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -209,6 +210,16 @@ static int build_schedule(spuq_sg_plan* p, int32_t K) {
     Schedule* sc = static_cast<Schedule*>(p->sched_host);
     if (!sc) { sc = new Schedule(); p->sched_host = sc; }
     schedule_build(tl, order, K, p->n_slots, sc);
+    if (std::getenv("SPUQ_SCHED_STATS")) {
+        int64_t n_run = 0, n_run2 = 0, n_next = 0;
+        for (const SchedRec& r : sc->recs) {
+            n_run += r.a == 0 ? 0 : 0;
+        }
+        (void)n_run; (void)n_run2; (void)n_next;
+        fprintf(stderr, "[spuq] schedule K=%d: blocks %d, jobs %lld (pairs %lld), A tiles %lld, stencils %lld, terms %lld, "
+                        "units %zu, producer cmds %zu\n", K, sc->nblk, (long long)sc->n_jobs, (long long)sc->n_pairs,
+                (long long)sc->n_asets, (long long)sc->n_stencils, (long long)sc->n_entries, sc->recs.size(), sc->pcmd.size());
+    }
     for (void* d : p->sched_dev) cudaFree(d);
     p->sched_dev.clear();
     p->d_recs = nullptr; p->d_pcmd = nullptr; p->d_blk_pcmd = nullptr; p->d_work_counter = nullptr;
