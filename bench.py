@@ -43,6 +43,8 @@ CONFIGS = {
     "c3": dict(n=1000, M=50, lam=("aniso", 50, 11.3), kind="hermite", mu=0.0),
     "c4": dict(n=500, M=30, lam=("prefix", 30, 3, 5000), kind="legendre", mu=0.0),
     # c3 on a 256 x 256 grid: same Lambda and schedule, 15x less work -- for ncu captures only
+    "c5t": dict(n=64, M=8, lam=("aniso", 8, 9.0), kind="hermite", mu=0.0),
+    "c3t": dict(n=64, M=50, lam=("aniso", 50, 11.3), kind="hermite", mu=0.0),
     "c3s": dict(n=256, M=50, lam=("aniso", 50, 11.3), kind="hermite", mu=0.0),
 }
 

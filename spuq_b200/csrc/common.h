@@ -142,7 +142,7 @@ struct spuq_sg_plan {
     // TMEM-accumulator kernel: schedule tables (host copy + device arrays) and the work counter
     std::vector<int32_t> h_nbr_up, h_nbr_dn;          // M x L, kept for the column order
     void* sched_host = nullptr;                        // spuq::Schedule*
-    int32_t sched_K = 0;
+    int32_t sched_K = 0, sched_C = 0;
     const void* d_recs = nullptr;
     const int32_t* d_pcmd = nullptr;
     const int32_t* d_blk_pcmd = nullptr;

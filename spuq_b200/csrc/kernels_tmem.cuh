@@ -179,15 +179,25 @@ __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
                  ::"r"(taddr), "r"(z) : "memory");
 }
 
-template <int K_, bool NINE_>
+template <int K_, bool NINE_, int G_>
 struct TmemCfg {
     static constexpr int K = K_;
     static constexpr bool NINE = NINE_;
+    // G consumer groups of 4 warps share the CTA: each owns 512/G TMEM columns (a block of 512/G/8 - 1
+    // output columns + the scratch accumulator), its own rings and its own work items.  Two groups put
+    // two warps on every SM sub-partition, which hides the barrier / LDS / tcgen05 round trips of one
+    // behind the arithmetic of the other.
+    static constexpr int G = G_;
     static constexpr int D = NINE ? 9 : 5;
     static constexpr int TILE_X = 64, TILE_Y = 8;
-    static constexpr int CONSUMER_WARPS = 4;
-    static constexpr int CONSUMERS = 32 * CONSUMER_WARPS;
-    static constexpr int THREADS = CONSUMERS + 32;
+    static constexpr int CONSUMER_WARPS = 4;                       // per group
+    // + one producer warp; with two groups the block is padded to three warpgroups so that
+    // setmaxnreg can move registers from the producer warpgroup to the consumers (the register file
+    // is split per SM sub-partition: 9 warps would cap every thread at 168 registers)
+    static constexpr int THREADS = (G == 1) ? 32 * (CONSUMER_WARPS + 1) : 384;
+    static constexpr int CONSUMER_REGS = 224, PRODUCER_REGS = 56;
+    static constexpr int TMEM_COLS = 512 / G;
+    static constexpr int BLOCK_COLS = TMEM_COLS / SCHED_ACC_STRIDE - 1;
     static constexpr int BOX_W = 68, WIN_ROWS = TILE_Y + 2;
     static constexpr int WIN_BYTES = BOX_W * WIN_ROWS * 8;
     static constexpr int WIN_STRIDE = (WIN_BYTES + 127) / 128 * 128;
@@ -195,55 +205,47 @@ struct TmemCfg {
     static constexpr int META_BYTES = SCHED_CHUNK_RECS * 16;
     // W ring: stages of W_GROUP windows under ONE full/empty barrier pair (a barrier round trip costs the
     // single consumer warp of a sub-partition 60-140 clk, so it is paid once per group, not per window)
-    static constexpr int W_GROUP = 4, W_STAGES = 4, W_SLOTS = W_GROUP * W_STAGES;
-    static constexpr int A_STAGES = NINE ? 2 : 4, M_STAGES = 4, I_STAGES = 4;
+    static constexpr int W_GROUP = (G == 1) ? 4 : 2, W_STAGES = 4, W_SLOTS = W_GROUP * W_STAGES;
+    static constexpr int A_STAGES = (G == 1) ? (NINE ? 2 : 4) : (NINE ? 1 : 2), M_STAGES = (G == 1) ? 4 : 3, I_STAGES = 4;
+    // per-group shared memory region
     static constexpr int OFF_A = W_SLOTS * WIN_STRIDE;
     static constexpr int OFF_M = OFF_A + A_STAGES * A_BYTES;
     static constexpr int OFF_I = OFF_M + M_STAGES * META_BYTES;
     static constexpr int OFF_BAR = OFF_I + I_STAGES * 16;
     static constexpr int N_BARS = 2 * (W_STAGES + A_STAGES + M_STAGES + I_STAGES);
-    static constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
+    static constexpr int GROUP_BYTES = (OFF_BAR + N_BARS * 8 + 127) / 128 * 128;
+    static constexpr int OFF_TMEM = G * GROUP_BYTES;
     static constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;       // + alignment slack
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int K, bool NINE>
-__global__ void __launch_bounds__(160, 1)
+template <int K, bool NINE, int G>
+__global__ void __launch_bounds__((G == 1) ? 160 : 384, 1)
 k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapA,
              const SchedRec* __restrict__ recs, const int32_t* __restrict__ pcmd,
              const int32_t* __restrict__ blk_pcmd, int32_t nblk, int32_t s, int32_t ny, int32_t nty,
              int64_t n_items, unsigned long long* __restrict__ work_counter,
              double* __restrict__ Y, int64_t ldy, const double* gate) {
-    using Cfg = TmemCfg<K, NINE>;
+    using Cfg = TmemCfg<K, NINE, G>;
     constexpr int D = Cfg::D;
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* wring = smem;
-    uint8_t* aring = smem + Cfg::OFF_A;
-    uint8_t* mring = smem + Cfg::OFF_M;
-    int4* iring = reinterpret_cast<int4*>(smem + Cfg::OFF_I);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_TMEM);
-    const uint32_t bar0 = smem_u32(smem + Cfg::OFF_BAR);
-    // barrier slots: full/empty pairs of the W, A, metadata and item rings
-    auto fullW = [&](int i) { return bar0 + 8u * i; };
-    auto emptyW = [&](int i) { return bar0 + 8u * (Cfg::W_STAGES + i); };
-    constexpr int BA = 2 * Cfg::W_STAGES;
-    auto fullA = [&](int i) { return bar0 + 8u * (BA + i); };
-    auto emptyA = [&](int i) { return bar0 + 8u * (BA + Cfg::A_STAGES + i); };
-    constexpr int BM = BA + 2 * Cfg::A_STAGES;
-    auto fullM = [&](int i) { return bar0 + 8u * (BM + i); };
-    auto emptyM = [&](int i) { return bar0 + 8u * (BM + Cfg::M_STAGES + i); };
-    constexpr int BI = BM + 2 * Cfg::M_STAGES;
-    auto fullI = [&](int i) { return bar0 + 8u * (BI + i); };
-    auto emptyI = [&](int i) { return bar0 + 8u * (BI + Cfg::I_STAGES + i); };
+    const uint32_t smem_s = smem_u32(smem);
+    // barrier slots of group g: full/empty pairs of its W, A, metadata and item rings
+    constexpr int BA = 2 * Cfg::W_STAGES, BM = BA + 2 * Cfg::A_STAGES, BI = BM + 2 * Cfg::M_STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < Cfg::W_STAGES; ++i) { mbar_init(fullW(i), Cfg::W_GROUP); mbar_init(emptyW(i), Cfg::CONSUMER_WARPS); }
-        for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(fullA(i), 1); mbar_init(emptyA(i), Cfg::CONSUMER_WARPS); }
-        for (int i = 0; i < Cfg::M_STAGES; ++i) { mbar_init(fullM(i), 1); mbar_init(emptyM(i), Cfg::CONSUMER_WARPS); }
-        for (int i = 0; i < Cfg::I_STAGES; ++i) { mbar_init(fullI(i), 1); mbar_init(emptyI(i), Cfg::CONSUMER_WARPS); }
+        for (int g = 0; g < G; ++g) {
+            const uint32_t b = smem_s + g * Cfg::GROUP_BYTES + Cfg::OFF_BAR;
+            for (int i = 0; i < Cfg::W_STAGES; ++i) { mbar_init(b + 8u * i, Cfg::W_GROUP); mbar_init(b + 8u * (Cfg::W_STAGES + i), Cfg::CONSUMER_WARPS); }
+            for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(b + 8u * (BA + i), 1); mbar_init(b + 8u * (BA + Cfg::A_STAGES + i), Cfg::CONSUMER_WARPS); }
+            for (int i = 0; i < Cfg::M_STAGES; ++i) { mbar_init(b + 8u * (BM + i), 1); mbar_init(b + 8u * (BM + Cfg::M_STAGES + i), Cfg::CONSUMER_WARPS); }
+            for (int i = 0; i < Cfg::I_STAGES; ++i) { mbar_init(b + 8u * (BI + i), 1); mbar_init(b + 8u * (BI + Cfg::I_STAGES + i), Cfg::CONSUMER_WARPS); }
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -254,94 +256,146 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    const uint32_t wring_s0 = smem_u32(wring), aring_s0 = smem_u32(aring), mring_s0 = smem_u32(mring);
-    if (warp == Cfg::CONSUMER_WARPS) {
+    if (warp >= Cfg::CONSUMER_WARPS * G) {
+        if (G > 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::PRODUCER_REGS));
+        if (warp >= Cfg::CONSUMER_WARPS * G + G) return;       // padding warps of the producer warpgroup
+        const int my_group = warp - Cfg::CONSUMER_WARPS * G;   // one producer warp per consumer group
         // ================================ producer warp ============================================
         // Every lane owns one command of a batch of 32: it computes its own ring stage from a ballot
         // prefix, waits for that stage to be free and issues its own copy, so the ~500 clk round trip
-        // of (barrier probe, expect_tx, TMA issue) is paid 32-fold in parallel, not per command.
-        uint32_t n_w = 0, n_a = 0, n_m = 0;               // fetches issued so far, per ring
-        int si = 0;
-        uint32_t pi = 0;
+        // of (barrier probe, expect_tx, TMA issue) is paid 32-fold in parallel, not per command.  Each
+        // consumer group has its own producer warp.
+        struct PState {
+            bool active = false, done = false;
+            int32_t xt = 0, yt = 0, c = 0, c1 = 0;
+            uint32_t n_w = 0, n_a = 0, n_m = 0;          // fetches issued so far, per ring
+            int si = 0;
+            uint32_t pi = 0;
+        };
+        PState st[G];
         const uint32_t lt = (1u << lane) - 1u;
-        for (;;) {
-            unsigned long long item = 0;
-            if (lane == 0) item = atomicAdd(work_counter, 1ull);
-            item = __shfl_sync(0xffffffffu, item, 0);
-            const bool valid = item < (unsigned long long)n_items;
-            int32_t xt = -1, yt = -1, blk = 0;
-            if (valid) {
-                blk = (int32_t)(item % (unsigned long long)nblk);
-                const int64_t tile = (int64_t)(item / (unsigned long long)nblk);
-                yt = (int32_t)(tile % nty) * Cfg::TILE_Y;
-                xt = (int32_t)(tile / nty) * Cfg::TILE_X;
-            }
-            if (lane == 0) {
-                mbar_wait(emptyI(si), pi ^ 1u);
-                iring[si] = make_int4(xt, yt, 0, 0);
-                mbar_arrive(fullI(si));
-            }
-            if (++si == Cfg::I_STAGES) { si = 0; pi ^= 1u; }
-            if (!valid) {
-                // complete the last, partly filled window group so that its consumers are released
-                if (lane == 0)
-                    for (uint32_t n = n_w; n % Cfg::W_GROUP != 0; ++n) mbar_arrive(fullW((n % Cfg::W_SLOTS) / Cfg::W_GROUP));
-                break;
-            }
-            const int32_t c0 = __ldg(blk_pcmd + blk), c1 = __ldg(blk_pcmd + blk + 1);
-            for (int32_t base = c0; base < c1; base += 32) {
-                const bool have = base + lane < c1;
+        bool all_done = false;
+        while (!all_done) {
+            all_done = true;
+            bool progress = false;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (g != my_group) continue;
+                PState& P = st[g];
+                if (P.done) continue;
+                all_done = false;
+                const uint32_t gs = smem_s + g * Cfg::GROUP_BYTES, b = gs + Cfg::OFF_BAR;
+                auto fullW = [&](uint32_t i) { return b + 8u * i; };
+                auto emptyW = [&](uint32_t i) { return b + 8u * (Cfg::W_STAGES + i); };
+                auto fullA = [&](uint32_t i) { return b + 8u * (BA + i); };
+                auto emptyA = [&](uint32_t i) { return b + 8u * (BA + Cfg::A_STAGES + i); };
+                auto fullM = [&](uint32_t i) { return b + 8u * (BM + i); };
+                auto emptyM = [&](uint32_t i) { return b + 8u * (BM + Cfg::M_STAGES + i); };
+                if (!P.active) {
+                    unsigned long long item = 0;
+                    if (lane == 0) item = atomicAdd(work_counter, 1ull);
+                    item = __shfl_sync(0xffffffffu, item, 0);
+                    const bool valid = item < (unsigned long long)n_items;
+                    int32_t blk = 0;
+                    P.xt = -1; P.yt = -1;
+                    if (valid) {
+                        blk = (int32_t)(item % (unsigned long long)nblk);
+                        const int64_t tile = (int64_t)(item / (unsigned long long)nblk);
+                        P.yt = (int32_t)(tile % nty) * Cfg::TILE_Y;
+                        P.xt = (int32_t)(tile / nty) * Cfg::TILE_X;
+                    }
+                    if (lane == 0) {
+                        mbar_wait(b + 8u * (BI + Cfg::I_STAGES + P.si), P.pi ^ 1u);
+                        *reinterpret_cast<int4*>(smem + g * Cfg::GROUP_BYTES + Cfg::OFF_I + 16 * P.si) = make_int4(P.xt, P.yt, 0, 0);
+                        mbar_arrive(b + 8u * (BI + P.si));
+                    }
+                    if (++P.si == Cfg::I_STAGES) { P.si = 0; P.pi ^= 1u; }
+                    if (!valid) { P.done = true; continue; }
+                    P.c = __ldg(blk_pcmd + blk); P.c1 = __ldg(blk_pcmd + blk + 1);
+                    P.active = true;
+                }
+                // ---- issue what can be issued NOW for this group, then turn to the next group: the
+                // longest prefix (in stream order) of the next 32 commands whose ring slots are free.
+                // No lane ever blocks, so a full ring of one group cannot starve the other; only the
+                // first lap of each ring is eligible, which also keeps the parity probes unambiguous.
+                const int32_t base = P.c;
+                const bool have = base + lane < P.c1;
                 const int32_t cmd = have ? __ldg(pcmd + base + lane) : 0;
                 const int32_t kind = cmd & PCMD_KIND_MASK, val = cmd & PCMD_VAL_MASK;
                 const bool is_w = have && kind == PCMD_WINDOW, is_a = have && kind == PCMD_ATILE,
                            is_m = have && kind == PCMD_META;
                 const uint32_t mw = __ballot_sync(0xffffffffu, is_w), ma = __ballot_sync(0xffffffffu, is_a),
                                mm = __ballot_sync(0xffffffffu, is_m);
-                // Two fetches of one batch that map to the same ring stage must not probe its barrier
-                // concurrently (a parity wait cannot tell "two phases behind" from "done"): a batch is
-                // issued in rounds of at most STAGES fetches per ring.
                 const uint32_t rw = __popc(mw & lt), ra = __popc(ma & lt), rm = __popc(mm & lt);
-                const uint32_t my_round = is_w ? rw / Cfg::W_SLOTS : (is_a ? ra / Cfg::A_STAGES : rm / Cfg::M_STAGES);
-                const uint32_t rounds = max(max((__popc(mw) + Cfg::W_SLOTS - 1) / Cfg::W_SLOTS,
-                                                (__popc(ma) + Cfg::A_STAGES - 1) / Cfg::A_STAGES),
-                                            (__popc(mm) + Cfg::M_STAGES - 1) / Cfg::M_STAGES);
-                for (uint32_t round = 0; round < rounds; ++round) {
-                    if (my_round == round) {
-                        if (is_w) {
-                            const uint32_t n = n_w + rw, slot = n % Cfg::W_SLOTS, st = slot / Cfg::W_GROUP,
-                                           par = (n / Cfg::W_SLOTS) & 1u;
-                            mbar_wait(emptyW(st), par ^ 1u);
-                            mbar_expect_tx(fullW(st), Cfg::WIN_BYTES);       // one arrival of W_GROUP + the bytes
-                            tma_load_3d(wring_s0 + slot * Cfg::WIN_STRIDE, &mapW, xt - 2, yt - 1, val, fullW(st));
-                        } else if (is_a) {
-                            const uint32_t n = n_a + ra, st = n % Cfg::A_STAGES, par = (n / Cfg::A_STAGES) & 1u;
-                            mbar_wait(emptyA(st), par ^ 1u);
-                            mbar_expect_tx(fullA(st), Cfg::A_BYTES);
-                            tma_load_3d(aring_s0 + st * Cfg::A_BYTES, &mapA, xt, yt, val * D, fullA(st));
-                        } else if (is_m) {
-                            const uint32_t n = n_m + rm, st = n % Cfg::M_STAGES, par = (n / Cfg::M_STAGES) & 1u;
-                            mbar_wait(emptyM(st), par ^ 1u);
-                            mbar_expect_tx(fullM(st), Cfg::META_BYTES);
-                            bulk_load(mring_s0 + st * Cfg::META_BYTES, recs + (size_t)val * SCHED_CHUNK_RECS, Cfg::META_BYTES, fullM(st));
-                        }
-                    }
-                    __syncwarp();
+                bool ok = false;
+                uint32_t slot = 0, sg = 0;
+                if (is_w) {
+                    const uint32_t n = P.n_w + rw;
+                    slot = n % Cfg::W_SLOTS; sg = slot / Cfg::W_GROUP;
+                    ok = rw < Cfg::W_SLOTS && mbar_test(emptyW(sg), ((n / Cfg::W_SLOTS) & 1u) ^ 1u);
+                } else if (is_a) {
+                    const uint32_t n = P.n_a + ra;
+                    sg = n % Cfg::A_STAGES;
+                    ok = ra < Cfg::A_STAGES && mbar_test(emptyA(sg), ((n / Cfg::A_STAGES) & 1u) ^ 1u);
+                } else if (is_m) {
+                    const uint32_t n = P.n_m + rm;
+                    sg = n % Cfg::M_STAGES;
+                    ok = rm < Cfg::M_STAGES && mbar_test(emptyM(sg), ((n / Cfg::M_STAGES) & 1u) ^ 1u);
                 }
-                n_w += __popc(mw); n_a += __popc(ma); n_m += __popc(mm);
+                const uint32_t blocked = ~__ballot_sync(0xffffffffu, ok);
+                const int npre = blocked ? (__ffs(blocked) - 1) : 32;          // commands issued this visit
+                if (lane < npre) {
+                    if (is_w) {
+                        mbar_expect_tx(fullW(sg), Cfg::WIN_BYTES);           // one arrival of W_GROUP + the bytes
+                        tma_load_3d(gs + slot * Cfg::WIN_STRIDE, &mapW, P.xt - 2, P.yt - 1, val, fullW(sg));
+                    } else if (is_a) {
+                        mbar_expect_tx(fullA(sg), Cfg::A_BYTES);
+                        tma_load_3d(gs + Cfg::OFF_A + sg * Cfg::A_BYTES, &mapA, P.xt, P.yt, val * D, fullA(sg));
+                    } else {
+                        mbar_expect_tx(fullM(sg), Cfg::META_BYTES);
+                        bulk_load(gs + Cfg::OFF_M + sg * Cfg::META_BYTES, recs + (size_t)val * SCHED_CHUNK_RECS, Cfg::META_BYTES, fullM(sg));
+                    }
+                }
                 __syncwarp();
+                const uint32_t below = npre >= 32 ? 0xffffffffu : ((1u << npre) - 1u);
+                P.n_w += __popc(mw & below); P.n_a += __popc(ma & below); P.n_m += __popc(mm & below);
+                P.c += npre;
+                if (P.c >= P.c1) {
+                    // A window group is never shared by two items (the last windows of this item must not
+                    // depend on fetches of the next one, which queue behind its metadata): complete the
+                    // partly filled group with plain arrivals; the consumers skip the unused slots.
+                    if (lane == 0)
+                        for (uint32_t n = P.n_w; n % Cfg::W_GROUP != 0; ++n) mbar_arrive(fullW((n % Cfg::W_SLOTS) / Cfg::W_GROUP));
+                    P.n_w = (P.n_w + Cfg::W_GROUP - 1) / Cfg::W_GROUP * Cfg::W_GROUP;
+                    P.active = false;
+                }
+                if (npre > 0) progress = true;
             }
+            if (!progress && !all_done) __nanosleep(100);
         }
         return;
     }
 
     // ==================================== consumer warps ===========================================
-    const uint32_t tmem_warp = *tmem_slot + ((uint32_t)(warp * 32) << 16);
-    int sw = 0, sa = 0, sm = 0, si = 0;
-    uint32_t pw = 0, pa = 0, pm = 0, pi = 0;
-    const uint32_t wring_s = wring_s0, aring_s = aring_s0, mring_s = mring_s0;
+    if (G > 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::CONSUMER_REGS));
+    const int grp = warp / Cfg::CONSUMER_WARPS, lw = warp % Cfg::CONSUMER_WARPS;     // lw = TMEM lane quarter
+    const uint32_t tmem_warp = *tmem_slot + ((uint32_t)(lw * 32) << 16) + (uint32_t)(grp * Cfg::TMEM_COLS);
+    int sa = 0, sm = 0, si = 0;
+    uint32_t pa = 0, pm = 0, pi = 0;
+    const uint32_t gs = smem_s + grp * Cfg::GROUP_BYTES;
+    const uint32_t wring_s = gs, aring_s = gs + Cfg::OFF_A, mring_s = gs + Cfg::OFF_M, iring_s = gs + Cfg::OFF_I;
+    const uint32_t bar0 = gs + Cfg::OFF_BAR;
+    auto fullW = [&](uint32_t i) { return bar0 + 8u * i; };
+    auto emptyW = [&](uint32_t i) { return bar0 + 8u * (Cfg::W_STAGES + i); };
+    auto fullA = [&](uint32_t i) { return bar0 + 8u * (BA + i); };
+    auto emptyA = [&](uint32_t i) { return bar0 + 8u * (BA + Cfg::A_STAGES + i); };
+    auto fullM = [&](uint32_t i) { return bar0 + 8u * (BM + i); };
+    auto emptyM = [&](uint32_t i) { return bar0 + 8u * (BM + Cfg::M_STAGES + i); };
+    auto fullI = [&](uint32_t i) { return bar0 + 8u * (BI + i); };
+    auto emptyI = [&](uint32_t i) { return bar0 + 8u * (BI + Cfg::I_STAGES + i); };
     // this thread's corner inside a staged window / A tile (bytes)
-    const uint32_t win_off = (uint32_t)(((2 * warp) * Cfg::BOX_W + 2 * lane) * 8);
-    const uint32_t a_off = (uint32_t)(((2 * warp) * Cfg::TILE_X + 2 * lane) * 8);
+    const uint32_t win_off = (uint32_t)(((2 * lw) * Cfg::BOX_W + 2 * lane) * 8);
+    const uint32_t a_off = (uint32_t)(((2 * lw) * Cfg::TILE_X + 2 * lane) * 8);
 
     double A[K][D][4];                    // [register set][diagonal][point r*2+p]
     double w0[4][4], w1[4][4];            // two window buffers: jobs alternate between them
@@ -493,16 +547,16 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     for (;;) {
         // ---- next work item -----------------------------------------------------------------------
         mbar_wait(fullI(si), pi);
-        const int4 it = lds_i32x4(smem_u32(iring + si));
+        const int4 it = lds_i32x4(iring_s + 16 * si);
         __syncwarp();
         if (lane == 0) mbar_arrive(emptyI(si));
         if (++si == Cfg::I_STAGES) { si = 0; pi ^= 1u; }
         if (it.x < 0) break;
-        const int32_t x0 = it.x + 2 * lane, y0 = it.y + 2 * warp;
+        const int32_t x0 = it.x + 2 * lane, y0 = it.y + 2 * lw;
 
         // accumulators <- 0 (tcgen05 operations of a warp complete in order)
 #pragma unroll
-        for (int c = 0; c < 512; c += 32) tmem_zero32(tmem_warp + c);
+        for (int c = 0; c < Cfg::TMEM_COLS; c += 32) tmem_zero32(tmem_warp + c);
         have_next = false;
 
         mbar_wait(fullM(sm), pm);
@@ -563,15 +617,19 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                 break;      // REC_END_ITEM
             }
         }
-        // END_ITEM: the rest of the chunk is padding
+        // END_ITEM: the rest of the chunk is padding, and so is the rest of a partly used window group
         __syncwarp();
-        if (lane == 0) mbar_arrive(emptyM(sm));
+        if (lane == 0) {
+            mbar_arrive(emptyM(sm));
+            if (nw % Cfg::W_GROUP != 0) mbar_arrive(emptyW((nw % Cfg::W_SLOTS) / Cfg::W_GROUP));
+        }
+        nw = (nw + Cfg::W_GROUP - 1) / Cfg::W_GROUP * Cfg::W_GROUP;
         if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
     }
 
     // all TMEM traffic of the CTA is complete (every load was waited for): release the columns
     asm volatile("tcgen05.fence::before_thread_sync;");
-    asm volatile("bar.sync 1, 128;");
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * G));
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(512));
 }

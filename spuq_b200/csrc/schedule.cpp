@@ -4,6 +4,7 @@
 #include "schedule.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -11,11 +12,11 @@
 
 namespace spuq {
 
-void schedule_column_order(int32_t L, int32_t M, const int32_t* nbr_up, const int32_t* nbr_dn,
+void schedule_column_order(int32_t L, int32_t M, const int32_t* nbr_up, const int32_t* nbr_dn, int32_t block_cols,
                            std::vector<int32_t>* perm) {
     perm->resize(L);
     std::iota(perm->begin(), perm->end(), 0);
-    if (M <= 0 || !nbr_up || !nbr_dn || L <= SCHED_BLOCK_COLS) return;
+    if (M <= 0 || !nbr_up || !nbr_dn || L <= block_cols) return;
 
     // multi-indices by propagation from the roots (columns without a down-neighbour)
     std::vector<int32_t> mu((size_t)L * M, 0);
@@ -109,13 +110,15 @@ struct Emitter {
 }  // namespace
 
 void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, int32_t K, int32_t n_slots,
-                    Schedule* out) {
+                    int32_t block_cols, Schedule* out) {
     Schedule& s = *out;
     s = Schedule{};
     if (K > SCHED_MAX_K) K = SCHED_MAX_K;
     s.K = K;
+    s.block_cols = block_cols;
     const int32_t L = terms.L;
-    const int32_t C = SCHED_BLOCK_COLS;
+    const int32_t C = block_cols;
+    const int32_t TRASH = block_cols;
     s.nblk = (L + C - 1) / C;
     s.blk_cols.assign((size_t)s.nblk * C, -1);
     s.blk_pcmd.push_back(0);
@@ -220,7 +223,7 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                     if (used[i]) continue;
                     used[i] = 1;
                     size_t partner = r.jobs.size();
-                    for (size_t j = i + 1; r.S <= 2 && j < r.jobs.size() && j < i + 64; ++j)
+                    for (size_t j = i + 1; r.S <= 2 && !std::getenv("SPUQ_NO_PAIRS") && j < r.jobs.size() && j < i + 64; ++j)
                         if (!used[j] && !(outs[i] & outs[j])) { partner = j; break; }
                     if (partner < r.jobs.size()) { used[partner] = 1; pairs.push_back({(int32_t)i, (int32_t)partner}); }
                     else singles.push_back((int32_t)i);
@@ -230,7 +233,7 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                 int32_t packs[SCHED_MAX_K] = {0, 0, 0};
                 for (int32_t k = 0; k < K; ++k)
                     for (int32_t sl = 0; sl < SCHED_MAX_S; ++sl) {
-                        const int32_t o = (sl < (int32_t)j.es[k].size()) ? j.es[k][sl].out : SCHED_TRASH_ACC;
+                        const int32_t o = (sl < (int32_t)j.es[k].size()) ? j.es[k][sl].out : TRASH;
                         packs[k] |= o << (9 * sl);
                     }
                 const int32_t ch = em.unit_words(REC_JOB, packs[0], packs[1], packs[2]);
@@ -297,7 +300,7 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                        const double* dia, const double* W, int64_t ldw, double* Y, int64_t ldy) {
     const int64_t N = (int64_t)nx * ny;
     const int32_t K = s.K;
-    std::vector<double> acc((size_t)(SCHED_TRASH_ACC + 1) * N), S(N);
+    std::vector<double> acc((size_t)(s.block_cols + 1) * N), S(N);
     std::vector<int32_t> set_slot(std::max(K, 1), -1);
     auto fail = [&]() { Y[0] = 0.0 / 0.0; };
     auto words = [](const SchedRec& r, int32_t (&w)[4]) {
@@ -369,7 +372,7 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                                 }
                             for (int32_t sl = 0; sl < Sn; ++sl) {
                                 const int32_t o = (w[1 + k] >> (9 * sl)) & 511;
-                                if (o != SCHED_TRASH_ACC) my_out |= 1ull << o;
+                                if (o != s.block_cols) my_out |= 1ull << o;
                                 const SchedRec& cr = s.recs[cbase + (size_t)k * cu + sl / 2];
                                 double coef;
                                 if (sl % 2 == 0) std::memcpy(&coef, &cr.a, 8); else coef = cr.c;

@@ -38,7 +38,7 @@ static_assert(sizeof(SchedRec) == 16, "unit must be 16 bytes");
 //                                  unit 1+..  for every kk (used or not) ceil(S/2) units holding the
 //                                             slot coefficients (two doubles per unit)
 //                                A slot that is not needed points at the scratch accumulator
-//                                (SCHED_TRASH_ACC) with coefficient 0, so the loop over a run is
+//                                (number block_cols) with coefficient 0, so the loop over a run is
 //                                branch-free in the data: window -> registers, then for every matrix
 //                                of kmask the stencil (20 DFMA) and S read-modify-writes of TMEM.
 //                                A job never straddles a chunk; `more` = another RUN follows in this
@@ -72,8 +72,8 @@ enum : int32_t {
 
 constexpr int SCHED_CHUNK_RECS = 128;            // 2 KB
 constexpr int SCHED_CHUNK_USABLE = 127;          // the last unit of a chunk is always NEXT_CHUNK / END
-constexpr int SCHED_BLOCK_COLS = 63;             // output columns per block (64 accumulators - scratch)
-constexpr int SCHED_TRASH_ACC = 63;              // scratch accumulator for padded slots
+// A block holds block_cols output columns + one scratch accumulator for padded slots: 63 + 1 when one
+// consumer group owns all 512 TMEM columns, 31 + 1 when two groups share them.
 constexpr int SCHED_ACC_STRIDE = 8;              // TMEM columns per accumulator (4 doubles)
 constexpr int SCHED_MAX_K = 3;                   // register sets (limited by the job unit layout)
 constexpr int SCHED_MAX_S = 3;
@@ -88,6 +88,7 @@ enum : int32_t {                                  // producer commands
 
 struct Schedule {
     int32_t K = 0;                         // register sets
+    int32_t block_cols = 63;               // output columns per block; the scratch accumulator is number block_cols
     int32_t nblk = 0;
     std::vector<SchedRec> recs;            // all chunks, SCHED_CHUNK_RECS records each
     std::vector<int32_t> pcmd;             // producer commands
@@ -110,12 +111,12 @@ struct TermLists {
 // tables (every index is its down-neighbour plus e_m) and sorts them with the dimension that
 // carries the most neighbour pairs varying fastest, so that a block holds indices with a common
 // "light" tail.  Falls back to the identity when tables are absent.  perm[k] = column at position k.
-void schedule_column_order(int32_t L, int32_t M, const int32_t* nbr_up, const int32_t* nbr_dn,
+void schedule_column_order(int32_t L, int32_t M, const int32_t* nbr_up, const int32_t* nbr_dn, int32_t block_cols,
                            std::vector<int32_t>* perm);
 
 // Build the schedule for K register sets.  `order` = column order from schedule_column_order.
 void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, int32_t K, int32_t n_slots,
-                    Schedule* out);
+                    int32_t block_cols, Schedule* out);
 
 // Host interpreter of a schedule: executes the record stream with plain loops on diagonal storage
 // (dia[(slot*D + d)*N + i], offsets off[d]).  Used by the CPU emulation build and by the tests to

@@ -198,7 +198,7 @@ static int build_blocks(spuq_sg_plan* p, int32_t C) {
 
 
 // ---- schedule of the TMEM-accumulator kernel (schedule.h), rebuilt when K changes ----------------
-static int build_schedule(spuq_sg_plan* p, int32_t K) {
+static int build_schedule(spuq_sg_plan* p, int32_t K, int32_t block_cols) {
     std::vector<int32_t> slot(p->h_term_mat.size());
     for (size_t t = 0; t < slot.size(); ++t) slot[t] = p->slot_of_mat[p->h_term_mat[t]];
     TermLists tl;
@@ -206,24 +206,24 @@ static int build_schedule(spuq_sg_plan* p, int32_t K) {
     tl.col = p->h_term_col.data(); tl.coef = p->h_term_coef.data();
     std::vector<int32_t> order;
     schedule_column_order(p->L, p->M, p->h_nbr_up.empty() ? nullptr : p->h_nbr_up.data(),
-                          p->h_nbr_dn.empty() ? nullptr : p->h_nbr_dn.data(), &order);
+                          p->h_nbr_dn.empty() ? nullptr : p->h_nbr_dn.data(), block_cols, &order);
     Schedule* sc = static_cast<Schedule*>(p->sched_host);
     if (!sc) { sc = new Schedule(); p->sched_host = sc; }
-    schedule_build(tl, order, K, p->n_slots, sc);
+    schedule_build(tl, order, K, p->n_slots, block_cols, sc);
     if (std::getenv("SPUQ_SCHED_STATS")) {
         int64_t n_run = 0, n_run2 = 0, n_next = 0;
         for (const SchedRec& r : sc->recs) {
             n_run += r.a == 0 ? 0 : 0;
         }
         (void)n_run; (void)n_run2; (void)n_next;
-        fprintf(stderr, "[spuq] schedule K=%d: blocks %d, jobs %lld (pairs %lld), A tiles %lld, stencils %lld, terms %lld, "
-                        "units %zu, producer cmds %zu\n", K, sc->nblk, (long long)sc->n_jobs, (long long)sc->n_pairs,
+        fprintf(stderr, "[spuq] schedule K=%d C=%d: blocks %d, jobs %lld (pairs %lld), A tiles %lld, stencils %lld, terms %lld, "
+                        "units %zu, producer cmds %zu\n", K, block_cols, sc->nblk, (long long)sc->n_jobs, (long long)sc->n_pairs,
                 (long long)sc->n_asets, (long long)sc->n_stencils, (long long)sc->n_entries, sc->recs.size(), sc->pcmd.size());
     }
     for (void* d : p->sched_dev) cudaFree(d);
     p->sched_dev.clear();
     p->d_recs = nullptr; p->d_pcmd = nullptr; p->d_blk_pcmd = nullptr; p->d_work_counter = nullptr;
-    p->sched_K = 0;
+    p->sched_K = 0; p->sched_C = 0;
     int rc;
     SchedRec* d_recs; int32_t *d_pcmd, *d_blk; 
     const size_t first = p->owned_dev.size();
@@ -237,6 +237,7 @@ static int build_schedule(spuq_sg_plan* p, int32_t K) {
     p->owned_dev.resize(first);
     p->d_recs = d_recs; p->d_pcmd = d_pcmd; p->d_blk_pcmd = d_blk; p->d_work_counter = d_cnt;
     p->sched_K = K;
+    p->sched_C = block_cols;
     return SPUQ_OK;
 }
 
@@ -522,10 +523,10 @@ static int launch_tma(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, 
     return SPUQ_OK;
 }
 
-template <int K, bool NINE>
+template <int K, bool NINE, int G>
 static int launch_tmem(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t ldy,
                        cudaStream_t stream, const double* gate) {
-    using Cfg = TmemCfg<K, NINE>;
+    using Cfg = TmemCfg<K, NINE, G>;
     int rc;
     if (p->tmap_a_rows != Cfg::TILE_Y) {
         if ((rc = encode_3d(p->tmap_a, p->dia_vals, p->st.s, p->ny, (int64_t)p->n_slots * Cfg::D, p->st.s, p->st.N,
@@ -536,7 +537,7 @@ static int launch_tmem(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y,
         if ((rc = encode_3d(p->tmap_w, W, p->st.s, p->ny, p->L, p->st.s, ldw, Cfg::BOX_W, Cfg::WIN_ROWS, 1))) return rc;
         p->tmap_w_ptr = W; p->tmap_w_ld = ldw; p->tmap_w_rows = Cfg::WIN_ROWS;
     }
-    auto kern = k_apply_tmem<K, NINE>;
+    auto kern = k_apply_tmem<K, NINE, G>;
     static bool attr_done = false;
     if (!attr_done) {
         SPUQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -546,7 +547,7 @@ static int launch_tmem(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y,
     const int32_t ntx = (p->st.s + Cfg::TILE_X - 1) / Cfg::TILE_X;
     const int32_t nty = (p->ny + Cfg::TILE_Y - 1) / Cfg::TILE_Y;
     const int64_t items = (int64_t)ntx * nty * sc->nblk;
-    const int64_t grid = std::min<int64_t>(items, (int64_t)p->n_sm);
+    const int64_t grid = std::min<int64_t>((items + G - 1) / G, (int64_t)p->n_sm);
     SPUQ_CUDA_TRY(cudaMemsetAsync(p->d_work_counter, 0, sizeof(unsigned long long), stream));
     CUtensorMap mw, ma;
     std::memcpy(&mw, p->tmap_w, sizeof(mw));
@@ -555,7 +556,7 @@ static int launch_tmem(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y,
         mw, ma, static_cast<const SchedRec*>(p->d_recs), p->d_pcmd, p->d_blk_pcmd, sc->nblk, p->st.s, p->ny, nty,
         items, p->d_work_counter, Y, ldy, gate);
     char name[80];
-    snprintf(name, sizeof(name), "k_apply_tmem<K=%d,%s>", K, NINE ? "9pt" : "5pt");
+    snprintf(name, sizeof(name), "k_apply_tmem<K=%d,G=%d,%s>", K, G, NINE ? "9pt" : "5pt");
     p->kernel_name = name;
     return SPUQ_OK;
 }
@@ -619,12 +620,16 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
         // automatic choice: the TMEM-accumulator kernel whenever its alignment conditions hold
         const bool use_tmem = aligned && p->n_slots > 0 && (p->variant == 4 || p->variant == 0);
         if (use_tmem) {
-            const int32_t Kdef = p->nine ? 2 : 3;
-            const int32_t K = p->cols_per_block > 0 ? p->cols_per_block : Kdef;
-            SPUQ_REQUIRE(K >= 1 && K <= (p->nine ? 2 : 3), "apply: TMEM kernel supports 1..%d register sets (got %d)",
-                         p->nine ? 2 : 3, K);
-            if (p->sched_K != K) {
-                int rc = build_schedule(p, K);
+            // rows_per_thread selects the number of consumer groups G (0 = default 2); cols_per_block = K
+            const int32_t G = p->rows_per_thread > 0 ? p->rows_per_thread : 2;
+            SPUQ_REQUIRE(G == 1 || G == 2, "apply: TMEM kernel supports 1 or 2 consumer groups (got %d)", G);
+            const int32_t Kmax = p->nine ? (G == 1 ? 2 : 1) : (G == 1 ? 3 : 2);
+            const int32_t K = p->cols_per_block > 0 ? p->cols_per_block : Kmax;
+            SPUQ_REQUIRE(K >= 1 && K <= Kmax, "apply: TMEM kernel with %d group(s) supports 1..%d register sets (got %d)",
+                         G, Kmax, K);
+            const int32_t block_cols = 512 / G / SCHED_ACC_STRIDE - 1;
+            if (p->sched_K != K || p->sched_C != block_cols) {
+                int rc = build_schedule(p, K, block_cols);
                 if (rc) return rc;
             }
 #ifdef SPUQ_EMU
@@ -633,27 +638,29 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
                               p->dia_vals, W, ldw, Y, ldy);
             {
                 char name[64];
-                snprintf(name, sizeof(name), "schedule_run_host<K=%d,%s>", K, p->nine ? "9pt" : "5pt");
+                snprintf(name, sizeof(name), "schedule_run_host<K=%d,G=%d,%s>", K, G, p->nine ? "9pt" : "5pt");
                 p->kernel_name = name;
             }
+            p->last_launches = 1;
+            return SPUQ_OK;
 #else
-            int rc = SPUQ_OK;
-            bool launched = false;
-#define SPUQ_TMEM(k)                                                                              \
-    if (!launched && K == k) {                                                                    \
-        rc = p->nine ? (k <= 2 ? launch_tmem<(k <= 2 ? k : 2), true>(p, W, ldw, Y, ldy, stream, gate) : SPUQ_E_UNSUPPORTED) \
-                     : launch_tmem<k, false>(p, W, ldw, Y, ldy, stream, gate);                    \
-        launched = true;                                                                          \
-    }
-            SPUQ_TMEM(1) SPUQ_TMEM(2) SPUQ_TMEM(3)
-#undef SPUQ_TMEM
+            int rc = SPUQ_E_UNSUPPORTED;
+            if (!p->nine) {
+                if (G == 1 && K == 1) rc = launch_tmem<1, false, 1>(p, W, ldw, Y, ldy, stream, gate);
+                else if (G == 1 && K == 2) rc = launch_tmem<2, false, 1>(p, W, ldw, Y, ldy, stream, gate);
+                else if (G == 1 && K == 3) rc = launch_tmem<3, false, 1>(p, W, ldw, Y, ldy, stream, gate);
+                else if (G == 2 && K == 1) rc = launch_tmem<1, false, 2>(p, W, ldw, Y, ldy, stream, gate);
+                else if (G == 2 && K == 2) rc = launch_tmem<2, false, 2>(p, W, ldw, Y, ldy, stream, gate);
+            } else {
+                if (G == 1 && K == 1) rc = launch_tmem<1, true, 1>(p, W, ldw, Y, ldy, stream, gate);
+                else if (G == 1 && K == 2) rc = launch_tmem<2, true, 1>(p, W, ldw, Y, ldy, stream, gate);
+                else if (G == 2 && K == 1) rc = launch_tmem<1, true, 2>(p, W, ldw, Y, ldy, stream, gate);
+            }
             if (rc) return rc;
             p->last_launches = 2;      // counter reset + kernel
             SPUQ_CUDA_TRY(cudaGetLastError());
             return SPUQ_OK;
 #endif
-            p->last_launches = 1;
-            return SPUQ_OK;
         }
         // TMA pipeline on grids at least one box wide/tall, else loads through registers
         const bool use_tma = can_tma && p->variant == 3;
