@@ -346,8 +346,12 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                 const int npre = blocked ? (__ffs(blocked) - 1) : 32;          // commands issued this visit
                 if (lane < npre) {
                     if (is_w) {
-                        mbar_expect_tx(fullW(sg), Cfg::WIN_BYTES);           // one arrival of W_GROUP + the bytes
-                        tma_load_3d(gs + slot * Cfg::WIN_STRIDE, &mapW, P.xt - 2, P.yt - 1, val, fullW(sg));
+                        if (val == PCMD_WINDOW_PAD) {
+                            mbar_arrive(fullW(sg));                          // pad slot: arrival without bytes
+                        } else {
+                            mbar_expect_tx(fullW(sg), Cfg::WIN_BYTES);       // one arrival of W_GROUP + the bytes
+                            tma_load_3d(gs + slot * Cfg::WIN_STRIDE, &mapW, P.xt - 2, P.yt - 1, val, fullW(sg));
+                        }
                     } else if (is_a) {
                         mbar_expect_tx(fullA(sg), Cfg::A_BYTES);
                         tma_load_3d(gs + Cfg::OFF_A + sg * Cfg::A_BYTES, &mapA, P.xt, P.yt, val * D, fullA(sg));
@@ -360,15 +364,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                 const uint32_t below = npre >= 32 ? 0xffffffffu : ((1u << npre) - 1u);
                 P.n_w += __popc(mw & below); P.n_a += __popc(ma & below); P.n_m += __popc(mm & below);
                 P.c += npre;
-                if (P.c >= P.c1) {
-                    // A window group is never shared by two items (the last windows of this item must not
-                    // depend on fetches of the next one, which queue behind its metadata): complete the
-                    // partly filled group with plain arrivals; the consumers skip the unused slots.
-                    if (lane == 0)
-                        for (uint32_t n = P.n_w; n % Cfg::W_GROUP != 0; ++n) mbar_arrive(fullW((n % Cfg::W_SLOTS) / Cfg::W_GROUP));
-                    P.n_w = (P.n_w + Cfg::W_GROUP - 1) / Cfg::W_GROUP * Cfg::W_GROUP;
-                    P.active = false;
-                }
+                if (P.c >= P.c1) P.active = false;      // (window groups end with the block: pad commands)
                 if (npre > 0) progress = true;
             }
             if (!progress && !all_done) __nanosleep(100);
@@ -426,6 +422,14 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             if (lane == 0) mbar_arrive(emptyW(st));
         }
         ++nw;
+    };
+    // the rest of a partly used window group is padding (groups end at A-set and block boundaries)
+    auto skip_window_group = [&]() {
+        if (nw % Cfg::W_GROUP != 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(emptyW((nw % Cfg::W_SLOTS) / Cfg::W_GROUP));
+            nw = (nw + Cfg::W_GROUP - 1) / Cfg::W_GROUP * Cfg::W_GROUP;
+        }
     };
     uint32_t rptr = 0;                    // shared address of the next unit of the record stream
     auto next_chunk = [&]() {
@@ -579,6 +583,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                 if (S == 1) run_pairs(std::integral_constant<int, 1>{}, kmask, u.y);
                 else run_pairs(std::integral_constant<int, 2>{}, kmask, u.y);
             } else if (type == REC_ASET) {
+                skip_window_group();
                 const int cnt = (u.x >> REC_CNT_SHIFT) & 0xF;
 #pragma unroll
                 for (int kk = 0; kk < K; ++kk) {
@@ -618,12 +623,9 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             }
         }
         // END_ITEM: the rest of the chunk is padding, and so is the rest of a partly used window group
+        skip_window_group();
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(emptyM(sm));
-            if (nw % Cfg::W_GROUP != 0) mbar_arrive(emptyW((nw % Cfg::W_SLOTS) / Cfg::W_GROUP));
-        }
-        nw = (nw + Cfg::W_GROUP - 1) / Cfg::W_GROUP * Cfg::W_GROUP;
+        if (lane == 0) mbar_arrive(emptyM(sm));
         if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
     }
 

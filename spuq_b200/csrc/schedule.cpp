@@ -68,10 +68,12 @@ struct Emitter {
     Schedule* s;
     std::vector<std::vector<int32_t>> chunk_cmds;   // producer commands by chunk of the current block
     int32_t chunk0 = 0;                              // first chunk of the current block
+    int32_t n_win = 0;                               // window commands of the current block so far
 
     void begin_block() {
         chunk0 = (int32_t)(s->recs.size() / SCHED_CHUNK_RECS);
         chunk_cmds.clear();
+        n_win = 0;
     }
     int32_t pos() const { return (int32_t)(s->recs.size() % SCHED_CHUNK_RECS); }
     // make room for n contiguous units in the current chunk (else link to a fresh chunk)
@@ -92,10 +94,19 @@ struct Emitter {
         std::memcpy(&c, &bits, 8);
         return unit(w0, w1, c);
     }
-    void cmd(int32_t chunk, int32_t c) { chunk_cmds[chunk].push_back(c); }
+    void cmd(int32_t chunk, int32_t c) {
+        chunk_cmds[chunk].push_back(c);
+        if ((c & PCMD_KIND_MASK) == PCMD_WINDOW) ++n_win;
+    }
+    // A window group (one W-ring stage) must not straddle an A-set or block boundary: the consumer waits
+    // for the WHOLE group, and its later windows would queue behind fetches (A tiles, metadata) that
+    // can only be issued after the consumer has moved on.  Complete the group with pad commands.
+    void pad_window_group(int32_t chunk) {
+        while (n_win % s->w_group != 0) cmd(chunk, PCMD_WINDOW | PCMD_WINDOW_PAD);
+    }
     void end_block() {
         ensure(1);
-        unit(REC_END_ITEM, 0, 0.0);
+        pad_window_group(unit(REC_END_ITEM, 0, 0.0));
         while (pos() != 0) s->recs.push_back(SchedRec{REC_END_ITEM, 0, 0.0});
         const int32_t nch = (int32_t)chunk_cmds.size();
         // producer stream: metadata chunks run two ahead of the fetches they describe
@@ -110,12 +121,13 @@ struct Emitter {
 }  // namespace
 
 void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, int32_t K, int32_t n_slots,
-                    int32_t block_cols, Schedule* out) {
+                    int32_t block_cols, int32_t w_group, Schedule* out) {
     Schedule& s = *out;
     s = Schedule{};
     if (K > SCHED_MAX_K) K = SCHED_MAX_K;
     s.K = K;
     s.block_cols = block_cols;
+    s.w_group = w_group;
     const int32_t L = terms.L;
     const int32_t C = block_cols;
     const int32_t TRASH = block_cols;
@@ -205,6 +217,7 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                 const int32_t cnt = std::min<int32_t>(K, (int32_t)slots.size() - cur_set * K);
                 em.ensure(1);
                 const int32_t ch = em.unit(REC_ASET | (cnt << REC_CNT_SHIFT), 0, 0.0);
+                em.pad_window_group(ch);
                 for (int32_t k = 0; k < cnt; ++k) em.cmd(ch, PCMD_ATILE | slots[(size_t)cur_set * K + k]);
                 s.n_asets += cnt;
             }
@@ -312,12 +325,18 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
         // what the producer would fetch, in order, and the chunks of the block
         int32_t chunk0 = -1;
         std::vector<int32_t> fetches, metas;
+        int32_t n_win = 0;
         for (int32_t p = s.blk_pcmd[b]; p < s.blk_pcmd[b + 1]; ++p) {
             const int32_t cmd = s.pcmd[p];
+            if ((cmd & PCMD_KIND_MASK) == PCMD_WINDOW) ++n_win;
+            if (cmd == (PCMD_WINDOW | PCMD_WINDOW_PAD)) continue;
+            // a group may only be padded, never split, at an A-set boundary
+            if ((cmd & PCMD_KIND_MASK) == PCMD_ATILE && !fetches.empty() && (fetches.back() & PCMD_KIND_MASK) == PCMD_WINDOW
+                && n_win % s.w_group != 0) { fail(); return; }
             if ((cmd & PCMD_KIND_MASK) == PCMD_META) { if (chunk0 < 0) chunk0 = cmd & PCMD_VAL_MASK; metas.push_back(cmd & PCMD_VAL_MASK); }
             else fetches.push_back(cmd);
         }
-        if (chunk0 < 0) { fail(); return; }
+        if (chunk0 < 0 || n_win % s.w_group != 0) { fail(); return; }
         for (size_t i = 0; i < metas.size(); ++i) if (metas[i] != chunk0 + (int32_t)i) { fail(); return; }
         std::fill(acc.begin(), acc.end(), 0.0);
         size_t r = (size_t)chunk0 * SCHED_CHUNK_RECS, f = 0, chunks_seen = 1;

@@ -84,11 +84,13 @@ enum : int32_t {                                  // producer commands
     PCMD_META = 2 << 30,    // low bits: absolute chunk index
     PCMD_KIND_MASK = 3 << 30,
     PCMD_VAL_MASK = (1 << 30) - 1,
+    PCMD_WINDOW_PAD = PCMD_VAL_MASK,   // WINDOW with this value: no fetch, just complete the window group
 };
 
 struct Schedule {
     int32_t K = 0;                         // register sets
     int32_t block_cols = 63;               // output columns per block; the scratch accumulator is number block_cols
+    int32_t w_group = 1;                   // windows per W-ring stage: groups are padded at A-set and block ends
     int32_t nblk = 0;
     std::vector<SchedRec> recs;            // all chunks, SCHED_CHUNK_RECS records each
     std::vector<int32_t> pcmd;             // producer commands
@@ -116,7 +118,7 @@ void schedule_column_order(int32_t L, int32_t M, const int32_t* nbr_up, const in
 
 // Build the schedule for K register sets.  `order` = column order from schedule_column_order.
 void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, int32_t K, int32_t n_slots,
-                    int32_t block_cols, Schedule* out);
+                    int32_t block_cols, int32_t w_group, Schedule* out);
 
 // Host interpreter of a schedule: executes the record stream with plain loops on diagonal storage
 // (dia[(slot*D + d)*N + i], offsets off[d]).  Used by the CPU emulation build and by the tests to

