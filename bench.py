@@ -186,26 +186,6 @@ class CpuReference:
 
 
 # ---- GPU arm ----------------------------------------------------------------------------------------
-def shard_ranges(tables, M, G):
-    """Contiguous m-ranges per rank balanced by term count (the mean block's L terms go to rank 0)."""
-    import numpy as np
-    w = np.array([(tables.nbr_up[m] >= 0).sum() + (tables.nbr_dn[m] >= 0).sum()
-                  + (tables.beta_0[m] != 0).sum() for m in range(M)], dtype=np.float64)
-    total = w.sum() + tables.L
-    target = total / G
-    ranges, lo, acc = [], 0, float(tables.L)
-    for g in range(G):
-        hi = lo
-        if g == G - 1:
-            hi = M
-        else:
-            while hi < M and acc + w[hi] / 2 <= target * (g + 1):
-                acc += w[hi]; hi += 1
-        ranges.append((lo, hi))
-        lo = hi
-    return ranges
-
-
 def run_gpu(args):
     import numpy as np
     import torch
@@ -231,12 +211,10 @@ def run_gpu(args):
 
     rowptr, colidx, vals = synthetic.fd_blocks(n, M, device=dev)
     blocks = DeviceBlocks(rowptr, colidx, vals, (N, N))
-    if world > 1:
-        ranges = shard_ranges(tables, M, world)
-        A = sp.MultiOperator.from_blocks(blocks, rvs, m_range=ranges[rank], include_mean=(rank == 0))
-    else:
-        A = sp.MultiOperator.from_blocks(blocks, rvs)
-    Lp = ((L + world - 1) // world) * world                 # pad columns for equal reduce-scatter shares
+    from spuq_b200.sharding import ShardedApply
+    sharded = ShardedApply(blocks, rvs, tables)             # world == 1: the whole operator
+    A = sharded.op
+    Lp = sharded.cols * world                               # columns padded for equal reduce-scatter shares
     g = torch.Generator(device=dev); g.manual_seed(1234)
     Wt = torch.rand((L, N), dtype=torch.float64, device=dev, generator=g)
     w = sp.SlabMultiVector(idx, slab=Wt, _sorted=True)
@@ -328,6 +306,16 @@ def run_gpu(args):
         return
     peak, peak_src = measured_peaks()
     achieved = info["algorithmic_bytes"] / (kernel_ms * 1e-3) / 1e9
+    # DRAM traffic per launch of the same kernel on the same workload, from the committed
+    # `ncu --set full` capture (profiles/): dram__bytes_read.sum + dram__bytes_write.sum
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f).get("%s|%s" % (args.config, plan.kernel_name))
+        if tr and world == 1:
+            traffic = tr["dram_bytes"]
+    except Exception:
+        pass
     out = {
         "metric": "SG operator apply throughput (N*|Lambda| per apply)",
         "value": N * L / (ms_per_step * 1e-3) / 1e9, "unit": "GDoF/s",
@@ -341,7 +329,7 @@ def run_gpu(args):
                    "l2_note": "input slab %.1f GB >> 126 MB L2, no flush needed" % (N * L * 8 / 1e9),
                    "kernel": plan.kernel_name, "path": info["path"]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes": info["algorithmic_bytes"], "kernel_ms": kernel_ms,
                      "fp64_gflops": info["algorithmic_flops"] / (kernel_ms * 1e-3) / 1e9},
         "clocks": clocks, "gpu_launches": launches,
