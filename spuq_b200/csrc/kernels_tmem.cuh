@@ -171,6 +171,15 @@ __device__ __forceinline__ void tmem_st8p(uint32_t taddr, const uint32_t* r) {
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t* r, uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
 // 32 TMEM columns of this warp's lanes <- 0
 __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
     const uint32_t z = 0u;
@@ -439,28 +448,30 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         mbar_wait(fullM(sm), pm);
         rptr = mring_s + (uint32_t)sm * Cfg::META_BYTES;
     };
-    bool have_next = false;               // the buffer `cur` already holds the window of the next job
     int cur = 0;                          // buffer of the next job: 0 = w0, 1 = w1
 
-    // one RUN: n jobs with the same matrices (kmask) and S accumulation slots per matrix
-    auto run_jobs = [&](auto s_tag, const uint32_t kmask, const int n, const bool more) {
+    // one RUN: n jobs with S accumulation slots per matrix; unit 0 of a job names its matrices (kmask)
+    auto run_jobs = [&](auto s_tag, const int n) {
         constexpr int S = decltype(s_tag)::value;
         constexpr int CU = (S + 1) / 2, JU = 1 + K * CU;
+        int4 d = lds_i32x4(rptr);
         // one job: window in wc (already loaded); the window after it is fetched into wp
         auto job = [&](double (&wc)[4][4], double (&wp)[4][4], const bool prefetch) {
-            int4 d = lds_i32x4(rptr);
             if ((d.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); d = lds_i32x4(rptr); }
+            const int4 dc = d;
+            const uint32_t kmask = (uint32_t)(dc.x >> REC_JOB_KMASK_SHIFT) & 0xFu;
             double cf[K][2 * CU];
 #pragma unroll
             for (int kk = 0; kk < K; ++kk)
 #pragma unroll
                 for (int u = 0; u < CU; ++u) lds_f64x2(rptr + 16 * (1 + kk * CU + u), cf[kk][2 * u], cf[kk][2 * u + 1]);
             rptr += 16 * JU;
+            d = lds_i32x4(rptr);                    // unit 0 of the next job (or whatever follows the run)
             if (prefetch) load_window(wp);
 #pragma unroll
             for (int kk = 0; kk < K; ++kk) {
                 if (kmask >> kk & 1u) {
-                    const uint32_t pack = (uint32_t)(kk == 0 ? d.y : (kk == 1 ? d.z : d.w));
+                    const uint32_t pack = (uint32_t)(kk == 0 ? dc.y : (kk == 1 ? dc.z : dc.w));
                     uint32_t ar[S * 8];
                     uint32_t ta[S];
 #pragma unroll
@@ -484,30 +495,31 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             }
         };
         if (n <= 0) return;
-        if (!have_next) { if (cur == 0) load_window(w0); else load_window(w1); }
+        if (cur == 0) load_window(w0); else load_window(w1);
         int j = 0;
-        if (cur == 1) { job(w1, w0, n > 1 || more); cur = 0; j = 1; }
+        if (cur == 1) { job(w1, w0, n > 1); cur = 0; j = 1; }
         for (; j + 1 < n; j += 2) {
             job(w0, w1, true);
-            job(w1, w0, (j + 2 < n) || more);
+            job(w1, w0, j + 2 < n);
         }
-        if (j < n) { job(w0, w1, more); cur = 1; }
-        have_next = more;
+        if (j < n) { job(w0, w1, false); cur = 1; }
     };
 
-    // one RUN2: n pairs of jobs (disjoint output columns) with the same matrices and S <= 2 slots; both
-    // windows of a pair go through the stencil in one basic block
-    auto run_pairs = [&](auto s_tag, const uint32_t kmask, const int n) {
+    // one RUN2: n pairs of jobs (same matrices, disjoint output columns, S <= 2 slots); both windows of
+    // a pair go through the stencil in one basic block
+    auto run_pairs = [&](auto s_tag, const int n) {
         constexpr int S = decltype(s_tag)::value;
         constexpr int CU = (S + 1) / 2, JU = 1 + K * CU;
+        int4 da = lds_i32x4(rptr), db = lds_i32x4(rptr + 16);
         for (int j = 0; j < n; ++j) {
-            int4 da = lds_i32x4(rptr);
-            if ((da.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); da = lds_i32x4(rptr); }
-            const int4 db = lds_i32x4(rptr + 16);
+            if ((da.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); da = lds_i32x4(rptr); db = lds_i32x4(rptr + 16); }
+            const int4 ca = da, cb = db;
+            const uint32_t kmask = (uint32_t)(ca.x >> REC_JOB_KMASK_SHIFT) & 0xFu;
             load_window(w0);
             load_window(w1);
             const uint32_t cbase = rptr + 32;
             rptr += 16 * 2 * JU;
+            da = lds_i32x4(rptr); db = lds_i32x4(rptr + 16);     // unit 0s of the next pair
 #pragma unroll
             for (int kk = 0; kk < K; ++kk) {
                 if (kmask >> kk & 1u) {
@@ -517,8 +529,8 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                         lds_f64x2(cbase + 16 * (kk * CU + u), cf[0][2 * u], cf[0][2 * u + 1]);
                         lds_f64x2(cbase + 16 * (K * CU + kk * CU + u), cf[1][2 * u], cf[1][2 * u + 1]);
                     }
-                    const uint32_t pa2 = (uint32_t)(kk == 0 ? da.y : (kk == 1 ? da.z : da.w));
-                    const uint32_t pb2 = (uint32_t)(kk == 0 ? db.y : (kk == 1 ? db.z : db.w));
+                    const uint32_t pa2 = (uint32_t)(kk == 0 ? ca.y : (kk == 1 ? ca.z : ca.w));
+                    const uint32_t pb2 = (uint32_t)(kk == 0 ? cb.y : (kk == 1 ? cb.z : cb.w));
                     uint32_t ar[2 * S * 8];
                     uint32_t ta[2 * S];
 #pragma unroll
@@ -545,7 +557,6 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                 }
             }
         }
-        have_next = false;
     };
 
     for (;;) {
@@ -561,7 +572,6 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         // accumulators <- 0 (tcgen05 operations of a warp complete in order)
 #pragma unroll
         for (int c = 0; c < Cfg::TMEM_COLS; c += 32) tmem_zero32(tmem_warp + c);
-        have_next = false;
 
         mbar_wait(fullM(sm), pm);
         rptr = mring_s + (uint32_t)sm * Cfg::META_BYTES;
@@ -570,18 +580,15 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             const int type = u.x & REC_TYPE_MASK;
             if (type == REC_NEXT_CHUNK) { next_chunk(); continue; }
             rptr += 16;
-            if (type == REC_RUN) {
-                const uint32_t kmask = (uint32_t)(u.x >> REC_RUN_KMASK_SHIFT) & 0xFu;
+            if (type == REC_RUN2) {
                 const int S = (u.x >> REC_RUN_S_SHIFT) & 3;
-                const bool more = (u.x & REC_RUN_MORE) != 0;
-                if (S == 1) run_jobs(std::integral_constant<int, 1>{}, kmask, u.y, more);
-                else if (S == 2) run_jobs(std::integral_constant<int, 2>{}, kmask, u.y, more);
-                else run_jobs(std::integral_constant<int, 3>{}, kmask, u.y, more);
-            } else if (type == REC_RUN2) {
-                const uint32_t kmask = (uint32_t)(u.x >> REC_RUN_KMASK_SHIFT) & 0xFu;
+                if (S == 1) run_pairs(std::integral_constant<int, 1>{}, u.y);
+                else run_pairs(std::integral_constant<int, 2>{}, u.y);
+            } else if (type == REC_RUN) {
                 const int S = (u.x >> REC_RUN_S_SHIFT) & 3;
-                if (S == 1) run_pairs(std::integral_constant<int, 1>{}, kmask, u.y);
-                else run_pairs(std::integral_constant<int, 2>{}, kmask, u.y);
+                if (S == 1) run_jobs(std::integral_constant<int, 1>{}, u.y);
+                else if (S == 2) run_jobs(std::integral_constant<int, 2>{}, u.y);
+                else run_jobs(std::integral_constant<int, 3>{}, u.y);
             } else if (type == REC_ASET) {
                 skip_window_group();
                 const int cnt = (u.x >> REC_CNT_SHIFT) & 0xF;
@@ -600,22 +607,28 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                         if (++sa == Cfg::A_STAGES) { sa = 0; pa ^= 1u; }
                     }
                 }
-            } else if (type == REC_STORE) {
+            } else if (type == REC_STOREALL) {
+                // all accumulators of the block -> Y, four at a time (32 TMEM columns per load)
                 tmem_wait_st();
-                uint32_t r16[16];
-                tmem_ld16(r16, tmem_warp + (uint32_t)u.y);
-                tmem_wait_ld16(r16);
-                const int32_t cols[2] = {u.z, u.w};
+                const bool xin = x0 < s;
+                for (int q = 0; q < u.y; ++q) {
+                    const int4 cols4 = lds_i32x4(rptr);
+                    rptr += 16;
+                    uint32_t r32[32];
+                    tmem_ld32(r32, tmem_warp + (uint32_t)(q * 4 * SCHED_ACC_STRIDE));
+                    TmemWait<32>::run(r32);
+                    const int32_t cols[4] = {cols4.x, cols4.y, cols4.z, cols4.w};
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    if (cols[q] >= 0 && x0 < s) {
-                        double* yp = Y + (int64_t)cols[q] * ldy + (int64_t)y0 * s + x0;
+                    for (int t = 0; t < 4; ++t) {
+                        if (cols[t] >= 0 && xin) {
+                            double* yp = Y + (int64_t)cols[t] * ldy + (int64_t)y0 * s + x0;
 #pragma unroll
-                        for (int r = 0; r < 2; ++r)
-                            if (y0 + r < ny)
-                                *reinterpret_cast<double2*>(yp + (int64_t)r * s) =
-                                    make_double2(__hiloint2double((int)r16[8 * q + 4 * r + 1], (int)r16[8 * q + 4 * r]),
-                                                 __hiloint2double((int)r16[8 * q + 4 * r + 3], (int)r16[8 * q + 4 * r + 2]));
+                            for (int r = 0; r < 2; ++r)
+                                if (y0 + r < ny)
+                                    *reinterpret_cast<double2*>(yp + (int64_t)r * s) =
+                                        make_double2(__hiloint2double((int)r32[8 * t + 4 * r + 1], (int)r32[8 * t + 4 * r]),
+                                                     __hiloint2double((int)r32[8 * t + 4 * r + 3], (int)r32[8 * t + 4 * r + 2]));
+                        }
                     }
                 }
             } else {

@@ -193,15 +193,16 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                     jobs.push_back(std::move(j));
                 }
             }
+            // one run per slot count; inside it jobs with the same matrices are adjacent (pair partners)
             std::stable_sort(jobs.begin(), jobs.end(), [](const Job& x, const Job& y) {
-                if (x.kmask != y.kmask) return x.kmask > y.kmask;
-                return x.S > y.S;
+                if (x.S != y.S) return x.S < y.S;
+                return x.kmask > y.kmask;
             });
             for (size_t i = 0; i < jobs.size();) {
                 size_t j = i;
-                while (j < jobs.size() && jobs[j].kmask == jobs[i].kmask && jobs[j].S == jobs[i].S) ++j;
+                while (j < jobs.size() && jobs[j].S == jobs[i].S) ++j;
                 Run r;
-                r.set = set; r.kmask = jobs[i].kmask; r.S = jobs[i].S;
+                r.set = set; r.kmask = 0; r.S = jobs[i].S;
                 r.jobs.assign(std::make_move_iterator(jobs.begin() + i), std::make_move_iterator(jobs.begin() + j));
                 runs.push_back(std::move(r));
                 i = j;
@@ -237,7 +238,7 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                     used[i] = 1;
                     size_t partner = r.jobs.size();
                     for (size_t j = i + 1; r.S <= 2 && !std::getenv("SPUQ_NO_PAIRS") && j < r.jobs.size() && j < i + 64; ++j)
-                        if (!used[j] && !(outs[i] & outs[j])) { partner = j; break; }
+                        if (!used[j] && r.jobs[j].kmask == r.jobs[i].kmask && !(outs[i] & outs[j])) { partner = j; break; }
                     if (partner < r.jobs.size()) { used[partner] = 1; pairs.push_back({(int32_t)i, (int32_t)partner}); }
                     else singles.push_back((int32_t)i);
                 }
@@ -249,12 +250,12 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                         const int32_t o = (sl < (int32_t)j.es[k].size()) ? j.es[k][sl].out : TRASH;
                         packs[k] |= o << (9 * sl);
                     }
-                const int32_t ch = em.unit_words(REC_JOB, packs[0], packs[1], packs[2]);
+                const int32_t ch = em.unit_words(REC_JOB | ((int32_t)j.kmask << REC_JOB_KMASK_SHIFT), packs[0], packs[1], packs[2]);
                 em.cmd(ch, PCMD_WINDOW | j.in_col);
             };
             auto coef_units = [&](const Job& j) {
                 for (int32_t k = 0; k < K; ++k) {
-                    if (r.kmask >> k & 1u) { s.n_stencils += 1; s.n_entries += (int64_t)j.es[k].size(); }
+                    if (j.kmask >> k & 1u) { s.n_stencils += 1; s.n_entries += (int64_t)j.es[k].size(); }
                     for (int32_t u = 0; u < cu; ++u) {
                         double c2[2] = {0.0, 0.0};
                         for (int q = 0; q < 2; ++q)
@@ -299,11 +300,15 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                 }
             }
         }
-        for (int32_t o = 0; o < ncols; o += 2) {
-            const int32_t c0 = s.blk_cols[(size_t)b * C + o];
-            const int32_t c1 = (o + 1 < ncols) ? s.blk_cols[(size_t)b * C + o + 1] : -1;
-            em.ensure(1);
-            em.unit_words(REC_STORE, o * SCHED_ACC_STRIDE, c0, c1);
+        {
+            const int32_t nq = (ncols + 3) / 4;
+            em.ensure(1 + nq);
+            em.unit(REC_STOREALL, nq, 0.0);
+            for (int32_t q = 0; q < nq; ++q) {
+                int32_t c4[4];
+                for (int32_t t = 0; t < 4; ++t) c4[t] = (4 * q + t < ncols) ? s.blk_cols[(size_t)b * C + 4 * q + t] : -1;
+                em.unit_words(c4[0], c4[1], c4[2], c4[3]);
+            }
         }
         em.end_block();
     }
@@ -358,7 +363,7 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
             case REC_RUN:
             case REC_RUN2: {
                 const bool two = (rec.a & REC_TYPE_MASK) == REC_RUN2;
-                const uint32_t kmask = (uint32_t)(rec.a >> REC_RUN_KMASK_SHIFT) & 0xFu;
+                uint32_t kmask = 0;
                 const int32_t Sn = (rec.a >> REC_RUN_S_SHIFT) & 3, n = rec.b;
                 const int32_t cu = (Sn + 1) / 2, job_units = 1 + K * cu;
                 const int32_t group_units = two ? 2 * job_units : job_units, per = two ? 2 : 1;
@@ -369,7 +374,10 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                     for (int32_t q = 0; q < per; ++q) {
                         int32_t w[4];
                         words(s.recs[r + q], w);
-                        if (w[0] != REC_JOB) { fail(); return; }
+                        if ((w[0] & REC_TYPE_MASK) != REC_JOB) { fail(); return; }
+                        const uint32_t km = (uint32_t)(w[0] >> REC_JOB_KMASK_SHIFT) & 0xFu;
+                        if (q > 0 && km != kmask) { fail(); return; }       // pair partners use the same matrices
+                        kmask = km;
                         if (f >= fetches.size() || (fetches[f] & PCMD_KIND_MASK) != PCMD_WINDOW) { fail(); return; }
                         const int32_t in_col = fetches[f++] & PCMD_VAL_MASK;
                         const double* wv = W + (int64_t)in_col * ldw;
@@ -407,12 +415,14 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                 }
                 break;
             }
-            case REC_STORE: {
-                int32_t w[4];
-                words(rec, w);
-                for (int q = 0; q < 2; ++q)
-                    if (w[2 + q] >= 0)
-                        std::memcpy(Y + (int64_t)w[2 + q] * ldy, &acc[(size_t)(w[1] / SCHED_ACC_STRIDE + q) * N], sizeof(double) * N);
+            case REC_STOREALL: {
+                for (int32_t q = 0; q < rec.b; ++q) {
+                    int32_t w[4];
+                    words(s.recs[r++], w);
+                    for (int t = 0; t < 4; ++t)
+                        if (w[t] >= 0)
+                            std::memcpy(Y + (int64_t)w[t] * ldy, &acc[(size_t)(4 * q + t) * N], sizeof(double) * N);
+                }
                 break;
             }
             default: fail(); return;

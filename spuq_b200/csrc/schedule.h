@@ -31,9 +31,10 @@ static_assert(sizeof(SchedRec) == 16, "unit must be 16 bytes");
 // Stream of a block (all units 16 bytes, read by the consumer warps from the metadata ring):
 //
 //   ASET  cnt                    load the next cnt A tiles of the A ring into register sets 0..cnt-1
-//   RUN   kmask S n more         n jobs follow that all use the matrices in kmask with S accumulation
-//                                slots per matrix.  Every job is 1 + K*ceil(S/2) units:
-//                                  unit 0     a = REC_JOB, words 1..3: for register set kk the
+//   RUN   S n                    n jobs follow, all with S accumulation slots per matrix.  Every job is
+//                                1 + K*ceil(S/2) units:
+//                                  unit 0     a = REC_JOB | kmask << 4 (matrices of the set the job
+//                                             uses), words 1..3: for register set kk the
 //                                             accumulator numbers of its S slots, 9 bits each
 //                                  unit 1+..  for every kk (used or not) ceil(S/2) units holding the
 //                                             slot coefficients (two doubles per unit)
@@ -47,7 +48,8 @@ static_assert(sizeof(SchedRec) == 16, "unit must be 16 bytes");
 //                                both windows in one basic block (eight independent DFMA chains and
 //                                2S TMEM read-modify-writes in flight).  A pair is
 //                                  [unit 0 of job a][unit 0 of job b][coef units of a][coef units of b]
-//   STORE taddr col0 col1        write two accumulators to Y
+//   STOREALL n                   write all accumulators to Y: n units follow, each naming the output
+//                                columns of four consecutive accumulators (-1 = none)
 //   NEXT_CHUNK                   continue in the next ring stage (rest of this chunk is unused)
 //   END_ITEM
 //
@@ -62,6 +64,8 @@ enum : int32_t {
     REC_RUN = 6,
     REC_JOB = 7,
     REC_RUN2 = 8,             // like RUN, but b = number of job PAIRS (see below)
+    REC_STOREALL = 9,         // b = number of accumulator quadruples; followed by that many units of 4 output columns
+    REC_JOB_KMASK_SHIFT = 4,  // JOB unit 0: matrices used by the job in bits 4..7
     REC_TYPE_MASK = 0xF,
     REC_CNT_SHIFT = 4,        // ASET: count in bits 4..7
     REC_RUN_KMASK_SHIFT = 4,  // RUN: kmask in bits 4..7
