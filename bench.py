@@ -20,9 +20,13 @@ Workloads (BASELINE.json configs, synthetic inputs of SURVEY.md 8d):
   c2  512 x 512 grid, M = 20, total degree 3 (1771 indices), Legendre
   c4  500 x 500 grid, M = 30, first 5000 indices of the degree-3 set, Legendre
   c1  32 x 32 grid, M = 5, total degree 2 (21 indices): the reference's CPU-runnable case
-Multi-GPU (N > 1): the M expansion terms are sharded over the ranks (balanced by term count), every
-rank applies its terms to a full replica of w and the partial results are combined with an NCCL
-reduce-scatter along the Lambda (column) axis; total work is fixed => "scaling": "strong".
+Multi-GPU (N > 1), total work fixed => "scaling": "strong".  Default `--shard rows`: the grid rows are
+sharded over the ranks (every rank owns N/G spatial dofs of all |Lambda| columns); one step = exchange
+of the two boundary grid rows with the neighbouring ranks (point to point over NCCL) + the single-GPU
+kernel on the local grid.  `--shard m` is the decomposition BASELINE.json's north_star describes: the M
+expansion terms are sharded (balanced by term count), every rank applies its terms to a full replica
+of w and the partial results are combined with an NCCL reduce-scatter along Lambda; it moves a whole
+slab over NVLink per step and cannot scale against a fused kernel.
 """
 import argparse
 import json
@@ -209,26 +213,49 @@ def run_gpu(args):
     rvs = synthetic.make_rvs(cfg["kind"], M, cfg["mu"])
     tables = lambda_tables.LambdaTables(idx, rvs)
 
-    rowptr, colidx, vals = synthetic.fd_blocks(n, M, device=dev)
-    blocks = DeviceBlocks(rowptr, colidx, vals, (N, N))
-    from spuq_b200.sharding import ShardedApply
-    sharded = ShardedApply(blocks, rvs, tables)             # world == 1: the whole operator
-    A = sharded.op
-    Lp = sharded.cols * world                               # columns padded for equal reduce-scatter shares
-    g = torch.Generator(device=dev); g.manual_seed(1234)
-    Wt = torch.rand((L, N), dtype=torch.float64, device=dev, generator=g)
+    rows_mode = world > 1 and args.shard == "rows"
+    g = torch.Generator(device=dev); g.manual_seed(1234 + (rank if rows_mode else 0))
+    if rows_mode:
+        # spatial rows sharded over the ranks, one halo grid row on each side, halo exchange per step
+        from spuq_b200.sharding import RowShardedApply, row_ranges
+        y0, y1 = row_ranges(n, world)[rank]
+        nyl = y1 - y0 + 2
+        Nloc = nyl * n
+        rowptr, colidx, vals = synthetic.fd_blocks_rows(n, M, y0, y1, device=dev)
+        blocks = DeviceBlocks(rowptr, colidx, vals, (Nloc, Nloc))
+        sharded = RowShardedApply(blocks, rvs, n, y0, y1)
+        A = sharded.op
+        Lp = L
+        Wt = torch.rand((L, Nloc), dtype=torch.float64, device=dev, generator=g)
+    else:
+        rowptr, colidx, vals = synthetic.fd_blocks(n, M, device=dev)
+        blocks = DeviceBlocks(rowptr, colidx, vals, (N, N))
+        from spuq_b200.sharding import ShardedApply
+        sharded = ShardedApply(blocks, rvs, tables)             # world == 1: the whole operator
+        A = sharded.op
+        Lp = sharded.cols * world                               # columns padded for equal reduce-scatter shares
+        Nloc = N
+        Wt = torch.rand((L, N), dtype=torch.float64, device=dev, generator=g)
     w = sp.SlabMultiVector(idx, slab=Wt, _sorted=True)
     plan = A.plan_for(w)
     if args.variant or args.cols or args.rows:
         plan.tune(args.variant, args.cols, args.rows, 0)
-    Yfull = torch.zeros((Lp, N), dtype=torch.float64, device=dev)
-    Yown = torch.empty((Lp // world, N), dtype=torch.float64, device=dev) if world > 1 else None
+    Yfull = torch.zeros((Lp, Nloc), dtype=torch.float64, device=dev)
+    Yown = torch.empty((Lp // world, N), dtype=torch.float64, device=dev) if (world > 1 and not rows_mode) else None
     info = plan.info()
 
-    def step():
-        plan.apply(Wt, Yfull[:L])
-        if world > 1:
+    def comm_before():
+        if rows_mode:
+            sharded.exchange_halos(Wt)
+
+    def comm_after():
+        if world > 1 and not rows_mode:
             dist.reduce_scatter_tensor(Yown, Yfull, op=dist.ReduceOp.SUM)
+
+    def step():
+        comm_before()
+        plan.apply(Wt, Yfull[:L])
+        comm_after()
 
     def barrier():
         if world > 1:
@@ -247,11 +274,11 @@ def run_gpu(args):
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0.record()
     for k in range(args.steps):
+        comm_before()
         kev[k][0].record()
         plan.apply(Wt, Yfull[:L])
         kev[k][1].record()
-        if world > 1:
-            dist.reduce_scatter_tensor(Yown, Yfull, op=dist.ReduceOp.SUM)
+        comm_after()
     ev1.record()
     barrier()
     total_ms = ev0.elapsed_time(ev1)
@@ -268,15 +295,16 @@ def run_gpu(args):
     e2e = None
     if not args.no_e2e:
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        h_in = torch.empty((L, N), dtype=torch.float64, pin_memory=True)
-        h_out = torch.empty((Lp // world if world > 1 else L, N), dtype=torch.float64, pin_memory=True)
+        h_in = torch.empty((L, Nloc), dtype=torch.float64, pin_memory=True)
+        h_out = torch.empty((L, Nloc) if (rows_mode or world == 1) else (Lp // world, N), dtype=torch.float64, pin_memory=True)
         h_in.copy_(Wt)
         torch.cuda.synchronize()
 
         def e2e_step():
             Wt.copy_(h_in, non_blocking=True)                     # H2D of this step's input slab
+            comm_before()
             y = A.apply(w)                                        # public API: MultiOperator.apply
-            if world > 1:
+            if world > 1 and not rows_mode:
                 Yfull[:L].copy_(y.slab)
                 dist.reduce_scatter_tensor(Yown, Yfull, op=dist.ReduceOp.SUM)
                 h_out.copy_(Yown, non_blocking=True)
@@ -325,7 +353,9 @@ def run_gpu(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config), "N": N, "L": L, "M": M,
                    "n_terms": info["n_terms"], "nnz_per_block": info["nnz"],
-                   "parallelism": ("M-sharded x%d + NCCL reduce-scatter over Lambda" % world) if world > 1 else "1 GPU",
+                   "parallelism": ("1 GPU" if world == 1 else
+                                   ("grid rows sharded x%d, halo rows exchanged point-to-point (NCCL) every step" % world) if rows_mode
+                                   else ("M-sharded x%d + NCCL reduce-scatter over Lambda" % world)),
                    "l2_note": "input slab %.1f GB >> 126 MB L2, no flush needed" % (N * L * 8 / 1e9),
                    "kernel": plan.kernel_name, "path": info["path"]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -388,6 +418,8 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--cols", type=int, default=0)
     ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--shard", default="rows", choices=["rows", "m"],
+                    help="multi-GPU decomposition: grid rows + halo exchange (default) or expansion terms + reduce-scatter")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)

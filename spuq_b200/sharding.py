@@ -12,7 +12,7 @@ import torch.distributed as dist
 
 from .multi_operator import MultiOperator
 
-__all__ = ["shard_ranges", "padded_columns", "ShardedApply"]
+__all__ = ["shard_ranges", "padded_columns", "ShardedApply", "row_ranges", "RowShardedApply"]
 
 
 def shard_ranges(tables, M, world):
@@ -76,3 +76,68 @@ class ShardedApply:
             dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.group)
             Yown.copy_(tmp[self.rank * self.cols:(self.rank + 1) * self.cols])
         return Yown
+
+
+# ---- row sharding ---------------------------------------------------------------------------------
+def row_ranges(ny, world, align=8):
+    """Contiguous grid-row ranges per rank, multiples of `align` rows (the kernel's tile height)
+    except for the last one."""
+    per = -(-ny // world)
+    per = -(-per // align) * align
+    return [(min(r * per, ny), min((r + 1) * per, ny)) for r in range(world)]
+
+
+class RowShardedApply:
+    """The SG operator with the SPATIAL rows sharded over the ranks (axis 3).
+
+    Rank r owns the grid rows [y0, y1) for all |Lambda| columns; its local slab carries one halo grid
+    row above and below (local grid (y1 - y0 + 2) x nx).  One apply = exchange of the two boundary
+    rows with the neighbouring ranks (2 x nx x L doubles per neighbour, point to point) followed by
+    the single-GPU kernel on the local grid; output halo rows are not meaningful.  No reduction of
+    Y is needed, so the traffic per rank is 1/world of the single-GPU traffic plus the halos.
+
+    ``blocks``: local blocks from synthetic.fd_blocks_rows(n, M, y0, y1) (or any assembly of the same
+    rows); ``W`` slabs are L x ((y1-y0+2)*nx)."""
+
+    def __init__(self, blocks, rvs, nx, y0, y1, group=None, path=0):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.nx, self.y0, self.y1 = nx, y0, y1
+        self.nyl = y1 - y0 + 2
+        self.op = MultiOperator.from_blocks(blocks, rvs, path=path)
+        self._bufs = None
+
+    def plan_for(self, w):
+        return self.op.plan_for(w)
+
+    def exchange_halos(self, W):
+        """Fill the halo rows of the local slab W (L x nyl*nx) from the neighbours' boundary rows."""
+        if self.world == 1:
+            return
+        L = W.shape[0]
+        W3 = W.view(L, self.nyl, self.nx)
+        if self._bufs is None or self._bufs[0].shape[0] != L:
+            mk = lambda: torch.empty((L, self.nx), dtype=W.dtype, device=W.device)      # noqa: E731
+            self._bufs = (mk(), mk(), mk(), mk())
+        s_up, s_dn, r_up, r_dn = self._bufs
+        ops = []
+        if self.rank > 0:
+            s_up.copy_(W3[:, 1, :])                              # my first owned row -> bottom halo of rank-1
+            ops += [dist.P2POp(dist.isend, s_up, self.rank - 1, self.group),
+                    dist.P2POp(dist.irecv, r_up, self.rank - 1, self.group)]
+        if self.rank < self.world - 1:
+            s_dn.copy_(W3[:, self.nyl - 2, :])                   # my last owned row -> top halo of rank+1
+            ops += [dist.P2POp(dist.isend, s_dn, self.rank + 1, self.group),
+                    dist.P2POp(dist.irecv, r_dn, self.rank + 1, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if self.rank > 0:
+            W3[:, 0, :].copy_(r_up)
+        if self.rank < self.world - 1:
+            W3[:, self.nyl - 1, :].copy_(r_dn)
+
+    def apply(self, plan, W, Y):
+        self.exchange_halos(W)
+        plan.apply(W, Y)
+        return Y

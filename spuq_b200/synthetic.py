@@ -29,7 +29,7 @@ from .lambda_tables import sort_permutation
 from .random_variable import NormalRV, UniformRV
 
 __all__ = ["kl_frequencies", "kl_amplitudes", "fd_pattern", "fd_values", "fd_blocks",
-           "complete_order_indices", "anisotropic_indices", "truncated_complete_indices",
+           "fd_blocks_rows", "fd_pattern_rect", "complete_order_indices", "anisotropic_indices", "truncated_complete_indices",
            "make_rvs", "blocks_to_scipy"]
 
 
@@ -94,6 +94,46 @@ def fd_blocks(n, M, device="cpu", gamma=0.9, decay=2.0, mean=1.0):
     for m, (k1, k2) in enumerate(kl_frequencies(M)):
         vals[1 + m] = fd_values(_coefficient(n, k1, k2, amps[m], device), valid)
     return rowptr, colidx, vals
+
+
+def fd_blocks_rows(n, M, y0, y1, device="cpu", gamma=0.9, decay=2.0, mean=1.0):
+    """Blocks of the ROW SHARD [y0, y1) of the n x n grid with one halo grid row on each side: the
+    local grid has (y1 - y0 + 2) x n points, local row j <-> global row y0 - 1 + j.  Values are the
+    global stencil values of those rows; couplings that leave the local grid are dropped (they only
+    touch the halo rows, whose outputs are not used), and a halo row outside the global grid (first /
+    last shard) is empty.  Returns rowptr, colidx, vals[(M+1), nnz] on the local 5-point pattern."""
+    nyl = y1 - y0 + 2
+    rowptr, colidx, valid = fd_pattern_rect(n, nyl, device)
+
+    def local_vals(a_nodal):
+        c = a_nodal[1:-1, 1:-1]
+        cs = 0.5 * (c + a_nodal[:-2, 1:-1]); cn = 0.5 * (c + a_nodal[2:, 1:-1])
+        cw = 0.5 * (c + a_nodal[1:-1, :-2]); ce = 0.5 * (c + a_nodal[1:-1, 2:])
+        full = torch.stack([-cs, -cw, cs + cw + ce + cn, -ce, -cn], dim=2)           # [n, n, 5] global rows
+        pad = torch.zeros((1, n, 5), dtype=full.dtype, device=full.device)
+        full = torch.cat([pad, full, pad], dim=0)                                   # global rows -1 .. n
+        loc = full[y0:y1 + 2].reshape(-1, 5)                                        # global rows y0-1 .. y1
+        return loc[valid]
+
+    vals = torch.empty((M + 1, colidx.numel()), dtype=torch.float64, device=device)
+    vals[0] = local_vals(torch.full((n + 2, n + 2), float(mean), dtype=torch.float64, device=device))
+    amps = kl_amplitudes(M, gamma, decay)
+    for m, (k1, k2) in enumerate(kl_frequencies(M)):
+        vals[1 + m] = local_vals(_coefficient(n, k1, k2, amps[m], device))
+    return rowptr, colidx, vals
+
+
+def fd_pattern_rect(nx, ny, device="cpu"):
+    """fd_pattern for an nx (fast) x ny grid."""
+    N = nx * ny
+    i = torch.arange(N, device=device, dtype=torch.int64)
+    ix, iy = i % nx, i // nx
+    cols = torch.stack([i - nx, i - 1, i, i + 1, i + nx], dim=1)
+    valid = torch.stack([iy > 0, ix > 0, torch.ones_like(ix, dtype=torch.bool), ix < nx - 1, iy < ny - 1], dim=1)
+    counts = valid.sum(dim=1)
+    rowptr = torch.zeros(N + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(counts, 0)
+    return rowptr.to(torch.int32), cols[valid].to(torch.int32), valid
 
 
 def blocks_to_scipy(rowptr, colidx, vals, n_rows):
