@@ -7,7 +7,8 @@ line on rank 0.  A step is one application y = A w of the stochastic-Galerkin op
   value      whole-job GDoF/s with the input slab already resident in HBM (CUDA events, max over
              ranks, barrier + synchronize on both sides)
   e2e        same metric through the public API with HOST buffers: pinned host slab -> H2D ->
-             MultiOperator kernel -> D2H of the result, every step
+             MultiOperator.apply -> D2H of the result, every step (copies of neighbouring steps overlap
+             the kernel on separate streams; the PCIe link bounds it)
   roofline   algorithmic (compulsory) bytes of one apply / kernel time vs the measured HBM peak
   cpu_baseline  the oracle port of the reference's CPU path (dict of vectors, one scipy SpMV per
              (mu, m)) timed on a bounded sample of output columns of the same workload
@@ -300,23 +301,57 @@ def run_gpu(args):
         h_in.copy_(Wt)
         torch.cuda.synchronize()
 
-        def e2e_step():
-            Wt.copy_(h_in, non_blocking=True)                     # H2D of this step's input slab
-            comm_before()
-            y = A.apply(w)                                        # public API: MultiOperator.apply
-            if world > 1 and not rows_mode:
+        pipelined = (world == 1 or rows_mode)
+        if pipelined:
+            # H2D of step k+1 and D2H of step k-1 overlap the kernel of step k (PCIe is full duplex):
+            # two device input slabs, copies on their own streams, every step still moves its whole
+            # input from pinned host memory and its whole result back.
+            cur = torch.cuda.current_stream()
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            Wdev = [Wt, torch.empty_like(Wt)]
+            wv = [w, w.like(Wdev[1])]
+            ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+            ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+            ev_out = torch.cuda.Event()
+            for e in ev_done:
+                e.record(cur)
+
+            def e2e_step(k):
+                b = k % 2
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(ev_done[b])                   # the kernel that last read this slab is done
+                    Wdev[b].copy_(h_in, non_blocking=True)        # H2D of this step's input slab
+                    ev_in[b].record(s_in)
+                cur.wait_event(ev_in[b])
+                if rows_mode:
+                    sharded.exchange_halos(Wdev[b])
+                y = A.apply(wv[b])                                # public API: MultiOperator.apply
+                ev_done[b].record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[b])
+                    h_out.copy_(y.slab, non_blocking=True)        # D2H of the result
+                    y.slab.record_stream(s_out)
+                    ev_out.record(s_out)
+                return y
+        else:
+            def e2e_step(k):
+                Wt.copy_(h_in, non_blocking=True)                 # H2D of this step's input slab
+                y = A.apply(w)                                    # public API: MultiOperator.apply
                 Yfull[:L].copy_(y.slab)
                 dist.reduce_scatter_tensor(Yown, Yfull, op=dist.ReduceOp.SUM)
-                h_out.copy_(Yown, non_blocking=True)
-            else:
-                h_out.copy_(y.slab, non_blocking=True)            # D2H of the result
-            return y
+                h_out.copy_(Yown, non_blocking=True)              # D2H of the rank's share of the result
+                return y
 
-        e2e_step(); barrier()
+        e2e_step(0); e2e_step(1)
+        if pipelined:
+            torch.cuda.current_stream().wait_event(ev_out)
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
+        for k in range(e2e_steps):
+            e2e_step(k)
+        if pipelined:
+            torch.cuda.current_stream().wait_event(ev_out)
         e1.record()
         barrier()
         te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

@@ -625,9 +625,11 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
 #pragma unroll
                             for (int r = 0; r < 2; ++r)
                                 if (y0 + r < ny)
-                                    *reinterpret_cast<double2*>(yp + (int64_t)r * s) =
-                                        make_double2(__hiloint2double((int)r32[8 * t + 4 * r + 1], (int)r32[8 * t + 4 * r]),
-                                                     __hiloint2double((int)r32[8 * t + 4 * r + 3], (int)r32[8 * t + 4 * r + 2]));
+                                    // streaming store: Y is written once and must not evict the
+                                    // windows that other blocks of the tile still re-read from L2
+                                    __stcs(reinterpret_cast<double2*>(yp + (int64_t)r * s),
+                                           make_double2(__hiloint2double((int)r32[8 * t + 4 * r + 1], (int)r32[8 * t + 4 * r]),
+                                                        __hiloint2double((int)r32[8 * t + 4 * r + 3], (int)r32[8 * t + 4 * r + 2])));
                         }
                     }
                 }
