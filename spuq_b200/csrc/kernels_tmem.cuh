@@ -432,6 +432,28 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         }
         ++nw;
     };
+    // both windows of a pair when a window group holds exactly two windows and the pair starts on a
+    // group boundary (the host emits the pair runs of an A-set first): one barrier wait, sixteen
+    // loads, one release -- no per-window bookkeeping
+    auto load_window_pair = [&]() {
+        const uint32_t slot = nw % Cfg::W_SLOTS, st = slot / Cfg::W_GROUP;
+        mbar_wait(fullW(st), (nw / Cfg::W_SLOTS) & 1u);
+        const uint32_t base = wring_s + slot * Cfg::WIN_STRIDE + win_off;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            lds_f64x2(base + (rr * Cfg::BOX_W + 2) * 8, w0[rr][1], w0[rr][2]);
+            lds_f64x2(base + Cfg::WIN_STRIDE + (rr * Cfg::BOX_W + 2) * 8, w1[rr][1], w1[rr][2]);
+            if (NINE || rr == 1 || rr == 2) {
+                w0[rr][0] = lds_f64(base + (rr * Cfg::BOX_W + 1) * 8);
+                w0[rr][3] = lds_f64(base + (rr * Cfg::BOX_W + 4) * 8);
+                w1[rr][0] = lds_f64(base + Cfg::WIN_STRIDE + (rr * Cfg::BOX_W + 1) * 8);
+                w1[rr][3] = lds_f64(base + Cfg::WIN_STRIDE + (rr * Cfg::BOX_W + 4) * 8);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(emptyW(st));
+        nw += 2;
+    };
     // the rest of a partly used window group is padding (groups end at A-set and block boundaries)
     auto skip_window_group = [&]() {
         if (nw % Cfg::W_GROUP != 0) {
@@ -515,8 +537,12 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             if ((da.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); da = lds_i32x4(rptr); db = lds_i32x4(rptr + 16); }
             const int4 ca = da, cb = db;
             const uint32_t kmask = (uint32_t)(ca.x >> REC_JOB_KMASK_SHIFT) & 0xFu;
-            load_window(w0);
-            load_window(w1);
+            if (Cfg::W_GROUP == 2) {
+                load_window_pair();
+            } else {
+                load_window(w0);
+                load_window(w1);
+            }
             const uint32_t cbase = rptr + 32;
             rptr += 16 * 2 * JU;
             da = lds_i32x4(rptr); db = lds_i32x4(rptr + 16);     // unit 0s of the next pair

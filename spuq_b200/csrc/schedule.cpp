@@ -209,12 +209,59 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
             }
         }
 
-        // ---- emit
-        int32_t cur_set = -1;
+        // ---- pair up jobs of a run that use the same matrices and have disjoint output columns (both
+        // windows then go through the stencil in one basic block)
+        struct Split { std::vector<std::pair<int32_t, int32_t>> pairs; std::vector<int32_t> singles; };
+        std::vector<Split> split(runs.size());
         for (size_t ri = 0; ri < runs.size(); ++ri) {
             const Run& r = runs[ri];
-            if (r.set != cur_set) {
-                cur_set = r.set;
+            std::vector<uint64_t> outs(r.jobs.size(), 0);
+            for (size_t i = 0; i < r.jobs.size(); ++i)
+                for (int32_t k = 0; k < K; ++k)
+                    for (const Entry& e : r.jobs[i].es[k]) outs[i] |= 1ull << e.out;
+            std::vector<char> used(r.jobs.size(), 0);
+            for (size_t i = 0; i < r.jobs.size(); ++i) {
+                if (used[i]) continue;
+                used[i] = 1;
+                size_t partner = r.jobs.size();
+                for (size_t j = i + 1; r.S <= 2 && !std::getenv("SPUQ_NO_PAIRS") && j < r.jobs.size() && j < i + 64; ++j)
+                    if (!used[j] && r.jobs[j].kmask == r.jobs[i].kmask && !(outs[i] & outs[j])) { partner = j; break; }
+                if (partner < r.jobs.size()) { used[partner] = 1; split[ri].pairs.push_back({(int32_t)i, (int32_t)partner}); }
+                else split[ri].singles.push_back((int32_t)i);
+            }
+        }
+
+        // ---- emit, set by set: A tiles, then all pair runs (so that a pair always starts on a window
+        // group boundary when groups hold two windows), then the runs of single jobs
+        auto unit0 = [&](const Job& j) {
+            int32_t packs[SCHED_MAX_K] = {0, 0, 0};
+            for (int32_t k = 0; k < K; ++k)
+                for (int32_t sl = 0; sl < SCHED_MAX_S; ++sl) {
+                    const int32_t o = (sl < (int32_t)j.es[k].size()) ? j.es[k][sl].out : TRASH;
+                    packs[k] |= o << (9 * sl);
+                }
+            const int32_t ch = em.unit_words(REC_JOB | ((int32_t)j.kmask << REC_JOB_KMASK_SHIFT), packs[0], packs[1], packs[2]);
+            em.cmd(ch, PCMD_WINDOW | j.in_col);
+        };
+        auto coef_units = [&](const Job& j, int32_t cu) {
+            for (int32_t k = 0; k < K; ++k) {
+                if (j.kmask >> k & 1u) { s.n_stencils += 1; s.n_entries += (int64_t)j.es[k].size(); }
+                for (int32_t u = 0; u < cu; ++u) {
+                    double c2[2] = {0.0, 0.0};
+                    for (int q = 0; q < 2; ++q)
+                        if (2 * u + q < (int32_t)j.es[k].size()) c2[q] = j.es[k][2 * u + q].coef;
+                    SchedRec rec;
+                    std::memcpy(&rec.a, &c2[0], 8);       // a,b = first coefficient, c = second
+                    rec.c = c2[1];
+                    s.recs.push_back(rec);
+                }
+            }
+        };
+        for (size_t r0 = 0; r0 < runs.size();) {
+            size_t r1 = r0;
+            while (r1 < runs.size() && runs[r1].set == runs[r0].set) ++r1;
+            const int32_t cur_set = runs[r0].set;
+            {
                 const int32_t cnt = std::min<int32_t>(K, (int32_t)slots.size() - cur_set * K);
                 em.ensure(1);
                 const int32_t ch = em.unit(REC_ASET | (cnt << REC_CNT_SHIFT), 0, 0.0);
@@ -222,83 +269,36 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                 for (int32_t k = 0; k < cnt; ++k) em.cmd(ch, PCMD_ATILE | slots[(size_t)cur_set * K + k]);
                 s.n_asets += cnt;
             }
-            const int32_t cu = (r.S + 1) / 2;               // coefficient units per register set
-            const int32_t job_units = 1 + K * cu;
-            // ---- pair up jobs whose output columns are disjoint (both windows in one basic block)
-            std::vector<std::pair<int32_t, int32_t>> pairs;
-            std::vector<int32_t> singles;
-            {
-                std::vector<uint64_t> outs(r.jobs.size(), 0);
-                for (size_t i = 0; i < r.jobs.size(); ++i)
-                    for (int32_t k = 0; k < K; ++k)
-                        for (const Entry& e : r.jobs[i].es[k]) outs[i] |= 1ull << e.out;
-                std::vector<char> used(r.jobs.size(), 0);
-                for (size_t i = 0; i < r.jobs.size(); ++i) {
-                    if (used[i]) continue;
-                    used[i] = 1;
-                    size_t partner = r.jobs.size();
-                    for (size_t j = i + 1; r.S <= 2 && !std::getenv("SPUQ_NO_PAIRS") && j < r.jobs.size() && j < i + 64; ++j)
-                        if (!used[j] && r.jobs[j].kmask == r.jobs[i].kmask && !(outs[i] & outs[j])) { partner = j; break; }
-                    if (partner < r.jobs.size()) { used[partner] = 1; pairs.push_back({(int32_t)i, (int32_t)partner}); }
-                    else singles.push_back((int32_t)i);
-                }
-            }
-            auto unit0 = [&](const Job& j) {
-                int32_t packs[SCHED_MAX_K] = {0, 0, 0};
-                for (int32_t k = 0; k < K; ++k)
-                    for (int32_t sl = 0; sl < SCHED_MAX_S; ++sl) {
-                        const int32_t o = (sl < (int32_t)j.es[k].size()) ? j.es[k][sl].out : TRASH;
-                        packs[k] |= o << (9 * sl);
-                    }
-                const int32_t ch = em.unit_words(REC_JOB | ((int32_t)j.kmask << REC_JOB_KMASK_SHIFT), packs[0], packs[1], packs[2]);
-                em.cmd(ch, PCMD_WINDOW | j.in_col);
-            };
-            auto coef_units = [&](const Job& j) {
-                for (int32_t k = 0; k < K; ++k) {
-                    if (j.kmask >> k & 1u) { s.n_stencils += 1; s.n_entries += (int64_t)j.es[k].size(); }
-                    for (int32_t u = 0; u < cu; ++u) {
-                        double c2[2] = {0.0, 0.0};
-                        for (int q = 0; q < 2; ++q)
-                            if (2 * u + q < (int32_t)j.es[k].size()) c2[q] = j.es[k][2 * u + q].coef;
-                        SchedRec rec;
-                        std::memcpy(&rec.a, &c2[0], 8);       // a,b = first coefficient, c = second
-                        rec.c = c2[1];
-                        s.recs.push_back(rec);
+            for (int pass = 0; pass < 2; ++pass)
+                for (size_t ri = r0; ri < r1; ++ri) {
+                    const Run& r = runs[ri];
+                    const int32_t cu = (r.S + 1) / 2;               // coefficient units per register set
+                    const int32_t job_units = 1 + K * cu;
+                    if (pass == 0) {
+                        s.n_jobs += (int64_t)r.jobs.size();
+                        if (split[ri].pairs.empty()) continue;
+                        em.ensure(1 + 2 * job_units);
+                        em.unit(REC_RUN2 | (r.S << REC_RUN_S_SHIFT), (int32_t)split[ri].pairs.size(), 0.0);
+                        for (const auto& pr : split[ri].pairs) {
+                            em.ensure(2 * job_units);
+                            unit0(r.jobs[pr.first]);
+                            unit0(r.jobs[pr.second]);
+                            coef_units(r.jobs[pr.first], cu);
+                            coef_units(r.jobs[pr.second], cu);
+                        }
+                        s.n_pairs += (int64_t)split[ri].pairs.size();
+                    } else {
+                        if (split[ri].singles.empty()) continue;
+                        em.ensure(1 + job_units);                    // header and first job in one chunk
+                        em.unit(REC_RUN | (r.S << REC_RUN_S_SHIFT), (int32_t)split[ri].singles.size(), 0.0);
+                        for (int32_t i : split[ri].singles) {
+                            em.ensure(job_units);
+                            unit0(r.jobs[i]);
+                            coef_units(r.jobs[i], cu);
+                        }
                     }
                 }
-            };
-            s.n_jobs += (int64_t)r.jobs.size();
-            const bool more_after = ri + 1 < runs.size();
-            if (!pairs.empty()) {
-                em.ensure(1 + 2 * job_units);
-                em.unit(REC_RUN2 | ((int32_t)r.kmask << REC_RUN_KMASK_SHIFT) | (r.S << REC_RUN_S_SHIFT), (int32_t)pairs.size(), 0.0);
-                for (const auto& pr : pairs) {
-                    em.ensure(2 * job_units);
-                    unit0(r.jobs[pr.first]);
-                    unit0(r.jobs[pr.second]);
-                    coef_units(r.jobs[pr.first]);
-                    coef_units(r.jobs[pr.second]);
-                }
-                s.n_pairs += (int64_t)pairs.size();
-            }
-            if (!singles.empty()) {
-                em.ensure(1 + job_units);                    // header and first job in one chunk
-                // `more`: the next run's first window may be prefetched by this run's last job -- only
-                // when that run is a RUN of single jobs too (pair runs load their windows themselves)
-                bool more = false;
-                if (more_after) {
-                    // conservative: look ahead is resolved after emission; pairs of the next run are not
-                    // known yet, so prefetch across runs is disabled
-                    more = false;
-                }
-                em.unit(REC_RUN | ((int32_t)r.kmask << REC_RUN_KMASK_SHIFT) | (r.S << REC_RUN_S_SHIFT) | (more ? REC_RUN_MORE : 0),
-                        (int32_t)singles.size(), 0.0);
-                for (int32_t i : singles) {
-                    em.ensure(job_units);
-                    unit0(r.jobs[i]);
-                    coef_units(r.jobs[i]);
-                }
-            }
+            r0 = r1;
         }
         {
             const int32_t nq = (ncols + 3) / 4;
@@ -345,6 +345,7 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
         for (size_t i = 0; i < metas.size(); ++i) if (metas[i] != chunk0 + (int32_t)i) { fail(); return; }
         std::fill(acc.begin(), acc.end(), 0.0);
         size_t r = (size_t)chunk0 * SCHED_CHUNK_RECS, f = 0, chunks_seen = 1;
+        int32_t win_seen = 0;
         auto next_chunk = [&]() { r = (r / SCHED_CHUNK_RECS + 1) * SCHED_CHUNK_RECS; ++chunks_seen; };
         bool running = true;
         while (running) {
@@ -353,6 +354,7 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
             switch (rec.a & REC_TYPE_MASK) {
             case REC_END_ITEM: running = false; break;
             case REC_ASET: {
+                win_seen = (win_seen + s.w_group - 1) / s.w_group * s.w_group;      // the group is padded here
                 const int32_t cnt = (rec.a >> REC_CNT_SHIFT) & 0xF;
                 for (int32_t k = 0; k < cnt; ++k) {
                     if (f >= fetches.size() || (fetches[f] & PCMD_KIND_MASK) != PCMD_ATILE) { fail(); return; }
@@ -370,6 +372,7 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                 for (int32_t j = 0; j < n; ++j) {
                     if ((s.recs[r].a & REC_TYPE_MASK) == REC_NEXT_CHUNK) next_chunk();
                     if (r % SCHED_CHUNK_RECS + group_units > SCHED_CHUNK_USABLE) { fail(); return; }
+                    if (two && s.w_group == 2 && win_seen % 2 != 0) { fail(); return; }   // pairs are group aligned
                     uint64_t seen_out = 0;
                     for (int32_t q = 0; q < per; ++q) {
                         int32_t w[4];
@@ -380,6 +383,7 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                         kmask = km;
                         if (f >= fetches.size() || (fetches[f] & PCMD_KIND_MASK) != PCMD_WINDOW) { fail(); return; }
                         const int32_t in_col = fetches[f++] & PCMD_VAL_MASK;
+                        ++win_seen;
                         const double* wv = W + (int64_t)in_col * ldw;
                         const size_t cbase = r + per + (size_t)q * K * cu;
                         uint64_t my_out = 0;
