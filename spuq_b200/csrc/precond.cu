@@ -15,13 +15,58 @@
 //     2. for every mode k and column: tridiagonal solve (T_y + lam_k I) uhat = rhat along y
 //                             (Thomas with precomputed reciprocal pivots; lanes along k)
 //     3. S = Uhat Q           (the same GEMM)
-// The GEMM is a hand-written register-tiled fp64 kernel (CUDA cores; no tensor cores on this path).
+// The two products are plain dense fp64 GEMMs ((L*ny) x nx by nx x nx): they go to cuBLAS DGEMM when
+// libcublas can be loaded at run time (dlopen, no link-time dependency); k_rowgemm below is the
+// in-house register-tiled fallback (CUDA cores) and the reference for the host-emulated build.
 #include <cmath>
 #include <vector>
 
 #include "precond.h"
 
+#ifndef SPUQ_EMU
+#include <dlfcn.h>
+#endif
+
 namespace spuq {
+
+#ifndef SPUQ_EMU
+// ---- minimal run-time binding of cuBLAS (v2 API) ---------------------------------------------------
+struct CublasApi {
+    int (*create)(void**) = nullptr;
+    int (*destroy)(void*) = nullptr;
+    int (*set_stream)(void*, cudaStream_t) = nullptr;
+    int (*dgemm)(void*, int, int, int, int, int, const double*, const double*, int, const double*, int,
+                 const double*, double*, int) = nullptr;
+    bool ok = false;
+};
+static CublasApi& cublas_api() {
+    static CublasApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libcublas.so.12", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libcublas.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.create = reinterpret_cast<decltype(api.create)>(dlsym(h, "cublasCreate_v2"));
+            api.destroy = reinterpret_cast<decltype(api.destroy)>(dlsym(h, "cublasDestroy_v2"));
+            api.set_stream = reinterpret_cast<decltype(api.set_stream)>(dlsym(h, "cublasSetStream_v2"));
+            api.dgemm = reinterpret_cast<decltype(api.dgemm)>(dlsym(h, "cublasDgemm_v2"));
+            api.ok = api.create && api.destroy && api.set_stream && api.dgemm;
+        }
+    }
+    return api;
+}
+// C[M x n] = A[M x n] * Q[n x n] (row-major, Q symmetric)  ==  column-major  C^T = Q * A^T
+static bool blas_rowgemm(spuq_sg_precond* p, int64_t Mrows, int32_t n, const double* A, const double* Q, double* C,
+                         cudaStream_t stream) {
+    CublasApi& api = cublas_api();
+    if (!api.ok || Mrows > 0x7fffffffLL) return false;
+    if (!p->blas && api.create(&p->blas) != 0) { p->blas = nullptr; return false; }
+    if (api.set_stream(p->blas, stream) != 0) return false;
+    const double one = 1.0, zero = 0.0;
+    return api.dgemm(p->blas, /*CUBLAS_OP_N*/ 0, 0, n, (int)Mrows, n, &one, Q, n, A, n, &zero, C, n) == 0;
+}
+#endif
 
 constexpr int GM = 128, GN = 64, GK = 8;      // CTA tile; 256 threads, each 8 x 4 outputs
 constexpr int G_THREADS = 256;
@@ -146,6 +191,9 @@ int mean_fd_destroy(spuq_sg_precond* p) {
     cudaFree(p->q_dev);
     cudaFree(p->piv_dev);
     p->q_dev = p->piv_dev = nullptr;
+#ifndef SPUQ_EMU
+    if (p->blas) { cublas_api().destroy(p->blas); p->blas = nullptr; }
+#endif
     return SPUQ_OK;
 }
 
@@ -160,11 +208,17 @@ int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, dou
     double* T = static_cast<double*>(work);
     const int64_t Mrows = (int64_t)L * p->ny;
     const dim3 grid((unsigned)((Mrows + GM - 1) / GM), (unsigned)((p->nx + GN - 1) / GN));
-    SPUQ_LAUNCH(k_rowgemm, grid, dim3(G_THREADS), 0, stream, Mrows, p->nx, R, p->q_dev, T, gate);
+    auto rowgemm = [&](const double* src, double* dst) {
+#ifndef SPUQ_EMU
+        if (blas_rowgemm(p, Mrows, p->nx, src, p->q_dev, dst, stream)) return;
+#endif
+        SPUQ_LAUNCH(k_rowgemm, grid, dim3(G_THREADS), 0, stream, Mrows, p->nx, src, p->q_dev, dst, gate);
+    };
+    rowgemm(R, T);
     const int64_t nthreads = (int64_t)L * p->nx;
     SPUQ_LAUNCH(k_thomas_y, dim3((unsigned)((nthreads + 127) / 128)), dim3(128), 0, stream, p->nx, p->ny, L,
                 p->oy, p->piv_dev, T, gate);
-    SPUQ_LAUNCH(k_rowgemm, grid, dim3(G_THREADS), 0, stream, Mrows, p->nx, T, p->q_dev, S, gate);
+    rowgemm(T, S);
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }

@@ -13,6 +13,7 @@ struct spuq_sg_precond {
     double* q_dev = nullptr;         // nx x nx sine-transform matrix (symmetric, orthogonal)
     double* lam_dev = nullptr;       // nx eigenvalues of the x part
     double* piv_dev = nullptr;       // nx x ny Thomas pivots of (T_y + lam_k I)
+    void* blas = nullptr;            // cublasHandle_t when libcublas could be loaded (else the in-house GEMM)
 };
 
 namespace spuq {

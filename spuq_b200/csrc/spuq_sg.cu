@@ -211,11 +211,6 @@ static int build_schedule(spuq_sg_plan* p, int32_t K, int32_t block_cols, int32_
     if (!sc) { sc = new Schedule(); p->sched_host = sc; }
     schedule_build(tl, order, K, p->n_slots, block_cols, w_group, sc);
     if (std::getenv("SPUQ_SCHED_STATS")) {
-        int64_t n_run = 0, n_run2 = 0, n_next = 0;
-        for (const SchedRec& r : sc->recs) {
-            n_run += r.a == 0 ? 0 : 0;
-        }
-        (void)n_run; (void)n_run2; (void)n_next;
         fprintf(stderr, "[spuq] schedule K=%d C=%d: blocks %d, jobs %lld (pairs %lld), A tiles %lld, stencils %lld, terms %lld, "
                         "units %zu, producer cmds %zu\n", K, block_cols, sc->nblk, (long long)sc->n_jobs, (long long)sc->n_pairs,
                 (long long)sc->n_asets, (long long)sc->n_stencils, (long long)sc->n_entries, sc->recs.size(), sc->pcmd.size());
