@@ -372,7 +372,7 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                 for (int32_t j = 0; j < n; ++j) {
                     if ((s.recs[r].a & REC_TYPE_MASK) == REC_NEXT_CHUNK) next_chunk();
                     if (r % SCHED_CHUNK_RECS + group_units > SCHED_CHUNK_USABLE) { fail(); return; }
-                    if (two && s.w_group == 2 && win_seen % 2 != 0) { fail(); return; }   // pairs are group aligned
+                    if (two && s.w_group % 2 == 0 && win_seen % 2 != 0) { fail(); return; }   // pairs are group aligned
                     uint64_t seen_out = 0;
                     for (int32_t q = 0; q < per; ++q) {
                         int32_t w[4];

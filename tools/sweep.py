@@ -68,6 +68,8 @@ def main():
     import spuq_b200 as sp
     from spuq_b200 import _abi, synthetic
     from spuq_b200.multi_operator import DeviceBlocks
+    if os.environ.get("SPUQ_LIB"):                      # A/B builds of the library (development only)
+        _abi.use_library(os.environ["SPUQ_LIB"], "cuda:0")
     dev = _abi.device()
     if args.micro:
         micro()
