@@ -214,7 +214,7 @@ struct TmemCfg {
     static constexpr int META_BYTES = SCHED_CHUNK_RECS * 16;
     // W ring: stages of W_GROUP windows under ONE full/empty barrier pair (a barrier round trip costs the
     // single consumer warp of a sub-partition 60-140 clk, so it is paid once per group, not per window)
-    static constexpr int W_GROUP = (G == 1) ? 4 : 2, W_STAGES = (G == 1) ? 4 : 5, W_SLOTS = W_GROUP * W_STAGES;
+    static constexpr int W_GROUP = (G == 1) ? 4 : 2, W_STAGES = (G == 1) ? 4 : 6, W_SLOTS = W_GROUP * W_STAGES;
     static constexpr int A_STAGES = (G == 1) ? (NINE ? 2 : 4) : (NINE ? 1 : 2), M_STAGES = (G == 1) ? 4 : 3, I_STAGES = 4;
     // per-group shared memory region
     static constexpr int OFF_A = W_SLOTS * WIN_STRIDE;
