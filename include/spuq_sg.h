@@ -57,7 +57,7 @@ extern "C" {
 #define SPUQ_PATH_AUTO     0   /* stencil path when the pattern allows it, else ELL, else CSR */
 #define SPUQ_PATH_CSR      1   /* general CSR, one thread per (row, column)                   */
 #define SPUQ_PATH_ELL      2   /* padded ELL copy of the values, coalesced                     */
-#define SPUQ_PATH_STENCIL  3   /* 9-point-window diagonal storage, register-tiled              */
+#define SPUQ_PATH_STENCIL  3   /* 9-point-window diagonal storage: TMA-fed, accumulators in TMEM */
 #define SPUQ_PATH_MASK     0xF
 
 typedef struct spuq_sg_plan spuq_sg_plan;
@@ -125,7 +125,14 @@ SPUQ_API int spuq_sg_plan_info(const spuq_sg_plan* plan, int32_t* path_out, int6
                       int64_t* nnz_out, int64_t* algorithmic_bytes_out,
                       int64_t* algorithmic_flops_out);
 
-/* Tunables of the stencil path (for the sweep in bench.py --tune); 0 keeps the default. */
+/* Tunables of the stencil path (development sweeps, tools/sweep.py); 0 keeps the default.
+ *   variant 0  automatic: the TMEM-accumulator kernel (4) whenever the grid width and the leading
+ *              dimensions are even and the slabs 16-byte aligned, else the simple stencil kernel
+ *   variant 1  k_apply_stencil_simple            (one thread per pair of rows)
+ *   variant 2  k_apply_tiled  (cols_per_block = C, rows_per_thread = RY)   registers only
+ *   variant 3  k_apply_tma    (same tiling, operands through TMA rings)
+ *   variant 4  k_apply_tmem   (cols_per_block = K register sets of block matrices, 1..3;
+ *              rows_per_thread = consumer groups per CTA, 1 or 2; accumulators in tensor memory) */
 SPUQ_API int spuq_sg_plan_tune(spuq_sg_plan* plan, int32_t variant, int32_t cols_per_block,
                       int32_t rows_per_thread, int32_t ctas_per_sm);
 

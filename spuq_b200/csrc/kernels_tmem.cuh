@@ -12,18 +12,19 @@
 //     register file to hold K block-matrix tiles at once, so ONE window read from shared memory
 //     serves every (matrix, output column) pair of the block that needs that input column.
 //
-// A CTA is 4 consumer warps (2 x 2 grid points per thread, lanes along x: a 64 x 8 tile) and one
-// producer warp.  The producer pulls work items (tile, column block) from a global counter and
-// walks the block's command list (schedule.h), issuing with cp.async.bulk[.tensor] and mbarriers
+// A CTA holds G consumer groups of 4 warps (2 x 2 grid points per thread, lanes along x: a 64 x 8 tile
+// per group) and one producer warp per group.  A producer pulls work items (tile, column block) from
+// a global counter and walks the block's command list (schedule.h); each of its 32 lanes owns one
+// command and issues, with cp.async.bulk[.tensor] and mbarriers, whatever ring slot is free:
 //     - the W window of every job   (box 68 x 10 of the slab seen as (x, y, column); zero fill
 //                                    outside the grid = the homogeneous boundary),
 //     - the A tile of every matrix  (box 64 x 8 x D of the diagonal storage),
-//     - the 512-byte chunks of the block's record stream,
-// into three shared-memory rings.  The consumers interpret the records: ASET loads an A tile into
-// register set k, JOB switches to the next window (already prefetched into registers), ENTRY
-// evaluates the stencil (20 DFMA) if the matrix changed and accumulates coef * S into the TMEM
-// accumulator of the output column, STORE writes two finished columns of Y.  Control flow is
-// warp-uniform throughout.
+//     - the 2 KB chunks of the block's record stream,
+// into three shared-memory rings per group.  The consumers interpret the stream: ASET loads the A
+// tiles of a set into registers, RUN / RUN2 loop over regular (padded) jobs -- window(s) from shared
+// memory into registers, for every matrix of the job the stencil (20 DFMA per window) and S
+// read-modify-writes of TMEM accumulators -- and STOREALL writes the finished columns of Y.
+// Control flow is warp-uniform throughout.
 //
 // Reference semantics: MultiOperator.apply, application/egsz/multi_operator2.py:38-84; only the
 // order in which the terms of a column are summed differs (grouped by register set and input).
@@ -234,7 +235,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
              const SchedRec* __restrict__ recs, const int32_t* __restrict__ pcmd,
              const int32_t* __restrict__ blk_pcmd, int32_t nblk, int32_t s, int32_t ny, int32_t nty,
              int64_t n_items, unsigned long long* __restrict__ work_counter,
-             double* __restrict__ Y, int64_t ldy, const double* gate) {
+             double* __restrict__ Y, int64_t ldy, const double* gate, int32_t debug_flags) {
     using Cfg = TmemCfg<K, NINE, G>;
     constexpr int D = Cfg::D;
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
@@ -330,7 +331,11 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                 const int32_t base = P.c;
                 const bool have = base + lane < P.c1;
                 const int32_t cmd = have ? __ldg(pcmd + base + lane) : 0;
-                const int32_t kind = cmd & PCMD_KIND_MASK, val = cmd & PCMD_VAL_MASK;
+                const int32_t kind = cmd & PCMD_KIND_MASK;
+                int32_t val = cmd & PCMD_VAL_MASK;
+                // development switch (SPUQ_KDEBUG=1): every window / A tile fetch hits the same column / matrix,
+                // i.e. always L2 -- wrong results, but the time shows what the arithmetic alone costs
+                if ((debug_flags & 1) && val != PCMD_WINDOW_PAD && kind != PCMD_META) val = 0;
                 const bool is_w = have && kind == PCMD_WINDOW, is_a = have && kind == PCMD_ATILE,
                            is_m = have && kind == PCMD_META;
                 const uint32_t mw = __ballot_sync(0xffffffffu, is_w), ma = __ballot_sync(0xffffffffu, is_a),

@@ -507,6 +507,7 @@ static int launch_tma(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, 
     const int64_t items = (int64_t)ntx * nty * p->bv.nblk;
     const int per_sm = p->ctas_per_sm > 0 ? std::min(p->ctas_per_sm, ctas_per_sm) : ctas_per_sm;
     const int64_t grid = std::min<int64_t>(items, (int64_t)p->n_sm * per_sm);
+    static const int32_t debug_flags = std::getenv("SPUQ_KDEBUG") ? std::atoi(std::getenv("SPUQ_KDEBUG")) : 0;
     CUtensorMap mw, ma;
     std::memcpy(&mw, p->tmap_w, sizeof(mw));
     std::memcpy(&ma, p->tmap_a, sizeof(ma));
@@ -544,12 +545,13 @@ static int launch_tmem(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y,
     const int64_t items = (int64_t)ntx * nty * sc->nblk;
     const int64_t grid = std::min<int64_t>((items + G - 1) / G, (int64_t)p->n_sm);
     SPUQ_CUDA_TRY(cudaMemsetAsync(p->d_work_counter, 0, sizeof(unsigned long long), stream));
+    static const int32_t debug_flags = std::getenv("SPUQ_KDEBUG") ? std::atoi(std::getenv("SPUQ_KDEBUG")) : 0;
     CUtensorMap mw, ma;
     std::memcpy(&mw, p->tmap_w, sizeof(mw));
     std::memcpy(&ma, p->tmap_a, sizeof(ma));
     kern<<<dim3((unsigned)grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream>>>(
         mw, ma, static_cast<const SchedRec*>(p->d_recs), p->d_pcmd, p->d_blk_pcmd, sc->nblk, p->st.s, p->ny, nty,
-        items, p->d_work_counter, Y, ldy, gate);
+        items, p->d_work_counter, Y, ldy, gate, debug_flags);
     char name[80];
     snprintf(name, sizeof(name), "k_apply_tmem<K=%d,G=%d,%s>", K, G, NINE ? "9pt" : "5pt");
     p->kernel_name = name;
