@@ -287,11 +287,13 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                             coef_units(r.jobs[pr.second], cu);
                         }
                         s.n_pairs += (int64_t)split[ri].pairs.size();
+                        for (const auto& pr : split[ri].pairs) s.hist_pairs[std::min<int>(r.S, 3) - 1][r.jobs[pr.first].kmask & 7] += 1;
                     } else {
                         if (split[ri].singles.empty()) continue;
                         em.ensure(1 + job_units);                    // header and first job in one chunk
                         em.unit(REC_RUN | (r.S << REC_RUN_S_SHIFT), (int32_t)split[ri].singles.size(), 0.0);
                         for (int32_t i : split[ri].singles) {
+                            s.hist_singles[std::min<int>(r.S, 3) - 1][r.jobs[i].kmask & 7] += 1;
                             em.ensure(job_units);
                             unit0(r.jobs[i]);
                             coef_units(r.jobs[i], cu);

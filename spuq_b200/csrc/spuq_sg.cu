@@ -214,6 +214,11 @@ static int build_schedule(spuq_sg_plan* p, int32_t K, int32_t block_cols, int32_
         fprintf(stderr, "[spuq] schedule K=%d C=%d: blocks %d, jobs %lld (pairs %lld), A tiles %lld, stencils %lld, terms %lld, "
                         "units %zu, producer cmds %zu\n", K, block_cols, sc->nblk, (long long)sc->n_jobs, (long long)sc->n_pairs,
                 (long long)sc->n_asets, (long long)sc->n_stencils, (long long)sc->n_entries, sc->recs.size(), sc->pcmd.size());
+        for (int S = 0; S < 3; ++S)
+            for (int km = 1; km < 8; ++km)
+                if (sc->hist_pairs[S][km] || sc->hist_singles[S][km])
+                    fprintf(stderr, "[spuq]   S=%d kmask=%d: pairs %lld singles %lld\n", S + 1, km,
+                            (long long)sc->hist_pairs[S][km], (long long)sc->hist_singles[S][km]);
     }
     for (void* d : p->sched_dev) cudaFree(d);
     p->sched_dev.clear();
