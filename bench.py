@@ -267,7 +267,7 @@ def run_gpu(args):
         step()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
         time.sleep(0.3)
     barrier()
@@ -455,6 +455,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--shard", default="rows", choices=["rows", "m"],
                     help="multi-GPU decomposition: grid rows + halo exchange (default) or expansion terms + reduce-scatter")
+    ap.add_argument("--no-clocks", action="store_true", help="development: do not run the nvidia-smi clock sampler")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
