@@ -389,10 +389,12 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     // ==================================== consumer warps ===========================================
     if (G > 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::CONSUMER_REGS));
     const int grp = warp / Cfg::CONSUMER_WARPS, lw = warp % Cfg::CONSUMER_WARPS;     // lw = TMEM lane quarter
-    const uint32_t tmem_warp = *tmem_slot + ((uint32_t)(lw * 32) << 16) + (uint32_t)(grp * Cfg::TMEM_COLS);
+    uint32_t tmem_warp = *tmem_slot + ((uint32_t)(lw * 32) << 16) + (uint32_t)(grp * Cfg::TMEM_COLS);
+    asm volatile("" : "+r"(tmem_warp));
     int sa = 0, sm = 0, si = 0;
     uint32_t pa = 0, pm = 0, pi = 0;
-    const uint32_t gs = smem_s + grp * Cfg::GROUP_BYTES;
+    uint32_t gs = smem_s + grp * Cfg::GROUP_BYTES;
+    asm volatile("" : "+r"(gs));
     const uint32_t wring_s = gs, aring_s = gs + Cfg::OFF_A, mring_s = gs + Cfg::OFF_M, iring_s = gs + Cfg::OFF_I;
     const uint32_t bar0 = gs + Cfg::OFF_BAR;
     auto fullW = [&](uint32_t i) { return bar0 + 8u * i; };
@@ -404,8 +406,11 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     auto fullI = [&](uint32_t i) { return bar0 + 8u * (BI + i); };
     auto emptyI = [&](uint32_t i) { return bar0 + 8u * (BI + Cfg::I_STAGES + i); };
     // this thread's corner inside a staged window / A tile (bytes)
-    const uint32_t win_off = (uint32_t)(((2 * lw) * Cfg::BOX_W + 2 * lane) * 8);
-    const uint32_t a_off = (uint32_t)(((2 * lw) * Cfg::TILE_X + 2 * lane) * 8);
+    uint32_t win_off = (uint32_t)(((2 * lw) * Cfg::BOX_W + 2 * lane) * 8);
+    uint32_t a_off = (uint32_t)(((2 * lw) * Cfg::TILE_X + 2 * lane) * 8);
+    // loop invariants the compiler would otherwise re-derive from special registers in every job
+    // (it rematerialises under register pressure): make them opaque so they stay in registers
+    asm volatile("" : "+r"(win_off), "+r"(a_off));
 
     double A[K][D][4];                    // [register set][diagonal][point r*2+p]
     double w0[4][4], w1[4][4];            // two window buffers: jobs alternate between them
@@ -416,12 +421,18 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
 #pragma unroll
     for (int r = 0; r < 4; ++r) w0[r][0] = w0[r][1] = w0[r][2] = w0[r][3] = w1[r][0] = w1[r][1] = w1[r][2] = w1[r][3] = 0.0;
 
-    uint32_t nw = 0;                      // windows taken from the W ring so far
+    // position in the W ring: slot of the next window and the parity of its lap (kept incrementally:
+    // the ring length is not a power of two)
+    uint32_t wslot = 0, wpar = 0;
+    auto w_advance = [&](const uint32_t by) {
+        wslot += by;
+        if (wslot >= Cfg::W_SLOTS) { wslot -= Cfg::W_SLOTS; wpar ^= 1u; }
+    };
     // next window of the W ring -> buf; a group of W_GROUP windows shares one barrier pair
     auto load_window = [&](double (&buf)[4][4]) {
-        const uint32_t slot = nw % Cfg::W_SLOTS, st = slot / Cfg::W_GROUP, sub = slot % Cfg::W_GROUP;
-        if (sub == 0) mbar_wait(fullW(st), (nw / Cfg::W_SLOTS) & 1u);
-        const uint32_t base = wring_s + slot * Cfg::WIN_STRIDE + win_off;
+        const uint32_t st = wslot / Cfg::W_GROUP, sub = wslot % Cfg::W_GROUP;
+        if (sub == 0) mbar_wait(fullW(st), wpar);
+        const uint32_t base = wring_s + wslot * Cfg::WIN_STRIDE + win_off;
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             // box element e <-> x = x_tile - 2 + e; this thread's x0 = x_tile + 2*lane
@@ -435,15 +446,15 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive(emptyW(st));
         }
-        ++nw;
+        w_advance(1);
     };
     // both windows of a pair when a window group holds exactly two windows and the pair starts on a
     // group boundary (the host emits the pair runs of an A-set first): one barrier wait, sixteen
     // loads, one release -- no per-window bookkeeping
     auto load_window_pair = [&]() {
-        const uint32_t slot = nw % Cfg::W_SLOTS, st = slot / Cfg::W_GROUP;
-        mbar_wait(fullW(st), (nw / Cfg::W_SLOTS) & 1u);
-        const uint32_t base = wring_s + slot * Cfg::WIN_STRIDE + win_off;
+        const uint32_t st = wslot / Cfg::W_GROUP;
+        mbar_wait(fullW(st), wpar);
+        const uint32_t base = wring_s + wslot * Cfg::WIN_STRIDE + win_off;
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             lds_f64x2(base + (rr * Cfg::BOX_W + 2) * 8, w0[rr][1], w0[rr][2]);
@@ -457,14 +468,15 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(emptyW(st));
-        nw += 2;
+        w_advance(2);
     };
     // the rest of a partly used window group is padding (groups end at A-set and block boundaries)
     auto skip_window_group = [&]() {
-        if (nw % Cfg::W_GROUP != 0) {
+        const uint32_t sub = wslot % Cfg::W_GROUP;
+        if (sub != 0) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(emptyW((nw % Cfg::W_SLOTS) / Cfg::W_GROUP));
-            nw = (nw + Cfg::W_GROUP - 1) / Cfg::W_GROUP * Cfg::W_GROUP;
+            if (lane == 0) mbar_arrive(emptyW(wslot / Cfg::W_GROUP));
+            w_advance(Cfg::W_GROUP - sub);
         }
     };
     uint32_t rptr = 0;                    // shared address of the next unit of the record stream
