@@ -410,7 +410,8 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     uint32_t a_off = (uint32_t)(((2 * lw) * Cfg::TILE_X + 2 * lane) * 8);
     // loop invariants the compiler would otherwise re-derive from special registers in every job
     // (it rematerialises under register pressure): make them opaque so they stay in registers
-    asm volatile("" : "+r"(win_off), "+r"(a_off));
+    uint32_t lane0 = (lane == 0) ? 1u : 0u;                 // this lane signals the ring barriers
+    asm volatile("" : "+r"(win_off), "+r"(a_off), "+r"(lane0));
 
     double A[K][D][4];                    // [register set][diagonal][point r*2+p]
     double w0[4][4], w1[4][4];            // two window buffers: jobs alternate between them
@@ -444,7 +445,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         }
         if (sub == Cfg::W_GROUP - 1) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(emptyW(st));
+            if (lane0) mbar_arrive(emptyW(st));
         }
         w_advance(1);
     };
@@ -467,7 +468,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(emptyW(st));
+        if (lane0) mbar_arrive(emptyW(st));
         w_advance(2);
     };
     // the rest of a partly used window group is padding (groups end at A-set and block boundaries)
@@ -475,14 +476,14 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         const uint32_t sub = wslot % Cfg::W_GROUP;
         if (sub != 0) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(emptyW(wslot / Cfg::W_GROUP));
+            if (lane0) mbar_arrive(emptyW(wslot / Cfg::W_GROUP));
             w_advance(Cfg::W_GROUP - sub);
         }
     };
     uint32_t rptr = 0;                    // shared address of the next unit of the record stream
     auto next_chunk = [&]() {
         __syncwarp();
-        if (lane == 0) mbar_arrive(emptyM(sm));
+        if (lane0) mbar_arrive(emptyM(sm));
         if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
         mbar_wait(fullM(sm), pm);
         rptr = mring_s + (uint32_t)sm * Cfg::META_BYTES;
@@ -515,7 +516,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                     uint32_t ta[S];
 #pragma unroll
                     for (int sl = 0; sl < S; ++sl) {
-                        ta[sl] = tmem_warp + ((pack >> (9 * sl)) & 511u) * SCHED_ACC_STRIDE;
+                        ta[sl] = tmem_warp + ((pack >> (9 * sl)) & 511u);
                         tmem_ld8p(ar + 8 * sl, ta[sl]);
                     }
                     double Sv[4];
@@ -578,8 +579,8 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                     uint32_t ta[2 * S];
 #pragma unroll
                     for (int sl = 0; sl < S; ++sl) {
-                        ta[sl] = tmem_warp + ((pa2 >> (9 * sl)) & 511u) * SCHED_ACC_STRIDE;
-                        ta[S + sl] = tmem_warp + ((pb2 >> (9 * sl)) & 511u) * SCHED_ACC_STRIDE;
+                        ta[sl] = tmem_warp + ((pa2 >> (9 * sl)) & 511u);
+                        ta[S + sl] = tmem_warp + ((pb2 >> (9 * sl)) & 511u);
                     }
 #pragma unroll
                     for (int sl = 0; sl < 2 * S; ++sl) tmem_ld8p(ar + 8 * sl, ta[sl]);
@@ -607,7 +608,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         mbar_wait(fullI(si), pi);
         const int4 it = lds_i32x4(iring_s + 16 * si);
         __syncwarp();
-        if (lane == 0) mbar_arrive(emptyI(si));
+        if (lane0) mbar_arrive(emptyI(si));
         if (++si == Cfg::I_STAGES) { si = 0; pi ^= 1u; }
         if (it.x < 0) break;
         const int32_t x0 = it.x + 2 * lane, y0 = it.y + 2 * lw;
@@ -646,7 +647,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                             for (int r = 0; r < 2; ++r)
                                 lds_f64x2(base + ((d * Cfg::TILE_Y + r) * Cfg::TILE_X) * 8, A[kk][d][2 * r], A[kk][d][2 * r + 1]);
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(emptyA(sa));
+                        if (lane0) mbar_arrive(emptyA(sa));
                         if (++sa == Cfg::A_STAGES) { sa = 0; pa ^= 1u; }
                     }
                 }
@@ -683,7 +684,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         // END_ITEM: the rest of the chunk is padding, and so is the rest of a partly used window group
         skip_window_group();
         __syncwarp();
-        if (lane == 0) mbar_arrive(emptyM(sm));
+        if (lane0) mbar_arrive(emptyM(sm));
         if (++sm == Cfg::M_STAGES) { sm = 0; pm ^= 1u; }
     }
 

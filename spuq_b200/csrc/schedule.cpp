@@ -238,7 +238,7 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
             for (int32_t k = 0; k < K; ++k)
                 for (int32_t sl = 0; sl < SCHED_MAX_S; ++sl) {
                     const int32_t o = (sl < (int32_t)j.es[k].size()) ? j.es[k][sl].out : TRASH;
-                    packs[k] |= o << (9 * sl);
+                    packs[k] |= (o * SCHED_ACC_STRIDE) << (9 * sl);      // TMEM column offset of the accumulator (< 512)
                 }
             const int32_t ch = em.unit_words(REC_JOB | ((int32_t)j.kmask << REC_JOB_KMASK_SHIFT), packs[0], packs[1], packs[2]);
             em.cmd(ch, PCMD_WINDOW | j.in_col);
@@ -404,7 +404,7 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                                     S[i] = v;
                                 }
                             for (int32_t sl = 0; sl < Sn; ++sl) {
-                                const int32_t o = (w[1 + k] >> (9 * sl)) & 511;
+                                const int32_t o = ((w[1 + k] >> (9 * sl)) & 511) / SCHED_ACC_STRIDE;
                                 if (o != s.block_cols) my_out |= 1ull << o;
                                 const SchedRec& cr = s.recs[cbase + (size_t)k * cu + sl / 2];
                                 double coef;

@@ -34,8 +34,8 @@ static_assert(sizeof(SchedRec) == 16, "unit must be 16 bytes");
 //   RUN   S n                    n jobs follow, all with S accumulation slots per matrix.  Every job is
 //                                1 + K*ceil(S/2) units:
 //                                  unit 0     a = REC_JOB | kmask << 4 (matrices of the set the job
-//                                             uses), words 1..3: for register set kk the
-//                                             accumulator numbers of its S slots, 9 bits each
+//                                             uses), words 1..3: for register set kk the TMEM column
+//                                             offsets (accumulator number * 8) of its S slots, 9 bits each
 //                                  unit 1+..  for every kk (used or not) ceil(S/2) units holding the
 //                                             slot coefficients (two doubles per unit)
 //                                A slot that is not needed points at the scratch accumulator
