@@ -494,7 +494,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     auto run_jobs = [&](auto s_tag, const int n) {
         constexpr int S = decltype(s_tag)::value;
         constexpr int CU = (S + 1) / 2, JU = 1 + K * CU;
-        int4 d = lds_i32x4(rptr);
+        int4 d = make_int4(0, 0, 0, 0);
         // one job: window in wc (already loaded); the window after it is fetched into wp
         auto job = [&](double (&wc)[4][4], double (&wp)[4][4], const bool prefetch) {
             if ((d.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); d = lds_i32x4(rptr); }
@@ -535,6 +535,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             }
         };
         if (n <= 0) return;
+        d = lds_i32x4(rptr);
         if (cur == 0) load_window(w0); else load_window(w1);
         int j = 0;
         if (cur == 1) { job(w1, w0, n > 1); cur = 0; j = 1; }
@@ -550,6 +551,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     auto run_pairs = [&](auto s_tag, const int n) {
         constexpr int S = decltype(s_tag)::value;
         constexpr int CU = (S + 1) / 2, JU = 1 + K * CU;
+        if (n <= 0) return;
         int4 da = lds_i32x4(rptr), db = lds_i32x4(rptr + 16);
         for (int j = 0; j < n; ++j) {
             if ((da.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); da = lds_i32x4(rptr); db = lds_i32x4(rptr + 16); }
@@ -624,18 +626,11 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             const int type = u.x & REC_TYPE_MASK;
             if (type == REC_NEXT_CHUNK) { next_chunk(); continue; }
             rptr += 16;
-            if (type == REC_RUN2) {
-                const int S = (u.x >> REC_RUN_S_SHIFT) & 3;
-                if (S == 1) run_pairs(std::integral_constant<int, 1>{}, u.y);
-                else run_pairs(std::integral_constant<int, 2>{}, u.y);
-            } else if (type == REC_RUN) {
-                const int S = (u.x >> REC_RUN_S_SHIFT) & 3;
-                if (S == 1) run_jobs(std::integral_constant<int, 1>{}, u.y);
-                else if (S == 2) run_jobs(std::integral_constant<int, 2>{}, u.y);
-                else run_jobs(std::integral_constant<int, 3>{}, u.y);
-            } else if (type == REC_ASET) {
+            if (type == REC_ASET) {
                 skip_window_group();
                 const int cnt = (u.x >> REC_CNT_SHIFT) & 0xF;
+                const int4 n4 = lds_i32x4(rptr);
+                rptr += 16;
 #pragma unroll
                 for (int kk = 0; kk < K; ++kk) {
                     if (kk < cnt) {
@@ -651,6 +646,12 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                         if (++sa == Cfg::A_STAGES) { sa = 0; pa ^= 1u; }
                     }
                 }
+                // the five runs of the set; their lengths sit in the header (u.y and the unit after it)
+                run_pairs(std::integral_constant<int, 1>{}, n4.x);
+                run_pairs(std::integral_constant<int, 2>{}, n4.y);
+                run_jobs(std::integral_constant<int, 1>{}, n4.z);
+                run_jobs(std::integral_constant<int, 2>{}, n4.w);
+                run_jobs(std::integral_constant<int, 3>{}, u.y);
             } else if (type == REC_STOREALL) {
                 // all accumulators of the block -> Y, four at a time (32 TMEM columns per load)
                 tmem_wait_st();

@@ -262,9 +262,18 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
             while (r1 < runs.size() && runs[r1].set == runs[r0].set) ++r1;
             const int32_t cur_set = runs[r0].set;
             {
+                // one SET header per register set: matrices to load and the lengths of its five runs
+                // (pairs with S = 1, 2, then single jobs with S = 1, 2, 3), in the order they are emitted
+                int32_t np[2] = {0, 0}, ns[3] = {0, 0, 0};
+                for (size_t ri = r0; ri < r1; ++ri) {
+                    const int32_t S1 = runs[ri].S - 1;
+                    if (S1 < 2) np[S1] += (int32_t)split[ri].pairs.size();
+                    ns[S1] += (int32_t)split[ri].singles.size();
+                }
                 const int32_t cnt = std::min<int32_t>(K, (int32_t)slots.size() - cur_set * K);
-                em.ensure(1);
-                const int32_t ch = em.unit(REC_ASET | (cnt << REC_CNT_SHIFT), 0, 0.0);
+                em.ensure(2);
+                const int32_t ch = em.unit_words(REC_ASET | (cnt << REC_CNT_SHIFT), ns[2], 0, 0);
+                em.unit_words(np[0], np[1], ns[0], ns[1]);
                 em.pad_window_group(ch);
                 for (int32_t k = 0; k < cnt; ++k) em.cmd(ch, PCMD_ATILE | slots[(size_t)cur_set * K + k]);
                 s.n_asets += cnt;
@@ -277,8 +286,6 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                     if (pass == 0) {
                         s.n_jobs += (int64_t)r.jobs.size();
                         if (split[ri].pairs.empty()) continue;
-                        em.ensure(1 + 2 * job_units);
-                        em.unit(REC_RUN2 | (r.S << REC_RUN_S_SHIFT), (int32_t)split[ri].pairs.size(), 0.0);
                         for (const auto& pr : split[ri].pairs) {
                             em.ensure(2 * job_units);
                             unit0(r.jobs[pr.first]);
@@ -290,8 +297,6 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                         for (const auto& pr : split[ri].pairs) s.hist_pairs[std::min<int>(r.S, 3) - 1][r.jobs[pr.first].kmask & 7] += 1;
                     } else {
                         if (split[ri].singles.empty()) continue;
-                        em.ensure(1 + job_units);                    // header and first job in one chunk
-                        em.unit(REC_RUN | (r.S << REC_RUN_S_SHIFT), (int32_t)split[ri].singles.size(), 0.0);
                         for (int32_t i : split[ri].singles) {
                             s.hist_singles[std::min<int>(r.S, 3) - 1][r.jobs[i].kmask & 7] += 1;
                             em.ensure(job_units);
@@ -362,13 +367,14 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                     if (f >= fetches.size() || (fetches[f] & PCMD_KIND_MASK) != PCMD_ATILE) { fail(); return; }
                     set_slot[k] = fetches[f++] & PCMD_VAL_MASK;
                 }
-                break;
-            }
-            case REC_RUN:
-            case REC_RUN2: {
-                const bool two = (rec.a & REC_TYPE_MASK) == REC_RUN2;
+                // run lengths: pairs S=1,2 then singles S=1,2,3 (the second header unit holds the first four)
+                int32_t cw[4];
+                words(s.recs[r++], cw);
+                const int32_t run_n[5] = {cw[0], cw[1], cw[2], cw[3], rec.b};
+                for (int32_t ri = 0; ri < 5; ++ri) {
+                const bool two = ri < 2;
                 uint32_t kmask = 0;
-                const int32_t Sn = (rec.a >> REC_RUN_S_SHIFT) & 3, n = rec.b;
+                const int32_t Sn = two ? ri + 1 : ri - 1, n = run_n[ri];
                 const int32_t cu = (Sn + 1) / 2, job_units = 1 + K * cu;
                 const int32_t group_units = two ? 2 * job_units : job_units, per = two ? 2 : 1;
                 for (int32_t j = 0; j < n; ++j) {
@@ -418,6 +424,7 @@ void schedule_run_host(const Schedule& s, int32_t D, const int32_t* dx, const in
                         seen_out |= my_out;
                     }
                     r += group_units;
+                }
                 }
                 break;
             }
