@@ -429,6 +429,11 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         wslot += by;
         if (wslot >= Cfg::W_SLOTS) { wslot -= Cfg::W_SLOTS; wpar ^= 1u; }
     };
+    // Releasing a window group: the warp is converged here (the barrier wait above reconverges it) and
+    // shared-memory reads and mbarrier arrives of a warp go through one in-order pipe, so lane 0's
+    // arrive cannot overtake the other lanes' loads; a full __syncwarp() costs a divergence-check
+    // branch per window, which a lone warp per scheduler cannot hide.  Compiler ordering only.
+    auto window_reads_issued = [] { asm volatile("" ::: "memory"); };
     // next window of the W ring -> buf; a group of W_GROUP windows shares one barrier pair
     auto load_window = [&](double (&buf)[4][4]) {
         const uint32_t st = wslot / Cfg::W_GROUP, sub = wslot % Cfg::W_GROUP;
@@ -444,7 +449,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             }
         }
         if (sub == Cfg::W_GROUP - 1) {
-            __syncwarp();
+            window_reads_issued();
             if (lane0) mbar_arrive(emptyW(st));
         }
         w_advance(1);
@@ -456,18 +461,21 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         const uint32_t st = wslot / Cfg::W_GROUP;
         mbar_wait(fullW(st), wpar);
         const uint32_t base = wring_s + wslot * Cfg::WIN_STRIDE + win_off;
+        // all of w0 first: its stencil can start while the loads of w1 are still draining
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            lds_f64x2(base + (rr * Cfg::BOX_W + 2) * 8, w0[rr][1], w0[rr][2]);
-            lds_f64x2(base + Cfg::WIN_STRIDE + (rr * Cfg::BOX_W + 2) * 8, w1[rr][1], w1[rr][2]);
-            if (NINE || rr == 1 || rr == 2) {
-                w0[rr][0] = lds_f64(base + (rr * Cfg::BOX_W + 1) * 8);
-                w0[rr][3] = lds_f64(base + (rr * Cfg::BOX_W + 4) * 8);
-                w1[rr][0] = lds_f64(base + Cfg::WIN_STRIDE + (rr * Cfg::BOX_W + 1) * 8);
-                w1[rr][3] = lds_f64(base + Cfg::WIN_STRIDE + (rr * Cfg::BOX_W + 4) * 8);
+        for (int q = 0; q < 2; ++q) {
+            double (&buf)[4][4] = *(q == 0 ? &w0 : &w1);
+            const uint32_t b = base + q * Cfg::WIN_STRIDE;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                lds_f64x2(b + (rr * Cfg::BOX_W + 2) * 8, buf[rr][1], buf[rr][2]);
+                if (NINE || rr == 1 || rr == 2) {
+                    buf[rr][0] = lds_f64(b + (rr * Cfg::BOX_W + 1) * 8);
+                    buf[rr][3] = lds_f64(b + (rr * Cfg::BOX_W + 4) * 8);
+                }
             }
         }
-        __syncwarp();
+        window_reads_issued();
         if (lane0) mbar_arrive(emptyW(st));
         w_advance(2);
     };
@@ -497,7 +505,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         int4 d = make_int4(0, 0, 0, 0);
         // one job: window in wc (already loaded); the window after it is fetched into wp
         auto job = [&](double (&wc)[4][4], double (&wp)[4][4], const bool prefetch) {
-            if ((d.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); d = lds_i32x4(rptr); }
+            while ((d.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); d = lds_i32x4(rptr); }
             const int4 dc = d;
             const uint32_t kmask = (uint32_t)(dc.x >> REC_JOB_KMASK_SHIFT) & 0xFu;
             double cf[K][2 * CU];
@@ -554,7 +562,8 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         if (n <= 0) return;
         int4 da = lds_i32x4(rptr), db = lds_i32x4(rptr + 16);
         for (int j = 0; j < n; ++j) {
-            if ((da.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); da = lds_i32x4(rptr); db = lds_i32x4(rptr + 16); }
+            // (a loop, not an if: the compiler moves loop bodies out of line, so the common path falls through)
+            while ((da.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); da = lds_i32x4(rptr); db = lds_i32x4(rptr + 16); }
             const int4 ca = da, cb = db;
             const uint32_t kmask = (uint32_t)(ca.x >> REC_JOB_KMASK_SHIFT) & 0xFu;
             if (Cfg::W_GROUP == 2) {
