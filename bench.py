@@ -482,7 +482,7 @@ def main():
     ap.add_argument("--no-clocks", action="store_true", help="development: do not run the nvidia-smi clock sampler")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-cols", type=int, default=24)
     ap.add_argument("--ref-cols", type=int, default=4, help="sampled output columns per process of the reference arm")
     ap.add_argument("--ref-procs", type=int, default=0, help="processes of the reference arm (0 = all host cpus, at most 32)")

@@ -411,7 +411,22 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     // loop invariants the compiler would otherwise re-derive from special registers in every job
     // (it rematerialises under register pressure): make them opaque so they stay in registers
     uint32_t lane0 = (lane == 0) ? 1u : 0u;                 // this lane signals the ring barriers
-    asm volatile("" : "+r"(win_off), "+r"(a_off), "+r"(lane0));
+    // x-halo loads (8 bytes out of every 16-byte lane slot) would hit each bank twice per half warp;
+    // lanes 8-15 and 24-31 therefore fetch their RIGHT halo in the instruction in which the others
+    // fetch their LEFT one (the two hit complementary banks) and swap the results afterwards:
+    // 2 instead of 4 wavefronts per halo load, the largest single item of the shared-memory budget
+#ifdef SPUQ_T_NOHALOSWZ
+    uint32_t halo_x = 0u;
+#else
+    uint32_t halo_x = (lane & 8) ? 24u : 0u;
+#endif
+    asm volatile("" : "+r"(win_off), "+r"(a_off), "+r"(lane0), "+r"(halo_x));
+    auto load_halos = [&](const uint32_t row_addr, double& left, double& right) {
+        const double a = lds_f64(row_addr + 8 + halo_x);          // element 1 (or 4)
+        const double b = lds_f64(row_addr + 32 - halo_x);         // element 4 (or 1)
+        left = halo_x ? b : a;
+        right = halo_x ? a : b;
+    };
 
     double A[K][D][4];                    // [register set][diagonal][point r*2+p]
     double w0[4][4], w1[4][4];            // two window buffers: jobs alternate between them
@@ -443,10 +458,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         for (int rr = 0; rr < 4; ++rr) {
             // box element e <-> x = x_tile - 2 + e; this thread's x0 = x_tile + 2*lane
             lds_f64x2(base + (rr * Cfg::BOX_W + 2) * 8, buf[rr][1], buf[rr][2]);
-            if (NINE || rr == 1 || rr == 2) {
-                buf[rr][0] = lds_f64(base + (rr * Cfg::BOX_W + 1) * 8);
-                buf[rr][3] = lds_f64(base + (rr * Cfg::BOX_W + 4) * 8);
-            }
+            if (NINE || rr == 1 || rr == 2) load_halos(base + rr * Cfg::BOX_W * 8, buf[rr][0], buf[rr][3]);
         }
         if (sub == Cfg::W_GROUP - 1) {
             window_reads_issued();
@@ -469,10 +481,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
                 lds_f64x2(b + (rr * Cfg::BOX_W + 2) * 8, buf[rr][1], buf[rr][2]);
-                if (NINE || rr == 1 || rr == 2) {
-                    buf[rr][0] = lds_f64(b + (rr * Cfg::BOX_W + 1) * 8);
-                    buf[rr][3] = lds_f64(b + (rr * Cfg::BOX_W + 4) * 8);
-                }
+                if (NINE || rr == 1 || rr == 2) load_halos(b + rr * Cfg::BOX_W * 8, buf[rr][0], buf[rr][3]);
             }
         }
         window_reads_issued();

@@ -151,11 +151,92 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                 slot_count[terms.slot[t]] += 1;
             }
         }
+        {   // what any grouping of this block's matrices into sets of K could reach at best
+            std::map<int32_t, std::vector<int32_t>> mats_of;
+            for (const Term& t : ts) mats_of[t.in_col].push_back(t.slot);
+            for (auto& kv : mats_of) {
+                std::sort(kv.second.begin(), kv.second.end());
+                const int64_t d = std::unique(kv.second.begin(), kv.second.end()) - kv.second.begin();
+                s.n_inputs += 1;
+                s.n_jobs_bound += (d + K - 1) / K;
+            }
+        }
         // matrices of this block, busiest first; K at a time form a register set
         std::vector<int32_t> slots;
         for (int32_t sl = 0; sl < (int32_t)slot_count.size(); ++sl)
             if (slot_count[sl] > 0) slots.push_back(sl);
         std::stable_sort(slots.begin(), slots.end(), [&](int32_t a, int32_t c2) { return slot_count[a] > slot_count[c2]; });
+        // ... regrouped greedily so that the matrices of a set act on the same input columns: one
+        // window load then serves up to K stencils (a job is an (input column, set) incidence)
+        if (K > 1 && !std::getenv("SPUQ_NO_COGROUP")) {
+            std::vector<std::vector<int32_t>> cols_of(slot_count.size());
+            for (const Term& t : ts) cols_of[t.slot].push_back(t.in_col);
+            for (auto& v : cols_of) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+            auto common = [&](int32_t a, int32_t c2) {
+                const auto &x = cols_of[a], &y = cols_of[c2];
+                size_t i = 0, j = 0, n = 0;
+                while (i < x.size() && j < y.size()) {
+                    if (x[i] < y[j]) ++i; else if (y[j] < x[i]) ++j; else { ++n; ++i; ++j; }
+                }
+                return (int64_t)n;
+            };
+            std::vector<int32_t> rest = slots, grouped;
+            if (K == 2) {
+                // maximum-weight matching on the co-occurrence graph, greedy by edge weight, then improved
+                // by exchanging partners between two pairs while that raises the total
+                const size_t n = slots.size();
+                std::vector<std::vector<int64_t>> w(n, std::vector<int64_t>(n, 0));
+                struct Edge { int64_t w; size_t a, b; };
+                std::vector<Edge> edges;
+                for (size_t a = 0; a < n; ++a)
+                    for (size_t c2 = a + 1; c2 < n; ++c2) {
+                        w[a][c2] = w[c2][a] = common(slots[a], slots[c2]);
+                        edges.push_back(Edge{w[a][c2], a, c2});
+                    }
+                std::stable_sort(edges.begin(), edges.end(), [](const Edge& x, const Edge& y) { return x.w > y.w; });
+                std::vector<int64_t> mate(n, -1);
+                for (const Edge& e : edges)
+                    if (mate[e.a] < 0 && mate[e.b] < 0) { mate[e.a] = (int64_t)e.b; mate[e.b] = (int64_t)e.a; }
+                for (bool improved = true; improved;) {
+                    improved = false;
+                    for (size_t a = 0; a < n; ++a) {
+                        if (mate[a] < 0) continue;
+                        for (size_t c2 = a + 1; c2 < n; ++c2) {
+                            if (mate[c2] < 0 || (size_t)mate[a] == c2) continue;
+                            const size_t b = (size_t)mate[a], d = (size_t)mate[c2];
+                            const int64_t cur = w[a][b] + w[c2][d];
+                            if (w[a][c2] + w[b][d] > cur) { mate[a] = (int64_t)c2; mate[c2] = (int64_t)a; mate[b] = (int64_t)d; mate[d] = (int64_t)b; improved = true; }
+                            else if (w[a][d] + w[b][c2] > cur) { mate[a] = (int64_t)d; mate[d] = (int64_t)a; mate[b] = (int64_t)c2; mate[c2] = (int64_t)b; improved = true; }
+                        }
+                    }
+                }
+                std::vector<char> done(n, 0);
+                for (size_t a = 0; a < n; ++a) {             // busiest pair first, an unmatched matrix last
+                    if (done[a] || mate[a] < 0) continue;
+                    grouped.push_back(slots[a]); grouped.push_back(slots[(size_t)mate[a]]);
+                    done[a] = done[(size_t)mate[a]] = 1;
+                }
+                for (size_t a = 0; a < n; ++a) if (!done[a]) grouped.push_back(slots[a]);
+                rest.clear();
+            }
+            while (!rest.empty()) {
+                std::vector<int32_t> grp{rest.front()};
+                rest.erase(rest.begin());
+                while ((int32_t)grp.size() < K && !rest.empty()) {
+                    size_t best = 0;
+                    int64_t best_w = -1;
+                    for (size_t i = 0; i < rest.size(); ++i) {
+                        int64_t w = 0;
+                        for (int32_t g : grp) w += common(g, rest[i]);
+                        if (w > best_w) { best_w = w; best = i; }      // ties: the busier one (rest keeps that order)
+                    }
+                    grp.push_back(rest[best]);
+                    rest.erase(rest.begin() + best);
+                }
+                grouped.insert(grouped.end(), grp.begin(), grp.end());
+            }
+            slots.swap(grouped);
+        }
         std::vector<int32_t> k_of_slot(slot_count.size(), -1), set_of_slot(slot_count.size(), -1);
         for (size_t i = 0; i < slots.size(); ++i) {
             set_of_slot[slots[i]] = (int32_t)(i / K);

@@ -102,6 +102,7 @@ struct Schedule {
     std::vector<int32_t> blk_cols;         // nblk*64 output columns (-1 = padding), for reporting
     // statistics (reported through plan_info / used by DESIGN.md numbers)
     int64_t n_jobs = 0, n_pairs = 0, n_asets = 0, n_entries = 0, n_stencils = 0;
+    int64_t n_inputs = 0, n_jobs_bound = 0;   // (input column, block) incidences; sum of ceil(matrices of an incidence / K)
     int64_t hist_pairs[3][8] = {}, hist_singles[3][8] = {};     // [S-1][kmask]
 };
 

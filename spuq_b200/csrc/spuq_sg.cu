@@ -212,8 +212,9 @@ static int build_schedule(spuq_sg_plan* p, int32_t K, int32_t block_cols, int32_
     schedule_build(tl, order, K, p->n_slots, block_cols, w_group, sc);
     if (std::getenv("SPUQ_SCHED_STATS")) {
         fprintf(stderr, "[spuq] schedule K=%d C=%d: blocks %d, jobs %lld (pairs %lld), A tiles %lld, stencils %lld, terms %lld, "
-                        "units %zu, producer cmds %zu\n", K, block_cols, sc->nblk, (long long)sc->n_jobs, (long long)sc->n_pairs,
-                (long long)sc->n_asets, (long long)sc->n_stencils, (long long)sc->n_entries, sc->recs.size(), sc->pcmd.size());
+                        "units %zu, producer cmds %zu, inputs %lld, job bound %lld\n", K, block_cols, sc->nblk, (long long)sc->n_jobs, (long long)sc->n_pairs,
+                (long long)sc->n_asets, (long long)sc->n_stencils, (long long)sc->n_entries, sc->recs.size(), sc->pcmd.size(),
+                (long long)sc->n_inputs, (long long)sc->n_jobs_bound);
         for (int S = 0; S < 3; ++S)
             for (int km = 1; km < 8; ++km)
                 if (sc->hist_pairs[S][km] || sc->hist_singles[S][km])
