@@ -7,6 +7,8 @@ Restates
   * ``PreconditioningOperator``     reference src/spuq/application/egsz/multi_operator2.py:139-165
   * ``pcg``                         reference src/spuq/application/egsz/pcg.py:15-53
   * ``ForgetfulVector``             reference src/spuq/utils/forgetful_vector.py:46-66
+  * ``prepare_rhs`` / ``pcg_solve`` reference src/spuq/application/egsz/adaptive_solver2.py:39-85,
+                                    ``error_norm`` src/spuq/fem/fenics/fenics_utils.py:140-159
   * batched form / Delta matrices   reference src/spuq/linalg/tensor_operator.py:65-79,
                                     src/spuq/polyquad/structure_coefficients.py:11-41
 Test infrastructure only (see oracle/__init__.py).
@@ -271,6 +273,62 @@ def pcg(A, f, P, w0, eps=1e-4, maxiter=100, history=None):
         zeta[i] = inner(rho[i], s[i])
         v[i] = s[i] + zeta[i] / zeta[i - 1] * v[i - 1]
     raise Exception("PCG did not converge")
+
+
+# ---- the direct caller of pcg: right-hand side and solve ------------------
+def prepare_rhs(A, w, coeff_field, pde):
+    """Right-hand side of the SG system; adaptive_solver2.py:39-68.
+
+    ``pde`` is the discretisation object of the reference (``FEMDiscretisation``,
+    fem_discretisation.py:256-352) reduced to what this path calls: ``assemble_rhs(basis, coeff,
+    withDirichletBC, withNeumannBC, f)`` returning the coefficient array and
+    ``set_dirichlet_bc_entries(vec, homogeneous)``.  The zero load the reference builds as a FEniCS
+    function (:45-50) is the scalar 0.0 here."""
+    b = 0 * w                                                               # :40
+    assert b.active_indices() == w.active_indices()                        # :41
+    zero = Multiindex()
+    b[zero].coeffs = pde.assemble_rhs(basis=b[zero].basis, coeff=coeff_field.mean_func,
+                                      withNeumannBC=True)                  # :43-44
+    zero_func = 0.0
+    for m in range(w.max_order):                                           # :52
+        eps_m = zero.inc(m)
+        am_f, am_rv = coeff_field[m]
+        beta = am_rv.orth_polys.get_beta(0)
+        if eps_m in b.active_indices():                                    # :57
+            g0 = b[eps_m].copy()
+            g0.coeffs = pde.assemble_rhs(basis=b[eps_m].basis, coeff=am_f, withNeumannBC=False, f=zero_func)
+            pde.set_dirichlet_bc_entries(g0, homogeneous=True)
+            b[eps_m] += beta[1] * g0                                       # :61
+        g0 = b[zero].copy()
+        g0.coeffs = pde.assemble_rhs(basis=b[zero].basis, coeff=am_f, f=zero_func)
+        pde.set_dirichlet_bc_entries(g0, homogeneous=True)
+        b[zero] += beta[0] * g0                                            # :66
+    return b
+
+
+def error_norm(vec1, vec2, normstr, pde):
+    """sqrt(sum_mu norm(vec1[mu] - vec2[mu])^2); fenics_utils.py:140-152.  ``normstr`` is a norm
+    name handed to ``pde.norm`` (dolfin's ``norm`` in the reference) or a callable."""
+    assert vec1.active_indices() == vec2.active_indices()
+    e = 0.0
+    for mi in vec1.keys():
+        err = vec1[mi].coeffs - vec2[mi].coeffs
+        e += (pde.norm(err, normstr) if isinstance(normstr, str) else normstr(err)) ** 2
+    return float(np.sqrt(e))
+
+
+def pcg_solve(A, w, coeff_field, pde, stats, pcg_eps, pcg_maxiter):
+    """adaptive_solver2.py:71-85: right-hand side, mean-based preconditioner, PCG from w, residual
+    of the returned iterate in two norms."""
+    b = prepare_rhs(A, w, coeff_field, pde)
+    P = PreconditioningOperator(coeff_field.mean_func, pde.assemble_solve_operator)
+    w, zeta, numit = pcg(A, b, P, w0=w, eps=pcg_eps, maxiter=pcg_maxiter)
+    b2 = A * w                                                             # :79
+    stats["RESIDUAL-L2"] = error_norm(b, b2, "L2", pde)
+    stats["RESIDUAL-H1A"] = error_norm(b, b2, pde.energy_norm, pde)
+    stats["DOFS"] = sum(b[mu].basis.dim for mu in b.keys())
+    stats["CELLS"] = sum(pde.num_cells(b[mu].basis) for mu in b.keys())
+    return w, zeta
 
 
 # ---- structural helpers used by the parity tests -----------------------------------------------

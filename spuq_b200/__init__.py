@@ -2,7 +2,7 @@
 
 Drop-in surface (same names as the reference):
     Multiindex, MultiindexSet, MultiVector, MultiVectorSharedBasis, SlabMultiVector,
-    MultiOperator, PreconditioningOperator, pcg, inner, FlatVector, the leaf operators,
+    MultiOperator, PreconditioningOperator, pcg, prepare_rhs, pcg_solve, inner, FlatVector, the leaf operators,
     ListCoefficientField, NormalRV, UniformRV.
 """
 from .multiindex import Multiindex, MultiindexSet
@@ -16,5 +16,6 @@ from .linalg import (Basis, CanonicalBasis, BasisMismatchError, Vector, FlatVect
 from .multi_vector import MultiVector, MultiVectorSharedBasis, SlabMultiVector
 from .multi_operator import MultiOperator, PreconditioningOperator, DeviceBlocks
 from .pcg import pcg
+from .adaptive_solver import prepare_rhs, pcg_solve, error_norm
 
 __version__ = "0.1.0"

@@ -30,7 +30,7 @@ from .random_variable import NormalRV, UniformRV
 
 __all__ = ["kl_frequencies", "kl_amplitudes", "fd_pattern", "fd_values", "fd_blocks",
            "fd_blocks_rows", "fd_pattern_rect", "complete_order_indices", "anisotropic_indices", "truncated_complete_indices",
-           "make_rvs", "blocks_to_scipy"]
+           "make_rvs", "blocks_to_scipy", "FDDiscretisation"]
 
 
 def kl_frequencies(M):
@@ -192,3 +192,92 @@ def make_rvs(kind, M, mu=0.0):
     else:
         raise ValueError("unknown polynomial family %r" % kind)
     return [rv] * M
+
+
+class FDDiscretisation:
+    """Finite-difference stand-in for the reference's ``FEMDiscretisation``
+    (spuq/application/egsz/fem_discretisation.py:228-352) on the synthetic blocks above: the
+    methods ``prepare_rhs`` / ``pcg_solve`` call on it (adaptive_solver2.py:39-85), with the
+    reference's names and argument meaning.  A coefficient is the token the coefficient field
+    yields: ``"mean"`` or the term number m.  Unknowns are the interior nodes, so Dirichlet data
+    enter only through the right-hand side (the coupling of an interior node to a boundary node
+    times the boundary value) and ``set_dirichlet_bc_entries`` has nothing to overwrite.
+
+    ``linalg`` is the module that provides ``ScipyOperator`` / ``ScipySolveOperator`` (this package,
+    or the oracle's restatement in the tests): the discretisation is an INPUT of the path, the same
+    object feeds both sides of a parity test."""
+
+    def __init__(self, n, M, linalg, f=1.0, uD=None, gamma=0.9, decay=2.0, mean=1.0):
+        self.n, self.M, self.h = int(n), int(M), 1.0 / (n + 1)
+        self._la = linalg
+        self.f, self.uD = f, uD
+        _, _, self._valid = fd_pattern(n)
+        rowptr, colidx, _ = fd_pattern(n)
+        self._rowptr, self._colidx = rowptr.numpy().astype(np.int64), colidx.numpy().astype(np.int64)
+        amps = kl_amplitudes(M, gamma, decay)
+        self._nodal = {"mean": torch.full((n + 2, n + 2), float(mean), dtype=torch.float64)}
+        for m, (k1, k2) in enumerate(kl_frequencies(M)):
+            self._nodal[m] = _coefficient(n, k1, k2, amps[m], "cpu")
+        self._lhs = {}
+        x = np.linspace(0.0, 1.0, n + 2)
+        self._x1, self._x2 = np.meshgrid(x, x)            # [iy, ix]: x1 along ix, as in _coefficient
+
+    def _on_nodes(self, g):
+        if g is None:
+            return np.zeros((self.n + 2, self.n + 2))
+        if callable(g):
+            return np.asarray(g(self._x1, self._x2), dtype=np.float64)
+        return np.full((self.n + 2, self.n + 2), float(g))
+
+    def assemble_lhs(self, basis=None, coeff="mean", withDirichletBC=True):
+        if coeff not in self._lhs:
+            vals = fd_values(self._nodal[coeff], self._valid).numpy()
+            N = self.n * self.n
+            self._lhs[coeff] = sps.csr_matrix((vals, self._colidx, self._rowptr), shape=(N, N))
+        return self._lhs[coeff]
+
+    def assemble_operator(self, basis, coeff="mean", withDirichletBC=True):
+        return self._la.ScipyOperator(self.assemble_lhs(basis, coeff), basis, basis)
+
+    assemble_operator_inner_dofs = assemble_operator
+
+    def assemble_solve_operator(self, basis, coeff="mean", withDirichletBC=True):
+        return self._la.ScipySolveOperator(self.assemble_lhs(basis, coeff), basis, basis)
+
+    def assemble_rhs(self, basis=None, coeff="mean", withDirichletBC=True, withNeumannBC=True, f=None):
+        """h^2 f at the interior nodes plus, with Dirichlet conditions, the lifted boundary values
+        (there is no Neumann boundary in this model problem)."""
+        a = self._nodal[coeff].numpy()
+        F = (self.h ** 2) * self._on_nodes(self.f if f is None else f)[1:-1, 1:-1].copy()
+        if withDirichletBC and self.uD is not None:
+            g = self._on_nodes(self.uD)
+            c = a[1:-1, 1:-1]
+            F[0, :] += 0.5 * (c[0, :] + a[0, 1:-1]) * g[0, 1:-1]
+            F[-1, :] += 0.5 * (c[-1, :] + a[-1, 1:-1]) * g[-1, 1:-1]
+            F[:, 0] += 0.5 * (c[:, 0] + a[1:-1, 0]) * g[1:-1, 0]
+            F[:, -1] += 0.5 * (c[:, -1] + a[1:-1, -1]) * g[1:-1, -1]
+        return F.reshape(-1)
+
+    def set_dirichlet_bc_entries(self, u, homogeneous=False):
+        return None
+
+    def norm(self, v, kind="L2"):
+        v = np.asarray(v)
+        if kind == "L2":
+            return float(self.h * np.linalg.norm(v))
+        if kind == "l2":
+            return float(np.linalg.norm(v))
+        raise ValueError("unknown norm %r" % (kind,))
+
+    @property
+    def energy_norm(self):
+        K0 = self.assemble_lhs(None, "mean")
+        return lambda v: float(np.sqrt(max(float(np.dot(v, K0 @ v)), 0.0)))
+
+    def num_cells(self, basis=None):
+        return (self.n + 1) ** 2
+
+    # what a slab-native caller may use instead of per-column norm calls
+    @property
+    def l2_weight(self):
+        return self.h ** 2

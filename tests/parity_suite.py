@@ -260,6 +260,56 @@ def check_apply_multiblock():
         assert relerr(total, c.Y) <= TOL
 
 
+# ---- the caller of pcg: right-hand side and solve --------------------------
+def check_pcg_solve(n=10, M=3, p=2, kind="hermite", mu=0.5):
+    """prepare_rhs / pcg_solve (adaptive_solver2.py:39-85) against the oracle's restatement on the
+    same discretisation object: inhomogeneous Dirichlet data so that every term contributes, a
+    non-symmetric random variable so that beta[0] != 0 (the mean column collects all terms)."""
+    idx = synthetic.complete_order_indices(M, p)
+    c = fd_case(n, M, idx, kind, mu)
+    uD = lambda x1, x2: 1.0 + x1 + 0.5 * x2 * x2          # noqa: E731
+    load = lambda x1, x2: 1.0 + np.sin(3.0 * x1) * x2     # noqa: E731
+    pde_o = synthetic.FDDiscretisation(n, M, olin, f=load, uD=uD)
+    pde_p = synthetic.FDDiscretisation(n, M, sp, f=load, uD=uD)
+    w0_o = 0 * c.w
+    b_o = osg.prepare_rhs(c.A, w0_o, c.cf, pde_o)
+    stats_o = {}
+    x_o, zeta_o = osg.pcg_solve(c.A, w0_o, c.cf, pde_o, stats_o, 1e-9, 100)
+
+    A = sp.MultiOperator.from_blocks(device_blocks(c), c.rvs)
+    cf = sp.ListCoefficientField("mean", list(range(M)), c.rvs)
+    w0 = sp.SlabMultiVector.from_array(idx, np.zeros_like(c.W))
+    b = sp.prepare_rhs(A, w0, cf, pde_p)
+    assert isinstance(b, sp.SlabMultiVector) and b.active_indices() == w0.active_indices()
+    B, B_o = b.to_array(), b_o.to_slab()
+    assert np.max(np.abs(B - B_o)) <= 1e-14 * np.max(np.abs(B_o))
+    nonzero = [k for k in range(B.shape[1]) if np.any(B[:, k] != 0.0)]
+    assert len(nonzero) == M + 1                          # the mean column and one column per e_m
+    stats = {}
+    x, zeta = sp.pcg_solve(A, w0, cf, pde_p, stats, 1e-9, 100)
+    assert isinstance(x, sp.SlabMultiVector)
+    assert np.max(np.abs(x.to_array() - x_o.to_slab())) <= 1e-8 * np.max(np.abs(x_o.to_slab()))
+    assert stats["DOFS"] == stats_o["DOFS"] == c.N * idx.shape[0]
+    assert stats["CELLS"] == stats_o["CELLS"] == (n + 1) ** 2 * idx.shape[0]
+    for key in ("RESIDUAL-L2", "RESIDUAL-H1A"):
+        # residuals of two converged runs: same size, both tiny against the right-hand side
+        assert stats[key] <= 1e-6 and stats_o[key] <= 1e-6, (key, stats[key], stats_o[key])
+    # the norms themselves, on a residual that is not tiny: one PCG pass only
+    s1, s1_o = {}, {}
+    with pytest.raises(Exception, match="PCG did not converge"):
+        sp.pcg_solve(A, w0, cf, pde_p, s1, 1e-14, 2)
+    r_p = sp.error_norm(b, A * (0.5 * b), "L2", pde_p)
+    r_o = osg.error_norm(b_o, c.A * (0.5 * b_o), "L2", pde_o)
+    assert abs(r_p - r_o) <= 1e-12 * r_o
+    from spuq_b200.adaptive_solver import _EnergyNorm
+    e_p = sp.error_norm(b, A * (0.5 * b), _EnergyNorm(pde_p.energy_norm, pde_p.assemble_lhs(None, "mean")), pde_p)
+    e_o = osg.error_norm(b_o, c.A * (0.5 * b_o), pde_o.energy_norm, pde_o)
+    assert abs(e_p - e_o) <= 1e-11 * e_o
+    # a dictionary MultiVector in, as the reference's callers hold it
+    x2, _ = sp.pcg_solve(A, w0.to_multivector(), cf, pde_p, {}, 1e-9, 100)
+    assert np.max(np.abs(x2.to_array() - x.to_array())) <= 1e-12
+
+
 # ---- vectors ------------------------------------------------------------------------------------
 def check_slab_multivector_api():
     FV = sp.FlatVector

@@ -74,3 +74,7 @@ def test_mean_preconditioner():
 
 def test_pcg_sg_mean():
     ps.check_pcg_sg_mean()
+
+
+def test_pcg_solve_and_prepare_rhs():
+    ps.check_pcg_solve()

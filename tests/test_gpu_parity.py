@@ -149,6 +149,11 @@ def test_pcg_sg_mean():
     ps.check_pcg_sg_mean()
 
 
+def test_pcg_solve_and_prepare_rhs():
+    ps.check_pcg_solve()
+    ps.check_pcg_solve(n=16, M=4, p=2, kind="legendre", mu=0.0)
+
+
 # ---- full-size configurations ---------------------------------------------------------------------
 def _oracle_columns(mats_vals, rowptr, colidx, N, tables, W, cols):
     """Oracle y[mu] for a few columns: the per-mu body of MultiOperator.apply
