@@ -410,7 +410,7 @@ def run_gpu(args):
                                          "MultiOperator.apply (cached scipy CSR leaves, one SpMV per (mu, m)); "
                                          "%.1f s; per-column cost is independent of the other columns" % (ncols, L, secs),
                                "host_cpus": os.cpu_count()}
-    print(json.dumps(out))
+    print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -464,7 +464,10 @@ def run_reference(args):
                                       "columns" % (ncols, L, len(parts)),
                             "host_cpus": os.cpu_count()},
            "e2e": {"value": value, "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    print(json.dumps(out), file=_JSON_OUT, flush=True)
+
+
+_JSON_OUT = sys.stdout
 
 
 def main():
@@ -487,6 +490,12 @@ def main():
     ap.add_argument("--ref-cols", type=int, default=4, help="sampled output columns per process of the reference arm")
     ap.add_argument("--ref-procs", type=int, default=0, help="processes of the reference arm (0 = all host cpus, at most 32)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: libraries that print there (NCCL's version banner
+    # under NCCL_DEBUG=VERSION) are sent to stderr for the duration of the run
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
