@@ -415,11 +415,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     // lanes 8-15 and 24-31 therefore fetch their RIGHT halo in the instruction in which the others
     // fetch their LEFT one (the two hit complementary banks) and swap the results afterwards:
     // 2 instead of 4 wavefronts per halo load, the largest single item of the shared-memory budget
-#ifdef SPUQ_T_NOHALOSWZ
-    uint32_t halo_x = 0u;
-#else
     uint32_t halo_x = (lane & 8) ? 24u : 0u;
-#endif
     asm volatile("" : "+r"(win_off), "+r"(a_off), "+r"(lane0), "+r"(halo_x));
     auto load_halos = [&](const uint32_t row_addr, double& left, double& right) {
         const double a = lds_f64(row_addr + 8 + halo_x);          // element 1 (or 4)
@@ -511,11 +507,10 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     auto run_jobs = [&](auto s_tag, const int n) {
         constexpr int S = decltype(s_tag)::value;
         constexpr int CU = (S + 1) / 2, JU = 1 + K * CU;
-        int4 d = make_int4(0, 0, 0, 0);
         // one job: window in wc (already loaded); the window after it is fetched into wp
         auto job = [&](double (&wc)[4][4], double (&wp)[4][4], const bool prefetch) {
-            while ((d.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); d = lds_i32x4(rptr); }
-            const int4 dc = d;
+            int4 dc = lds_i32x4(rptr);
+            while ((dc.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); dc = lds_i32x4(rptr); }
             const uint32_t kmask = (uint32_t)(dc.x >> REC_JOB_KMASK_SHIFT) & 0xFu;
             double cf[K][2 * CU];
 #pragma unroll
@@ -523,7 +518,6 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
 #pragma unroll
                 for (int u = 0; u < CU; ++u) lds_f64x2(rptr + 16 * (1 + kk * CU + u), cf[kk][2 * u], cf[kk][2 * u + 1]);
             rptr += 16 * JU;
-            d = lds_i32x4(rptr);                    // unit 0 of the next job (or whatever follows the run)
             if (prefetch) load_window(wp);
 #pragma unroll
             for (int kk = 0; kk < K; ++kk) {
@@ -552,7 +546,6 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             }
         };
         if (n <= 0) return;
-        d = lds_i32x4(rptr);
         if (cur == 0) load_window(w0); else load_window(w1);
         int j = 0;
         if (cur == 1) { job(w1, w0, n > 1); cur = 0; j = 1; }
@@ -569,11 +562,12 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         constexpr int S = decltype(s_tag)::value;
         constexpr int CU = (S + 1) / 2, JU = 1 + K * CU;
         if (n <= 0) return;
-        int4 da = lds_i32x4(rptr), db = lds_i32x4(rptr + 16);
         for (int j = 0; j < n; ++j) {
+            // unit 0 of both jobs (not prefetched in the previous pass: the copies that keeps alive
+            // cost more than the load latency, which the barrier wait below covers anyway)
+            int4 ca = lds_i32x4(rptr), cb = lds_i32x4(rptr + 16);
             // (a loop, not an if: the compiler moves loop bodies out of line, so the common path falls through)
-            while ((da.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); da = lds_i32x4(rptr); db = lds_i32x4(rptr + 16); }
-            const int4 ca = da, cb = db;
+            while ((ca.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); ca = lds_i32x4(rptr); cb = lds_i32x4(rptr + 16); }
             const uint32_t kmask = (uint32_t)(ca.x >> REC_JOB_KMASK_SHIFT) & 0xFu;
             if (Cfg::W_GROUP == 2) {
                 load_window_pair();
@@ -583,7 +577,6 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             }
             const uint32_t cbase = rptr + 32;
             rptr += 16 * 2 * JU;
-            da = lds_i32x4(rptr); db = lds_i32x4(rptr + 16);     // unit 0s of the next pair
 #pragma unroll
             for (int kk = 0; kk < K; ++kk) {
                 if (kmask >> kk & 1u) {
