@@ -15,9 +15,13 @@
 //     2. for every mode k and column: tridiagonal solve (T_y + lam_k I) uhat = rhat along y
 //                             (Thomas with precomputed reciprocal pivots; lanes along k)
 //     3. S = Uhat Q           (the same GEMM)
+// For even nx the transform is split by the parity of the mode (Q[nx-1-j][k] = (-1)^k Q[j][k]): the
+// sums and differences of mirrored entries of a grid row go through two half-size products, which
+// halves the flops of steps 1 and 3 at the price of two element-wise passes.
 // The two products are plain dense fp64 GEMMs ((L*ny) x nx by nx x nx): they go to cuBLAS DGEMM when
 // libcublas can be loaded at run time (dlopen, no link-time dependency); k_rowgemm below is the
 // in-house register-tiled fallback (CUDA cores) and the reference for the host-emulated build.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -56,15 +60,16 @@ static CublasApi& cublas_api() {
     }
     return api;
 }
-// C[M x n] = A[M x n] * Q[n x n] (row-major, Q symmetric)  ==  column-major  C^T = Q * A^T
-static bool blas_rowgemm(spuq_sg_precond* p, int64_t Mrows, int32_t n, const double* A, const double* Q, double* C,
-                         cudaStream_t stream) {
+// C[M x nc] = A[M x nk] * Q[nk x nc], all row-major (row strides lda, ldc, nc)  ==  column-major
+// C^T = Q^T * A^T with Q^T = the row-major Q read column-major
+static bool blas_rowgemm(spuq_sg_precond* p, int64_t Mrows, int32_t nk, int32_t nc, const double* A, int32_t lda,
+                         const double* Q, double* C, int32_t ldc, cudaStream_t stream) {
     CublasApi& api = cublas_api();
     if (!api.ok || Mrows > 0x7fffffffLL) return false;
     if (!p->blas && api.create(&p->blas) != 0) { p->blas = nullptr; return false; }
     if (api.set_stream(p->blas, stream) != 0) return false;
     const double one = 1.0, zero = 0.0;
-    return api.dgemm(p->blas, /*CUBLAS_OP_N*/ 0, 0, n, (int)Mrows, n, &one, Q, n, A, n, &zero, C, n) == 0;
+    return api.dgemm(p->blas, /*CUBLAS_OP_N*/ 0, 0, nc, (int)Mrows, nk, &one, Q, nc, A, lda, &zero, C, ldc) == 0;
 }
 #endif
 
@@ -72,10 +77,10 @@ constexpr int GM = 128, GN = 64, GK = 8;      // CTA tile; 256 threads, each 8 x
 constexpr int G_THREADS = 256;
 
 #ifndef SPUQ_EMU
-// C[M x n] = A[M x n] * Q[n x n]; A, C row-major with leading dimension n; Q symmetric.
+// C[M x nc] = A[M x nk] * Q[nk x nc]; A, C row-major with row strides lda, ldc; Q row-major, stride nc.
 __global__ void __launch_bounds__(G_THREADS)
-k_rowgemm(int64_t Mrows, int32_t n, const double* __restrict__ A, const double* __restrict__ Q,
-          double* __restrict__ C, const double* gate) {
+k_rowgemm(int64_t Mrows, int32_t nk, int32_t nc, const double* __restrict__ A, int32_t lda,
+          const double* __restrict__ Q, double* __restrict__ C, int32_t ldc, const double* gate) {
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
     __shared__ double As[2][GK][GM + 2];
     __shared__ double Bs[2][GK][GN];
@@ -98,13 +103,13 @@ k_rowgemm(int64_t Mrows, int32_t n, const double* __restrict__ A, const double* 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int k = k0 + a_k + q;
-            ra[q] = (r < Mrows && k < n) ? A[r * n + k] : 0.0;
+            ra[q] = (r < Mrows && k < nk) ? A[r * lda + k] : 0.0;
         }
         const int k = k0 + b_k;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int c = col0 + b_c + q;
-            rb[q] = (k < n && c < n) ? Q[(int64_t)k * n + c] : 0.0;
+            rb[q] = (k < nk && c < nc) ? Q[(int64_t)k * nc + c] : 0.0;
         }
     };
     auto store = [&](int buf) {
@@ -117,8 +122,8 @@ k_rowgemm(int64_t Mrows, int32_t n, const double* __restrict__ A, const double* 
     store(0);
     __syncthreads();
     int buf = 0;
-    for (int k0 = 0; k0 < n; k0 += GK) {
-        const bool more = k0 + GK < n;
+    for (int k0 = 0; k0 < nk; k0 += GK) {
+        const bool more = k0 + GK < nk;
         if (more) load(k0 + GK);
 #pragma unroll
         for (int k = 0; k < GK; ++k) {
@@ -143,22 +148,60 @@ k_rowgemm(int64_t Mrows, int32_t n, const double* __restrict__ A, const double* 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = col0 + tc + 16 * j;
-            if (c < n) C[r * n + c] = acc[i][j];
+            if (c < nc) C[r * ldc + c] = acc[i][j];
         }
     }
 }
 #else
-void k_rowgemm(int64_t Mrows, int32_t n, const double* A, const double* Q, double* C, const double* gate) {
+void k_rowgemm(int64_t Mrows, int32_t nk, int32_t nc, const double* A, int32_t lda, const double* Q, double* C,
+               int32_t ldc, const double* gate) {
     if (gate != nullptr && *gate != (double)SPUQ_PCG_RUNNING) return;
     if (threadIdx.x != 0 || blockIdx.x != 0 || blockIdx.y != 0) return;
     for (int64_t r = 0; r < Mrows; ++r)
-        for (int c = 0; c < n; ++c) {
+        for (int c = 0; c < nc; ++c) {
             double s = 0.0;
-            for (int k = 0; k < n; ++k) s += A[r * n + k] * Q[(int64_t)k * n + c];
-            C[r * n + c] = s;
+            for (int k = 0; k < nk; ++k) s += A[r * lda + k] * Q[(int64_t)k * nc + c];
+            C[r * ldc + c] = s;
         }
 }
 #endif
+
+// Mirror sums and differences of every grid row (n even, h = n/2):  out[r][j] = in[r][j] + in[r][n-1-j],
+// out[r][h+j] = in[r][j] - in[r][n-1-j]
+__global__ void __launch_bounds__(256)
+k_mirror_split(int64_t Mrows, int32_t n, const double* __restrict__ in, double* __restrict__ out, const double* gate) {
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+    const int32_t h = n / 2;
+    const int64_t total = Mrows * h;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / h;
+        const int32_t j = (int32_t)(t % h);
+        const double a = in[r * n + j], b = in[r * n + (n - 1 - j)];
+        out[r * n + j] = a + b;
+        out[r * n + h + j] = a - b;
+    }
+}
+// Its inverse, in place: X[r] holds P (first half) and M (second half); X[r][j] = P[j] + M[j],
+// X[r][n-1-j] = P[j] - M[j].  One thread owns the pair (j, h-1-j): the four positions it reads are the
+// four it writes.
+__global__ void __launch_bounds__(256)
+k_mirror_merge(int64_t Mrows, int32_t n, double* __restrict__ X, const double* gate) {
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+    const int32_t h = n / 2, hp = (h + 1) / 2;
+    const int64_t total = Mrows * hp;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / hp;
+        const int32_t j = (int32_t)(t % hp), j2 = h - 1 - j;
+        double* x = X + r * n;
+        const double p1 = x[j], m1 = x[h + j], p2 = x[j2], m2 = x[h + j2];
+        x[j] = p1 + m1;
+        x[h + j2] = p1 - m1;          // position n-1-j
+        if (j2 != j) {
+            x[j2] = p2 + m2;
+            x[h + j] = p2 - m2;       // position n-1-j2
+        }
+    }
+}
 
 // Thomas solves along y, in place on X (L columns of ny x nx): one thread per (column, mode k),
 // lanes along k.  ipiv[y*nx + k] = reciprocal pivot of (T_y + lam_k I) at row y.
@@ -190,7 +233,9 @@ int mean_fd_destroy(spuq_sg_precond* p) {
     cudaSetDevice(p->device);
     cudaFree(p->q_dev);
     cudaFree(p->piv_dev);
-    p->q_dev = p->piv_dev = nullptr;
+    cudaFree(p->qsplit_dev);
+    cudaFree(p->piv_split_dev);
+    p->q_dev = p->piv_dev = p->qsplit_dev = p->piv_split_dev = nullptr;
 #ifndef SPUQ_EMU
     if (p->blas) { cublas_api().destroy(p->blas); p->blas = nullptr; }
 #endif
@@ -207,18 +252,33 @@ int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, dou
     SPUQ_REQUIRE(work != nullptr, "precond_mean_fd: workspace missing");
     double* T = static_cast<double*>(work);
     const int64_t Mrows = (int64_t)L * p->ny;
-    const dim3 grid((unsigned)((Mrows + GM - 1) / GM), (unsigned)((p->nx + GN - 1) / GN));
-    auto rowgemm = [&](const double* src, double* dst) {
+    auto rowgemm = [&](const double* src, double* dst, int32_t nk, int32_t nc, const double* Q) {
 #ifndef SPUQ_EMU
-        if (blas_rowgemm(p, Mrows, p->nx, src, p->q_dev, dst, stream)) return;
+        if (blas_rowgemm(p, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, stream)) return;
 #endif
-        SPUQ_LAUNCH(k_rowgemm, grid, dim3(G_THREADS), 0, stream, Mrows, p->nx, src, p->q_dev, dst, gate);
+        const dim3 g((unsigned)((Mrows + GM - 1) / GM), (unsigned)((nc + GN - 1) / GN));
+        SPUQ_LAUNCH(k_rowgemm, g, dim3(G_THREADS), 0, stream, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, gate);
     };
-    rowgemm(R, T);
     const int64_t nthreads = (int64_t)L * p->nx;
-    SPUQ_LAUNCH(k_thomas_y, dim3((unsigned)((nthreads + 127) / 128)), dim3(128), 0, stream, p->nx, p->ny, L,
-                p->oy, p->piv_dev, T, gate);
-    rowgemm(T, S);
+    const int32_t h = p->half;
+    if (h > 0 && R != S) {
+        // sums / differences of mirrored entries -> S (scratch), two half-size products each way
+        const size_t hh = (size_t)h * h;
+        const unsigned eb = (unsigned)std::min<int64_t>((Mrows * h + 255) / 256, 1 << 20);
+        SPUQ_LAUNCH(k_mirror_split, dim3(eb), dim3(256), 0, stream, Mrows, p->nx, R, S, gate);
+        rowgemm(S, T, h, h, p->qsplit_dev);
+        rowgemm(S + h, T + h, h, h, p->qsplit_dev + hh);
+        SPUQ_LAUNCH(k_thomas_y, dim3((unsigned)((nthreads + 127) / 128)), dim3(128), 0, stream, p->nx, p->ny, L,
+                    p->oy, p->piv_split_dev, T, gate);
+        rowgemm(T, S, h, h, p->qsplit_dev + 2 * hh);
+        rowgemm(T + h, S + h, h, h, p->qsplit_dev + 3 * hh);
+        SPUQ_LAUNCH(k_mirror_merge, dim3(eb), dim3(256), 0, stream, Mrows, p->nx, S, gate);
+    } else {
+        rowgemm(R, T, p->nx, p->nx, p->q_dev);
+        SPUQ_LAUNCH(k_thomas_y, dim3((unsigned)((nthreads + 127) / 128)), dim3(128), 0, stream, p->nx, p->ny, L,
+                    p->oy, p->piv_dev, T, gate);
+        rowgemm(T, S, p->nx, p->nx, p->q_dev);
+    }
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }
@@ -262,6 +322,35 @@ extern "C" int spuq_sg_precond_mean_fd(spuq_sg_precond** out, int device, int32_
     }
     p->q_dev = static_cast<double*>(dq);
     p->piv_dev = static_cast<double*>(dp);
+    if (nx % 2 == 0 && nx >= 4) {
+        const int32_t h = nx / 2;
+        const size_t hh = (size_t)h * h;
+        std::vector<double> qs(4 * hh), pvs(piv.size());
+        for (int32_t j = 0; j < h; ++j)
+            for (int32_t c = 0; c < h; ++c) {
+                const double e = q[(size_t)j * nx + 2 * c], o = q[(size_t)j * nx + 2 * c + 1];
+                qs[(size_t)j * h + c] = e;                  // Qe   [j][c]  (modes 2c)
+                qs[hh + (size_t)j * h + c] = o;             // Qo   [j][c]  (modes 2c+1)
+                qs[2 * hh + (size_t)c * h + j] = e;         // Qe^T [c][j]
+                qs[3 * hh + (size_t)c * h + j] = o;         // Qo^T [c][j]
+            }
+        for (int32_t y = 0; y < ny; ++y)
+            for (int32_t c = 0; c < h; ++c) {
+                pvs[(size_t)y * nx + c] = piv[(size_t)y * nx + 2 * c];
+                pvs[(size_t)y * nx + h + c] = piv[(size_t)y * nx + 2 * c + 1];
+            }
+        void* dqs = nullptr; void* dps = nullptr;
+        if (cudaMalloc(&dqs, sizeof(double) * qs.size()) == cudaSuccess &&
+            cudaMalloc(&dps, sizeof(double) * pvs.size()) == cudaSuccess) {
+            p->qsplit_dev = static_cast<double*>(dqs);
+            p->piv_split_dev = static_cast<double*>(dps);
+            cudaMemcpy(p->qsplit_dev, qs.data(), sizeof(double) * qs.size(), cudaMemcpyHostToDevice);
+            cudaMemcpy(p->piv_split_dev, pvs.data(), sizeof(double) * pvs.size(), cudaMemcpyHostToDevice);
+            p->half = h;
+        } else {
+            cudaFree(dqs);          // not fatal: the full-size transform still works
+        }
+    }
     cudaMemcpy(p->q_dev, q.data(), sizeof(double) * q.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(p->piv_dev, piv.data(), sizeof(double) * piv.size(), cudaMemcpyHostToDevice);
     *out = p;

@@ -14,6 +14,10 @@ struct spuq_sg_precond {
     double* lam_dev = nullptr;       // nx eigenvalues of the x part
     double* piv_dev = nullptr;       // nx x ny Thomas pivots of (T_y + lam_k I)
     void* blas = nullptr;            // cublasHandle_t when libcublas could be loaded (else the in-house GEMM)
+    // even nx: the sine transform split by the parity of the mode (two products of half the size)
+    int32_t half = 0;                // nx / 2 when the split is used, else 0
+    double* qsplit_dev = nullptr;    // four half x half matrices: Qe, Qo (forward), Qe^T, Qo^T (inverse)
+    double* piv_split_dev = nullptr; // pivots with the modes ordered even | odd
 };
 
 namespace spuq {

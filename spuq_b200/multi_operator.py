@@ -212,6 +212,7 @@ class MeanSolveSlabOperator:
         if not np.all(diag == d):
             raise _abi.SpuqError("mean block is not constant-coefficient (diagonal varies)")
         coo = csr.tocoo()
+        coo.eliminate_zeros()                 # explicitly stored zeros are not couplings
         off = coo.col - coo.row
         far = np.abs(off[np.abs(off) > 1])
         nx = int(far.min()) if far.size else N

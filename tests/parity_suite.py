@@ -495,7 +495,8 @@ def check_mean_preconditioner():
     import scipy.sparse.linalg as spla
     from spuq_b200.multi_operator import MeanSolveSlabOperator
     rng = np.random.RandomState(21)
-    for nx, ny, L in [(12, 12, 5), (70, 9, 3), (9, 33, 4), (130, 2, 2), (17, 1, 3)]:
+    # even nx takes the parity-split transform (half sizes 6, 35, 65, 2, 3: even and odd; nx < 4 keeps the full transform), odd nx the full one
+    for nx, ny, L in [(12, 12, 5), (70, 9, 3), (9, 33, 4), (130, 2, 2), (17, 1, 3), (4, 3, 2), (6, 7, 3)]:
         T = lambda n, o, dd: sps.diags([o, dd, o], [-1, 0, 1], shape=(n, n))      # noqa: E731
         if ny > 1:
             A0 = sps.kron(sps.identity(ny), T(nx, -1.0, 2.0)) + sps.kron(T(ny, -1.0, 2.0), sps.identity(nx))
@@ -513,6 +514,9 @@ def check_mean_preconditioner():
         err = np.max(np.linalg.norm(St.cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1))
         assert err <= 1e-12, (nx, ny, err)
         assert torch.equal(Rt.cpu(), torch.from_numpy(R))
+        solver.apply_slab(Rt, Rt)                                   # in place (input and output alias)
+        err = np.max(np.linalg.norm(Rt.cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1))
+        assert err <= 1e-12, (nx, ny, err, "in place")
     with pytest.raises(_abi.SpuqError, match="constant-coefficient"):
         MeanSolveSlabOperator(sps.csr_matrix(sps.diags([np.arange(1.0, 10.0)], [0])), 1)
 
