@@ -193,11 +193,17 @@ class MeanSolveSlabOperator:
     """Exact solve with the mean block on every column (K4): recognises a constant-coefficient
     5-point block on an nx x ny grid and uses the fast-diagonalisation solver of libspuq_sg."""
 
-    def __init__(self, csr, n_columns=1):
-        csr = sps.csr_matrix(csr, dtype=np.float64)
-        self.N = csr.shape[0]
+    def __init__(self, csr, n_columns=1, stencil=None):
+        """``stencil`` = (nx, ny, d, ox, oy) skips the recognition (and the need for the matrix)."""
+        if stencil is None:
+            csr = sps.csr_matrix(csr, dtype=np.float64)
+            self.N = csr.shape[0]
+            nx, ny, d, ox, oy = self._recognise(csr)
+        else:
+            nx, ny, d, ox, oy = stencil
+            self.N = int(nx) * int(ny)
+        self.stencil = (int(nx), int(ny), float(d), float(ox), float(oy))
         self.L = int(n_columns)
-        nx, ny, d, ox, oy = self._recognise(csr)
         handle = C.c_void_p()
         _abi.check(_abi.lib().spuq_sg_precond_mean_fd(C.byref(handle), _abi.device_index(), nx, ny, d, ox, oy),
                    "precond_mean_fd")

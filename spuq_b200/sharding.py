@@ -10,9 +10,12 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .multi_operator import MultiOperator
+from .multi_operator import MeanSolveSlabOperator, MultiOperator
+from .multi_vector import _axpy, _dot, _scal
+from .pcg import PCG_MESSAGES
+from . import _abi
 
-__all__ = ["shard_ranges", "padded_columns", "ShardedApply", "row_ranges", "RowShardedApply"]
+__all__ = ["shard_ranges", "padded_columns", "ShardedApply", "row_ranges", "RowShardedApply", "RowShardedPCG"]
 
 
 def shard_ranges(tables, M, world):
@@ -141,3 +144,150 @@ class RowShardedApply:
         self.exchange_halos(W)
         plan.apply(W, Y)
         return Y
+
+
+class RowShardedPCG:
+    """``pcg`` (application/egsz/pcg.py:15-53) on row-sharded slabs.
+
+    Every vector lives as the local slab of ``RowShardedApply`` (L x (y1-y0+2)*nx, halo rows zero
+    except in the search direction right after its halo exchange).  Per pass:
+      * ``z = A v``: halo exchange + the single-GPU kernel, then the output halo rows are zeroed, so
+        that every inner product can run over the whole local slab;
+      * the two inner products are local sums + one all-reduce of a scalar each;
+      * the mean-based preconditioner solves with A_0 column by column and needs whole columns: the
+        residual is transposed to a COLUMN sharding (rank q gets columns Lambda_q of all rows: every
+        rank sends contiguous blocks, all-to-all over NVLink), solved with the single-GPU exact solver
+        and transposed back.  With ``mean_stencil=None`` the identity is used.
+    The reference's four failure conditions are checked on the all-reduced scalars, so all ranks
+    take the same branch."""
+
+    def __init__(self, sharded_apply, nx, ny, ranges, mean_stencil=None):
+        self.A = sharded_apply
+        self.group = sharded_apply.group
+        self.world, self.rank = sharded_apply.world, sharded_apply.rank
+        self.nx, self.ny = int(nx), int(ny)
+        self.ranges = list(ranges)                       # (y0, y1) of every rank
+        self.y0, self.y1 = self.ranges[self.rank]
+        self.nyl = self.y1 - self.y0 + 2
+        self.mean_stencil = mean_stencil                 # (d, ox, oy) of the constant-coefficient mean block
+        self._solver = None
+        self.last_history = []
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def _zero_halos(self, X):
+        X3 = X.view(X.shape[0], self.nyl, self.nx)
+        X3[:, 0, :].zero_()
+        X3[:, self.nyl - 1, :].zero_()
+
+    def _allreduce(self, value, dev):
+        if self.world == 1:
+            return float(value)
+        t = torch.tensor([value], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return float(t[0].item())
+
+    def _col_range(self, q, L):
+        per = padded_columns(L, self.world)
+        return min(q * per, L), min((q + 1) * per, L)
+
+    def _exchange(self, send, recv):
+        """send[q] -> rank q, recv[q] <- rank q (lists of contiguous tensors, possibly empty)."""
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_to_all(recv, send, group=self.group)
+            return
+        ops = []
+        for q in range(self.world):
+            if q == self.rank:
+                recv[q].copy_(send[q])
+                continue
+            if send[q].numel():
+                ops.append(dist.P2POp(dist.isend, send[q], q, self.group))
+            if recv[q].numel():
+                ops.append(dist.P2POp(dist.irecv, recv[q], q, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def precondition(self, R, S):
+        """S = A_0^{-1} R on the owned rows (halo rows of S zero)."""
+        if self.mean_stencil is None:
+            S.copy_(R)
+            self._zero_halos(S)
+            return S
+        L = R.shape[0]
+        dev = R.device
+        c0, c1 = self._col_range(self.rank, L)
+        if self._solver is None:
+            d, ox, oy = self.mean_stencil
+            self._solver = MeanSolveSlabOperator(None, max(c1 - c0, 1), stencil=(self.nx, self.ny, d, ox, oy))
+        R3 = R.view(L, self.nyl, self.nx)
+        S3 = S.view(L, self.nyl, self.nx)
+        if self.world == 1:
+            Rc = R3[:, 1:-1, :].reshape(L, self.ny * self.nx)
+            Sc = torch.empty_like(Rc)
+            self._solver.apply_slab(Rc, Sc)
+            S3.zero_()
+            S3[:, 1:-1, :].copy_(Sc.view(L, self.ny, self.nx))
+            return S
+        own = self.y1 - self.y0
+        send = [R3[q0:q1, 1:-1, :].contiguous() for q0, q1 in (self._col_range(q, L) for q in range(self.world))]
+        recv = [torch.empty((c1 - c0, r1 - r0, self.nx), dtype=R.dtype, device=dev) for r0, r1 in self.ranges]
+        self._exchange(send, recv)
+        Rc = torch.empty((c1 - c0, self.ny, self.nx), dtype=R.dtype, device=dev)
+        for (r0, r1), blk in zip(self.ranges, recv):
+            Rc[:, r0:r1, :].copy_(blk)
+        Sc = torch.empty_like(Rc)
+        if c1 > c0:
+            self._solver.apply_slab(Rc.view(c1 - c0, -1), Sc.view(c1 - c0, -1))
+        back = [Sc[:, r0:r1, :].contiguous() for r0, r1 in self.ranges]
+        got = [torch.empty((q1 - q0, own, self.nx), dtype=R.dtype, device=dev)
+               for q0, q1 in (self._col_range(q, L) for q in range(self.world))]
+        self._exchange(back, got)
+        S3.zero_()
+        for q, blk in enumerate(got):
+            q0, q1 = self._col_range(q, L)
+            S3[q0:q1, 1:-1, :].copy_(blk)
+        return S
+
+    # ---- the solver ----------------------------------------------------------------------------
+    def solve(self, plan, F, W0, eps=1e-4, maxiter=100):
+        """F, W0: local slabs (halo rows ignored).  Returns (W, zeta, numit) like ``pcg``; raises
+        the reference's exceptions."""
+        dev = F.device
+        W = W0.clone()
+        self._zero_halos(W)
+        rho = F.clone()
+        self._zero_halos(rho)
+        z = torch.empty_like(W)
+        self.A.apply(plan, W, z)                          # rho = f - A w0      (pcg.py:26)
+        self._zero_halos(z)
+        self._zero_halos(W)
+        _axpy(-1.0, z, rho)
+        s = torch.empty_like(W)
+        self.precondition(rho, s)                         # s = P rho           (:27)
+        v = s.clone()                                     # v = s               (:28)
+        zeta = self._allreduce(_dot(rho, s), dev)         # zeta = <rho, s>     (:30)
+        self.last_history = []
+        for i in range(1, maxiter):                       # (:31)
+            self.last_history.append(zeta)
+            if zeta < 0:
+                raise Exception(PCG_MESSAGES[_abi.PCG_PRECOND_NOT_PD] % zeta)
+            if zeta <= eps ** 2:
+                self._zero_halos(W)
+                return W, zeta, i
+            self.A.apply(plan, v, z)                      # z = A v             (:40)
+            self._zero_halos(z)
+            alpha = self._allreduce(_dot(z, v), dev)      # (:41)
+            if alpha == 0:
+                raise Exception(PCG_MESSAGES[_abi.PCG_SINGULAR] % alpha)
+            if alpha < 0:
+                raise Exception(PCG_MESSAGES[_abi.PCG_NOT_PD] % alpha)
+            _axpy(zeta / alpha, v, W)                     # (:47)
+            _axpy(-zeta / alpha, z, rho)                  # (:48)
+            self.precondition(rho, s)                     # (:49)
+            zeta_new = self._allreduce(_dot(rho, s), dev)  # (:50)
+            _scal(zeta_new / zeta, v)                     # v = s + zeta_new / zeta * v   (:51)
+            _axpy(1.0, s, v)
+            self._zero_halos(v)
+            zeta = zeta_new
+        raise Exception(PCG_MESSAGES[_abi.PCG_NOT_CONVERGED])

@@ -103,3 +103,71 @@ def test_row_sharded_apply_two_ranks(tmp_path, emu):
     out = tmp_path / "err.txt"
     mp.spawn(_row_worker, args=(2, _free_port(), str(out)), nprocs=2, join=True)
     assert float(out.read_text()) <= 1e-12
+
+
+def _pcg_worker(rank, world, port, out_path, precond):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import spuq_b200 as sp
+        from spuq_b200 import _abi, synthetic
+        from spuq_b200.multi_operator import DeviceBlocks
+        from spuq_b200.sharding import RowShardedApply, RowShardedPCG, row_ranges
+        from tests.cases import fd_case
+        from oracle import linalg as olin, sg as osg
+        _abi.use_library(conftest.EMU_LIB, "cpu")
+        n, M = 16, 3
+        idx = synthetic.complete_order_indices(M, 2)
+        c = fd_case(n, M, idx, "legendre")                         # global problem, x* = c.W
+        L = idx.shape[0]
+        ranges = row_ranges(n, world)
+        y0, y1 = ranges[rank]
+        nyl = y1 - y0 + 2
+        rowptr, colidx, vals = synthetic.fd_blocks_rows(n, M, y0, y1)
+        blocks = DeviceBlocks(rowptr, colidx, vals, (nyl * n, nyl * n))
+        sh = RowShardedApply(blocks, c.rvs, n, y0, y1)
+        Fg = torch.from_numpy(np.ascontiguousarray(c.Y.T)).view(L, n, n)      # f = A x*, global
+        F = torch.zeros((L, nyl, n), dtype=torch.float64)
+        F[:, 1:-1, :] = Fg[:, y0:y1, :]
+        F = F.view(L, nyl * n)
+        w = sp.SlabMultiVector(idx, slab=torch.zeros_like(F), _sorted=True)
+        plan = sh.plan_for(w)
+        d = float(c.mats[0].diagonal()[0])
+        solver = RowShardedPCG(sh, n, n, ranges, mean_stencil=(d, -1.0, -1.0) if precond == "mean" else None)
+        X, zeta, it = solver.solve(plan, F, torch.zeros_like(F), eps=1e-9, maxiter=200)
+        own = X.view(L, nyl, n)[:, 1:-1, :].contiguous()
+        parts = [torch.empty_like(own) for _ in range(world)]
+        dist.all_gather(parts, own)
+        if rank == 0:
+            Xg = torch.cat(parts, dim=1).reshape(L, n * n).numpy().T
+            # the oracle's PCG on the same numbers, with the same preconditioner
+            basis = olin.CanonicalBasis(c.N)
+            if precond == "mean":
+                lu = olin.ScipySolveOperator(c.mats[0], basis, basis, factor=True)
+                P = osg.PreconditioningOperator("mean", lambda b, f: lu)
+            else:
+                class _Id(olin.Operator):
+                    def apply(self, v):
+                        return v.copy()
+                P = _Id()
+            oh = []
+            x_o, zeta_o, it_o = osg.pcg(c.A, c.A * c.w, P, 0 * c.w, eps=1e-9, maxiter=200, history=oh)
+            k = min(len(oh), len(solver.last_history), 6)
+            traj = float(np.max(np.abs(np.array(solver.last_history[:k]) - np.array(oh[:k])) / np.array(oh[:k])))
+            err = float(np.max(np.abs(Xg - x_o.to_slab())))
+            with open(out_path, "w") as f:
+                f.write("%r %r %r %r\n" % (err, traj, it, it_o))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("precond", ["mean", "identity"])
+def test_row_sharded_pcg_two_ranks(tmp_path, emu, precond):
+    """PCG on row-sharded slabs (halo exchange for A, all-reduced scalars, preconditioner through a
+    transposition to column shards) against the oracle's PCG on the global problem."""
+    out = tmp_path / "res.txt"
+    mp.spawn(_pcg_worker, args=(2, _free_port(), str(out), precond), nprocs=2, join=True)
+    err, traj, it, it_o = [float(v) for v in out.read_text().split()]
+    assert abs(it - it_o) <= 1, (it, it_o)
+    assert traj <= 1e-9 and err <= 1e-8
