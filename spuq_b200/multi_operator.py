@@ -243,6 +243,8 @@ class MeanSolveSlabOperator:
     def apply_slab(self, R, S):
         lib = _abi.lib()
         L, N = R.shape
+        if not (R.is_contiguous() and S.is_contiguous() and S.shape == R.shape):
+            raise ValueError("MeanSolveSlabOperator.apply_slab needs contiguous L x N slabs of equal shape")
         need = int(lib.spuq_sg_precond_work_bytes(self.handle, N, L))
         if self._work is None or self._work.numel() * 8 < need:
             self._work = torch.empty(need // 8 + 1, dtype=torch.float64, device=R.device)

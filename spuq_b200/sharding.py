@@ -223,7 +223,7 @@ class RowShardedPCG:
         R3 = R.view(L, self.nyl, self.nx)
         S3 = S.view(L, self.nyl, self.nx)
         if self.world == 1:
-            Rc = R3[:, 1:-1, :].reshape(L, self.ny * self.nx)
+            Rc = R3[:, 1:-1, :].contiguous().view(L, self.ny * self.nx)     # (reshape alone keeps the column stride)
             Sc = torch.empty_like(Rc)
             self._solver.apply_slab(Rc, Sc)
             S3.zero_()

@@ -260,6 +260,40 @@ def check_apply_multiblock():
         assert relerr(total, c.Y) <= TOL
 
 
+def check_row_sharded_pcg_single_rank(n=16, M=3, p=2):
+    """RowShardedPCG with one rank (no process group): the halo'd local slab is the whole grid plus two
+    empty rows; the solve must agree with the oracle's PCG on the global problem (the two-rank form
+    of this check runs on gloo in tests/test_sharded_gloo.py)."""
+    from spuq_b200.sharding import RowShardedApply, RowShardedPCG
+    idx = synthetic.complete_order_indices(M, p)
+    c = fd_case(n, M, idx, "legendre")
+    L = idx.shape[0]
+    rowptr, colidx, vals = synthetic.fd_blocks_rows(n, M, 0, n)
+    nyl = n + 2
+    blocks = DeviceBlocks(_dev(rowptr), _dev(colidx), _dev(vals), (nyl * n, nyl * n))
+    sh = RowShardedApply(blocks, c.rvs, n, 0, n)
+    F = torch.zeros((L, nyl, n), dtype=torch.float64)
+    F[:, 1:-1, :] = torch.from_numpy(np.ascontiguousarray(c.Y.T)).view(L, n, n)
+    F = _dev(F.view(L, nyl * n))
+    w = sp.SlabMultiVector(idx, slab=torch.zeros_like(F), _sorted=True)
+    plan = sh.plan_for(w)
+    d = float(c.mats[0].diagonal()[0])
+    solver = RowShardedPCG(sh, n, n, [(0, n)], mean_stencil=(d, -1.0, -1.0))
+    X, zeta, it = solver.solve(plan, F, torch.zeros_like(F), eps=1e-9, maxiter=100)
+    basis = olin.CanonicalBasis(c.N)
+    lu = olin.ScipySolveOperator(c.mats[0], basis, basis, factor=True)
+    oh = []
+    x_o, zeta_o, it_o = osg.pcg(c.A, c.A * c.w, osg.PreconditioningOperator("mean", lambda b, f: lu), 0 * c.w,
+                                eps=1e-9, maxiter=100, history=oh)
+    assert abs(it - it_o) <= 1
+    k = min(len(oh), len(solver.last_history), 6)
+    assert np.allclose(solver.last_history[:k], oh[:k], rtol=1e-9)
+    Xg = X.view(L, nyl, n)[:, 1:-1, :].reshape(L, n * n).cpu().numpy().T
+    assert np.max(np.abs(Xg - x_o.to_slab())) <= 1e-8
+    with pytest.raises(Exception, match="PCG did not converge"):
+        solver.solve(plan, F, torch.zeros_like(F), eps=1e-14, maxiter=3)
+
+
 # ---- the caller of pcg: right-hand side and solve (SURVEY.md 8f, row f1) --------------------------
 def check_pcg_solve(n=10, M=3, p=2, kind="hermite", mu=0.5):
     """prepare_rhs / pcg_solve (adaptive_solver2.py:39-85) against the oracle's restatement on the

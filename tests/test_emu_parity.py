@@ -78,3 +78,7 @@ def test_pcg_sg_mean():
 
 def test_pcg_solve_and_prepare_rhs():
     ps.check_pcg_solve()
+
+
+def test_row_sharded_pcg_single_rank():
+    ps.check_row_sharded_pcg_single_rank()

@@ -149,6 +149,11 @@ def test_pcg_sg_mean():
     ps.check_pcg_sg_mean()
 
 
+def test_row_sharded_pcg_single_rank():
+    ps.check_row_sharded_pcg_single_rank()
+    ps.check_row_sharded_pcg_single_rank(n=32, M=4, p=2)
+
+
 def test_pcg_solve_and_prepare_rhs():
     ps.check_pcg_solve()
     ps.check_pcg_solve(n=16, M=4, p=2, kind="legendre", mu=0.0)
