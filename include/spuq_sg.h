@@ -174,6 +174,12 @@ SPUQ_API int spuq_sg_xpay(int64_t n, const double* num_dev, const double* den_de
                  const double* s_dev, double* v_dev, void* stream);
 /* x *= alpha_host */
 SPUQ_API int spuq_sg_scal(int64_t n, double alpha_host, double* x_dev, void* stream);
+/* out[s*ldo + i] = sum_mu coef_dev[s*L + mu] * W[i + ldw*mu]   for S coefficient vectors at once:
+ * the value of the expansion at S parameter samples, coef[s][mu] = prod_m P_{mu_m}(y^s_m).
+ * Replaces the sum over Lambda in compute_parametric_sample_solution,
+ * application/egsz/sampling.py:59-75 (one pass over the slab per 8 samples). */
+SPUQ_API int spuq_sg_combine(int64_t n, int32_t L, int32_t S, const double* W_dev, int64_t ldw,
+                    const double* coef_dev, double* out_dev, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4: preconditioners  s[mu] = P rho[mu]  applied to every column.

@@ -14,6 +14,8 @@ x p_n = beta[1] p_{n+1} - beta[0] p_n + beta[-1] p_{n-1}.
 """
 import math
 
+import numpy as np
+
 import scipy.special
 
 
@@ -144,6 +146,10 @@ class PolynomialFamily:
     def eval(self, n, x, all_degrees=False):
         vals = compute_poly(self._rc, n, x)
         return vals if all_degrees else vals[-1]
+
+    def __getitem__(self, n):
+        """The polynomial of degree n as a numpy.poly1d; polynomials.py:33-35."""
+        return self.eval(n, np.poly1d([1, 0]))
 
     def norm(self, n, sqrt=True):
         if self._normalised:

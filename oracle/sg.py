@@ -7,6 +7,9 @@ Restates
   * ``PreconditioningOperator``     reference src/spuq/application/egsz/multi_operator2.py:139-165
   * ``pcg``                         reference src/spuq/application/egsz/pcg.py:15-53
   * ``ForgetfulVector``             reference src/spuq/utils/forgetful_vector.py:46-66
+  * ``sample_realization``, ``compute_parametric_sample_solution``
+                                    reference src/spuq/application/egsz/coefficient_field.py:45-52,
+                                    src/spuq/application/egsz/sampling.py:59-75
   * ``prepare_rhs`` / ``pcg_solve`` reference src/spuq/application/egsz/adaptive_solver2.py:39-85,
                                     ``error_norm`` src/spuq/fem/fenics/fenics_utils.py:140-159
   * batched form / Delta matrices   reference src/spuq/linalg/tensor_operator.py:65-79,
@@ -145,6 +148,14 @@ class ListCoefficientField:
     def __getitem__(self, i):
         assert i < len(self._funcs), "invalid index"
         return self._funcs[i], self._rvs[i]
+
+    def sample_realization(self, Lambda, RV_samples):
+        """sample_map[mu] = prod_m P_{mu_m}(y_m) over the stored part of mu; coefficient_field.py:45-52."""
+        sample_map = {}
+        for mu in Lambda:
+            univariate_vals = [self[m][1].orth_polys[mu[m]](RV_samples[m]) for m in range(len(mu))]
+            sample_map[mu] = float(np.prod(univariate_vals)) if univariate_vals else 1.0
+        return sample_map, RV_samples
 
 
 class MultiOperator(Operator):
@@ -329,6 +340,15 @@ def pcg_solve(A, w, coeff_field, pde, stats, pcg_eps, pcg_maxiter):
     stats["DOFS"] = sum(b[mu].basis.dim for mu in b.keys())
     stats["CELLS"] = sum(pde.num_cells(b[mu].basis) for mu in b.keys())
     return w, zeta
+
+
+def compute_parametric_sample_solution(RV_samples, coeff_field, w, proj_basis=None, cache=None):
+    """The expansion evaluated at one parameter sample, sum_mu w[mu] * prod_m P_{mu_m}(y_m);
+    sampling.py:59-75 with all vectors already on the projection basis (shared basis: the projection
+    of :46-52 is the identity)."""
+    Lambda = w.active_indices()
+    sample_map, _ = coeff_field.sample_realization(Lambda, RV_samples)
+    return sum(w[mu] * sample_map[mu] for mu in Lambda)
 
 
 # ---- structural helpers used by the parity tests -----------------------------------------------

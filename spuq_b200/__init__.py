@@ -17,5 +17,6 @@ from .multi_vector import MultiVector, MultiVectorSharedBasis, SlabMultiVector
 from .multi_operator import MultiOperator, PreconditioningOperator, DeviceBlocks
 from .pcg import pcg
 from .adaptive_solver import prepare_rhs, pcg_solve, error_norm
+from .sampling import compute_parametric_sample_solution, sample_solutions
 
 __version__ = "0.1.0"

@@ -21,6 +21,19 @@ class CoefficientField:
     def __getitem__(self, i):  # pragma: no cover - abstract
         raise NotImplementedError
 
+    def sample_realization(self, Lambda, RV_samples):
+        """``sample_map[mu] = prod_m P_{mu_m}(y_m)`` over the stored entries of mu, and the samples
+        back (coefficient_field.py:45-52; the reference's ``sample_rvs`` default is broken there,
+        :103-104, so the samples must be given)."""
+        sample_map = {}
+        for mu in Lambda:
+            vals = [self[m][1].orth_polys[mu[m]](RV_samples[m]) for m in range(len(mu))]
+            p = 1.0
+            for v in vals:
+                p = p * v
+            sample_map[mu] = float(p)
+        return sample_map, RV_samples
+
 
 class ListCoefficientField(CoefficientField):
     def __init__(self, mean_func, funcs, rvs):

@@ -111,6 +111,93 @@ __device__ __forceinline__ double ratio_of(double alpha, const double* num, cons
     return a;
 }
 
+// out[s][i] = sum_mu coef[s][mu] * W[i + ldw*mu], SC samples per pass (coefficients staged in shared
+// memory in chunks of COMBINE_LCHUNK columns).  One thread owns two consecutive rows; a warp reads 512
+// contiguous bytes of a column per step: a pure streaming kernel, 8 n L bytes per SC samples.
+#ifndef SPUQ_EMU
+constexpr int COMBINE_LCHUNK = 512;
+// out[s][i] = sum_mu coef[s][mu] * W[i + ldw*mu], SC samples per pass.  One thread owns four consecutive
+// rows (two 16-byte loads per column, a warp reads 1 KB of a column per step) and keeps 4 x SC sums in
+// registers (two rows when 8 samples are summed at once, to keep three blocks per SM in flight); the
+// coefficients of a chunk of columns are staged in shared memory, sample index fastest,
+// so that one 16-byte shared load feeds 8 FMAs.  A pure streaming kernel: 8 n L bytes per SC samples.
+template <int SC, int R>
+__global__ void __launch_bounds__(256)
+k_combine(int64_t n, int32_t L, int32_t S, int32_t s0, const double* __restrict__ W, int64_t ldw,
+          const double* __restrict__ coef, double* __restrict__ out, int64_t ldo) {
+    static_assert(SC % 2 == 0 && R % 2 == 0, "samples and rows are handled in pairs");
+    __shared__ __align__(16) double cs[COMBINE_LCHUNK][SC];
+    const int64_t ngrp = (n + R - 1) / R;
+    const bool aligned = ((ldw & 1) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    for (int64_t qb = (int64_t)blockIdx.x * blockDim.x; qb < ngrp; qb += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = R * (qb + threadIdx.x);
+        const int nin = i < n ? (int)min((int64_t)R, n - i) : 0;
+        const bool vec = aligned && nin == R;
+        double acc[R][SC];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int q = 0; q < SC; ++q) acc[r][q] = 0.0;
+        for (int32_t l0 = 0; l0 < L; l0 += COMBINE_LCHUNK) {
+            const int32_t lc = min(COMBINE_LCHUNK, L - l0);
+            __syncthreads();
+            for (int t = threadIdx.x; t < SC * lc; t += blockDim.x) {
+                const int q = t / lc, l = t % lc;
+                cs[l][q] = (s0 + q < S) ? coef[(int64_t)(s0 + q) * L + l0 + l] : 0.0;
+            }
+            __syncthreads();
+            if (nin == 0) continue;
+            const double* w = W + i + ldw * (int64_t)l0;
+#pragma unroll 4
+            for (int32_t l = 0; l < lc; ++l, w += ldw) {
+                double x[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) x[r] = 0.0;
+                if (vec) {
+#pragma unroll
+                    for (int r = 0; r < R; r += 2) {
+                        const double2 v = *reinterpret_cast<const double2*>(w + r);
+                        x[r] = v.x; x[r + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) if (r < nin) x[r] = w[r];
+                }
+#pragma unroll
+                for (int q = 0; q < SC; q += 2) {
+                    const double2 c2 = *reinterpret_cast<const double2*>(&cs[l][q]);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        acc[r][q] = fma(c2.x, x[r], acc[r][q]);
+                        acc[r][q + 1] = fma(c2.y, x[r], acc[r][q + 1]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SC; ++q)
+            if (s0 + q < S) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) if (r < nin) out[(int64_t)(s0 + q) * ldo + i + r] = acc[r][q];
+            }
+    }
+}
+
+#else
+// host-emulated build: the same sums, evaluated by the first emulated thread
+template <int SC, int R>
+void k_combine(int64_t n, int32_t L, int32_t S, int32_t s0, const double* W, int64_t ldw, const double* coef,
+               double* out, int64_t ldo) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int q = 0; q < SC && s0 + q < S; ++q)
+        for (int64_t i = 0; i < n; ++i) {
+            double a = 0.0;
+            for (int32_t l = 0; l < L; ++l) a = std::fma(coef[(int64_t)(s0 + q) * L + l], W[i + ldw * (int64_t)l], a);
+            out[(int64_t)(s0 + q) * ldo + i] = a;
+        }
+}
+#endif
+
 // y += a*x
 __global__ void __launch_bounds__(256)
 k_axpy(int64_t n, double alpha, const double* num, const double* den,

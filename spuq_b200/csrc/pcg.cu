@@ -91,6 +91,30 @@ extern "C" int spuq_sg_xpay(int64_t n, const double* num, const double* den, con
     return SPUQ_OK;
 }
 
+extern "C" int spuq_sg_combine(int64_t n, int32_t L, int32_t S, const double* W, int64_t ldw,
+                               const double* coef, double* out, int64_t ldo, void* stream) {
+    SPUQ_REQUIRE(n >= 0 && L >= 0 && S >= 0, "combine: negative size");
+    if (n == 0 || S == 0) return SPUQ_OK;
+    SPUQ_REQUIRE(W && coef && out && ldw >= n && ldo >= n, "combine: null argument or leading dimension too small");
+    auto blocks = [&](int rows) {
+        return dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>(((n + rows - 1) / rows + 255) / 256, (int64_t)cur_sm_count() * 8)));
+    };
+    for (int32_t s0 = 0; s0 < S; s0 += 8) {
+        if (S - s0 >= 5) {
+            SPUQ_LAUNCH((k_combine<8, 2>), blocks(2), dim3(256), 0, static_cast<cudaStream_t>(stream), n, L, S, s0, W, ldw,
+                        coef, out, ldo);
+        } else if (S - s0 >= 3) {
+            SPUQ_LAUNCH((k_combine<4, 4>), blocks(4), dim3(256), 0, static_cast<cudaStream_t>(stream), n, L, S, s0, W, ldw,
+                        coef, out, ldo);
+        } else {
+            SPUQ_LAUNCH((k_combine<2, 4>), blocks(4), dim3(256), 0, static_cast<cudaStream_t>(stream), n, L, S, s0, W, ldw,
+                        coef, out, ldo);
+        }
+    }
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+
 extern "C" int spuq_sg_scal(int64_t n, double alpha, double* x, void* stream) {
     SPUQ_REQUIRE(n >= 0 && x, "scal: null argument");
     SPUQ_LAUNCH(k_scal, dim3(blas_grid(n, cur_sm_count(), 256)), dim3(256), 0,

@@ -344,6 +344,38 @@ def check_pcg_solve(n=10, M=3, p=2, kind="hermite", mu=0.5):
     assert np.max(np.abs(x2.to_array() - x.to_array())) <= 1e-12
 
 
+# ---- evaluation at parameter samples ---------------------------------------
+def check_parametric_samples():
+    """compute_parametric_sample_solution (sampling.py:59-75) and its many-sample form against the
+    oracle's restatement: odd and even n, |Lambda| above and below the kernel's coefficient chunk,
+    sample counts that exercise every accumulator width."""
+    rng = np.random.RandomState(5)
+    for n, M, p, kind, mu, S in [(9, 3, 3, "hermite", 0.5, 11), (8, 4, 2, "legendre", 0.0, 2), (4, 7, 5, "legendre", 0.0, 5),
+                                 (5, 2, 2, "hermite", 0.0, 1)]:
+        idx = synthetic.complete_order_indices(M, p)
+        c = fd_case(n, M, idx, kind, mu)
+        cf_p = sp.ListCoefficientField("mean", list(range(M)), c.rvs)
+        w = sp.SlabMultiVector.from_array(idx, c.W)
+        samples = rng.uniform(-0.9, 0.9, size=(S, M))
+        vals = sp.sample_solutions(samples, cf_p, w)
+        assert tuple(vals.shape) == (S, c.N)
+        vals = vals.cpu().numpy()
+        for s_ in range(S):
+            ref = osg.compute_parametric_sample_solution(list(samples[s_]), c.cf, c.w)
+            assert np.max(np.abs(vals[s_] - ref.coeffs)) <= 1e-12 * max(1.0, np.max(np.abs(ref.coeffs))), (n, M, p, s_)
+        one = sp.compute_parametric_sample_solution(list(samples[0]), cf_p, w)
+        assert isinstance(one, sp.FlatVector) and np.array_equal(one.coeffs, vals[0])
+        # the sample map itself: bit-exact products of the same polynomial values
+        sm_p, _ = cf_p.sample_realization(w.active_indices(), list(samples[0]))
+        sm_o, _ = c.cf.sample_realization(c.w.active_indices(), list(samples[0]))
+        assert [sm_p[k] for k in w.active_indices()] == [sm_o[k] for k in c.w.active_indices()]
+    # a dictionary MultiVector in
+    one2 = sp.compute_parametric_sample_solution(list(samples[0]), cf_p, w.to_multivector())
+    assert np.max(np.abs(one2.coeffs - one.coeffs)) <= 1e-14
+    with pytest.raises(TypeError):
+        sp.sample_solutions(samples, cf_p, 3)
+
+
 # ---- vectors ------------------------------------------------------------------------------------
 def check_slab_multivector_api():
     FV = sp.FlatVector

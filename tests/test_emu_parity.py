@@ -82,3 +82,7 @@ def test_pcg_solve_and_prepare_rhs():
 
 def test_row_sharded_pcg_single_rank():
     ps.check_row_sharded_pcg_single_rank()
+
+
+def test_parametric_samples():
+    ps.check_parametric_samples()

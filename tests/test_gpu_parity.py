@@ -249,3 +249,7 @@ def test_full_size_config3_hermite_shifted():
     from spuq_b200 import synthetic
     idx = synthetic.anisotropic_indices(50, 11.3)
     _full_size(1000, 50, idx, "hermite", 0.5, [0, 3, 50, 500, 987], [(2, 4, 2, 0), (3, 8, 2, 0), (4, 3, 1, 0)])
+
+
+def test_parametric_samples():
+    ps.check_parametric_samples()
