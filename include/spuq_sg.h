@@ -132,7 +132,8 @@ SPUQ_API int spuq_sg_plan_info(const spuq_sg_plan* plan, int32_t* path_out, int6
  *   variant 2  k_apply_tiled  (cols_per_block = C, rows_per_thread = RY)   registers only
  *   variant 3  k_apply_tma    (same tiling, operands through TMA rings)
  *   variant 4  k_apply_tmem   (cols_per_block = K register sets of block matrices, 1..3;
- *              rows_per_thread = consumer groups per CTA, 1 or 2; accumulators in tensor memory) */
+ *              rows_per_thread = consumer groups per CTA, 1 or 2, or 3 = one fused
+ *              group of eight warps on 64 x 16 tiles; accumulators in tensor memory) */
 SPUQ_API int spuq_sg_plan_tune(spuq_sg_plan* plan, int32_t variant, int32_t cols_per_block,
                       int32_t rows_per_thread, int32_t ctas_per_sm);
 

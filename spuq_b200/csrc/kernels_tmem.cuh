@@ -197,16 +197,21 @@ struct TmemCfg {
     // output columns + the scratch accumulator), its own rings and its own work items.  Two groups put
     // two warps on every SM sub-partition, which hides the barrier / LDS / tcgen05 round trips of one
     // behind the arithmetic of the other.
-    static constexpr int G = G_;
+    // G_ = 3 is the FUSED form of two groups: ONE group of eight warps on a 64 x 16 tile (the two halves
+    // of the tile use the two halves of TMEM), one job stream, one producer warp: 10 % fewer halo rows
+    // to stage and half the producer work per grid point.
+    static constexpr bool FUSED = (G_ == 3);
+    static constexpr int G = FUSED ? 1 : G_;                       // consumer groups (own rings, own items)
     static constexpr int D = NINE ? 9 : 5;
-    static constexpr int TILE_X = 64, TILE_Y = 8;
-    static constexpr int CONSUMER_WARPS = 4;                       // per group
+    static constexpr int TILE_X = 64, TILE_Y = FUSED ? 16 : 8;
+    static constexpr int CONSUMER_WARPS = FUSED ? 8 : 4;           // per group
     // + one producer warp; with two groups the block is padded to three warpgroups so that
     // setmaxnreg can move registers from the producer warpgroup to the consumers (the register file
     // is split per SM sub-partition: 9 warps would cap every thread at 168 registers)
-    static constexpr int THREADS = (G == 1) ? 32 * (CONSUMER_WARPS + 1) : 384;
+    static constexpr bool WIDE = (G_ != 1);                        // 384-thread block with setmaxnreg
+    static constexpr int THREADS = WIDE ? 384 : 32 * (CONSUMER_WARPS + 1);
     static constexpr int CONSUMER_REGS = 224, PRODUCER_REGS = 56;
-    static constexpr int TMEM_COLS = 512 / G;
+    static constexpr int TMEM_COLS = WIDE ? 256 : 512;             // per consumer warp
     static constexpr int BLOCK_COLS = TMEM_COLS / SCHED_ACC_STRIDE - 1;
     static constexpr int BOX_W = 68, WIN_ROWS = TILE_Y + 2;
     static constexpr int WIN_BYTES = BOX_W * WIN_ROWS * 8;
@@ -215,8 +220,8 @@ struct TmemCfg {
     static constexpr int META_BYTES = SCHED_CHUNK_RECS * 16;
     // W ring: stages of W_GROUP windows under ONE full/empty barrier pair (a barrier round trip costs the
     // single consumer warp of a sub-partition 60-140 clk, so it is paid once per group, not per window)
-    static constexpr int W_GROUP = (G == 1) ? 4 : 2, W_STAGES = (G == 1) ? 4 : 6, W_SLOTS = W_GROUP * W_STAGES;
-    static constexpr int A_STAGES = (G == 1) ? (NINE ? 2 : 4) : (NINE ? 1 : 2), M_STAGES = (G == 1) ? 4 : 3, I_STAGES = 4;
+    static constexpr int W_GROUP = WIDE ? 2 : 4, W_STAGES = FUSED ? 7 : (WIDE ? 6 : 4), W_SLOTS = W_GROUP * W_STAGES;
+    static constexpr int A_STAGES = WIDE ? (NINE ? 1 : 2) : (NINE ? 2 : 4), M_STAGES = WIDE ? 3 : 4, I_STAGES = 4;
     // per-group shared memory region
     static constexpr int OFF_A = W_SLOTS * WIN_STRIDE;
     static constexpr int OFF_M = OFF_A + A_STAGES * A_BYTES;
@@ -229,15 +234,16 @@ struct TmemCfg {
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int K, bool NINE, int G>
-__global__ void __launch_bounds__((G == 1) ? 160 : 384, 1)
+template <int K, bool NINE, int G_>
+__global__ void __launch_bounds__((G_ == 1) ? 160 : 384, 1)
 k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapA,
              const SchedRec* __restrict__ recs, const int32_t* __restrict__ pcmd,
              const int32_t* __restrict__ blk_pcmd, int32_t nblk, int32_t s, int32_t ny, int32_t nty,
              int64_t n_items, unsigned long long* __restrict__ work_counter,
              double* __restrict__ Y, int64_t ldy, const double* gate, int32_t debug_flags) {
-    using Cfg = TmemCfg<K, NINE, G>;
+    using Cfg = TmemCfg<K, NINE, G_>;
     constexpr int D = Cfg::D;
+    constexpr int G = Cfg::G;
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
 
     extern __shared__ uint8_t smem_raw[];
@@ -267,7 +273,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     asm volatile("tcgen05.fence::after_thread_sync;");
 
     if (warp >= Cfg::CONSUMER_WARPS * G) {
-        if (G > 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::PRODUCER_REGS));
+        if (Cfg::WIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::PRODUCER_REGS));
         if (warp >= Cfg::CONSUMER_WARPS * G + G) return;       // padding warps of the producer warpgroup
         const int my_group = warp - Cfg::CONSUMER_WARPS * G;   // one producer warp per consumer group
         // ================================ producer warp ============================================
@@ -387,9 +393,12 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     }
 
     // ==================================== consumer warps ===========================================
-    if (G > 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::CONSUMER_REGS));
-    const int grp = warp / Cfg::CONSUMER_WARPS, lw = warp % Cfg::CONSUMER_WARPS;     // lw = TMEM lane quarter
-    uint32_t tmem_warp = *tmem_slot + ((uint32_t)(lw * 32) << 16) + (uint32_t)(grp * Cfg::TMEM_COLS);
+    if (Cfg::WIDE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::CONSUMER_REGS));
+    // grp: ring set / work items; lw = TMEM lane quarter (warp % 4); half: which 256 TMEM columns and, in
+    // the fused form, which eight rows of the 64 x 16 tile
+    const int grp = warp / Cfg::CONSUMER_WARPS, lw = warp % 4, half = warp / 4;
+    const int row0 = Cfg::FUSED ? 8 * half + 2 * lw : 2 * lw;                          // first tile row of the thread
+    uint32_t tmem_warp = *tmem_slot + ((uint32_t)(lw * 32) << 16) + (uint32_t)((Cfg::WIDE ? half : 0) * Cfg::TMEM_COLS);
     asm volatile("" : "+r"(tmem_warp));
     int sa = 0, sm = 0, si = 0;
     uint32_t pa = 0, pm = 0, pi = 0;
@@ -406,8 +415,8 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     auto fullI = [&](uint32_t i) { return bar0 + 8u * (BI + i); };
     auto emptyI = [&](uint32_t i) { return bar0 + 8u * (BI + Cfg::I_STAGES + i); };
     // this thread's corner inside a staged window / A tile (bytes)
-    uint32_t win_off = (uint32_t)(((2 * lw) * Cfg::BOX_W + 2 * lane) * 8);
-    uint32_t a_off = (uint32_t)(((2 * lw) * Cfg::TILE_X + 2 * lane) * 8);
+    uint32_t win_off = (uint32_t)((row0 * Cfg::BOX_W + 2 * lane) * 8);
+    uint32_t a_off = (uint32_t)((row0 * Cfg::TILE_X + 2 * lane) * 8);
     // loop invariants the compiler would otherwise re-derive from special registers in every job
     // (it rematerialises under register pressure): make them opaque so they stay in registers
     uint32_t lane0 = (lane == 0) ? 1u : 0u;                 // this lane signals the ring barriers
@@ -624,7 +633,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         if (lane0) mbar_arrive(emptyI(si));
         if (++si == Cfg::I_STAGES) { si = 0; pi ^= 1u; }
         if (it.x < 0) break;
-        const int32_t x0 = it.x + 2 * lane, y0 = it.y + 2 * lw;
+        const int32_t x0 = it.x + 2 * lane, y0 = it.y + row0;
 
         // accumulators <- 0 (tcgen05 operations of a warp complete in order)
 #pragma unroll
@@ -702,7 +711,7 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
 
     // all TMEM traffic of the CTA is complete (every load was waited for): release the columns
     asm volatile("tcgen05.fence::before_thread_sync;");
-    asm volatile("bar.sync 1, %0;" ::"n"(128 * G));
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::CONSUMER_WARPS * G));
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(512));
 }

@@ -549,7 +549,7 @@ static int launch_tmem(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y,
     const int32_t ntx = (p->st.s + Cfg::TILE_X - 1) / Cfg::TILE_X;
     const int32_t nty = (p->ny + Cfg::TILE_Y - 1) / Cfg::TILE_Y;
     const int64_t items = (int64_t)ntx * nty * sc->nblk;
-    const int64_t grid = std::min<int64_t>((items + G - 1) / G, (int64_t)p->n_sm);
+    const int64_t grid = std::min<int64_t>((items + Cfg::G - 1) / Cfg::G, (int64_t)p->n_sm);
     SPUQ_CUDA_TRY(cudaMemsetAsync(p->d_work_counter, 0, sizeof(unsigned long long), stream));
     static const int32_t debug_flags = std::getenv("SPUQ_KDEBUG") ? std::atoi(std::getenv("SPUQ_KDEBUG")) : 0;
     CUtensorMap mw, ma;
@@ -625,12 +625,12 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
         if (use_tmem) {
             // rows_per_thread selects the number of consumer groups G (0 = default 2); cols_per_block = K
             const int32_t G = p->rows_per_thread > 0 ? p->rows_per_thread : 2;
-            SPUQ_REQUIRE(G == 1 || G == 2, "apply: TMEM kernel supports 1 or 2 consumer groups (got %d)", G);
+            SPUQ_REQUIRE(G >= 1 && G <= 3, "apply: TMEM kernel supports 1 or 2 consumer groups, or 3 = one fused 8-warp group (got %d)", G);
             const int32_t Kmax = p->nine ? (G == 1 ? 2 : 1) : (G == 1 ? 3 : 2);
             const int32_t K = p->cols_per_block > 0 ? p->cols_per_block : Kmax;
             SPUQ_REQUIRE(K >= 1 && K <= Kmax, "apply: TMEM kernel with %d group(s) supports 1..%d register sets (got %d)",
                          G, Kmax, K);
-            const int32_t block_cols = 512 / G / SCHED_ACC_STRIDE - 1;
+            const int32_t block_cols = (G == 1 ? 512 : 256) / SCHED_ACC_STRIDE - 1;
             if (p->sched_K != K || p->sched_C != block_cols) {
                 int rc = build_schedule(p, K, block_cols, G == 1 ? 4 : 2);      // = TmemCfg::W_GROUP
                 if (rc) return rc;
@@ -654,10 +654,13 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
                 else if (G == 1 && K == 3) rc = launch_tmem<3, false, 1>(p, W, ldw, Y, ldy, stream, gate);
                 else if (G == 2 && K == 1) rc = launch_tmem<1, false, 2>(p, W, ldw, Y, ldy, stream, gate);
                 else if (G == 2 && K == 2) rc = launch_tmem<2, false, 2>(p, W, ldw, Y, ldy, stream, gate);
+                else if (G == 3 && K == 1) rc = launch_tmem<1, false, 3>(p, W, ldw, Y, ldy, stream, gate);
+                else if (G == 3 && K == 2) rc = launch_tmem<2, false, 3>(p, W, ldw, Y, ldy, stream, gate);
             } else {
                 if (G == 1 && K == 1) rc = launch_tmem<1, true, 1>(p, W, ldw, Y, ldy, stream, gate);
                 else if (G == 1 && K == 2) rc = launch_tmem<2, true, 1>(p, W, ldw, Y, ldy, stream, gate);
                 else if (G == 2 && K == 1) rc = launch_tmem<1, true, 2>(p, W, ldw, Y, ldy, stream, gate);
+                else if (G == 3 && K == 1) rc = launch_tmem<1, true, 3>(p, W, ldw, Y, ldy, stream, gate);
             }
             if (rc) return rc;
             p->last_launches = 2;      // counter reset + kernel

@@ -55,7 +55,7 @@ def check_apply_paths(n=12, M=4, p=2, kind="legendre", mu=0.0):
         seen.add(plan.kernel_name)
     assert {"k_apply_csr", "k_apply_ell<8>"} <= seen
     for tune in [(1, 0, 0, 0), (2, 8, 2, 0), (2, 4, 2, 0), (2, 16, 2, 0), (2, 8, 1, 0), (2, 16, 1, 0), (2, 4, 4, 0),
-                 (4, 1, 0, 0), (4, 2, 0, 0), (4, 1, 1, 0), (4, 2, 1, 0), (4, 3, 1, 0)]:
+                 (4, 1, 0, 0), (4, 2, 0, 0), (4, 1, 1, 0), (4, 2, 1, 0), (4, 3, 1, 0), (4, 2, 3, 0)]:
         Y, plan = product_apply(c, _abi.PATH_STENCIL, tune)
         assert relerr(Y, c.Y) <= TOL, (tune, plan.kernel_name, relerr(Y, c.Y))
     info = plan.info()
@@ -249,7 +249,7 @@ def check_apply_multiblock():
     for n, idx, M, kind, mu in cases:
         assert idx.shape[0] > 64
         c = fd_case(n, M, idx, kind, mu)
-        for tune in [(4, 1, 0, 0), (4, 3, 1, 0), (4, 2, 1, 0), None]:
+        for tune in [(4, 1, 0, 0), (4, 3, 1, 0), (4, 2, 1, 0), (4, 2, 3, 0), None]:
             Y, plan = product_apply(c, _abi.PATH_STENCIL, tune)
             assert relerr(Y, c.Y) <= TOL, (tune, plan.kernel_name, relerr(Y, c.Y))
         total = np.zeros_like(c.Y)

@@ -62,7 +62,7 @@ def test_apply_tmem_variants(n, M, p, kind, mu):
     from tests.cases import fd_case, relerr
     idx = synthetic.complete_order_indices(M, p)
     c = fd_case(n, M, idx, kind, mu)
-    for tune in [(4, 1, 0, 0), (4, 2, 0, 0), (4, 1, 1, 0), (4, 2, 1, 0), (4, 3, 1, 0)]:
+    for tune in [(4, 1, 0, 0), (4, 2, 0, 0), (4, 1, 1, 0), (4, 2, 1, 0), (4, 3, 1, 0), (4, 2, 3, 0), (4, 1, 3, 0)]:
         Y, plan = ps.product_apply(c, _abi.PATH_STENCIL, tune)
         assert "tmem" in plan.kernel_name
         assert relerr(Y, c.Y) <= ps.TOL, (tune, plan.kernel_name, relerr(Y, c.Y))
@@ -72,7 +72,7 @@ def test_apply_tmem_nine_point():
     from spuq_b200 import _abi, synthetic
     from tests.cases import relerr
     c = ps.nine_point_case(72, 40, 3, synthetic.complete_order_indices(3, 2))
-    for tune in [(4, 1, 0, 0), (4, 1, 1, 0), (4, 2, 1, 0)]:
+    for tune in [(4, 1, 0, 0), (4, 1, 1, 0), (4, 2, 1, 0), (4, 1, 3, 0)]:
         Y, plan = ps.product_apply(c, _abi.PATH_STENCIL, tune)
         assert "tmem" in plan.kernel_name and "9pt" in plan.kernel_name
         assert relerr(Y, c.Y) <= ps.TOL, (tune, relerr(Y, c.Y))
@@ -248,7 +248,7 @@ def test_full_size_config3_hermite_shifted():
     reference's default NormalRV(mu=0.5) (beta0 != 0): 8 GB per slab."""
     from spuq_b200 import synthetic
     idx = synthetic.anisotropic_indices(50, 11.3)
-    _full_size(1000, 50, idx, "hermite", 0.5, [0, 3, 50, 500, 987], [(2, 4, 2, 0), (3, 8, 2, 0), (4, 3, 1, 0)])
+    _full_size(1000, 50, idx, "hermite", 0.5, [0, 3, 50, 500, 987], [(2, 4, 2, 0), (3, 8, 2, 0), (4, 3, 1, 0), (4, 2, 3, 0)])
 
 
 def test_parametric_samples():
