@@ -7,6 +7,7 @@ Restates
   * ``PreconditioningOperator``     reference src/spuq/application/egsz/multi_operator2.py:139-165
   * ``pcg``                         reference src/spuq/application/egsz/pcg.py:15-53
   * ``ForgetfulVector``             reference src/spuq/utils/forgetful_vector.py:46-66
+  * ``refine_y``                    reference src/spuq/application/egsz/marking2.py:205-208
   * ``sample_realization``, ``compute_parametric_sample_solution``
                                     reference src/spuq/application/egsz/coefficient_field.py:45-52,
                                     src/spuq/application/egsz/sampling.py:59-75
@@ -340,6 +341,15 @@ def pcg_solve(A, w, coeff_field, pde, stats, pcg_eps, pcg_maxiter):
     stats["DOFS"] = sum(b[mu].basis.dim for mu in b.keys())
     stats["CELLS"] = sum(pde.num_cells(b[mu].basis) for mu in b.keys())
     return w, zeta
+
+
+def refine_y(w, new_mi):
+    """Marking.refine_y, marking2.py:205-208: a zero vector for every new multi-index."""
+    some = w[w.active_indices()[0]]
+    for mu in new_mi:
+        z = some.copy()
+        z.coeffs = np.zeros_like(some.coeffs)
+        w[mu] = z
 
 
 def compute_parametric_sample_solution(RV_samples, coeff_field, w, proj_basis=None, cache=None):

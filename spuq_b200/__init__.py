@@ -18,5 +18,6 @@ from .multi_operator import MultiOperator, PreconditioningOperator, DeviceBlocks
 from .pcg import pcg
 from .adaptive_solver import prepare_rhs, pcg_solve, error_norm
 from .sampling import compute_parametric_sample_solution, sample_solutions
+from .marking import Marking
 
 __version__ = "0.1.0"

@@ -344,6 +344,50 @@ def check_pcg_solve(n=10, M=3, p=2, kind="hermite", mu=0.5):
     assert np.max(np.abs(x2.to_array() - x.to_array())) <= 1e-12
 
 
+# ---- growth of Lambda between solves ---------------------------------------
+def check_lambda_growth():
+    """Marking.refine_y (marking2.py:205-208) on a slab: the grown vector has the oracle's keys in the
+    oracle's order, old columns untouched, new ones zero; the operator applied to it (fresh neighbour
+    tables for the grown set) matches the oracle; batched insertion == one-by-one insertion."""
+    M = 4
+    idx_all = synthetic.complete_order_indices(M, 3)
+    start = [k for k in range(idx_all.shape[0]) if idx_all[k].sum() <= 2]
+    idx0 = idx_all[start]
+    rest = [k for k in range(idx_all.shape[0]) if idx_all[k].sum() == 3]
+    new_rows = [idx_all[k] for k in rest[::3]]                          # a scattered third of the degree-3 shell
+    c = fd_case(8, M, idx0, "hermite", 0.5)
+    new_o = [omi.Multiindex(np.asarray(r, dtype=np.int64)) for r in new_rows]
+    new_p = [sp.Multiindex(r) for r in new_rows]
+    w_o = c.w.copy()
+    osg.refine_y(w_o, new_o)
+    w = sp.SlabMultiVector.from_array(idx0, c.W)
+    before = {mu: w[mu].as_array().copy() for mu in w.active_indices()}
+    sp.Marking.refine_y(w, new_p)
+    assert len(w) == len(w_o) == idx0.shape[0] + len(new_rows)
+    assert [tuple(mu.as_array) for mu in w.active_indices()] == [tuple(mu.as_array) for mu in w_o.active_indices()]
+    for mu in w.active_indices():
+        col = w[mu].as_array()
+        assert np.array_equal(col, before[mu]) if mu in before else not col.any()
+    # one by one gives the same slab and the same order
+    w1 = sp.SlabMultiVector.from_array(idx0, c.W)
+    for mu in new_p:
+        w1[mu] = sp.FlatVector(np.zeros(c.N), w1.spatial_basis)
+    assert w1.active_indices() == w.active_indices() and torch.equal(w1.slab, w.slab)
+    sp.Marking.refine_y(w, new_p[:2])                                   # already active: nothing changes
+    assert torch.equal(w1.slab, w.slab)
+    # the operator on the grown set: new columns receive contributions from their neighbours
+    A = sp.MultiOperator.from_blocks(device_blocks(c), c.rvs)
+    Y = A.apply(w).to_array()
+    Y_o = (c.A * w_o).to_slab()
+    assert relerr(Y, Y_o) <= TOL
+    grown_cols = [k for k, mu in enumerate(w.active_indices()) if mu not in before]
+    assert np.abs(Y[:, grown_cols]).max() > 0.0
+    # a dictionary MultiVector grows the reference's way
+    wd = sp.SlabMultiVector.from_array(idx0, c.W).to_multivector()
+    sp.Marking.refine_y(wd, new_p)
+    assert len(wd) == len(w)
+
+
 # ---- evaluation at parameter samples (SURVEY.md 8f, row f4) ---------------------------------------
 def check_parametric_samples():
     """compute_parametric_sample_solution (sampling.py:59-75) and its many-sample form against the

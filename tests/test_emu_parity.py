@@ -86,3 +86,7 @@ def test_row_sharded_pcg_single_rank():
 
 def test_parametric_samples():
     ps.check_parametric_samples()
+
+
+def test_lambda_growth():
+    ps.check_lambda_growth()

@@ -253,3 +253,7 @@ def test_full_size_config3_hermite_shifted():
 
 def test_parametric_samples():
     ps.check_parametric_samples()
+
+
+def test_lambda_growth():
+    ps.check_lambda_growth()
