@@ -2,13 +2,14 @@
 // tensor memory.
 //
 // Why this shape (rates measured with tools/microbench.cu on a B200):
-//   * an SM issues 64 DFMA/clk but its shared-memory pipe moves 128 B/clk (16 doubles) and a
-//     conflict-free LDS of the 5-point window costs 4 doubles per grid point, so a kernel that reads
-//     one operand per term from shared memory is bound by LDS at < 40 % of the FP64 rate;
+//   * an SM issues 64 DFMA/clk but its shared-memory pipe moves 128 B/clk (16 doubles) and the window
+//     of the 5-point stencil costs 3 doubles per grid point, so a kernel that reads one operand per
+//     term from shared memory is bound by LDS at < 40 % of the FP64 rate (and this one still is the
+//     shared-memory pipe's customer first: see the halo loads below);
 //   * tensor memory is a second, private, 256 KB on-chip store with its own datapath (measured
 //     385 B/clk/SM load, 650 B/clk/SM store) -- the tcgen05 accumulator file.  This kernel uses it
 //     the way a tcgen05 GEMM does, as the accumulator home, but fills it from the FP64 CUDA cores
-//     (tcgen05.ld / DFMA / tcgen05.st): 64 output columns x 4 grid points per thread.  That frees the
+//     (tcgen05.ld / DFMA / tcgen05.st): 32 or 64 output columns x 4 grid points per thread.  That frees the
 //     register file to hold K block-matrix tiles at once, so ONE window read from shared memory
 //     serves every (matrix, output column) pair of the block that needs that input column.
 //
@@ -20,10 +21,11 @@
 //                                    outside the grid = the homogeneous boundary),
 //     - the A tile of every matrix  (box 64 x 8 x D of the diagonal storage),
 //     - the 2 KB chunks of the block's record stream,
-// into three shared-memory rings per group.  The consumers interpret the stream: ASET loads the A
-// tiles of a set into registers, RUN / RUN2 loop over regular (padded) jobs -- window(s) from shared
-// memory into registers, for every matrix of the job the stencil (20 DFMA per window) and S
-// read-modify-writes of TMEM accumulators -- and STOREALL writes the finished columns of Y.
+// into three shared-memory rings per group.  The consumers interpret the stream: a SET header loads
+// the A tiles of a register set and gives the lengths of its five runs of regular (padded) jobs --
+// window(s) from shared memory into registers, for every matrix of the job the stencil (20 DFMA per
+// window) and S read-modify-writes of TMEM accumulators -- and STOREALL writes the finished columns
+// of Y.  G = 3 selects ONE fused group of eight warps on a 64 x 16 tile (TmemCfg).
 // Control flow is warp-uniform throughout.
 //
 // Reference semantics: MultiOperator.apply, application/egsz/multi_operator2.py:38-84; only the

@@ -5,12 +5,12 @@
 // Per SM the scarce resource is shared-memory bandwidth (128 B/clk against 64 DFMA/clk), so the
 // schedule keeps BOTH stencil operands in registers and the accumulators in tensor memory:
 //
-//   block   = up to 64 output columns of Y whose accumulators (4 grid points per thread) fill the
-//             512 TMEM columns of a CTA;
+//   block   = 63 (one consumer group) or 31 (two groups) output columns of Y whose accumulators
+//             (4 grid points per thread) fill the group's TMEM columns, plus one scratch accumulator;
 //   A-set   = up to K block matrices of that block whose tiles sit in registers at the same time;
 //   job     = one input column: its window is read from shared memory ONCE and used by every
-//             (matrix of the set, output column of the block) pair that needs it; jobs are processed
-//             two at a time (window buffers A and B);
+//             (matrix of the set, output column of the block) pair that needs it; jobs with the same
+//             matrices and disjoint outputs are processed two at a time (window buffers A and B);
 //   op      = one term: optional stencil evaluation S = A_k * window, then acc[out] += coef * S.
 //
 // The host flattens this into a stream of 16-byte records per block, cut into 2 KB chunks that
@@ -30,48 +30,43 @@ static_assert(sizeof(SchedRec) == 16, "unit must be 16 bytes");
 
 // Stream of a block (all units 16 bytes, read by the consumer warps from the metadata ring):
 //
-//   ASET  cnt                    load the next cnt A tiles of the A ring into register sets 0..cnt-1
-//   RUN   S n                    n jobs follow, all with S accumulation slots per matrix.  Every job is
-//                                1 + K*ceil(S/2) units:
-//                                  unit 0     a = REC_JOB | kmask << 4 (matrices of the set the job
-//                                             uses), words 1..3: for register set kk the TMEM column
-//                                             offsets (accumulator number * 8) of its S slots, 9 bits each
-//                                  unit 1+..  for every kk (used or not) ceil(S/2) units holding the
-//                                             slot coefficients (two doubles per unit)
-//                                A slot that is not needed points at the scratch accumulator
-//                                (number block_cols) with coefficient 0, so the loop over a run is
-//                                branch-free in the data: window -> registers, then for every matrix
-//                                of kmask the stencil (20 DFMA) and S read-modify-writes of TMEM.
-//                                A job never straddles a chunk; `more` = another RUN follows in this
-//                                block (its first window is prefetched by the last job of this one).
-//   RUN2  kmask S n              n PAIRS of jobs with disjoint output columns: the consumer evaluates
-//                                both windows in one basic block (eight independent DFMA chains and
-//                                2S TMEM read-modify-writes in flight).  A pair is
-//                                  [unit 0 of job a][unit 0 of job b][coef units of a][coef units of b]
+//   SET   two header units, then the jobs of one register set:
+//           unit 0   a = REC_ASET | cnt << 4: load the next cnt A tiles of the A ring into register
+//                    sets 0..cnt-1;  b = number of single jobs with S = 3
+//           unit 1   four counts: job PAIRS with S = 1, pairs with S = 2, single jobs with S = 1,
+//                    single jobs with S = 2
+//         followed, in exactly that order, by the pairs (S = 1, then S = 2) and the single jobs
+//         (S = 1, 2, 3).  S = accumulation slots per matrix.  A job is 1 + K*ceil(S/2) units:
+//           unit 0     a = REC_JOB | kmask << 4 (matrices of the set the job uses), words 1..3: for
+//                      register set kk the TMEM column offsets (accumulator number * 8) of its S
+//                      slots, 9 bits each
+//           unit 1+..  for every kk (used or not) ceil(S/2) units holding the slot coefficients
+//                      (two doubles per unit)
+//         A slot that is not needed points at the scratch accumulator (number block_cols) with
+//         coefficient 0, so a job is branch-free in the data: window -> registers, then for every
+//         matrix of kmask the stencil (20 DFMA) and S read-modify-writes of TMEM.  A PAIR is two jobs
+//         with the same kmask and disjoint output columns, laid out as
+//           [unit 0 of job a][unit 0 of job b][coef units of a][coef units of b]
+//         the consumer evaluates both windows in one basic block (eight independent DFMA chains,
+//         2S TMEM read-modify-writes in flight).  A job (a pair) never straddles a chunk.
 //   STOREALL n                   write all accumulators to Y: n units follow, each naming the output
 //                                columns of four consecutive accumulators (-1 = none)
-//   NEXT_CHUNK                   continue in the next ring stage (rest of this chunk is unused)
+//   NEXT_CHUNK                   continue in the next ring stage (rest of this chunk is unused); may
+//                                stand wherever a unit 0 of a job or a top-level unit is expected
 //   END_ITEM
 //
-// The consumer warps are ONE warp per SM sub-partition (TMEM lane ownership: 4 points x 64 columns
-// per thread), which exposes every branch (~10 clk) and every barrier round trip (30-50 clk);
-// hence the regular, padded run format instead of one record per term.
+// Each SM sub-partition runs at most two consumer warps (TMEM lane ownership, registers), which
+// exposes every branch (~10 clk) and every barrier round trip; hence the regular, padded job format
+// with counted runs instead of one record per term.
 enum : int32_t {
     REC_END_ITEM = 0,
     REC_ASET = 2,
-    REC_STORE = 4,
     REC_NEXT_CHUNK = 5,
-    REC_RUN = 6,
     REC_JOB = 7,
-    REC_RUN2 = 8,             // like RUN, but b = number of job PAIRS (see below)
     REC_STOREALL = 9,         // b = number of accumulator quadruples; followed by that many units of 4 output columns
     REC_JOB_KMASK_SHIFT = 4,  // JOB unit 0: matrices used by the job in bits 4..7
     REC_TYPE_MASK = 0xF,
     REC_CNT_SHIFT = 4,        // ASET: count in bits 4..7
-    REC_RUN_KMASK_SHIFT = 4,  // RUN: kmask in bits 4..7
-    REC_RUN_S_SHIFT = 8,      // RUN: S in bits 8..9
-    REC_RUN_MORE = 1 << 10,   // RUN: another RUN follows in this block
-                              // RUN: b = number of jobs
 };
 
 constexpr int SCHED_CHUNK_RECS = 128;            // 2 KB
