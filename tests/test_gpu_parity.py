@@ -251,6 +251,35 @@ def test_full_size_config3_hermite_shifted():
     _full_size(1000, 50, idx, "hermite", 0.5, [0, 3, 50, 500, 987], [(2, 4, 2, 0), (3, 8, 2, 0), (4, 3, 1, 0), (4, 2, 3, 0)])
 
 
+def test_full_size_config4_apply_and_pcg():
+    """500 x 500 grid, M = 30, first 5000 indices of the degree-3 set, Legendre (10 GB per slab): the
+    apply properties, then the solve of BASELINE config 4 -- mean-based preconditioner, eps = 1e-10 --
+    checked through its manufactured solution and the residual of the returned iterate."""
+    import spuq_b200 as sp
+    from spuq_b200 import _abi, synthetic
+    from spuq_b200.multi_operator import DeviceBlocks
+    n, M = 500, 30
+    idx = synthetic.truncated_complete_indices(30, 3, 5000)
+    _full_size(n, M, idx, "legendre", 0.0, [0, 31, 2500, 4999], [(4, 3, 1, 0), (4, 2, 3, 0)])
+    torch.cuda.empty_cache()
+    dev = _abi.device()
+    N, L = n * n, idx.shape[0]
+    rowptr, colidx, vals = synthetic.fd_blocks(n, M, device=dev)
+    blocks = DeviceBlocks(rowptr, colidx, vals, (N, N))
+    A = sp.MultiOperator.from_blocks(blocks, synthetic.make_rvs("legendre", M, 0.0))
+    g = torch.Generator(device=dev); g.manual_seed(1234)
+    X = torch.rand((L, N), dtype=torch.float64, device=dev, generator=g)
+    f = A.apply(sp.SlabMultiVector(idx, slab=X, _sorted=True))
+    A0 = synthetic.blocks_to_scipy(rowptr, colidx, vals[:1], N)[0]
+    P = sp.PreconditioningOperator("mean", lambda b, f_: sp.ScipySolveOperator(A0, b, b))
+    x, zeta, it = sp.pcg(A, f, P, 0 * f, eps=1e-10, maxiter=100)
+    assert it <= 25 and zeta <= 1e-20
+    assert float((x.slab - X).abs().max()) <= 1e-10
+    r = A.apply(x)
+    r -= f
+    assert float(torch.linalg.norm(r.slab)) <= 1e-9 * float(torch.linalg.norm(f.slab))
+
+
 def test_parametric_samples():
     ps.check_parametric_samples()
 
