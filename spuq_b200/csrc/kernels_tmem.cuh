@@ -344,6 +344,8 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                 // development switch (SPUQ_KDEBUG=1): every window / A tile fetch hits the same column / matrix,
                 // i.e. always L2 -- wrong results, but the time shows what the arithmetic alone costs
                 if ((debug_flags & 1) && val != PCMD_WINDOW_PAD && kind != PCMD_META) val = 0;
+                if ((debug_flags & 2) && kind == PCMD_ATILE) val = 0;                            // 2: A tiles only
+                if ((debug_flags & 4) && kind == PCMD_WINDOW && val != PCMD_WINDOW_PAD) val = 0;   // 4: windows only
                 const bool is_w = have && kind == PCMD_WINDOW, is_a = have && kind == PCMD_ATILE,
                            is_m = have && kind == PCMD_META;
                 const uint32_t mw = __ballot_sync(0xffffffffu, is_w), ma = __ballot_sync(0xffffffffu, is_a),
