@@ -211,13 +211,27 @@ void schedule_build(const TermLists& terms, const std::vector<int32_t>& order, i
                     }
                 }
                 std::vector<char> done(n, 0);
-                for (size_t a = 0; a < n; ++a) {             // busiest pair first, an unmatched matrix last
+                for (size_t a = 0; a < n; ++a) {
                     if (done[a] || mate[a] < 0) continue;
                     grouped.push_back(slots[a]); grouped.push_back(slots[(size_t)mate[a]]);
                     done[a] = done[(size_t)mate[a]] = 1;
                 }
                 for (size_t a = 0; a < n; ++a) if (!done[a]) grouped.push_back(slots[a]);
                 rest.clear();
+                {
+                    // sets in ascending order of their smallest matrix: the blocks of a tile, which run
+                    // concurrently, then ask for the A tiles of a matrix at about the same time
+                    std::vector<std::pair<int32_t, int32_t>> prs;
+                    for (size_t i = 0; i + 1 < grouped.size(); i += 2) prs.push_back({grouped[i], grouped[i + 1]});
+                    std::vector<int32_t> tail;
+                    if (grouped.size() % 2) tail.push_back(grouped.back());
+                    std::stable_sort(prs.begin(), prs.end(), [](const std::pair<int32_t, int32_t>& x, const std::pair<int32_t, int32_t>& y) {
+                        return std::min(x.first, x.second) < std::min(y.first, y.second);
+                    });
+                    grouped.clear();
+                    for (auto& pr : prs) { grouped.push_back(pr.first); grouped.push_back(pr.second); }
+                    for (int32_t t : tail) grouped.push_back(t);
+                }
             }
             while (!rest.empty()) {
                 std::vector<int32_t> grp{rest.front()};
