@@ -21,7 +21,7 @@ Workloads (BASELINE.json configs, synthetic inputs of SURVEY.md 8d):
   c2  512 x 512 grid, M = 20, total degree 3 (1771 indices), Legendre
   c4  500 x 500 grid, M = 30, first 5000 indices of the degree-3 set, Legendre
   c1  32 x 32 grid, M = 5, total degree 2 (21 indices): the reference's CPU-runnable case
-Multi-GPU (N > 1), total work fixed => "scaling": "strong".  Default `--shard rows`: the grid rows are
+The workload is the same for every N (total work fixed) => "scaling": "strong".  Default `--shard rows`: the grid rows are
 sharded over the ranks (every rank owns N/G spatial dofs of all |Lambda| columns); one step = exchange
 of the two boundary grid rows with the neighbouring ranks (point to point over NCCL) + the single-GPU
 kernel on the local grid.  `--shard m` is the decomposition BASELINE.json's north_star describes: the M
@@ -384,7 +384,7 @@ def run_gpu(args):
         "value": N * L / (ms_per_step * 1e-3) / 1e9, "unit": "GDoF/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config), "N": N, "L": L, "M": M,
                    "n_terms": info["n_terms"], "nnz_per_block": info["nnz"],
@@ -454,7 +454,7 @@ def run_reference(args):
     value = N * L / (ms * 1e-3) / 1e9
     out = {"impl": "reference", "metric": "SG operator apply throughput (N*|Lambda| per apply)",
            "value": value, "unit": "GDoF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload_name(args.config), "N": N, "L": L, "M": cfg["M"]},
            "cpu_baseline": {"value": value, "unit": "GDoF/s", "cores": len(parts), "kind": "port",
