@@ -663,7 +663,7 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
                 else if (G == 3 && K == 1) rc = launch_tmem<1, true, 3>(p, W, ldw, Y, ldy, stream, gate);
             }
             if (rc) return rc;
-            p->last_launches = 2;      // counter reset + kernel
+            p->last_launches = 1;      // the kernel (the work counter is reset by a memset node, not a kernel)
             SPUQ_CUDA_TRY(cudaGetLastError());
             return SPUQ_OK;
 #endif
