@@ -191,6 +191,28 @@ class CpuReference:
 
 
 # ---- GPU arm ----------------------------------------------------------------------------------------
+def _bind_to_gpu_numa_node(torch, local):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is
+    allocated: with several ranks the host<->device copies of the e2e leg otherwise cross the socket
+    interconnect for the GPUs of the other socket.  Best effort (sysfs); returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        dev = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + dev
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -200,6 +222,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus)
     torch.cuda.set_device(local)
+    numa = _bind_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import spuq_b200 as sp
@@ -392,7 +415,8 @@ def run_gpu(args):
                                    ("grid rows sharded x%d, halo rows exchanged point-to-point (NCCL) every step" % world) if rows_mode
                                    else ("M-sharded x%d + NCCL reduce-scatter over Lambda" % world)),
                    "l2_note": "input slab %.1f GB >> 126 MB L2, no flush needed" % (N * L * 8 / 1e9),
-                   "kernel": plan.kernel_name, "path": info["path"]},
+                   "kernel": plan.kernel_name, "path": info["path"],
+                   "host_numa_node_rank0": numa},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes": info["algorithmic_bytes"], "kernel_ms": kernel_ms,
