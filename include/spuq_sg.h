@@ -200,6 +200,20 @@ SPUQ_API int spuq_sg_precond_from_plan(spuq_sg_precond** out, spuq_sg_plan* plan
  * solve of ScipySolveOperator.apply / FEniCSSolveOperator.apply (linalg/scipy_operator.py:45-49). */
 SPUQ_API int spuq_sg_precond_mean_fd(spuq_sg_precond** out, int device, int32_t nx, int32_t ny,
                             double d, double ox, double oy);
+/* The mean_fd solve in two halves, for callers that complete the y direction themselves (grid rows
+ * sharded over GPUs: spuq_b200.sharding, partition method for the tridiagonal systems along y).
+ *   forward: T = (tridiagonal solves along the handle's ny rows)(sine transform in x of R), left in the
+ *            transformed domain; position c of a grid row holds mode order[c] (..._mode_order);
+ *            work: spuq_sg_precond_work_bytes; R and T must not alias
+ *   inverse: S = sine transform back of T; T and S must not alias
+ *   spuq_sg_spike_correct: T[col][y][c] -= zl[col][c]*sl[y][c] + zr[col][c]*sr[y][c]  (L x ny x nx) */
+SPUQ_API int spuq_sg_precond_mean_fd_forward(spuq_sg_precond* p, int64_t N, int32_t L, const double* R_dev,
+                                    double* T_dev, void* work, void* stream);
+SPUQ_API int spuq_sg_precond_mean_fd_inverse(spuq_sg_precond* p, int64_t N, int32_t L, const double* T_dev,
+                                    double* S_dev, void* stream);
+SPUQ_API int spuq_sg_precond_mean_fd_mode_order(const spuq_sg_precond* p, int32_t* order_host);
+SPUQ_API int spuq_sg_spike_correct(int32_t L, int32_t ny, int32_t nx, double* T_dev, const double* zl_dev,
+                          const double* zr_dev, const double* sl_dev, const double* sr_dev, void* stream);
 SPUQ_API int spuq_sg_precond_destroy(spuq_sg_precond* p);
 /* workspace (bytes) precond_apply needs for an N x L slab */
 SPUQ_API int64_t spuq_sg_precond_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L);

@@ -62,6 +62,10 @@ SIGNATURES = {
     "spuq_sg_axpy2": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spuq_sg_xpay": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "spuq_sg_scal": (C.c_int, [C.c_int64, C.c_double, _vp, _vp]),
+    "spuq_sg_precond_mean_fd_forward": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp]),
+    "spuq_sg_precond_mean_fd_inverse": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp]),
+    "spuq_sg_precond_mean_fd_mode_order": (C.c_int, [_vp, _vp]),
+    "spuq_sg_spike_correct": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spuq_sg_combine": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp]),
     "spuq_sg_precond_identity": (C.c_int, [C.POINTER(_vp), C.c_double]),
     "spuq_sg_precond_from_plan": (C.c_int, [C.POINTER(_vp), _vp]),

@@ -283,9 +283,118 @@ int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, dou
     return SPUQ_OK;
 }
 
+// ---- the solve split in two, for callers that finish the y direction themselves -------------------
+// forward: T = (local tridiagonal solves along y)(sine transform in x of R), in the transformed domain
+// (mode of transformed position c: mean_fd_mode_order); inverse: S = sine transform back of T.
+int mean_fd_forward(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* T, void* work,
+                    cudaStream_t stream) {
+    SPUQ_REQUIRE(N == (int64_t)p->nx * p->ny, "precond_mean_fd: slab rows %lld != nx*ny", (long long)N);
+    SPUQ_REQUIRE(R != T, "precond_mean_fd_forward: input and output must not alias");
+    const int64_t Mrows = (int64_t)L * p->ny;
+    const double* gate = nullptr;
+    auto rowgemm = [&](const double* src, double* dst, int32_t nk, int32_t nc, const double* Q) {
+#ifndef SPUQ_EMU
+        if (blas_rowgemm(p, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, stream)) return;
+#endif
+        const dim3 g((unsigned)((Mrows + GM - 1) / GM), (unsigned)((nc + GN - 1) / GN));
+        SPUQ_LAUNCH(k_rowgemm, g, dim3(G_THREADS), 0, stream, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, gate);
+    };
+    const int64_t nthreads = (int64_t)L * p->nx;
+    const int32_t h = p->half;
+    if (h > 0) {
+        SPUQ_REQUIRE(work != nullptr, "precond_mean_fd_forward: workspace missing");
+        double* U = static_cast<double*>(work);
+        const size_t hh = (size_t)h * h;
+        const unsigned eb = (unsigned)std::min<int64_t>((Mrows * h + 255) / 256, 1 << 20);
+        SPUQ_LAUNCH(k_mirror_split, dim3(eb), dim3(256), 0, stream, Mrows, p->nx, R, U, gate);
+        rowgemm(U, T, h, h, p->qsplit_dev);
+        rowgemm(U + h, T + h, h, h, p->qsplit_dev + hh);
+        SPUQ_LAUNCH(k_thomas_y, dim3((unsigned)((nthreads + 127) / 128)), dim3(128), 0, stream, p->nx, p->ny, L,
+                    p->oy, p->piv_split_dev, T, gate);
+    } else {
+        rowgemm(R, T, p->nx, p->nx, p->q_dev);
+        SPUQ_LAUNCH(k_thomas_y, dim3((unsigned)((nthreads + 127) / 128)), dim3(128), 0, stream, p->nx, p->ny, L,
+                    p->oy, p->piv_dev, T, gate);
+    }
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+
+int mean_fd_inverse(spuq_sg_precond* p, int64_t N, int32_t L, const double* T, double* S, cudaStream_t stream) {
+    SPUQ_REQUIRE(N == (int64_t)p->nx * p->ny, "precond_mean_fd: slab rows %lld != nx*ny", (long long)N);
+    SPUQ_REQUIRE(T != S, "precond_mean_fd_inverse: input and output must not alias");
+    const int64_t Mrows = (int64_t)L * p->ny;
+    const double* gate = nullptr;
+    auto rowgemm = [&](const double* src, double* dst, int32_t nk, int32_t nc, const double* Q) {
+#ifndef SPUQ_EMU
+        if (blas_rowgemm(p, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, stream)) return;
+#endif
+        const dim3 g((unsigned)((Mrows + GM - 1) / GM), (unsigned)((nc + GN - 1) / GN));
+        SPUQ_LAUNCH(k_rowgemm, g, dim3(G_THREADS), 0, stream, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, gate);
+    };
+    const int32_t h = p->half;
+    if (h > 0) {
+        const size_t hh = (size_t)h * h;
+        const unsigned eb = (unsigned)std::min<int64_t>((Mrows * h + 255) / 256, 1 << 20);
+        rowgemm(T, S, h, h, p->qsplit_dev + 2 * hh);
+        rowgemm(T + h, S + h, h, h, p->qsplit_dev + 3 * hh);
+        SPUQ_LAUNCH(k_mirror_merge, dim3(eb), dim3(256), 0, stream, Mrows, p->nx, S, gate);
+    } else {
+        rowgemm(T, S, p->nx, p->nx, p->q_dev);
+    }
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+
+// T[col][y][c] -= zl[col][c] * sl[y][c] + zr[col][c] * sr[y][c]: the interface corrections of the
+// partition method for tridiagonal systems split over ranks (lanes along the mode index c)
+__global__ void __launch_bounds__(256)
+k_spike_correct(int32_t L, int32_t ny, int32_t nx, double* __restrict__ T, const double* __restrict__ zl,
+                const double* __restrict__ zr, const double* __restrict__ sl, const double* __restrict__ sr) {
+    const int64_t total = (int64_t)L * ny * nx;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = (int32_t)(t % nx);
+        const int64_t r = t / nx;
+        const int32_t y = (int32_t)(r % ny);
+        const int64_t col = r / ny;
+        T[t] -= zl[col * nx + c] * sl[(int64_t)y * nx + c] + zr[col * nx + c] * sr[(int64_t)y * nx + c];
+    }
+}
+
 }  // namespace spuq
 
 using namespace spuq;
+
+extern "C" int spuq_sg_precond_mean_fd_forward(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* T,
+                                               void* work, void* stream) {
+    SPUQ_REQUIRE(p && p->kind == spuq_sg_precond::MEAN_FD && R && T, "precond_mean_fd_forward: needs a mean_fd handle");
+    return mean_fd_forward(p, N, L, R, T, work, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int spuq_sg_precond_mean_fd_inverse(spuq_sg_precond* p, int64_t N, int32_t L, const double* T, double* S,
+                                               void* stream) {
+    SPUQ_REQUIRE(p && p->kind == spuq_sg_precond::MEAN_FD && T && S, "precond_mean_fd_inverse: needs a mean_fd handle");
+    return mean_fd_inverse(p, N, L, T, S, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int spuq_sg_precond_mean_fd_mode_order(const spuq_sg_precond* p, int32_t* order) {
+    SPUQ_REQUIRE(p && p->kind == spuq_sg_precond::MEAN_FD && order, "precond_mean_fd_mode_order: needs a mean_fd handle");
+    const int32_t h = p->half;
+    for (int32_t c = 0; c < p->nx; ++c) order[c] = h > 0 ? (c < h ? 2 * c : 2 * (c - h) + 1) : c;
+    return SPUQ_OK;
+}
+
+extern "C" int spuq_sg_spike_correct(int32_t L, int32_t ny, int32_t nx, double* T, const double* zl, const double* zr,
+                                     const double* sl, const double* sr, void* stream) {
+    SPUQ_REQUIRE(L >= 0 && ny >= 1 && nx >= 1 && T && zl && zr && sl && sr, "spike_correct: bad argument");
+    const int64_t total = (int64_t)L * ny * nx;
+    if (total == 0) return SPUQ_OK;
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 1 << 20);
+    SPUQ_LAUNCH(k_spike_correct, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), L, ny, nx, T, zl, zr, sl, sr);
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+
 
 extern "C" int spuq_sg_precond_mean_fd(spuq_sg_precond** out, int device, int32_t nx, int32_t ny,
                                        double d, double ox, double oy) {

@@ -6,6 +6,9 @@ owning the r-th contiguous block of output columns.
 The reference has no multi-process code at all; the split is the sum over m
 of application/egsz/multi_operator2.py:59-82, which is independent per m.
 """
+import ctypes as C
+import math
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -15,7 +18,8 @@ from .multi_vector import _axpy, _dot, _scal
 from .pcg import PCG_MESSAGES
 from . import _abi
 
-__all__ = ["shard_ranges", "padded_columns", "ShardedApply", "row_ranges", "RowShardedApply", "RowShardedPCG"]
+__all__ = ["shard_ranges", "padded_columns", "ShardedApply", "row_ranges", "RowShardedApply", "RowShardedPCG",
+           "PartitionedMeanSolver"]
 
 
 def shard_ranges(tables, M, world):
@@ -146,6 +150,108 @@ class RowShardedApply:
         return Y
 
 
+def _const_tridiag_solve(b, o, rhs):
+    """Solve tridiag(o, b[k], o) x = rhs for all k at once (Thomas, vectorised over the last axis):
+    b: [nk], rhs: [n, nk] -> [n, nk]."""
+    n = rhs.shape[0]
+    piv = np.empty_like(rhs)
+    x = rhs.astype(np.float64).copy()
+    piv[0] = b
+    for y in range(1, n):
+        piv[y] = b - o * o / piv[y - 1]
+        x[y] -= o / piv[y - 1] * x[y - 1]
+    x[n - 1] /= piv[n - 1]
+    for y in range(n - 2, -1, -1):
+        x[y] = (x[y] - o * x[y + 1]) / piv[y]
+    return x
+
+
+class PartitionedMeanSolver:
+    """A_0^{-1} on ROW-sharded slabs without moving the slab: the mean block is diagonalised in x (rows
+    are whole on every rank) and the tridiagonal systems along y, which cross the ranks, are solved by
+    the partition method.  Rank p solves its own diagonal block for the right-hand side (library:
+    spuq_sg_precond_mean_fd_forward on the local nx x n_p grid); the influence of the two neighbouring
+    interface values enters through the block's first / last columns of its inverse (the spikes), which
+    depend on the mode and the block size only and are set-up data.  The 2P interface values of every
+    (mode, column) satisfy a 2P x 2P system whose matrix depends on the mode only: it is inverted at
+    set-up, every rank all-gathers the 2 x nx x |Lambda| boundary values and evaluates the two rows it
+    needs.  Per call: two streaming corrections and one small all-gather instead of two transpositions
+    of the whole slab."""
+
+    def __init__(self, nx, ny, ranges, rank, stencil, group=None):
+        from .multi_operator import MeanSolveSlabOperator
+        d, ox, oy = stencil
+        self.nx, self.ny, self.ranges, self.rank, self.group = int(nx), int(ny), list(ranges), int(rank), group
+        self.P = len(self.ranges)
+        sizes = [r1 - r0 for r0, r1 in self.ranges]
+        if ny < 2 or min(sizes) < 2:
+            raise ValueError("PartitionedMeanSolver needs at least two grid rows on every rank")
+        self.n_loc = sizes[rank]
+        self.local = MeanSolveSlabOperator(None, 1, stencil=(nx, self.n_loc, d, ox, oy))
+        order = np.empty(nx, dtype=np.int32)
+        _abi.check(_abi.lib().spuq_sg_precond_mean_fd_mode_order(self.local.handle, order.ctypes.data_as(C.c_void_p)),
+                   "mode_order")
+        k = order.astype(np.float64)
+        lam = 0.5 * d + 2.0 * ox * np.cos((k + 1.0) * math.pi / (nx + 1.0))       # eigenvalues of the x part
+        b = 0.5 * d + lam                                                         # diagonal of the y systems
+        P = self.P
+        first, last = [], []                                                      # spikes at the block ends, all ranks
+        mine = None
+        for q, nq in enumerate(sizes):
+            e0 = np.zeros((nq, nx)); e0[0] = 1.0
+            e1 = np.zeros((nq, nx)); e1[nq - 1] = 1.0
+            sl, sr = _const_tridiag_solve(b, oy, e0), _const_tridiag_solve(b, oy, e1)
+            first.append((sl[0], sr[0])); last.append((sl[nq - 1], sr[nq - 1]))
+            if q == rank:
+                mine = (sl, sr)
+        # reduced system in the unknowns (a_0, z_0, a_1, z_1, ...) = (first, last value of every block)
+        Mred = np.zeros((nx, 2 * P, 2 * P))
+        for q in range(P):
+            for row, (sl_v, sr_v) in ((2 * q, first[q]), (2 * q + 1, last[q])):
+                Mred[:, row, row] = 1.0
+                if q > 0:
+                    Mred[:, row, 2 * (q - 1) + 1] += oy * sl_v
+                if q < P - 1:
+                    Mred[:, row, 2 * (q + 1)] += oy * sr_v
+        Minv = np.linalg.inv(Mred)
+        dev = _abi.device()
+        zero = np.zeros((nx, 2 * P))
+        cz = Minv[:, 2 * (rank - 1) + 1, :] if rank > 0 else zero                 # z_{p-1} = cz . g
+        ca = Minv[:, 2 * (rank + 1), :] if rank < P - 1 else zero                 # a_{p+1} = ca . g
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)          # noqa: E731
+        self.cz, self.ca = up(cz.T), up(ca.T)                                     # [2P, nx]
+        self.sl, self.sr = up(oy * mine[0]), up(oy * mine[1])                     # [n_loc, nx], coupling folded in
+        self._work = None
+
+    def solve(self, Rc, Sc):
+        """Rc, Sc: contiguous L x (n_loc * nx) slabs of the owned rows; Sc = (A_0^{-1} R) restricted to them."""
+        lib = _abi.lib()
+        L = Rc.shape[0]
+        N = self.n_loc * self.nx
+        assert Rc.is_contiguous() and Sc.is_contiguous() and Rc.shape == (L, N) and Sc.shape == (L, N)
+        need = int(lib.spuq_sg_precond_work_bytes(self.local.handle, N, L))
+        if self._work is None or self._work.numel() * 8 < need:
+            self._work = torch.empty(need // 8 + 1, dtype=torch.float64, device=Rc.device)
+        T = torch.empty_like(Rc)
+        _abi.check(lib.spuq_sg_precond_mean_fd_forward(self.local.handle, N, L, _abi.ptr(Rc), _abi.ptr(T),
+                                                       _abi.ptr(self._work), _abi.stream_ptr()), "mean_fd_forward")
+        T3 = T.view(L, self.n_loc, self.nx)
+        mine = torch.stack([T3[:, 0, :], T3[:, self.n_loc - 1, :]]).contiguous()   # [2, L, nx]
+        if self.P > 1:
+            parts = [torch.empty_like(mine) for _ in range(self.P)]
+            dist.all_gather(parts, mine, group=self.group)
+            g = torch.cat(parts)                                                  # [2P, L, nx], unknown order
+        else:
+            g = mine
+        zl = torch.einsum("jk,jlk->lk", self.cz, g).contiguous()                   # [L, nx]
+        zr = torch.einsum("jk,jlk->lk", self.ca, g).contiguous()
+        _abi.check(lib.spuq_sg_spike_correct(L, self.n_loc, self.nx, _abi.ptr(T), _abi.ptr(zl), _abi.ptr(zr),
+                                             _abi.ptr(self.sl), _abi.ptr(self.sr), _abi.stream_ptr()), "spike_correct")
+        _abi.check(lib.spuq_sg_precond_mean_fd_inverse(self.local.handle, N, L, _abi.ptr(T), _abi.ptr(Sc),
+                                                       _abi.stream_ptr()), "mean_fd_inverse")
+        return Sc
+
+
 class RowShardedPCG:
     """``pcg`` (application/egsz/pcg.py:15-53) on row-sharded slabs.
 
@@ -161,7 +267,7 @@ class RowShardedPCG:
     The reference's four failure conditions are checked on the all-reduced scalars, so all ranks
     take the same branch."""
 
-    def __init__(self, sharded_apply, nx, ny, ranges, mean_stencil=None):
+    def __init__(self, sharded_apply, nx, ny, ranges, mean_stencil=None, mean_solver="partition"):
         self.A = sharded_apply
         self.group = sharded_apply.group
         self.world, self.rank = sharded_apply.world, sharded_apply.rank
@@ -170,7 +276,15 @@ class RowShardedPCG:
         self.y0, self.y1 = self.ranges[self.rank]
         self.nyl = self.y1 - self.y0 + 2
         self.mean_stencil = mean_stencil                 # (d, ox, oy) of the constant-coefficient mean block
+        # "partition": tridiagonal partition method, the slab stays row-sharded (default);
+        # "transpose": all-to-all to column shards and back around the single-GPU solver
+        if mean_solver not in ("partition", "transpose"):
+            raise ValueError("mean_solver must be 'partition' or 'transpose'")
+        self.mean_solver = mean_solver
+        if min(r1 - r0 for r0, r1 in self.ranges) < 2:
+            self.mean_solver = "transpose"
         self._solver = None
+        self._partition = None
         self.last_history = []
 
     # ---- helpers -------------------------------------------------------------------------------
@@ -216,6 +330,18 @@ class RowShardedPCG:
             return S
         L = R.shape[0]
         dev = R.device
+        if self.mean_solver == "partition":
+            if self._partition is None:
+                self._partition = PartitionedMeanSolver(self.nx, self.ny, self.ranges, self.rank, self.mean_stencil, self.group)
+            R3 = R.view(L, self.nyl, self.nx)
+            Rc = R3[:, 1:-1, :].contiguous().view(L, -1)
+            Sc = torch.empty_like(Rc)
+            self._partition.solve(Rc, Sc)
+            S3 = S.view(L, self.nyl, self.nx)
+            S3[:, 0, :].zero_()
+            S3[:, self.nyl - 1, :].zero_()
+            S3[:, 1:-1, :].copy_(Sc.view(L, self.nyl - 2, self.nx))
+            return S
         c0, c1 = self._col_range(self.rank, L)
         if self._solver is None:
             d, ox, oy = self.mean_stencil

@@ -260,6 +260,48 @@ def check_apply_multiblock():
         assert relerr(total, c.Y) <= TOL
 
 
+def check_partitioned_mean_solver():
+    """The partition method for the mean solve on row-sharded slabs (PartitionedMeanSolver), all ranks
+    simulated in one process: forward halves, the all-gather done by hand, corrections and inverse
+    halves must reproduce the global sparse direct solve; uneven partitions, even and odd nx."""
+    import scipy.sparse.linalg as spla
+    from spuq_b200.sharding import PartitionedMeanSolver
+    lib = _abi.lib()
+    rng = np.random.RandomState(3)
+    for nx, ny, ranges, L in [(6, 11, [(0, 4), (4, 7), (7, 11)], 3), (9, 8, [(0, 4), (4, 8)], 2), (16, 16, [(0, 16)], 2)]:
+        T = lambda n, o, dd: sps.diags([o, dd, o], [-1, 0, 1], shape=(n, n))      # noqa: E731
+        A0 = sps.csr_matrix(sps.kron(sps.identity(ny), T(nx, -1.0, 2.0)) + sps.kron(T(ny, -1.0, 2.0), sps.identity(nx)))
+        R = rng.random_sample((L, ny * nx))
+        lu = spla.splu(A0.tocsc())
+        ref = np.stack([lu.solve(R[k]) for k in range(L)])
+        solvers = [PartitionedMeanSolver(nx, ny, ranges, p, (4.0, -1.0, -1.0)) for p in range(len(ranges))]
+        Ts = []
+        for s_, (r0, r1) in zip(solvers, ranges):
+            Rc = _dev(torch.from_numpy(np.ascontiguousarray(R.reshape(L, ny, nx)[:, r0:r1, :]).reshape(L, -1)))
+            Tt = torch.empty_like(Rc)
+            work = torch.empty(int(lib.spuq_sg_precond_work_bytes(s_.local.handle, Rc.shape[1], L)) // 8 + 1,
+                               dtype=torch.float64, device=Rc.device)
+            _abi.check(lib.spuq_sg_precond_mean_fd_forward(s_.local.handle, Rc.shape[1], L, _abi.ptr(Rc), _abi.ptr(Tt),
+                                                           _abi.ptr(work), _abi.stream_ptr()), "forward")
+            Ts.append(Tt)
+        g = torch.cat([torch.stack([t.view(L, r1 - r0, nx)[:, 0, :], t.view(L, r1 - r0, nx)[:, -1, :]])
+                       for t, (r0, r1) in zip(Ts, ranges)])
+        out = np.zeros((L, ny, nx))
+        for s_, Tt, (r0, r1) in zip(solvers, Ts, ranges):
+            zl = torch.einsum("jk,jlk->lk", s_.cz, g).contiguous()
+            zr = torch.einsum("jk,jlk->lk", s_.ca, g).contiguous()
+            _abi.check(lib.spuq_sg_spike_correct(L, r1 - r0, nx, _abi.ptr(Tt), _abi.ptr(zl), _abi.ptr(zr), _abi.ptr(s_.sl),
+                                                 _abi.ptr(s_.sr), _abi.stream_ptr()), "correct")
+            Sc = torch.empty_like(Tt)
+            _abi.check(lib.spuq_sg_precond_mean_fd_inverse(s_.local.handle, Tt.shape[1], L, _abi.ptr(Tt), _abi.ptr(Sc),
+                                                           _abi.stream_ptr()), "inverse")
+            out[:, r0:r1, :] = Sc.view(L, r1 - r0, nx).cpu().numpy()
+        err = np.max(np.abs(out.reshape(L, -1) - ref)) / np.max(np.abs(ref))
+        assert err <= 1e-12, (nx, ny, ranges, err)
+    with pytest.raises(ValueError):
+        PartitionedMeanSolver(6, 5, [(0, 4), (4, 5)], 0, (4.0, -1.0, -1.0))
+
+
 def check_row_sharded_pcg_single_rank(n=16, M=3, p=2):
     """RowShardedPCG with one rank (no process group): the halo'd local slab is the whole grid plus two
     empty rows; the solve must agree with the oracle's PCG on the global problem (the two-rank form

@@ -90,3 +90,7 @@ def test_parametric_samples():
 
 def test_lambda_growth():
     ps.check_lambda_growth()
+
+
+def test_partitioned_mean_solver():
+    ps.check_partitioned_mean_solver()

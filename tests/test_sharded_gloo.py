@@ -134,7 +134,8 @@ def _pcg_worker(rank, world, port, out_path, precond):
         w = sp.SlabMultiVector(idx, slab=torch.zeros_like(F), _sorted=True)
         plan = sh.plan_for(w)
         d = float(c.mats[0].diagonal()[0])
-        solver = RowShardedPCG(sh, n, n, ranges, mean_stencil=(d, -1.0, -1.0) if precond == "mean" else None)
+        solver = RowShardedPCG(sh, n, n, ranges, mean_stencil=(d, -1.0, -1.0) if precond.startswith("mean") else None,
+                               mean_solver="transpose" if precond == "mean-transpose" else "partition")
         X, zeta, it = solver.solve(plan, F, torch.zeros_like(F), eps=1e-9, maxiter=200)
         own = X.view(L, nyl, n)[:, 1:-1, :].contiguous()
         parts = [torch.empty_like(own) for _ in range(world)]
@@ -143,7 +144,7 @@ def _pcg_worker(rank, world, port, out_path, precond):
             Xg = torch.cat(parts, dim=1).reshape(L, n * n).numpy().T
             # the oracle's PCG on the same numbers, with the same preconditioner
             basis = olin.CanonicalBasis(c.N)
-            if precond == "mean":
+            if precond.startswith("mean"):
                 lu = olin.ScipySolveOperator(c.mats[0], basis, basis, factor=True)
                 P = osg.PreconditioningOperator("mean", lambda b, f: lu)
             else:
@@ -162,10 +163,11 @@ def _pcg_worker(rank, world, port, out_path, precond):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precond", ["mean", "identity"])
+@pytest.mark.parametrize("precond", ["mean", "mean-transpose", "identity"])
 def test_row_sharded_pcg_two_ranks(tmp_path, emu, precond):
-    """PCG on row-sharded slabs (halo exchange for A, all-reduced scalars, preconditioner through a
-    transposition to column shards) against the oracle's PCG on the global problem."""
+    """PCG on row-sharded slabs (halo exchange for A, all-reduced scalars, mean preconditioner by the
+    tridiagonal partition method or through a transposition to column shards) against the oracle's
+    PCG on the global problem."""
     out = tmp_path / "res.txt"
     mp.spawn(_pcg_worker, args=(2, _free_port(), str(out), precond), nprocs=2, join=True)
     err, traj, it, it_o = [float(v) for v in out.read_text().split()]
