@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--eps", type=float, default=1e-10)
     ap.add_argument("--maxiter", type=int, default=200)
     ap.add_argument("--poll", type=int, default=8)
+    ap.add_argument("--mean-solver", default="partition", choices=["partition", "transpose"])
     args = ap.parse_args()
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         return main_sharded(args)
@@ -108,7 +109,7 @@ def main_sharded(args):
     plan = sh.plan_for(w)
     F = torch.empty_like(X)
     sh.apply(plan, X.clone(), F)
-    solver = RowShardedPCG(sh, n, n, ranges, mean_stencil=(4.0, -1.0, -1.0))
+    solver = RowShardedPCG(sh, n, n, ranges, mean_stencil=(4.0, -1.0, -1.0), mean_solver=args.mean_solver)
     solver._zero_halos(F)
     tmp = torch.empty_like(F)
     solver.precondition(F, tmp)                        # warm-up: solver set-up, cuBLAS handle, NCCL channels
@@ -123,7 +124,7 @@ def main_sharded(args):
     dist.all_reduce(err, op=dist.ReduceOp.MAX)
     passes = max(it - 1, 1)
     if rank == 0:
-        print(json.dumps({"config": args.config, "n_gpus": world, "sharding": "grid rows; preconditioner on column shards via all-to-all",
+        print(json.dumps({"config": args.config, "n_gpus": world, "sharding": "grid rows; mean preconditioner: " + solver.mean_solver,
                           "N": n * n, "L": L, "M": M, "eps": args.eps, "numit": it, "zeta": zeta, "seconds": dt,
                           "ms_per_pass": dt / passes * 1e3, "gdof_per_s_per_pass": n * n * L * passes / dt / 1e9,
                           "max_abs_error": float(err[0]), "zeta_history": solver.last_history[:6] + ["..."] + solver.last_history[-3:]}))
