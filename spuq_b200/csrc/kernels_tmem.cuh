@@ -581,7 +581,8 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
             int4 ca = lds_i32x4(rptr), cb = lds_i32x4(rptr + 16);
             // (a loop, not an if: the compiler moves loop bodies out of line, so the common path falls through)
             while ((ca.x & REC_TYPE_MASK) == REC_NEXT_CHUNK) { next_chunk(); ca = lds_i32x4(rptr); cb = lds_i32x4(rptr + 16); }
-            const uint32_t kmask = (uint32_t)(ca.x >> REC_JOB_KMASK_SHIFT) & 0xFu;
+            // (both jobs carry the same mask; reading it through both words lets unit 0 of job b come in one 16-byte load)
+            const uint32_t kmask = (uint32_t)((ca.x & cb.x) >> REC_JOB_KMASK_SHIFT) & 0xFu;
             if (Cfg::W_GROUP == 2) {
                 load_window_pair();
             } else {
