@@ -175,6 +175,13 @@ SPUQ_API int spuq_sg_xpay(int64_t n, const double* num_dev, const double* den_de
                  const double* s_dev, double* v_dev, void* stream);
 /* x *= alpha_host */
 SPUQ_API int spuq_sg_scal(int64_t n, double alpha_host, double* x_dev, void* stream);
+/* out[:, mu] = -b0[mu]*W[:, mu] + bu[mu]*W[:, up[mu]] + bd[mu]*W[:, dn[mu]]  for all L columns (absent
+ * neighbour: index < 0; all five tables on the device, rows of the plan's neighbour / beta tables for
+ * one term m).  The neighbour combination of residual_estimator2.py:111-131, same operation order. */
+SPUQ_API int spuq_sg_neighbour_combine(int64_t n, int32_t L, const double* W_dev, int64_t ldw,
+                              const int32_t* up_dev, const int32_t* dn_dev, const double* bu_dev,
+                              const double* bd_dev, const double* b0_dev, double* out_dev, int64_t ldo,
+                              void* stream);
 /* out[s*ldo + i] = sum_mu coef_dev[s*L + mu] * W[i + ldw*mu]   for S coefficient vectors at once:
  * the value of the expansion at S parameter samples, coef[s][mu] = prod_m P_{mu_m}(y^s_m).
  * Replaces the sum over Lambda in compute_parametric_sample_solution,

@@ -7,6 +7,7 @@ Restates
   * ``PreconditioningOperator``     reference src/spuq/application/egsz/multi_operator2.py:139-165
   * ``pcg``                         reference src/spuq/application/egsz/pcg.py:15-53
   * ``ForgetfulVector``             reference src/spuq/utils/forgetful_vector.py:46-66
+  * ``neighbour_combination``       reference src/spuq/application/egsz/residual_estimator2.py:107-131
   * ``refine_y``                    reference src/spuq/application/egsz/marking2.py:205-208
   * ``sample_realization``, ``compute_parametric_sample_solution``
                                     reference src/spuq/application/egsz/coefficient_field.py:45-52,
@@ -341,6 +342,25 @@ def pcg_solve(A, w, coeff_field, pde, stats, pcg_eps, pcg_maxiter):
     stats["DOFS"] = sum(b[mu].basis.dim for mu in b.keys())
     stats["CELLS"] = sum(pde.num_cells(b[mu].basis) for mu in b.keys())
     return w, zeta
+
+
+def neighbour_combination(w, coeff_field, m):
+    """res[mu] = -beta[0] w[mu] + beta[1] w[mu+e_m] + beta[-1] w[mu-e_m] for every active mu;
+    residual_estimator2.py:107-131 (the loop body for one m, before the FEM forms are applied)."""
+    Lambda = w.active_indices()
+    out = MultiVector()
+    am_f, am_rv = coeff_field[m]
+    for mu in Lambda:
+        beta = am_rv.orth_polys.get_beta(mu[m])
+        res = -beta[0] * w[mu]
+        mu1 = mu.inc(m)
+        if mu1 in Lambda:
+            res += beta[1] * w[mu1]
+        mu2 = mu.dec(m)
+        if mu2 in Lambda:
+            res += beta[-1] * w[mu2]
+        out[mu] = res
+    return out
 
 
 def refine_y(w, new_mi):

@@ -66,6 +66,7 @@ SIGNATURES = {
     "spuq_sg_precond_mean_fd_inverse": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp]),
     "spuq_sg_precond_mean_fd_mode_order": (C.c_int, [_vp, _vp]),
     "spuq_sg_spike_correct": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spuq_sg_neighbour_combine": (C.c_int, [C.c_int64, C.c_int32, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _vp]),
     "spuq_sg_combine": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp]),
     "spuq_sg_precond_identity": (C.c_int, [C.POINTER(_vp), C.c_double]),
     "spuq_sg_precond_from_plan": (C.c_int, [C.POINTER(_vp), _vp]),

@@ -47,6 +47,9 @@ static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 static inline int emu_sm_count() { return 4; }
 
+// round-to-nearest products and sums that the compiler may not contract (host: plain operators, -ffp-contract is off for this build)
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 
 template <typename F>

@@ -198,6 +198,31 @@ void k_combine(int64_t n, int32_t L, int32_t S, int32_t s0, const double* W, int
 }
 #endif
 
+// out[:, mu] = -b0[mu] * W[:, mu] + bu[mu] * W[:, up[mu]] + bd[mu] * W[:, dn[mu]]  (absent neighbours: index < 0)
+// The neighbour combination of one expansion term m, for every column at once: what the residual
+// estimator feeds to its flux forms (residual_estimator2.py:111-131) and, with the block matrices,
+// the inner sum of MultiOperator.apply.  Same operation order as the reference (no contraction), so
+// the result is bit-identical to the numpy expression.
+__global__ void __launch_bounds__(256)
+k_neighbour_combine(int64_t n, int32_t L, const double* __restrict__ W, int64_t ldw, const int32_t* __restrict__ up,
+                    const int32_t* __restrict__ dn, const double* __restrict__ bu, const double* __restrict__ bd,
+                    const double* __restrict__ b0, double* __restrict__ out, int64_t ldo) {
+    const int32_t mu = blockIdx.y;
+    if (mu >= L) return;
+    const int32_t u = up[mu], d = dn[mu];
+    const double cu = bu[mu], cd = bd[mu], c0 = -b0[mu];
+    const double* w = W + ldw * (int64_t)mu;
+    const double* wu = u >= 0 ? W + ldw * (int64_t)u : nullptr;
+    const double* wd = d >= 0 ? W + ldw * (int64_t)d : nullptr;
+    double* o = out + ldo * (int64_t)mu;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double r = __dmul_rn(c0, w[i]);
+        if (wu) r = __dadd_rn(r, __dmul_rn(cu, wu[i]));
+        if (wd) r = __dadd_rn(r, __dmul_rn(cd, wd[i]));
+        o[i] = r;
+    }
+}
+
 // y += a*x
 __global__ void __launch_bounds__(256)
 k_axpy(int64_t n, double alpha, const double* num, const double* den,

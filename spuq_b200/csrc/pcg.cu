@@ -115,6 +115,21 @@ extern "C" int spuq_sg_combine(int64_t n, int32_t L, int32_t S, const double* W,
     return SPUQ_OK;
 }
 
+extern "C" int spuq_sg_neighbour_combine(int64_t n, int32_t L, const double* W, int64_t ldw, const int32_t* up,
+                                         const int32_t* dn, const double* bu, const double* bd, const double* b0,
+                                         double* out, int64_t ldo, void* stream) {
+    SPUQ_REQUIRE(n >= 0 && L >= 0, "neighbour_combine: negative size");
+    if (n == 0 || L == 0) return SPUQ_OK;
+    SPUQ_REQUIRE(W && up && dn && bu && bd && b0 && out && ldw >= n && ldo >= n && W != out,
+                 "neighbour_combine: null argument, leading dimension too small, or in-place call");
+    SPUQ_REQUIRE(L <= 65535, "neighbour_combine: more than 65535 columns");
+    const unsigned bx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 64));
+    SPUQ_LAUNCH(k_neighbour_combine, dim3(bx, (unsigned)L), dim3(256), 0, static_cast<cudaStream_t>(stream), n, L, W, ldw,
+                up, dn, bu, bd, b0, out, ldo);
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+
 extern "C" int spuq_sg_scal(int64_t n, double alpha, double* x, void* stream) {
     SPUQ_REQUIRE(n >= 0 && x, "scal: null argument");
     SPUQ_LAUNCH(k_scal, dim3(blas_grid(n, cur_sm_count(), 256)), dim3(256), 0,

@@ -386,6 +386,27 @@ def check_pcg_solve(n=10, M=3, p=2, kind="hermite", mu=0.5):
     assert np.max(np.abs(x2.to_array() - x.to_array())) <= 1e-12
 
 
+# ---- neighbour combination of the residual estimator ------------------------
+def check_neighbour_combination():
+    """res = -beta0 w[mu] + beta1 w[mu+e_m] + beta-1 w[mu-e_m] (residual_estimator2.py:117-131) for all
+    columns of a term at once: BIT-identical to the oracle's loop (same operation order, no fused
+    multiply-add), for a symmetric and a shifted random variable; per-column energy norms."""
+    for n, M, p, kind, mu0 in [(7, 3, 3, "hermite", 0.5), (8, 4, 2, "legendre", 0.0)]:
+        idx = synthetic.complete_order_indices(M, p)
+        c = fd_case(n, M, idx, kind, mu0)
+        cf_p = sp.ListCoefficientField("mean", list(range(M)), c.rvs)
+        w = sp.SlabMultiVector.from_array(idx, c.W)
+        for m in range(M):
+            res = sp.neighbour_combination(w, cf_p, m)
+            ref = osg.neighbour_combination(c.w, c.cf, m).to_slab()
+            assert np.array_equal(res.to_array(), ref), (kind, m, np.max(np.abs(res.to_array() - ref)))
+        with pytest.raises(IndexError):
+            sp.neighbour_combination(w, cf_p, M)
+        norms = sp.column_energy_norms(w, c.mats[0]).cpu().numpy()
+        ref_n = np.sqrt(np.einsum("ik,ik->k", c.W, c.mats[0] @ c.W))
+        assert np.max(np.abs(norms - ref_n)) <= 1e-12 * np.max(ref_n)
+
+
 # ---- growth of Lambda between solves (SURVEY.md 8f, row f3) ---------------------------------------
 def check_lambda_growth():
     """Marking.refine_y (marking2.py:205-208) on a slab: the grown vector has the oracle's keys in the

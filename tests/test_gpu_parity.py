@@ -290,3 +290,7 @@ def test_lambda_growth():
 
 def test_partitioned_mean_solver():
     ps.check_partitioned_mean_solver()
+
+
+def test_neighbour_combination():
+    ps.check_neighbour_combination()
