@@ -1,5 +1,6 @@
 #!/bin/bash
 # A/B timing of library builds under build_ab/ on one box (development tool): tools/ab.sh c3 "4,2,2" base old ...
+# build the variants first:  mkdir -p build_ab && make -C spuq_b200/csrc -B OUT=../../build_ab/lib_old.so EXTRA="-DSOME_SWITCH"
 cfg=$1; var=$2; shift 2
 for round in 1 2; do
   for n in "$@"; do
