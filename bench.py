@@ -242,7 +242,9 @@ def run_gpu(args):
     if rows_mode:
         # spatial rows sharded over the ranks, one halo grid row on each side, halo exchange per step
         from spuq_b200.sharding import RowShardedApply, row_ranges
-        y0, y1 = row_ranges(n, world)[rank]
+        # balanced bands, NOT rounded to the kernel's tile height: 125 rows + 2 halo rows are 16 tile rows,
+        # 128 + 2 would spill into a seventeenth
+        y0, y1 = row_ranges(n, world, align=1)[rank]
         nyl = y1 - y0 + 2
         Nloc = nyl * n
         rowptr, colidx, vals = synthetic.fd_blocks_rows(n, M, y0, y1, device=dev)

@@ -260,6 +260,33 @@ def check_apply_multiblock():
         assert relerr(total, c.Y) <= TOL
 
 
+def check_row_bands_manual_exchange(n=24, M=3, bands=((0, 7), (7, 16), (16, 24))):
+    """The single-GPU kernel on row bands with halo rows, as RowShardedApply runs it, with all ranks
+    simulated in one process (halo rows copied by hand): bands of odd and even height that are not
+    multiples of the tile height must reproduce the global result."""
+    from spuq_b200.sharding import RowShardedApply
+    idx = synthetic.complete_order_indices(M, 2)
+    c = fd_case(n, M, idx, "hermite", 0.5)
+    L = idx.shape[0]
+    Wg = torch.from_numpy(np.ascontiguousarray(c.W.T)).view(L, n, n)
+    Yg = np.zeros((L, n, n))
+    for y0, y1 in bands:
+        nyl = y1 - y0 + 2
+        rowptr, colidx, vals = synthetic.fd_blocks_rows(n, M, y0, y1)
+        blocks = DeviceBlocks(_dev(rowptr), _dev(colidx), _dev(vals), (nyl * n, nyl * n))
+        sh = RowShardedApply(blocks, c.rvs, n, y0, y1)
+        W = torch.zeros((L, nyl, n), dtype=torch.float64)
+        lo, hi = max(y0 - 1, 0), min(y1 + 1, n)                     # owned rows + the neighbours' boundary rows
+        W[:, lo - (y0 - 1):hi - (y0 - 1), :] = Wg[:, lo:hi, :]
+        W = _dev(W.view(L, nyl * n))
+        w = sp.SlabMultiVector(idx, slab=W, _sorted=True)
+        plan = sh.plan_for(w)
+        Y = torch.empty_like(W)
+        plan.apply(W, Y)
+        Yg[:, y0:y1, :] = Y.view(L, nyl, n)[:, 1:-1, :].cpu().numpy()
+    assert relerr(Yg.reshape(L, n * n).T, c.Y) <= TOL
+
+
 def check_partitioned_mean_solver():
     """The partition method for the mean solve on row-sharded slabs (PartitionedMeanSolver), all ranks
     simulated in one process: forward halves, the all-gather done by hand, corrections and inverse

@@ -98,3 +98,7 @@ def test_partitioned_mean_solver():
 
 def test_neighbour_combination():
     ps.check_neighbour_combination()
+
+
+def test_row_bands_manual_exchange():
+    ps.check_row_bands_manual_exchange()

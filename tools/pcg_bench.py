@@ -94,7 +94,7 @@ def main_sharded(args):
     idx = bench.index_set(cfg)
     L = idx.shape[0]
     rvs = synthetic.make_rvs(cfg["kind"], M, cfg["mu"])
-    ranges = row_ranges(n, world)
+    ranges = row_ranges(n, world, align=1)
     y0, y1 = ranges[rank]
     nyl = y1 - y0 + 2
     rowptr, colidx, vals = synthetic.fd_blocks_rows(n, M, y0, y1, device=dev)
