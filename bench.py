@@ -142,44 +142,24 @@ class CpuReference:
     independently of all other columns, so the time of a sample of columns extrapolates linearly
     to |Lambda|.  The timed loop is oracle.sg.MultiOperator.apply restricted to the sampled
     columns (``only=``): dict-of-vectors MultiVector, Multiindex `in Lambda` scans, one scipy SpMV
-    per (mu, m), cached CSR leaves -- single-threaded, as the reference is."""
+    per (mu, m), cached CSR leaves -- single-threaded, as the reference is.
+
+    Everything on this side (index set, neighbour look-ups, beta values, blocks) is built by the
+    oracle package alone (oracle/synth.py, oracle/sampled.py): the product library is not loaded."""
 
     def __init__(self, cfg, n_cols, seed=1234):
         import numpy as np
-        from oracle import linalg as olin, multiindex as omi, polys as opolys, sg as osg
-        from spuq_b200 import synthetic, lambda_tables
+        from oracle import synth
+        from oracle.sampled import SampledApply
         n, M = cfg["n"], cfg["M"]
         self.N = N = n * n
-        idx = index_set(cfg)
+        idx = synth.index_set(cfg["lam"])
         self.L = L = idx.shape[0]
-        rowptr, colidx, vals = synthetic.fd_blocks(n, M)
-        mats = synthetic.blocks_to_scipy(rowptr, colidx, vals, N)
-        rv = opolys.UniformRV(-1, 1) if cfg["kind"] == "legendre" else opolys.NormalRV(cfg["mu"], 1)
-        cf = osg.ListCoefficientField("mean", list(range(M)), [rv] * M)
-        basis = olin.CanonicalBasis(N)
-        leaves = {}
-
-        def assemble(b, f):
-            k = 0 if f == "mean" else 1 + f
-            if k not in leaves:
-                leaves[k] = olin.ScipyOperator(mats[k], b, b)
-            return leaves[k]
-
-        self.A = osg.MultiOperator(cf, assemble)
+        mats = synth.fd_matrices(n, M)
         pick = np.unique(np.linspace(0, L - 1, min(n_cols, L)).astype(int))
-        up, dn = lambda_tables.neighbour_tables(idx)
-        touched = set(int(k) for k in pick)
-        for k in pick:
-            touched.update(int(v) for v in up[:, k] if v >= 0)
-            touched.update(int(v) for v in dn[:, k] if v >= 0)
         rng = np.random.RandomState(seed)
-        shared = olin.FlatVector(np.zeros(N), basis)     # untouched columns share one zero vector
-        keys = [omi.Multiindex(r.astype(np.int64)) for r in idx]
-        self.w = osg.MultiVector()
-        for k, mu in enumerate(keys):
-            self.w[mu] = olin.FlatVector(rng.random_sample(N), basis) if k in touched else shared
-        Lambda = self.w.active_indices()
-        self.only = [Lambda[k] for k in pick]
+        self.sa = SampledApply(mats, idx, cfg["kind"], cfg["mu"], pick, lambda k: rng.random_sample(N))
+        self.A, self.w, self.only = self.sa.A, self.sa.w, self.sa.only
         self.n_cols = len(pick)
 
     def run(self):

@@ -203,10 +203,21 @@ SPUQ_API int spuq_sg_precond_from_plan(spuq_sg_precond** out, spuq_sg_plan* plan
 /* P = A_0^{-1} for the mean block A_0 = 5-point stencil with CONSTANT coefficients on an
  * nx x ny grid (rows i = iy*nx + ix): diag `d`, x-coupling `ox`, y-coupling `oy` (so that
  * A_0 = tridiag_x(ox, d/2, ox) (+) tridiag_y(oy, d/2, oy)).  Exact to rounding: sine-transform
- * diagonalisation in x, tridiagonal (Thomas) solves in y.  Replaces the per-column sparse direct
+ * diagonalisation on strips of <= 32 grid rows held in shared memory plus an exact Schur-complement solve
+ * on the separator rows (csrc/precond_strip.cuh).  Replaces the per-column sparse direct
  * solve of ScipySolveOperator.apply / FEniCSSolveOperator.apply (linalg/scipy_operator.py:45-49). */
 SPUQ_API int spuq_sg_precond_mean_fd(spuq_sg_precond** out, int device, int32_t nx, int32_t ny,
                             double d, double ox, double oy);
+/* P = A_0^{-1} for a GENERAL sparse mean block (variable coefficients, unstructured meshes): the caller
+ * factorises once, Pr A_0 Pc = L U (scipy.sparse.linalg.splu, the solver behind the reference's
+ * ScipySolveOperator.apply, linalg/scipy_operator.py:45-49), and hands over the factors as host CSR
+ * arrays: the STRICT lower triangle of the unit-lower L, the STRICT upper triangle and the diagonal of U,
+ * and the permutations (Pr b)[perm_r[i]] = b[i], (Pc w)[i] = w[perm_c[i]].  The device runs both
+ * triangular solves for all slab columns in one launch (level-scheduled, one CTA per column group). */
+SPUQ_API int spuq_sg_precond_sparse_lu(spuq_sg_precond** out, int device, int64_t n,
+                              const int32_t* l_rowptr_host, const int32_t* l_colidx_host, const double* l_vals_host,
+                              const int32_t* u_rowptr_host, const int32_t* u_colidx_host, const double* u_vals_host,
+                              const double* u_diag_host, const int32_t* perm_r_host, const int32_t* perm_c_host);
 /* The mean_fd solve in two halves, for callers that complete the y direction themselves (grid rows
  * sharded over GPUs: spuq_b200.sharding, partition method for the tridiagonal systems along y).
  *   forward: T = (tridiagonal solves along the handle's ny rows)(sine transform in x of R), left in the

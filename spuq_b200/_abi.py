@@ -72,6 +72,7 @@ SIGNATURES = {
     "spuq_sg_precond_from_plan": (C.c_int, [C.POINTER(_vp), _vp]),
     "spuq_sg_precond_mean_fd": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int32, C.c_int32,
                                            C.c_double, C.c_double, C.c_double]),
+    "spuq_sg_precond_sparse_lu": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spuq_sg_precond_destroy": (C.c_int, [_vp]),
     "spuq_sg_precond_work_bytes": (C.c_int64, [_vp, C.c_int64, C.c_int32]),
     "spuq_sg_precond_apply": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp]),

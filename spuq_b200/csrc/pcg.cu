@@ -179,6 +179,7 @@ extern "C" int spuq_sg_precond_from_plan(spuq_sg_precond** out, spuq_sg_plan* pl
 extern "C" int spuq_sg_precond_destroy(spuq_sg_precond* p) {
     if (!p) return SPUQ_OK;
     if (p->kind == spuq_sg_precond::MEAN_FD) mean_fd_destroy(p);
+    if (p->kind == spuq_sg_precond::SPARSE_LU) lu_plan_destroy(p);
     delete p;
     return SPUQ_OK;
 }
@@ -186,6 +187,7 @@ extern "C" int spuq_sg_precond_destroy(spuq_sg_precond* p) {
 extern "C" int64_t spuq_sg_precond_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L) {
     if (!p) return 0;
     if (p->kind == spuq_sg_precond::MEAN_FD) return mean_fd_work_bytes(p, N, L);
+    if (p->kind == spuq_sg_precond::SPARSE_LU) return lu_work_bytes(p, N, L);
     return 0;
 }
 
@@ -209,6 +211,8 @@ int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
         return apply_impl(p->plan, R, N, S, N, stream, gate);
     case spuq_sg_precond::MEAN_FD:
         return mean_fd_apply(p, N, L, R, S, work, stream, gate);
+    case spuq_sg_precond::SPARSE_LU:
+        return lu_apply(p, N, L, R, S, work, stream, gate);
     }
     return SPUQ_E_INVALID;
 }

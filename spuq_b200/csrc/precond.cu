@@ -18,60 +18,22 @@
 // For even nx the transform is split by the parity of the mode (Q[nx-1-j][k] = (-1)^k Q[j][k]): the
 // sums and differences of mirrored entries of a grid row go through two half-size products, which
 // halves the flops of steps 1 and 3 at the price of two element-wise passes.
-// The two products are plain dense fp64 GEMMs ((L*ny) x nx by nx x nx): they go to cuBLAS DGEMM when
-// libcublas can be loaded at run time (dlopen, no link-time dependency); k_rowgemm below is the
-// in-house register-tiled fallback (CUDA cores) and the reference for the host-emulated build.
+// The two products are plain dense fp64 GEMMs ((L*ny) x nx by nx x nx) done by k_rowgemm below, an
+// in-house register-tiled kernel on the FP64 CUDA cores (no library on this path).
+//
+// ROUND 2: the full-length transform of every grid row is only the FALL-BACK now (and the engine of the
+// forward/inverse halves used by the row-sharded solver).  The default path is the two-level strip
+// partition of precond_strip.cuh, which needs the long transform for ~3 % of the rows only.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "precond.h"
 
-#ifndef SPUQ_EMU
-#include <dlfcn.h>
-#endif
+#include "precond_strip.cuh"
 
 namespace spuq {
-
-#ifndef SPUQ_EMU
-// ---- minimal run-time binding of cuBLAS (v2 API) ---------------------------------------------------
-struct CublasApi {
-    int (*create)(void**) = nullptr;
-    int (*destroy)(void*) = nullptr;
-    int (*set_stream)(void*, cudaStream_t) = nullptr;
-    int (*dgemm)(void*, int, int, int, int, int, const double*, const double*, int, const double*, int,
-                 const double*, double*, int) = nullptr;
-    bool ok = false;
-};
-static CublasApi& cublas_api() {
-    static CublasApi api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* h = dlopen("libcublas.so.12", RTLD_NOW | RTLD_GLOBAL);
-        if (!h) h = dlopen("libcublas.so", RTLD_NOW | RTLD_GLOBAL);
-        if (h) {
-            api.create = reinterpret_cast<decltype(api.create)>(dlsym(h, "cublasCreate_v2"));
-            api.destroy = reinterpret_cast<decltype(api.destroy)>(dlsym(h, "cublasDestroy_v2"));
-            api.set_stream = reinterpret_cast<decltype(api.set_stream)>(dlsym(h, "cublasSetStream_v2"));
-            api.dgemm = reinterpret_cast<decltype(api.dgemm)>(dlsym(h, "cublasDgemm_v2"));
-            api.ok = api.create && api.destroy && api.set_stream && api.dgemm;
-        }
-    }
-    return api;
-}
-// C[M x nc] = A[M x nk] * Q[nk x nc], all row-major (row strides lda, ldc, nc)  ==  column-major
-// C^T = Q^T * A^T with Q^T = the row-major Q read column-major
-static bool blas_rowgemm(spuq_sg_precond* p, int64_t Mrows, int32_t nk, int32_t nc, const double* A, int32_t lda,
-                         const double* Q, double* C, int32_t ldc, cudaStream_t stream) {
-    CublasApi& api = cublas_api();
-    if (!api.ok || Mrows > 0x7fffffffLL) return false;
-    if (!p->blas && api.create(&p->blas) != 0) { p->blas = nullptr; return false; }
-    if (api.set_stream(p->blas, stream) != 0) return false;
-    const double one = 1.0, zero = 0.0;
-    return api.dgemm(p->blas, /*CUBLAS_OP_N*/ 0, 0, nc, (int)Mrows, nk, &one, Q, nc, A, lda, &zero, C, ldc) == 0;
-}
-#endif
 
 constexpr int GM = 128, GN = 64, GK = 8;      // CTA tile; 256 threads, each 8 x 4 outputs
 constexpr int G_THREADS = 256;
@@ -229,6 +191,221 @@ k_thomas_y(int32_t nx, int32_t ny, int32_t L, double oy, const double* __restric
     }
 }
 
+// ---- two-level strip partition: plan (host tables) and driver ---------------------------------------
+struct StripPlan {
+    StripView sv{};
+    std::vector<void*> dev;               // device allocations
+    int32_t cmax = 0;                     // tallest strip
+    size_t smem_bytes = 0;
+    double* sy_ipiv = nullptr;            // [q][nx] separator system per x-mode (transform order of the GEMM path)
+    double* sy_off = nullptr;
+};
+
+// first column of (tridiag(o, b, o) of size n)^{-1}
+static void tri_first_column(int n, double b, double o, std::vector<double>* v) {
+    std::vector<double> piv(n);
+    v->assign(n, 0.0);
+    piv[0] = b;
+    for (int t = 1; t < n; ++t) piv[t] = b - o * o / piv[t - 1];
+    // forward elimination of e_0: z_0 = 1, z_t = -o z_{t-1} / piv_{t-1}
+    std::vector<double>& z = *v;
+    z[0] = 1.0;
+    for (int t = 1; t < n; ++t) z[t] = -o * z[t - 1] / piv[t - 1];
+    z[n - 1] /= piv[n - 1];
+    for (int t = n - 2; t >= 0; --t) z[t] = (z[t] - o * z[t + 1]) / piv[t];
+}
+
+// equal-as-possible pieces of n points separated by single separator points, each piece <= cap
+static void partition_line(int n, int cap, std::vector<int32_t>* start, std::vector<int32_t>* len) {
+    const int P = (n + 1 + cap) / (cap + 1);
+    const int q = P - 1, tot = n - q, h = tot / P, r = tot % P;
+    start->clear(); len->clear();
+    int pos = 0;
+    for (int p = 0; p < P; ++p) {
+        const int c = h + (p < r ? 1 : 0);
+        start->push_back(pos); len->push_back(c);
+        pos += c + 1;
+    }
+}
+
+template <typename T>
+static T* strip_upload(StripPlan* sp, const std::vector<T>& h) {
+    void* d = nullptr;
+    if (cudaMalloc(&d, sizeof(T) * std::max<size_t>(h.size(), 1)) != cudaSuccess) return nullptr;
+    sp->dev.push_back(d);
+    if (!h.empty()) cudaMemcpy(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice);
+    return static_cast<T*>(d);
+}
+
+void strip_plan_destroy(spuq_sg_precond* p) {
+    StripPlan* sp = static_cast<StripPlan*>(p->strip);
+    if (!sp) return;
+    for (void* d : sp->dev) cudaFree(d);
+    delete sp;
+    p->strip = nullptr;
+}
+
+int strip_plan_build(spuq_sg_precond* p) {
+    const int32_t nx = p->nx, ny = p->ny;
+    if (ny < 2 || nx < 2) return SPUQ_OK;                 // 1-D: the plain path
+    if (const char* e = std::getenv("SPUQ_PRECOND_PLAIN")) { if (e[0] == '1') return SPUQ_OK; }   // A/B switch (development)
+    const double pi = 3.14159265358979323846;
+    const double dxx = 0.5 * p->d, dyy = 0.5 * p->d, ox = p->ox, oy = p->oy;
+    // strip height: two CTAs per SM when that still allows >= 12 rows, else one
+    const size_t fixed = sizeof(double) * ((size_t)STRIP_CMAX * STRIP_HP + (size_t)STRIP_CMAX * 64);
+    auto rows_for = [&](size_t budget) { return budget > fixed ? (int)((budget - fixed) / (sizeof(double) * (size_t)nx)) : 0; };
+    int cap = std::min(STRIP_CMAX, rows_for(112 * 1024));
+    if (cap < 12) cap = std::min(STRIP_CMAX, rows_for(224 * 1024));
+    if (cap < 2) return SPUQ_OK;                          // grid too wide for shared memory: plain path
+    StripPlan* sp = new StripPlan();
+    StripView& sv = sp->sv;
+    std::vector<int32_t> ystart, ylen, xstart, xlen;
+    partition_line(ny, cap, &ystart, &ylen);
+    partition_line(nx, 31, &xstart, &xlen);
+    sv.nx = nx; sv.ny = ny; sv.ox = ox; sv.oy = oy;
+    sv.P = (int32_t)ystart.size(); sv.q = sv.P - 1;
+    sv.PX = (int32_t)xstart.size(); sv.qx = sv.PX - 1;
+    if (sv.qx > 64) { delete sp; return SPUQ_OK; }
+    sv.cxmax = *std::max_element(xlen.begin(), xlen.end());
+    sv.ch[0] = ylen.front(); sv.ch[1] = ylen.back();     // heights h+1 (first strips) and h
+    sv.xlen_cls_len[0] = xlen.front(); sv.xlen_cls_len[1] = xlen.back();
+    sp->cmax = sv.ch[0];
+    std::vector<int32_t> ycls(sv.P);
+    for (int i = 0; i < sv.P; ++i) ycls[i] = ylen[i] == sv.ch[0] ? 0 : 1;
+    sv.ystart = strip_upload(sp, ystart); sv.ycls = strip_upload(sp, ycls);
+    sv.xstart = strip_upload(sp, xstart); sv.xlen = strip_upload(sp, xlen);
+    bool ok = sv.ystart && sv.ycls && sv.xstart && sv.xlen;
+    const int cx = sv.cxmax, qx = sv.qx;
+    for (int cls = 0; cls < 2 && ok; ++cls) {
+        const int c = sv.ch[cls];
+        const int hp = (c + 1) / 2;
+        std::vector<double> qc((size_t)c * STRIP_HP, 0.0), ipx((size_t)c * cx), spk((size_t)2 * c * cx, 0.0),
+            sip((size_t)c * std::max(qx, 1), 0.0), sof((size_t)c * std::max(qx, 1), 0.0);
+        const double sc = std::sqrt(2.0 / (c + 1.0));
+        for (int j = 0; j < c; ++j) {
+            for (int i = 0; i < hp; ++i) qc[(size_t)j * STRIP_HP + i] = sc * std::sin((double)(i + 1) * (double)(j + 1) * pi / (c + 1.0));
+            const double b = dxx + dyy + 2.0 * oy * std::cos((double)(j + 1) * pi / (c + 1.0));
+            double pv = b;
+            for (int t = 0; t < cx; ++t) {
+                if (t > 0) pv = b - ox * ox / pv;
+                if (!(pv != 0.0) || !std::isfinite(pv)) ok = false;
+                ipx[(size_t)j * cx + t] = 1.0 / pv;
+            }
+            std::vector<double> v[2];
+            for (int lc = 0; lc < 2; ++lc) {
+                tri_first_column(sv.xlen_cls_len[lc], b, ox, &v[lc]);
+                for (int t = 0; t < sv.xlen_cls_len[lc]; ++t) spk[((size_t)lc * c + j) * cx + t] = v[lc][t];
+            }
+            // x-separator system: D_i = b - ox^2 (G_ll(chunk i) + G_00(chunk i+1)), E_i = -ox^2 G_0l(chunk i+1)
+            double prev_piv = 0.0, prev_off = 0.0;
+            for (int i = 0; i < qx; ++i) {
+                const int lcl = xlen[i] == sv.xlen_cls_len[0] ? 0 : 1, lcr = xlen[i + 1] == sv.xlen_cls_len[0] ? 0 : 1;
+                const double D = b - ox * ox * (v[lcl][0] + v[lcr][0]);
+                const double E = -ox * ox * v[lcr][xlen[i + 1] - 1];
+                double pvt = D;
+                if (i > 0) pvt = D - prev_off * prev_off / prev_piv;
+                if (!(pvt != 0.0) || !std::isfinite(pvt)) ok = false;
+                sip[(size_t)j * qx + i] = 1.0 / pvt;
+                sof[(size_t)j * qx + i] = E;
+                prev_piv = pvt; prev_off = E;
+            }
+        }
+        sv.qc[cls] = strip_upload(sp, qc); sv.ipivx[cls] = strip_upload(sp, ipx); sv.spike[cls] = strip_upload(sp, spk);
+        sv.sx_ipiv[cls] = strip_upload(sp, sip); sv.sx_off[cls] = strip_upload(sp, sof);
+        ok = ok && sv.qc[cls] && sv.ipivx[cls] && sv.spike[cls] && sv.sx_ipiv[cls] && sv.sx_off[cls];
+    }
+    // separator rows: per x-mode k a q x q tridiagonal system, stored in the order the row transform
+    // delivers the modes (even | odd when the transform is split by parity)
+    if (ok && sv.q > 0) {
+        const int q = sv.q, h = p->half;
+        std::vector<double> ip((size_t)q * nx), of((size_t)q * nx);
+        std::vector<double> v[2];
+        for (int32_t c0 = 0; c0 < nx && ok; ++c0) {
+            const int32_t k = h > 0 ? (c0 < h ? 2 * c0 : 2 * (c0 - h) + 1) : c0;
+            const double bb = dyy + dxx + 2.0 * ox * std::cos((double)(k + 1) * pi / (nx + 1.0));
+            for (int cls = 0; cls < 2; ++cls) tri_first_column(sv.ch[cls], bb, oy, &v[cls]);
+            double prev_piv = 0.0, prev_off = 0.0;
+            for (int j = 0; j < q; ++j) {
+                const int ca = ycls[j], cb = ycls[j + 1];
+                const double D = bb - oy * oy * (v[ca][0] + v[cb][0]);
+                const double E = -oy * oy * v[cb][sv.ch[cb] - 1];
+                double pvt = D;
+                if (j > 0) pvt = D - prev_off * prev_off / prev_piv;
+                if (!(pvt != 0.0) || !std::isfinite(pvt)) ok = false;
+                ip[(size_t)j * nx + c0] = 1.0 / pvt;
+                of[(size_t)j * nx + c0] = E;
+                prev_piv = pvt; prev_off = E;
+            }
+        }
+        sp->sy_ipiv = strip_upload(sp, ip); sp->sy_off = strip_upload(sp, of);
+        ok = ok && sp->sy_ipiv && sp->sy_off;
+    }
+    sp->smem_bytes = sizeof(double) * ((size_t)STRIP_CMAX * STRIP_HP + (size_t)STRIP_CMAX * std::max(qx, 1) + (size_t)sp->cmax * nx);
+    p->strip = sp;
+    if (!ok) { strip_plan_destroy(p); return SPUQ_OK; }       // not fatal: the plain path still works
+#ifndef SPUQ_EMU
+    if (cudaFuncSetAttribute(k_strip<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_strip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        strip_plan_destroy(p);
+    }
+#endif
+    return SPUQ_OK;
+}
+
+static int64_t strip_work_doubles(const StripPlan* sp, int32_t L) {
+    return (int64_t)L * sp->sv.nx * (2 * (int64_t)sp->sv.P + 2 * (int64_t)sp->sv.q);
+}
+
+static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
+                       cudaStream_t stream, const double* gate) {
+    StripPlan* sp = static_cast<StripPlan*>(p->strip);
+    const StripView& sv = sp->sv;
+    const int32_t nx = sv.nx, q = sv.q;
+    SPUQ_REQUIRE(N == (int64_t)nx * sv.ny, "precond_mean_fd: slab rows %lld != nx*ny", (long long)N);
+    SPUQ_REQUIRE(work != nullptr || q == 0, "precond_mean_fd: workspace missing");
+    SPUQ_REQUIRE((int64_t)L * sv.P < 0x7fffffffLL, "precond_mean_fd: too many strips for one launch");
+    double* Gf = static_cast<double*>(work);
+    double* Gl = Gf + (int64_t)L * sv.P * nx;
+    double* Z = Gl + (int64_t)L * sv.P * nx;
+    double* Z2 = Z + (int64_t)L * q * nx;
+    const dim3 grid((unsigned)((int64_t)L * sv.P)), block(STRIP_THREADS);
+    const double* U = nullptr;
+    if (q > 0) {
+        SPUQ_LAUNCH((k_strip<false>), grid, block, sp->smem_bytes, stream, sv, L, R, S, Gf, Gl, (const double*)nullptr, gate);
+        const int64_t Mrows = (int64_t)L * q;
+        const unsigned eb = (unsigned)std::min<int64_t>((Mrows * nx + 255) / 256, 1 << 20);
+        SPUQ_LAUNCH(k_sep_assemble, dim3(eb), dim3(256), 0, stream, sv, L, R, Gf, Gl, Z, gate);
+        auto rowgemm = [&](const double* src, double* dst, int32_t nk, int32_t nc, const double* Q) {
+            const dim3 g((unsigned)((Mrows + GM - 1) / GM), (unsigned)((nc + GN - 1) / GN));
+            SPUQ_LAUNCH(k_rowgemm, g, dim3(G_THREADS), 0, stream, Mrows, nk, nc, src, nx, Q, dst, nx, gate);
+        };
+        const int64_t nthreads = (int64_t)L * nx;
+        const dim3 tg((unsigned)((nthreads + 127) / 128));
+        const int32_t h = p->half;
+        if (h > 0) {
+            const size_t hh = (size_t)h * h;
+            const unsigned mb = (unsigned)std::min<int64_t>((Mrows * h + 255) / 256, 1 << 20);
+            SPUQ_LAUNCH(k_mirror_split, dim3(mb), dim3(256), 0, stream, Mrows, nx, Z, Z2, gate);
+            rowgemm(Z2, Z, h, h, p->qsplit_dev);
+            rowgemm(Z2 + h, Z + h, h, h, p->qsplit_dev + hh);
+            SPUQ_LAUNCH(k_thomas_sep, tg, dim3(128), 0, stream, nx, q, L, sp->sy_ipiv, sp->sy_off, Z, gate);
+            rowgemm(Z, Z2, h, h, p->qsplit_dev + 2 * hh);
+            rowgemm(Z + h, Z2 + h, h, h, p->qsplit_dev + 3 * hh);
+            SPUQ_LAUNCH(k_mirror_merge, dim3(mb), dim3(256), 0, stream, Mrows, nx, Z2, gate);
+            U = Z2;
+        } else {
+            rowgemm(Z, Z2, nx, nx, p->q_dev);
+            SPUQ_LAUNCH(k_thomas_sep, tg, dim3(128), 0, stream, nx, q, L, sp->sy_ipiv, sp->sy_off, Z2, gate);
+            rowgemm(Z2, Z, nx, nx, p->q_dev);
+            U = Z;
+        }
+    }
+    SPUQ_LAUNCH((k_strip<true>), grid, block, sp->smem_bytes, stream, sv, L, R, S, Gf, Gl, U, gate);
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+
 int mean_fd_destroy(spuq_sg_precond* p) {
     cudaSetDevice(p->device);
     cudaFree(p->q_dev);
@@ -236,26 +413,26 @@ int mean_fd_destroy(spuq_sg_precond* p) {
     cudaFree(p->qsplit_dev);
     cudaFree(p->piv_split_dev);
     p->q_dev = p->piv_dev = p->qsplit_dev = p->piv_split_dev = nullptr;
-#ifndef SPUQ_EMU
-    if (p->blas) { cublas_api().destroy(p->blas); p->blas = nullptr; }
-#endif
+    strip_plan_destroy(p);
     return SPUQ_OK;
 }
 
-int64_t mean_fd_work_bytes(const spuq_sg_precond*, int64_t N, int32_t L) {
-    return (int64_t)sizeof(double) * N * L;
+int64_t mean_fd_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L) {
+    // the strip path needs room for the first/last rows of every strip and the separator rows; callers
+    // of the forward/inverse halves still need a whole slab
+    int64_t need = (int64_t)sizeof(double) * N * L;
+    if (p->strip) need = std::max<int64_t>(need, (int64_t)sizeof(double) * strip_work_doubles(static_cast<const StripPlan*>(p->strip), L));
+    return need;
 }
 
 int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
                   cudaStream_t stream, const double* gate) {
     SPUQ_REQUIRE(N == (int64_t)p->nx * p->ny, "precond_mean_fd: slab rows %lld != nx*ny", (long long)N);
+    if (p->strip) return strip_apply(p, N, L, R, S, work, stream, gate);
     SPUQ_REQUIRE(work != nullptr, "precond_mean_fd: workspace missing");
     double* T = static_cast<double*>(work);
     const int64_t Mrows = (int64_t)L * p->ny;
     auto rowgemm = [&](const double* src, double* dst, int32_t nk, int32_t nc, const double* Q) {
-#ifndef SPUQ_EMU
-        if (blas_rowgemm(p, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, stream)) return;
-#endif
         const dim3 g((unsigned)((Mrows + GM - 1) / GM), (unsigned)((nc + GN - 1) / GN));
         SPUQ_LAUNCH(k_rowgemm, g, dim3(G_THREADS), 0, stream, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, gate);
     };
@@ -293,9 +470,6 @@ int mean_fd_forward(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, d
     const int64_t Mrows = (int64_t)L * p->ny;
     const double* gate = nullptr;
     auto rowgemm = [&](const double* src, double* dst, int32_t nk, int32_t nc, const double* Q) {
-#ifndef SPUQ_EMU
-        if (blas_rowgemm(p, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, stream)) return;
-#endif
         const dim3 g((unsigned)((Mrows + GM - 1) / GM), (unsigned)((nc + GN - 1) / GN));
         SPUQ_LAUNCH(k_rowgemm, g, dim3(G_THREADS), 0, stream, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, gate);
     };
@@ -326,9 +500,6 @@ int mean_fd_inverse(spuq_sg_precond* p, int64_t N, int32_t L, const double* T, d
     const int64_t Mrows = (int64_t)L * p->ny;
     const double* gate = nullptr;
     auto rowgemm = [&](const double* src, double* dst, int32_t nk, int32_t nc, const double* Q) {
-#ifndef SPUQ_EMU
-        if (blas_rowgemm(p, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, stream)) return;
-#endif
         const dim3 g((unsigned)((Mrows + GM - 1) / GM), (unsigned)((nc + GN - 1) / GN));
         SPUQ_LAUNCH(k_rowgemm, g, dim3(G_THREADS), 0, stream, Mrows, nk, nc, src, p->nx, Q, dst, p->nx, gate);
     };
@@ -462,6 +633,7 @@ extern "C" int spuq_sg_precond_mean_fd(spuq_sg_precond** out, int device, int32_
     }
     cudaMemcpy(p->q_dev, q.data(), sizeof(double) * q.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(p->piv_dev, piv.data(), sizeof(double) * piv.size(), cudaMemcpyHostToDevice);
+    strip_plan_build(p);
     *out = p;
     return SPUQ_OK;
 }

@@ -3,7 +3,7 @@
 #include "common.h"
 
 struct spuq_sg_precond {
-    enum Kind { IDENTITY = 0, PLAN = 1, MEAN_FD = 2 } kind = IDENTITY;
+    enum Kind { IDENTITY = 0, PLAN = 1, MEAN_FD = 2, SPARSE_LU = 3 } kind = IDENTITY;
     double scale = 1.0;              // IDENTITY
     spuq_sg_plan* plan = nullptr;    // PLAN (borrowed)
     // MEAN_FD: A_0 = tridiag_x(ox, dxx, ox) (+) tridiag_y(oy, dyy, oy) on an nx x ny grid
@@ -13,15 +13,27 @@ struct spuq_sg_precond {
     double* q_dev = nullptr;         // nx x nx sine-transform matrix (symmetric, orthogonal)
     double* lam_dev = nullptr;       // nx eigenvalues of the x part
     double* piv_dev = nullptr;       // nx x ny Thomas pivots of (T_y + lam_k I)
-    void* blas = nullptr;            // cublasHandle_t when libcublas could be loaded (else the in-house GEMM)
     // even nx: the sine transform split by the parity of the mode (two products of half the size)
     int32_t half = 0;                // nx / 2 when the split is used, else 0
     double* qsplit_dev = nullptr;    // four half x half matrices: Qe, Qo (forward), Qe^T, Qo^T (inverse)
     double* piv_split_dev = nullptr; // pivots with the modes ordered even | odd
+    // two-level strip partition (precond_strip.cuh): opaque spuq::StripPlan*, null when the shape does
+    // not allow it (then the full-length transform above is used)
+    void* strip = nullptr;
+    // SPARSE_LU: opaque spuq::LuPlan* (precond_lu.cu)
+    void* lu = nullptr;
 };
 
 namespace spuq {
 int mean_fd_destroy(spuq_sg_precond* p);
+// strip path (precond_strip.cuh / precond.cu)
+int strip_plan_build(spuq_sg_precond* p);
+void strip_plan_destroy(spuq_sg_precond* p);
+// general mean block through a sparse LU factorisation (precond_lu.cu)
+void lu_plan_destroy(spuq_sg_precond* p);
+int64_t lu_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L);
+int lu_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work, cudaStream_t stream,
+             const double* gate);
 int64_t mean_fd_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L);
 int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
                   cudaStream_t stream, const double* gate);

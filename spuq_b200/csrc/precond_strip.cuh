@@ -1,0 +1,294 @@
+// precond_strip.cuh -- K4, the fast form of the exact mean solve  S[:, mu] = A_0^{-1} R[:, mu]  for a
+// constant-coefficient 5-point block  A_0 = I_y (x) T_x + T_y (x) I_x  on an nx x ny grid
+// (replaces the per-column sparse direct solve of PreconditioningOperator.apply,
+// application/egsz/multi_operator2.py:151-165 / linalg/scipy_operator.py:45-49).
+//
+// Why this shape.  Fast diagonalisation needs a sine transform of length nx (or ny) per grid line.
+// For the grids of the configurations (500, 512, 1000: nx + 1 = 3*167, 27*19, 7*11*13) there is no
+// FFT to speak of, and a dense transform costs nx/2 multiply-adds per dof and direction: 1.25 TFLOP
+// per application on configuration 4 (54 ms in round 1, on cuBLAS).  This file removes the long
+// transform from the bulk of the data by an exact two-level partition (block elimination, no
+// approximation):
+//
+//   level 1 (grid rows): q separator rows cut the grid into strips of c <= 32 rows.  A strip of one
+//       slab column is c*nx contiguous doubles (<= 110 KB) and is solved entirely in shared memory:
+//         - sine transform of length c along y (one thread per grid column, c*c/2 DFMA, the matrix
+//           in shared memory, mirror sums/differences halve the work);
+//         - per y-mode a Toeplitz tridiagonal system along x, itself cut by x-separators into chunks
+//           of ~31 points: chunk-local Thomas sweeps (one thread per (mode, chunk)), a small
+//           separator system per mode, correction with the chunk's spike;
+//         - transform back.
+//       k_strip<false> does this for the right-hand side and keeps only the first and last row of each
+//       strip's solution (all the separator equations need), k_strip<true> repeats it with the separator
+//       values moved to the right-hand side and writes the solution.
+//   level 2 (separator rows, q/ny ~ 3 % of the data): the Schur complement of the separator rows is
+//       block tridiagonal with blocks that are functions of T_x, i.e. diagonal in the sine basis of
+//       length nx: dense transform of the q rows (the in-house fp64 GEMM of precond.cu), per mode a
+//       q x q tridiagonal solve, transform back.
+//
+// HBM traffic: R is read twice, S written once (24 N L bytes) instead of ten slab passes; flops per
+// dof ~ 2.5 c + 30 instead of 2 nx.  No library call anywhere on the path.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.h"
+#include "precond.h"
+
+namespace spuq {
+
+constexpr int STRIP_THREADS = 256;
+constexpr int STRIP_CMAX = 32;        // strip height limit (registers of the y-transform)
+constexpr int STRIP_HP = 16;          // ceil(CMAX / 2)
+
+// Device view of the strip plan (passed by value).
+struct StripView {
+    int32_t nx, ny, P, q;             // P strips, q = P - 1 separator rows
+    int32_t PX, qx;                   // x-chunks per row, x-separators (= PX - 1)
+    int32_t cxmax;                    // longest chunk
+    double ox, oy;
+    const int32_t* ystart;            // P: first grid row of strip p
+    const int32_t* ycls;              // P: height class of strip p
+    const int32_t* xstart;            // PX: first x of chunk ch
+    const int32_t* xlen;              // PX
+    int32_t ch[2];                    // heights of the two classes
+    // per class: Q (c x HP, parity folded), x-direction tables per mode j
+    const double* qc[2];              // [c][HP]
+    const double* ipivx[2];           // [c][cxmax]   reciprocal Thomas pivots of tridiag(ox, dxx + theta_j, ox)
+    const double* spike[2];           // [2][c][cxmax] first spike (T_len^{-1} e_0) for the two chunk lengths
+    const double* sx_ipiv[2];         // [c][qx]      x-separator system: reciprocal pivots
+    const double* sx_off[2];          // [c][qx]      ... off-diagonal between separator i and i+1
+    int32_t xlen_cls_len[2];          // chunk lengths of the two chunk classes
+};
+
+#ifdef SPUQ_EMU
+#define STRIP_T0 0
+#define STRIP_TS 1
+#define STRIP_SYNC()
+#else
+#define STRIP_T0 ((int)threadIdx.x)
+#define STRIP_TS ((int)blockDim.x)
+#define STRIP_SYNC() __syncthreads()
+#endif
+
+// y-transform of grid column x of the strip: out[j] = sum_i Q[j][i] strip[i][x] with the mirror symmetry
+// Q[j][c-1-i] = (-1)^j Q[j][i] folded: qc[j*HP + i] = Q[j][i] for i < ceil(c/2), 0 beyond.  All inputs
+// are read (mirror sums p, differences m) before `emit(j, value)` is called for the first row, so the
+// transform may overwrite its own column.
+template <typename Emit>
+__device__ __forceinline__ void strip_ytransform(const double* __restrict__ qc, const double* __restrict__ colx,
+                                                 int nx, int c, Emit emit) {
+    double p[STRIP_HP], m[STRIP_HP];
+    const int half = c >> 1;
+#pragma unroll
+    for (int s = 0; s < STRIP_HP; ++s) {
+        if (s < half) {
+            const double a = colx[(size_t)s * nx], b = colx[(size_t)(c - 1 - s) * nx];
+            p[s] = a + b; m[s] = a - b;
+        } else if (s == half && (c & 1)) {
+            p[s] = colx[(size_t)s * nx]; m[s] = 0.0;
+        } else {
+            p[s] = 0.0; m[s] = 0.0;
+        }
+    }
+    for (int j = 0; j < c; j += 2) {            // even modes: symmetric part
+        const double* q = qc + j * STRIP_HP;
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < STRIP_HP; ++i) acc = fma(q[i], p[i], acc);
+        emit(j, acc);
+    }
+    for (int j = 1; j < c; j += 2) {            // odd modes: antisymmetric part
+        const double* q = qc + j * STRIP_HP;
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < STRIP_HP; ++i) acc = fma(q[i], m[i], acc);
+        emit(j, acc);
+    }
+}
+
+// One strip of one slab column.  FINAL = false: Gf/Gl <- first / last row of A_strip^{-1} R_strip.
+// FINAL = true: S_strip <- A_strip^{-1} (R_strip - oy * separator values on the adjacent rows), and the
+// separator row below the strip is copied from U.
+template <bool FINAL>
+__global__ void __launch_bounds__(STRIP_THREADS, 2)
+k_strip(StripView sv, int32_t L, const double* __restrict__ R, double* __restrict__ S,
+        double* __restrict__ Gf, double* __restrict__ Gl, const double* __restrict__ U, const double* gate) {
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+#ifdef SPUQ_EMU
+    if (threadIdx.x != 0) return;
+    std::vector<double> smem_store((size_t)STRIP_CMAX * sv.nx + STRIP_CMAX * STRIP_HP + STRIP_CMAX * (sv.qx + 1));
+    double* smem = smem_store.data();
+#else
+    extern __shared__ __align__(16) double smem[];
+#endif
+    const int nx = sv.nx;
+    const int p = (int)(blockIdx.x % (unsigned)sv.P);
+    const int64_t col = blockIdx.x / (unsigned)sv.P;
+    if (col >= L) return;
+    const int cls = sv.ycls[p];
+    const int c = sv.ch[cls];
+    const int y0 = sv.ystart[p];
+    double* qc = smem;                                  // [c][HP]
+    double* sepv = qc + STRIP_CMAX * STRIP_HP;          // [c][qx]
+    double* strip = sepv + STRIP_CMAX * (sv.qx > 0 ? sv.qx : 1);   // [c][nx]
+    const int64_t N = (int64_t)nx * sv.ny;
+    const double* src = R + col * N + (int64_t)y0 * nx;
+
+    // ---- phase 0: strip and transform matrix into shared memory ------------------------------------
+    for (int i = STRIP_T0; i < c * STRIP_HP; i += STRIP_TS) qc[i] = sv.qc[cls][i];     // zero beyond ceil(c/2)
+    for (int i = STRIP_T0; i < c * nx; i += STRIP_TS) strip[i] = src[i];
+    if (FINAL) {
+        STRIP_SYNC();
+        const double oy = sv.oy;
+        for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
+            if (p > 0) strip[x] -= oy * U[(col * sv.q + (p - 1)) * nx + x];
+            if (p < sv.q) strip[(size_t)(c - 1) * nx + x] -= oy * U[(col * sv.q + p) * nx + x];
+        }
+        // separator row below this strip
+        if (p < sv.q) {
+            double* dst = S + col * N + (int64_t)(y0 + c) * nx;
+            const double* us = U + (col * sv.q + p) * nx;
+            for (int x = STRIP_T0; x < nx; x += STRIP_TS) dst[x] = us[x];
+        }
+    }
+    STRIP_SYNC();
+
+    // ---- phase 1: sine transform along y, one thread per grid column -------------------------------
+    for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
+        strip_ytransform(qc, strip + x, nx, c, [&](int j, double a) { strip[(size_t)j * nx + x] = a; });
+    }
+    STRIP_SYNC();
+
+    // ---- phase 2a: chunk-local Thomas sweeps along x, one thread per (mode, chunk) --------------------
+    const int PX = sv.PX, qx = sv.qx, cxmax = sv.cxmax;
+    const double ox = sv.ox;
+    const double* ipx = sv.ipivx[cls];
+    for (int task = STRIP_T0; task < c * PX; task += STRIP_TS) {
+        const int j = task / PX, ch = task - j * PX;
+        const int x0 = sv.xstart[ch], len = sv.xlen[ch];
+        double* r = strip + (size_t)j * nx + x0;
+        const double* ip = ipx + (size_t)j * cxmax;
+        // one dependent DFMA per step: the factors come from the table, not from the recurrence
+        double z = r[0];
+        for (int t = 1; t < len; ++t) {
+            z = fma(-ox * __ldg(ip + t - 1), z, r[t]);
+            r[t] = z;
+        }
+        double u = z * __ldg(ip + len - 1);
+        r[len - 1] = u;
+        for (int t = len - 2; t >= 0; --t) {
+            const double pv = __ldg(ip + t);
+            u = fma(-ox * pv, u, r[t] * pv);
+            r[t] = u;
+        }
+    }
+    STRIP_SYNC();
+
+    // ---- phase 2b: x-separator system of every mode (tridiagonal, qx unknowns) -------------------------
+    if (qx > 0) {
+        for (int j = STRIP_T0; j < c; j += STRIP_TS) {
+            double* row = strip + (size_t)j * nx;
+            const double* sip = sv.sx_ipiv[cls] + (size_t)j * qx;
+            const double* sof = sv.sx_off[cls] + (size_t)j * qx;
+            double* sv_j = sepv + (size_t)j * qx;
+            double z = 0.0;
+            for (int i = 0; i < qx; ++i) {
+                const int xs = sv.xstart[i] + sv.xlen[i];          // separator between chunk i and i+1
+                double rhs = row[xs] - ox * (row[xs - 1] + row[xs + 1]);
+                if (i > 0) rhs -= __ldg(sof + i - 1) * __ldg(sip + i - 1) * z;
+                z = rhs;
+                sv_j[i] = z;
+            }
+            double u = 0.0;
+            for (int i = qx - 1; i >= 0; --i) {
+                const double e = (i + 1 < qx) ? __ldg(sof + i) * u : 0.0;
+                u = (sv_j[i] - e) * __ldg(sip + i);
+                sv_j[i] = u;
+                row[sv.xstart[i] + sv.xlen[i]] = u;
+            }
+        }
+        STRIP_SYNC();
+        // ---- phase 2c: chunks corrected with their spikes ------------------------------------------
+        for (int task = STRIP_T0; task < c * PX; task += STRIP_TS) {
+            const int j = task / PX, ch = task - j * PX;
+            const int x0 = sv.xstart[ch], len = sv.xlen[ch];
+            const int lc = (len == sv.xlen_cls_len[0]) ? 0 : 1;
+            const double* sp = sv.spike[cls] + ((size_t)lc * c + j) * cxmax;
+            const double sl = (ch > 0) ? sepv[(size_t)j * qx + ch - 1] : 0.0;
+            const double sr = (ch < qx) ? sepv[(size_t)j * qx + ch] : 0.0;
+            double* r = strip + (size_t)j * nx + x0;
+            const double a = ox * sl, b = ox * sr;
+            for (int t = 0; t < len; ++t) r[t] -= a * __ldg(sp + t) + b * __ldg(sp + len - 1 - t);
+        }
+        STRIP_SYNC();
+    }
+
+    // ---- phase 3: transform back -------------------------------------------------------------------
+    if (FINAL) {
+        double* dst = S + col * N + (int64_t)y0 * nx;
+        for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
+            strip_ytransform(qc, strip + x, nx, c, [&](int j, double a) { dst[(size_t)j * nx + x] = a; });
+        }
+    } else {
+        double* gf = Gf + (col * sv.P + p) * nx;
+        double* gl = Gl + (col * sv.P + p) * nx;
+        for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
+            // rows 0 and c-1 of Q u: Q[0][j] and Q[c-1][j] = (-1)^j Q[0][j]
+            double se = 0.0, so = 0.0;
+            for (int j = 0; j < c; ++j) {
+                // Q[0][j] = Q[j][0] (symmetric) = qc[j*HP + 0]
+                const double t = qc[j * STRIP_HP] * strip[(size_t)j * nx + x];
+                if (j & 1) so += t; else se += t;
+            }
+            gf[x] = se + so;
+            gl[x] = se - so;
+        }
+    }
+}
+
+// Z[col][j][x] = R[col][ysep_j][x] - oy * (Gl[col][j][x] + Gf[col][j+1][x])
+__global__ void __launch_bounds__(256)
+k_sep_assemble(StripView sv, int32_t L, const double* __restrict__ R, const double* __restrict__ Gf,
+               const double* __restrict__ Gl, double* __restrict__ Z, const double* gate) {
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+    const int nx = sv.nx, q = sv.q;
+    const int64_t total = (int64_t)L * q * nx;
+    const int64_t N = (int64_t)nx * sv.ny;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(t % nx);
+        const int64_t r = t / nx;
+        const int j = (int)(r % q);
+        const int64_t col = r / q;
+        const int ys = sv.ystart[j] + sv.ch[sv.ycls[j]];
+        Z[t] = R[col * N + (int64_t)ys * nx + x]
+               - sv.oy * (Gl[(col * sv.P + j) * nx + x] + Gf[(col * sv.P + j + 1) * nx + x]);
+    }
+}
+
+// Tridiagonal solves of the separator system in the transformed domain, in place on X[col][j][k]:
+// one thread per (column, mode k), lanes along k.  ipiv[j*nx + k], off[j*nx + k] (coupling j <-> j+1).
+__global__ void __launch_bounds__(128)
+k_thomas_sep(int32_t nx, int32_t q, int32_t L, const double* __restrict__ ipiv, const double* __restrict__ off,
+             double* __restrict__ X, const double* gate) {
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)L * nx) return;
+    const int32_t k = (int32_t)(t % nx);
+    const int64_t col = t / nx;
+    double* x = X + col * (int64_t)nx * q + k;
+    double z = x[0];
+    for (int32_t j = 1; j < q; ++j) {
+        z = x[(int64_t)j * nx] - off[(int64_t)(j - 1) * nx + k] * ipiv[(int64_t)(j - 1) * nx + k] * z;
+        x[(int64_t)j * nx] = z;
+    }
+    double u = z * ipiv[(int64_t)(q - 1) * nx + k];
+    x[(int64_t)(q - 1) * nx] = u;
+    for (int32_t j = q - 2; j >= 0; --j) {
+        u = (x[(int64_t)j * nx] - off[(int64_t)j * nx + k] * u) * ipiv[(int64_t)j * nx + k];
+        x[(int64_t)j * nx] = u;
+    }
+}
+
+}  // namespace spuq

@@ -498,9 +498,9 @@ class ScipyOperator(_CsrLeaf):
 
 class ScipySolveOperator(BaseOperator):
     """Sparse direct solve block (scipy_operator.py:43-61): the callback result handed to
-    ``PreconditioningOperator``.  It only *describes* the mean block; the GPU preconditioner
-    recognises a constant-coefficient 5-point block and solves it exactly on the device
-    (multi_operator.PreconditioningOperator)."""
+    ``PreconditioningOperator``.  It only *describes* the mean block; the GPU preconditioner solves it
+    exactly on the device -- with the strip solver when it recognises a constant-coefficient 5-point
+    block, through a sparse LU factorisation otherwise (multi_operator.mean_solver_for)."""
 
     def __init__(self, matrix, domain=None, codomain=None):
         if not sps.issparse(matrix):
@@ -518,8 +518,8 @@ class ScipySolveOperator(BaseOperator):
         return sps.csr_matrix(self._matrix, dtype=np.float64)
 
     def apply(self, vec):
-        from .multi_operator import MeanSolveSlabOperator
+        from .multi_operator import mean_solver_for
         if getattr(self, "_solver", None) is None:
-            self._solver = MeanSolveSlabOperator(self.as_csr(), n_columns=1)
+            self._solver = mean_solver_for(self.as_csr(), n_columns=1)
         y = self._solver.apply_array(np.ascontiguousarray(vec.coeffs, dtype=np.float64))
         return type(vec)(y, self.codomain)

@@ -31,7 +31,7 @@ from .multi_vector import MultiVector, SlabMultiVector
 logger = logging.getLogger(__name__)
 
 __all__ = ["MultiOperator", "PreconditioningOperator", "DeviceBlocks", "CsrSlabOperator",
-           "MeanSolveSlabOperator", "SGPlan"]
+           "MeanSolveSlabOperator", "SparseLUSlabOperator", "mean_solver_for", "SGPlan"]
 
 
 # ---- spatial blocks on the device ----------------------------------------------------------------
@@ -266,6 +266,56 @@ class MeanSolveSlabOperator:
             pass
 
 
+class SparseLUSlabOperator:
+    """Exact solve with ANY sparse mean block on every column (K4, general form): the matrix is
+    factorised once on the host with SuperLU (``scipy.sparse.linalg.splu``, the solver behind the
+    reference's ``ScipySolveOperator.apply``, linalg/scipy_operator.py:45-49) and the triangular solves
+    run on the device for the whole slab (csrc/precond_lu.cu).  Same interface as
+    ``MeanSolveSlabOperator``."""
+
+    def __init__(self, csr, n_columns=1):
+        import scipy.sparse.linalg as spla
+        csr = sps.csr_matrix(csr, dtype=np.float64)
+        if csr.shape[0] != csr.shape[1]:
+            raise ValueError("the mean block must be square")
+        self.N = n = csr.shape[0]
+        self.L = int(n_columns)
+        lu = spla.splu(csr.tocsc())
+        Lr = sps.csr_matrix(lu.L)                      # unit lower triangular
+        Ur = sps.csr_matrix(lu.U)
+        Lr.sort_indices(); Ur.sort_indices()
+        Ls = sps.tril(Lr, k=-1, format="csr")
+        Us = sps.triu(Ur, k=1, format="csr")
+        diag = np.ascontiguousarray(Ur.diagonal(), dtype=np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)        # noqa: E731
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)      # noqa: E731
+        keep = [i32(Ls.indptr), i32(Ls.indices), f64(Ls.data), i32(Us.indptr), i32(Us.indices), f64(Us.data),
+                diag, i32(lu.perm_r), i32(lu.perm_c)]
+        self.nnz_factors = int(Ls.nnz + Us.nnz + n)
+        handle = C.c_void_p()
+        _abi.check(_abi.lib().spuq_sg_precond_sparse_lu(C.byref(handle), _abi.device_index(), n,
+                                                        *[_abi.ptr(a) for a in keep]), "precond_sparse_lu")
+        self.handle = handle
+        self._work = None
+
+    set_columns = MeanSolveSlabOperator.set_columns
+    apply_slab = MeanSolveSlabOperator.apply_slab
+    apply_array = MeanSolveSlabOperator.apply_array
+    __del__ = MeanSolveSlabOperator.__del__
+
+
+def mean_solver_for(csr, n_columns=1):
+    """The device solver for a mean block: the fast strip solver when the block is a constant-coefficient
+    5-point stencil on a tensor grid, the sparse-LU solver for everything else (variable coefficients,
+    permuted or unstructured numbering) -- the reference accepts any matrix here."""
+    try:
+        return MeanSolveSlabOperator(csr, n_columns)
+    except _abi.SpuqError as e:
+        if "mean block is not" not in str(e):
+            raise
+        return SparseLUSlabOperator(csr, n_columns)
+
+
 # ---- the SG operator -------------------------------------------------------------------------------
 class MultiOperator(Operator):
     """Discrete SG operator on one shared spatial basis (EGSZ (2.6) generalised to spuq's
@@ -394,14 +444,22 @@ class PreconditioningOperator(Operator):
         re-factorises per column and per iteration, multi_operator2.py:159)."""
         basis = w.spatial_basis
         if self._solver is None or self._solver[0] != basis:
+            # the reference computes `A0 * w[mu]` with whatever operator the callback returns
+            # (multi_operator2.py:159): dispatch on the operator TYPE -- a solve-type leaf becomes a device
+            # solver, a multiply-type leaf (ScipyOperator, MatrixOperator, DiagonalMatrixOperator, and
+            # MatrixSolveOperator through its explicit inverse) is applied as the matrix it is
+            from .linalg import ScipySolveOperator, _CsrLeaf
             op = self._assemble_solver(basis, self._mean_func)
             if hasattr(op, "slab_solver"):
                 solver = op.slab_solver()
-            elif hasattr(op, "as_matrix") and not hasattr(op, "matrix") and not hasattr(op, "_matrix"):
-                # explicit (dense) inverse, e.g. MatrixSolveOperator: apply it as a matrix
-                solver = CsrSlabOperator(sps.csr_matrix(np.asarray(op.as_matrix())), len(w))
+            elif isinstance(op, ScipySolveOperator):
+                solver = mean_solver_for(op.as_csr(), len(w))
+            elif isinstance(op, _CsrLeaf):
+                solver = CsrSlabOperator(op.as_csr(), len(w))
             else:
-                solver = MeanSolveSlabOperator(_block_to_csr(op), len(w))
+                raise TypeError("PreconditioningOperator: the assemble_solver callback returned %s, which has "
+                                "no device form (supported: ScipySolveOperator, MatrixSolveOperator, "
+                                "ScipyOperator, MatrixOperator, DiagonalMatrixOperator)" % type(op).__name__)
             self._solver = (basis, solver)
         return self._solver[1]
 

@@ -19,7 +19,7 @@ from . import _abi
 from .linalg import (DiagonalMatrixOperator, FlatVector, MatrixOperator, MatrixSolveOperator,
                      MultiplicationOperator, Operator, ScipyOperator, Vector, _CsrLeaf)
 from .multi_operator import (CsrSlabOperator, MeanSolveSlabOperator, MultiOperator,
-                             PreconditioningOperator, SGPlan)
+                             PreconditioningOperator, SGPlan, SparseLUSlabOperator)
 from .multi_vector import MultiVector, SlabMultiVector
 from .multiindex import Multiindex
 
@@ -52,7 +52,7 @@ class _Precond:
         return cls(h, keep=(plan, keep))
 
     def close(self):
-        if self.handle is not None and not isinstance(self.keep, MeanSolveSlabOperator):
+        if self.handle is not None and not isinstance(self.keep, (MeanSolveSlabOperator, SparseLUSlabOperator)):
             _abi.lib().spuq_sg_precond_destroy(self.handle)
         self.handle = None
 
@@ -70,7 +70,7 @@ def _precond_for(P, slab):
         return _Precond.identity(P._a)
     if isinstance(P, PreconditioningOperator):
         solver = P.slab_operator(slab)
-        if isinstance(solver, MeanSolveSlabOperator):
+        if isinstance(solver, (MeanSolveSlabOperator, SparseLUSlabOperator)):
             solver.set_columns(L)
             return _Precond(solver.handle, keep=solver)
         if solver.plan.L != L:

@@ -79,9 +79,12 @@ def fd_values(a_nodal, valid):
 
 
 def _coefficient(n, k1, k2, amp, device, dtype=torch.float64):
-    x = torch.linspace(0.0, 1.0, n + 2, device=device, dtype=dtype)
-    cx = torch.cos(math.pi * k1 * x)
-    cy = torch.cos(math.pi * k2 * x)
+    # the 1-D cosine factors are evaluated with numpy on the host (n + 2 values) so that every device and
+    # the oracle-side generator (oracle/synth.py) see bit-identical blocks; the outer product and the
+    # face averages are single IEEE operations and round the same everywhere
+    x = np.linspace(0.0, 1.0, n + 2)
+    cx = torch.from_numpy(np.cos(math.pi * k1 * x)).to(device=device, dtype=dtype)
+    cy = torch.from_numpy(np.cos(math.pi * k2 * x)).to(device=device, dtype=dtype)
     return amp * cy[:, None] * cx[None, :]          # [iy, ix]: x1 runs along ix
 
 

@@ -696,7 +696,10 @@ def check_mean_preconditioner():
     from spuq_b200.multi_operator import MeanSolveSlabOperator
     rng = np.random.RandomState(21)
     # even nx takes the parity-split transform (half sizes 6, 35, 65, 2, 3: even and odd; nx < 4 keeps the full transform), odd nx the full one
-    for nx, ny, L in [(12, 12, 5), (70, 9, 3), (9, 33, 4), (130, 2, 2), (17, 1, 3), (4, 3, 2), (6, 7, 3)]:
+    # ny > 32 and nx > 31 exercise the two-level strip partition (several strips of two heights, x-chunks
+    # of two lengths with their separator systems); the rest a single strip / the plain transform
+    for nx, ny, L in [(12, 12, 5), (70, 9, 3), (9, 33, 4), (130, 2, 2), (17, 1, 3), (4, 3, 2), (6, 7, 3),
+                      (70, 75, 3), (33, 67, 2), (95, 64, 2), (31, 100, 2), (64, 34, 2), (100, 133, 1)]:
         T = lambda n, o, dd: sps.diags([o, dd, o], [-1, 0, 1], shape=(n, n))      # noqa: E731
         if ny > 1:
             A0 = sps.kron(sps.identity(ny), T(nx, -1.0, 2.0)) + sps.kron(T(ny, -1.0, 2.0), sps.identity(nx))
@@ -719,6 +722,80 @@ def check_mean_preconditioner():
         assert err <= 1e-12, (nx, ny, err, "in place")
     with pytest.raises(_abi.SpuqError, match="constant-coefficient"):
         MeanSolveSlabOperator(sps.csr_matrix(sps.diags([np.arange(1.0, 10.0)], [0])), 1)
+
+
+def check_sparse_lu_preconditioner():
+    """Exact mean solve for blocks the strip solver does not recognise -- variable coefficients, a
+    renumbered grid, an unsymmetric matrix -- against scipy's sparse direct solve
+    (ScipySolveOperator.apply, linalg/scipy_operator.py:45-49)."""
+    import scipy.sparse.linalg as spla
+    from oracle import synth
+    from spuq_b200.multi_operator import SparseLUSlabOperator, mean_solver_for
+    rng = np.random.RandomState(5)
+    n = 20
+    mats = synth.fd_matrices(n, 2)
+    var = sps.csr_matrix(mats[0] + 0.7 * mats[1] + 0.2 * mats[2])            # variable mean field
+    perm = synth.tile_permutation(n, 5)
+    cases = {"variable": var, "permuted": synth.permuted([mats[0]], perm)[0],
+             "unsymmetric": sps.csr_matrix(var + sps.diags([0.3 * rng.random_sample(n * n - 1)], [1]))}
+    for name, A0 in cases.items():
+        N = A0.shape[0]
+        for L in (1, 7, 40):
+            R = rng.random_sample((L, N))
+            solver = mean_solver_for(A0, L)
+            assert isinstance(solver, SparseLUSlabOperator), name
+            Rt = _dev(torch.from_numpy(R.copy()))
+            St = torch.empty_like(Rt)
+            solver.apply_slab(Rt, St)
+            lu = spla.splu(A0.tocsc())
+            ref = np.stack([lu.solve(R[k]) for k in range(L)])
+            err = np.max(np.linalg.norm(St.cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1))
+            assert err <= 1e-12, (name, L, err)
+            solver.apply_slab(Rt, Rt)                               # in place
+            err = np.max(np.linalg.norm(Rt.cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1))
+            assert err <= 1e-12, (name, L, err, "in place")
+    # a constant-coefficient grid block still takes the strip solver
+    from spuq_b200.multi_operator import MeanSolveSlabOperator
+    assert isinstance(mean_solver_for(mats[0], 3), MeanSolveSlabOperator)
+
+
+def check_pcg_variable_mean(n=12, M=3, p=2, eps=1e-10):
+    """PCG with the mean-based preconditioner when the mean field is NOT constant (the case round 1
+    refused): zeta trajectory and solution against the oracle's PCG with a sparse direct solve; and a
+    MULTIPLY-type operator returned by assemble_solver is applied as a matrix, as the reference's
+    `A0 * w[mu]` does (multi_operator2.py:159), not inverted."""
+    idx = synthetic.complete_order_indices(M, p)
+    c = fd_case(n, M, idx, "legendre")
+    # variable mean: A_0 <- A_0 + 0.6 A_1 (still SPD), the other blocks unchanged
+    mats = list(c.mats)
+    mats[0] = sps.csr_matrix(mats[0] + 0.6 * mats[1])
+    A_o, _ = oracle_operator(mats, c.orvs)
+    basis_o = olin.CanonicalBasis(c.N)
+    solve_o = olin.ScipySolveOperator(mats[0], basis_o, basis_o, factor=True)
+    P_o = osg.PreconditioningOperator("mean", lambda b, f: solve_o)
+    f_o = A_o * c.w
+    oh = []
+    x_o, zeta_o, it_o = osg.pcg(A_o, f_o, P_o, 0 * c.w, eps=eps, maxiter=100, history=oh)
+
+    A = sp.MultiOperator.from_blocks(DeviceBlocks.from_scipy(mats), c.rvs)
+    f = A.apply(sp.SlabMultiVector.from_array(idx, c.W))
+    assert relerr(f.to_array(), f_o.to_slab()) <= TOL
+    P = sp.PreconditioningOperator("mean", lambda b, f_: sp.ScipySolveOperator(mats[0], b, b))
+    ph = []
+    x, zeta, it = sp.pcg(A, f, P, 0 * f, eps=eps, maxiter=100, history=ph)
+    assert abs(it - it_o) <= 1, (it, it_o)
+    k = min(len(ph), len(oh)) - 1
+    assert np.allclose(ph[:k], oh[:k], rtol=1e-9), (ph, oh)
+    assert np.max(np.abs(x.to_array() - x_o.to_slab())) <= 1e-8
+    # multiply-type leaf as "preconditioner": P * f == A_0 f column by column
+    Pm = sp.PreconditioningOperator("mean", lambda b, f_: sp.ScipyOperator(mats[0], b, b))
+    s = (Pm * f).to_array()
+    ref = mats[0] @ f.to_array()
+    assert np.max(np.abs(s - ref)) <= 1e-12 * np.max(np.abs(ref))
+    Pd = sp.PreconditioningOperator("mean", lambda b, f_: sp.DiagonalMatrixOperator(mats[0].diagonal(), b, b).inverse())
+    s = (Pd * f).to_array()
+    ref = f.to_array() / mats[0].diagonal()[:, None]
+    assert np.max(np.abs(s - ref)) <= 1e-12 * np.max(np.abs(ref))
 
 
 def check_pcg_sg_mean(n=12, M=3, p=2, eps=1e-10):

@@ -76,6 +76,14 @@ def test_pcg_sg_mean():
     ps.check_pcg_sg_mean()
 
 
+def test_sparse_lu_preconditioner():
+    ps.check_sparse_lu_preconditioner()
+
+
+def test_pcg_variable_mean():
+    ps.check_pcg_variable_mean()
+
+
 def test_pcg_solve_and_prepare_rhs():
     ps.check_pcg_solve()
 

@@ -149,6 +149,14 @@ def test_pcg_sg_mean():
     ps.check_pcg_sg_mean()
 
 
+def test_sparse_lu_preconditioner():
+    ps.check_sparse_lu_preconditioner()
+
+
+def test_pcg_variable_mean():
+    ps.check_pcg_variable_mean()
+
+
 def test_row_sharded_pcg_single_rank():
     ps.check_row_sharded_pcg_single_rank()
     ps.check_row_sharded_pcg_single_rank(n=32, M=4, p=2)
@@ -160,34 +168,21 @@ def test_pcg_solve_and_prepare_rhs():
 
 
 # ---- full-size configurations ---------------------------------------------------------------------
-def _oracle_columns(mats_vals, rowptr, colidx, N, tables, W, cols):
-    """Oracle y[mu] for a few columns: the per-mu body of MultiOperator.apply
-    (multi_operator2.py:52-83) with scipy CSR leaves."""
-    import scipy.sparse as sps
-    rp, ci = rowptr.cpu().numpy(), colidx.cpu().numpy()
-    mats = {}
-
-    def mat(k):
-        if k not in mats:
-            mats[k] = sps.csr_matrix((mats_vals[k].cpu().numpy(), ci, rp), shape=(N, N))
-        return mats[k]
-    out = {}
-    for mu in cols:
-        w_mu = W[mu].cpu().numpy()
-        cur_v = mat(0) @ w_mu
-        for m in range(tables.maxm):
-            cur_w = -tables.beta_0[m, mu] * w_mu
-            if tables.nbr_up[m, mu] >= 0:
-                cur_w = cur_w + tables.beta_up[m, mu] * W[int(tables.nbr_up[m, mu])].cpu().numpy()
-            if tables.nbr_dn[m, mu] >= 0:
-                cur_w = cur_w + tables.beta_dn[m, mu] * W[int(tables.nbr_dn[m, mu])].cpu().numpy()
-            if np.any(cur_w):
-                cur_v = cur_v + mat(1 + m) @ cur_w
-        out[mu] = cur_v
+def _oracle_columns(n, M, idx, kind, mu, W, cols):
+    """Oracle y[mu] for a few output columns: `oracle.sg.MultiOperator.apply(w, only=...)`, the unchanged
+    loop body of multi_operator2.py:52-83, on inputs the ORACLE side builds for itself -- blocks from
+    oracle/synth.py, index set, `in Lambda` look-ups and beta values from the oracle's own classes.
+    Nothing of the product's plan (neighbour / beta tables) enters the expected values."""
+    from oracle import synth
+    from oracle.sampled import SampledApply
+    oidx = synth.index_set(idx) if isinstance(idx, tuple) else idx
+    mats = synth.fd_matrices(n, M)
+    sa = SampledApply(mats, oidx, kind, mu, cols, lambda k: W[k].cpu().numpy())
+    out, _ = sa.run()
     return out
 
 
-def _full_size(n, M, idx, kind, mu, sample_cols, variants):
+def _full_size(n, M, idx, kind, mu, sample_cols, variants, lam_spec=None):
     import spuq_b200 as sp
     from spuq_b200 import _abi, synthetic
     from spuq_b200.multi_operator import DeviceBlocks
@@ -203,7 +198,10 @@ def _full_size(n, M, idx, kind, mu, sample_cols, variants):
     plan = A.plan_for(w)
     y = A.apply(w)
     # (i) sampled columns against the oracle formula
-    ref = _oracle_columns(vals, rowptr, colidx, N, plan.tables, W, sample_cols)
+    if lam_spec is not None:
+        from oracle import synth
+        assert np.array_equal(synth.index_set(lam_spec), idx)      # the oracle's own construction of Lambda
+    ref = _oracle_columns(n, M, idx, kind, mu, W, sample_cols)
     ynorm = float(torch.linalg.norm(y.slab))
     for mu_, r in ref.items():
         err = np.linalg.norm(y.slab[mu_].cpu().numpy() - r) / np.linalg.norm(r)
@@ -240,7 +238,7 @@ def test_full_size_config2():
     from spuq_b200 import synthetic
     idx = synthetic.complete_order_indices(20, 3)
     _full_size(512, 20, idx, "legendre", 0.0, [0, 1, 7, 230, 231, 1000, 1770],
-               [(1, 0, 0, 0), (2, 4, 2, 0), (3, 8, 2, 0), (4, 3, 1, 0)])
+               [(1, 0, 0, 0), (2, 4, 2, 0), (3, 8, 2, 0), (4, 3, 1, 0)], lam_spec=("td", 20, 3))
 
 
 def test_full_size_config3_hermite_shifted():
@@ -248,7 +246,15 @@ def test_full_size_config3_hermite_shifted():
     reference's default NormalRV(mu=0.5) (beta0 != 0): 8 GB per slab."""
     from spuq_b200 import synthetic
     idx = synthetic.anisotropic_indices(50, 11.3)
-    _full_size(1000, 50, idx, "hermite", 0.5, [0, 3, 50, 500, 987], [(2, 4, 2, 0), (3, 8, 2, 0), (4, 3, 1, 0), (4, 2, 3, 0)])
+    _full_size(1000, 50, idx, "hermite", 0.5, [0, 3, 50, 500, 987], [(2, 4, 2, 0), (3, 8, 2, 0), (4, 3, 1, 0), (4, 2, 3, 0)],
+               lam_spec=("aniso", 50, 11.3))
+
+
+def test_full_size_config3_benchmarked():
+    """The workload bench.py times: config 3 with NormalRV(mu=0) (beta0 = 0), default kernel only."""
+    from spuq_b200 import synthetic
+    idx = synthetic.anisotropic_indices(50, 11.3)
+    _full_size(1000, 50, idx, "hermite", 0.0, [0, 1, 17, 333, 612, 987], [], lam_spec=("aniso", 50, 11.3))
 
 
 def test_full_size_config4_apply_and_pcg():
@@ -260,7 +266,7 @@ def test_full_size_config4_apply_and_pcg():
     from spuq_b200.multi_operator import DeviceBlocks
     n, M = 500, 30
     idx = synthetic.truncated_complete_indices(30, 3, 5000)
-    _full_size(n, M, idx, "legendre", 0.0, [0, 31, 2500, 4999], [(4, 3, 1, 0), (4, 2, 3, 0)])
+    _full_size(n, M, idx, "legendre", 0.0, [0, 31, 2500, 4999], [(4, 3, 1, 0), (4, 2, 3, 0)], lam_spec=("prefix", 30, 3, 5000))
     torch.cuda.empty_cache()
     dev = _abi.device()
     N, L = n * n, idx.shape[0]

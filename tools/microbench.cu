@@ -49,6 +49,14 @@ __global__ void k_lds(double* out, int iters, long long* clk) {
             double v = sm[((idx >> 1) + it * 32) & 4095];
             acc0 += v;
         }
+        if (MODE == 7) {   // lanes 2i, 2i+1 read the same double: 16 distinct addresses (128 B) per warp
+            double v = sm[((threadIdx.x >> 1) + it * 16) & 4095];
+            acc0 += v;
+        }
+        if (MODE == 8) {   // lanes i, i+16 read the same double (pairs across the half-warps)
+            double v = sm[((threadIdx.x & 15) + 16 * (threadIdx.x >> 5) + it * 16) & 4095];
+            acc0 += v;
+        }
         if (MODE == 2) {
             u = __shfl_xor_sync(0xffffffffu, u, 1) + 1;
             u = __shfl_xor_sync(0xffffffffu, u, 2) + 1;
@@ -303,6 +311,8 @@ int main(int argc, char** argv) {
         for (int warps : {8, 16, 32}) {
             run(k_lds<0>, "LDS.128", 16, 0, 0, warps);
             run(k_lds<1>, "LDS.64", 8, 0, 0, warps);
+            run(k_lds<7>, "LDS.64 lanes paired (2i,2i+1)", 8, 0, 0, warps);
+            run(k_lds<8>, "LDS.64 lanes paired (i,i+16)", 8, 0, 0, warps);
             run(k_lds<2>, "LDS.128 + 2 SHFL", 16, 2, 0, warps);
             run(k_lds<3>, "4 SHFL", 0, 4, 0, warps);
             run(k_lds<6>, "LDS.128 + 2 DFMA", 16, 0, 2, warps);
