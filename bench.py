@@ -67,6 +67,12 @@ def workload_name(key):
         key, c["n"], c["n"], c["n"] ** 2, c["M"], ls, c["kind"])
 
 
+def bench_config(key, N, L, M):
+    """The `config` object of the JSON line: identical for the GPU arm and the reference arm."""
+    return {"workload": workload_name(key), "N": N, "L": L, "M": M,
+            "l2_note": "input slab %.1f GB >> 126 MB L2, no flush needed" % (N * L * 8 / 1e9)}
+
+
 def index_set(cfg):
     from spuq_b200 import synthetic
     lam = cfg["lam"]
@@ -147,7 +153,7 @@ class CpuReference:
     Everything on this side (index set, neighbour look-ups, beta values, blocks) is built by the
     oracle package alone (oracle/synth.py, oracle/sampled.py): the product library is not loaded."""
 
-    def __init__(self, cfg, n_cols, seed=1234):
+    def __init__(self, cfg, n_cols, seed=1234, get_column=None):
         import numpy as np
         from oracle import synth
         from oracle.sampled import SampledApply
@@ -158,15 +164,18 @@ class CpuReference:
         mats = synth.fd_matrices(n, M)
         pick = np.unique(np.linspace(0, L - 1, min(n_cols, L)).astype(int))
         rng = np.random.RandomState(seed)
-        self.sa = SampledApply(mats, idx, cfg["kind"], cfg["mu"], pick, lambda k: rng.random_sample(N))
+        # input columns: the caller's slab (parity check against the GPU result) or seeded random data
+        self.pick = [int(k) for k in pick]
+        self.sa = SampledApply(mats, idx, cfg["kind"], cfg["mu"], pick, get_column or (lambda k: rng.random_sample(N)))
         self.A, self.w, self.only = self.sa.A, self.sa.w, self.sa.only
         self.n_cols = len(pick)
 
     def run(self):
-        """(GDoF/s, seconds) for one pass over the sampled columns."""
+        """(GDoF/s, seconds) for one pass over the sampled columns; the result is kept in self.result."""
         t0 = time.perf_counter()
-        self.A.apply(self.w, only=self.only)
+        v = self.A.apply(self.w, only=self.only)
         dt = time.perf_counter() - t0
+        self.result = {k: v[mu].coeffs for k, mu in zip(self.pick, self.only)}
         return self.N * self.n_cols / dt / 1e9, dt
 
 
@@ -233,6 +242,11 @@ def run_gpu(args):
         A = sharded.op
         Lp = L
         Wt = torch.rand((L, Nloc), dtype=torch.float64, device=dev, generator=g)
+        # the halo row outside the global grid (first / last rank) is the homogeneous Dirichlet boundary
+        if rank == 0:
+            Wt.view(L, nyl, n)[:, 0, :] = 0.0
+        if rank == world - 1:
+            Wt.view(L, nyl, n)[:, -1, :] = 0.0
     else:
         rowptr, colidx, vals = synthetic.fd_blocks(n, M, device=dev)
         blocks = DeviceBlocks(rowptr, colidx, vals, (N, N))
@@ -368,6 +382,30 @@ def run_gpu(args):
                "d2h_bytes_per_step": int(h_out.numel() * 8)}
         launches += e2e_steps * plan.last_launches
 
+    # ---- inputs of the parity check: the few slab columns the sampled oracle apply reads, and the same
+    # output columns of this run's result, gathered to rank 0 (rows mode: band by band)
+    parity_in = None
+    if not args.no_cpu and (world == 1 or rows_mode):
+        from oracle import synth as osynth
+        oidx = osynth.index_set(cfg["lam"])
+        ncols = args.cpu_cols if world == 1 else min(args.cpu_cols, 4)
+        pick = [int(k) for k in np.unique(np.linspace(0, L - 1, min(ncols, L)).astype(int))]
+        touched = sorted(osynth.touched_columns(oidx, pick))
+        step()
+        torch.cuda.synchronize()
+
+        def gather_cols(T, cols):
+            if world == 1:
+                return {k: T[k].cpu().numpy() for k in cols}
+            band = T.view(T.shape[0], nyl, n)[cols, 1:-1, :].cpu().numpy()       # owned grid rows only
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object(band, parts, dst=0)
+            if rank != 0:
+                return None
+            full = np.concatenate(parts, axis=1).reshape(len(cols), -1)
+            return {k: full[i] for i, k in enumerate(cols)}
+        parity_in = (ncols, gather_cols(Wt, touched), gather_cols(Yfull[:L], pick))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -376,14 +414,19 @@ def run_gpu(args):
     achieved = info["algorithmic_bytes"] / (kernel_ms * 1e-3) / 1e9
     # DRAM traffic per launch of the same kernel on the same workload, from the committed
     # `ncu --set full` capture (profiles/): dram__bytes_read.sum + dram__bytes_write.sum
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            tr = json.load(f).get("%s|%s" % (args.config, plan.kernel_name))
-        if tr and world == 1:
-            traffic = tr["dram_bytes"]
-    except Exception:
-        pass
+    traffic, traffic_src = None, None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tr = json.load(f).get("%s|%s" % (args.config, plan.kernel_name))
+            if tr and world == 1:
+                traffic = tr["dram_bytes"]
+                traffic_src = ("profiles/%s: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on "
+                               "this workload from a committed `ncu --set full` capture (NOT measured in this run: a "
+                               "run under ncu is never a bench value)" % name)
+                break
+        except Exception:
+            pass
     out = {
         "metric": "SG operator apply throughput (N*|Lambda| per apply)",
         "value": N * L / (ms_per_step * 1e-3) / 1e9, "unit": "GDoF/s",
@@ -391,34 +434,109 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.config), "N": N, "L": L, "M": M,
-                   "n_terms": info["n_terms"], "nnz_per_block": info["nnz"],
-                   "parallelism": ("1 GPU" if world == 1 else
-                                   ("grid rows sharded x%d, halo rows exchanged point-to-point (NCCL) every step" % world) if rows_mode
-                                   else ("M-sharded x%d + NCCL reduce-scatter over Lambda" % world)),
-                   "l2_note": "input slab %.1f GB >> 126 MB L2, no flush needed" % (N * L * 8 / 1e9),
-                   "kernel": plan.kernel_name, "path": info["path"],
-                   "host_numa_node_rank0": numa},
+        "config": bench_config(args.config, N, L, M),
+        "parallelism": ("1 GPU" if world == 1 else
+                        ("grid rows sharded x%d, halo rows exchanged point-to-point (NCCL) every step" % world) if rows_mode
+                        else ("M-sharded x%d + NCCL reduce-scatter over Lambda" % world)),
+        "details": {"n_terms": info["n_terms"], "nnz_per_block": info["nnz"], "kernel": plan.kernel_name,
+                    "path": info["path"], "host_numa_node_rank0": numa},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes": info["algorithmic_bytes"], "kernel_ms": kernel_ms,
                      "fp64_gflops": info["algorithmic_flops"] / (kernel_ms * 1e-3) / 1e9},
         "clocks": clocks, "gpu_launches": launches,
     }
     if e2e:
         out["e2e"] = e2e
-    if world == 1 and not args.no_cpu:
-        ref = CpuReference(cfg, args.cpu_cols)
+    # ---- parity of this run's result against the oracle on sampled output columns, and the CPU baseline ----
+    # rank 0 owns the JSON line; in rows mode the touched input columns and the sampled output columns are
+    # gathered band by band (only those few columns travel)
+    if parity_in is not None:
+        ncols, win, yout = parity_in
+        ref = CpuReference(cfg, ncols, get_column=lambda k: win[k])
         v, secs = ref.run()
-        ncols = ref.n_cols
-        out["cpu_baseline"] = {"value": v, "unit": "GDoF/s", "cores": 1, "kind": "port",
-                               "sample": "%d of %d output columns of the same workload through the oracle port of "
-                                         "MultiOperator.apply (cached scipy CSR leaves, one SpMV per (mu, m)); "
-                                         "%.1f s; per-column cost is independent of the other columns" % (ncols, L, secs),
-                               "host_cpus": os.cpu_count()}
+        worst = 0.0
+        for k, r in ref.result.items():
+            worst = max(worst, float(np.linalg.norm(yout[k] - r) / np.linalg.norm(r)))
+        out["parity_relerr"] = worst
+        out["parity_note"] = ("max over %d sampled output columns of ||y_gpu - y_oracle|| / ||y_oracle|| on this run's "
+                              "input slab; oracle = oracle.sg.MultiOperator.apply(only=...)" % len(ref.result))
+        if world == 1:
+            out["cpu_baseline"] = {"value": v, "unit": "GDoF/s", "cores": 1, "kind": "port",
+                                   "sample": "%d of %d output columns of the same workload through the oracle port of "
+                                             "MultiOperator.apply (cached scipy CSR leaves, one SpMV per (mu, m)); "
+                                             "%.1f s; per-column cost is independent of the other columns" % (ref.n_cols, L, secs),
+                                   "host_cpus": os.cpu_count()}
+    if world == 1 and not args.no_pcg:
+        # free the apply benchmark's slabs before the solve (config 4 needs ~9 slabs of 10 GB)
+        del Wt, Yfull, w, plan, A, sharded, blocks, vals
+        if not args.no_e2e:
+            del Wdev, wv, h_in, h_out
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        out["pcg"] = pcg_block(args, peak)
     print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def pcg_block(args, peak_gbs):
+    """BASELINE.json config 4 on one GPU: PCG to 1e-10 with the exact mean-based preconditioner through
+    the public API (MultiOperator / PreconditioningOperator / pcg).  Manufactured solution x* ~ U(0,1),
+    f = A x*, w0 = 0.  `seconds` is the wall time of the `pcg` call (device-resident loop, the host polls
+    a status word every 8 passes), `bytes_model` the compulsory traffic of one pass:
+    apply + preconditioner (read rho, write s) + the fused vector updates and the two dots."""
+    import torch
+    import spuq_b200 as sp
+    from spuq_b200 import _abi, synthetic
+    from spuq_b200.multi_operator import DeviceBlocks
+    key = args.pcg_config
+    cfg = CONFIGS[key]
+    dev = _abi.device()
+    n, M = cfg["n"], cfg["M"]
+    N = n * n
+    idx = index_set(cfg)
+    L = idx.shape[0]
+    rvs = synthetic.make_rvs(cfg["kind"], M, cfg["mu"])
+    rowptr, colidx, vals = synthetic.fd_blocks(n, M, device=dev)
+    A = sp.MultiOperator.from_blocks(DeviceBlocks(rowptr, colidx, vals, (N, N)), rvs)
+    g = torch.Generator(device=dev); g.manual_seed(1234)
+    X = torch.rand((L, N), dtype=torch.float64, device=dev, generator=g)
+    x_true = sp.SlabMultiVector(idx, slab=X, _sorted=True)
+    f = A.apply(x_true)
+    info = A.plan_for(x_true).info()
+    A0 = synthetic.blocks_to_scipy(rowptr, colidx, vals[:1], N)[0]
+    P = sp.PreconditioningOperator("mean", lambda b, f_: sp.ScipySolveOperator(A0, b, b))
+    w0 = 0 * f
+    s = P * f                                   # set-up of the solver outside the timed solve
+    del s
+    hist = []
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    x, zeta, it = sp.pcg(A, f, P, w0, eps=args.pcg_eps, maxiter=200, poll_every=8, history=hist)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    err = float((x.slab - X).abs().max())
+    passes = max(it - 1, 1)
+
+    def ms(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    t_apply = ms(lambda: A.apply(x))
+    t_prec = ms(lambda: P * f)
+    model = info["algorithmic_bytes"] + (16 + 88) * N * L
+    return {"workload": workload_name(key), "eps": args.pcg_eps, "numit": it, "zeta": zeta, "seconds": dt,
+            "ms_per_pass": dt / passes * 1e3, "gdof_per_s_per_pass": N * L * passes / dt / 1e9,
+            "max_abs_error_vs_manufactured": err, "ms_apply": t_apply, "ms_precond": t_prec,
+            "bytes_model_per_pass": model, "bytes_model_frac": model / (dt / passes) / 1e9 / peak_gbs,
+            "preconditioner": "exact A_0^{-1} (strip partition, csrc/precond_strip.cuh)",
+            "gpu_launches": A.plan_for(x_true).last_launches}
 
 
 def _ref_worker(ref, only, q):
@@ -462,7 +580,7 @@ def run_reference(args):
            "value": value, "unit": "GDoF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(args.config), "N": N, "L": L, "M": cfg["M"]},
+           "config": bench_config(args.config, N, L, cfg["M"]),
            "cpu_baseline": {"value": value, "unit": "GDoF/s", "cores": len(parts), "kind": "port",
                             "sample": "each step = %d of %d output columns through the oracle port of the reference's "
                                       "MultiOperator.apply (Python + scipy SpMV as the reference; its loop over output "
@@ -491,6 +609,9 @@ def main():
     ap.add_argument("--no-clocks", action="store_true", help="development: do not run the nvidia-smi clock sampler")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pcg", action="store_true", help="skip the config-4 PCG solve appended to the 1-GPU line")
+    ap.add_argument("--pcg-config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--pcg-eps", type=float, default=1e-10)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-cols", type=int, default=24)
     ap.add_argument("--ref-cols", type=int, default=4, help="sampled output columns per process of the reference arm")

@@ -228,6 +228,20 @@ static void partition_line(int n, int cap, std::vector<int32_t>* start, std::vec
     }
 }
 
+// x-chunks of a strip row: chunks of `len` points at a pitch of len + 1 (the separator), the remainder in
+// the last chunk.  The pitch is ODD (len = 30): lanes that sweep consecutive chunks of a row then hit
+// shared-memory words 62 apart, i.e. 16 different bank pairs per half-warp -- a pitch of 32 doubles put
+// all 32 lanes on ONE bank pair (measured: 16-way conflicts made the sweeps 4x the rest of the kernel).
+static void partition_chunks(int n, int len, std::vector<int32_t>* start, std::vector<int32_t>* lens) {
+    start->clear(); lens->clear();
+    int pos = 0;
+    while (n - pos > len + 1) {                // room for a chunk, its separator and at least one more point
+        start->push_back(pos); lens->push_back(len);
+        pos += len + 1;
+    }
+    start->push_back(pos); lens->push_back(n - pos);     // last chunk: 1 .. len + 1 points
+}
+
 template <typename T>
 static T* strip_upload(StripPlan* sp, const std::vector<T>& h) {
     void* d = nullptr;
@@ -261,7 +275,7 @@ int strip_plan_build(spuq_sg_precond* p) {
     StripView& sv = sp->sv;
     std::vector<int32_t> ystart, ylen, xstart, xlen;
     partition_line(ny, cap, &ystart, &ylen);
-    partition_line(nx, 31, &xstart, &xlen);
+    partition_chunks(nx, 30, &xstart, &xlen);
     sv.nx = nx; sv.ny = ny; sv.ox = ox; sv.oy = oy;
     sv.P = (int32_t)ystart.size(); sv.q = sv.P - 1;
     sv.PX = (int32_t)xstart.size(); sv.qx = sv.PX - 1;
@@ -348,6 +362,11 @@ int strip_plan_build(spuq_sg_precond* p) {
         cudaFuncSetAttribute(k_strip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem_bytes) != cudaSuccess) {
         cudaGetLastError();
         strip_plan_destroy(p);
+    } else {
+        // two CTAs of ~110 KB per SM: ask for the largest shared-memory carve-out
+        cudaFuncSetAttribute(k_strip<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_strip<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaGetLastError();
     }
 #endif
     return SPUQ_OK;

@@ -93,18 +93,26 @@ __device__ __forceinline__ void strip_ytransform(const double* __restrict__ qc, 
         }
     }
     for (int j = 0; j < c; j += 2) {            // even modes: symmetric part
-        const double* q = qc + j * STRIP_HP;
-        double acc = 0.0;
+        const double2* q = reinterpret_cast<const double2*>(qc + j * STRIP_HP);     // 16-byte broadcast loads
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int i = 0; i < STRIP_HP; ++i) acc = fma(q[i], p[i], acc);
-        emit(j, acc);
+        for (int i = 0; i < STRIP_HP / 2; ++i) {
+            const double2 qq = q[i];
+            a0 = fma(qq.x, p[2 * i], a0);
+            a1 = fma(qq.y, p[2 * i + 1], a1);
+        }
+        emit(j, a0 + a1);
     }
     for (int j = 1; j < c; j += 2) {            // odd modes: antisymmetric part
-        const double* q = qc + j * STRIP_HP;
-        double acc = 0.0;
+        const double2* q = reinterpret_cast<const double2*>(qc + j * STRIP_HP);     // 16-byte broadcast loads
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int i = 0; i < STRIP_HP; ++i) acc = fma(q[i], m[i], acc);
-        emit(j, acc);
+        for (int i = 0; i < STRIP_HP / 2; ++i) {
+            const double2 qq = q[i];
+            a0 = fma(qq.x, m[2 * i], a0);
+            a1 = fma(qq.y, m[2 * i + 1], a1);
+        }
+        emit(j, a0 + a1);
     }
 }
 
@@ -138,6 +146,13 @@ k_strip(StripView sv, int32_t L, const double* __restrict__ R, double* __restric
 
     // ---- phase 0: strip and transform matrix into shared memory ------------------------------------
     for (int i = STRIP_T0; i < c * STRIP_HP; i += STRIP_TS) qc[i] = sv.qc[cls][i];     // zero beyond ceil(c/2)
+#ifndef SPUQ_EMU
+    if (((c * nx) & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(strip)) & 15) == 0) {
+        const double2* s2 = reinterpret_cast<const double2*>(src);
+        double2* d2 = reinterpret_cast<double2*>(strip);
+        for (int i = STRIP_T0; i < (c * nx) / 2; i += STRIP_TS) d2[i] = s2[i];
+    } else
+#endif
     for (int i = STRIP_T0; i < c * nx; i += STRIP_TS) strip[i] = src[i];
     if (FINAL) {
         STRIP_SYNC();

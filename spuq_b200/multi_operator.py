@@ -456,6 +456,10 @@ class PreconditioningOperator(Operator):
                 solver = mean_solver_for(op.as_csr(), len(w))
             elif isinstance(op, _CsrLeaf):
                 solver = CsrSlabOperator(op.as_csr(), len(w))
+            elif hasattr(op, "as_matrix"):
+                # any other operator that can state the matrix of its `apply` (operator.py:110-125)
+                m = op.as_matrix()
+                solver = CsrSlabOperator(sps.csr_matrix(m if sps.issparse(m) else np.asarray(m, dtype=np.float64)), len(w))
             else:
                 raise TypeError("PreconditioningOperator: the assemble_solver callback returned %s, which has "
                                 "no device form (supported: ScipySolveOperator, MatrixSolveOperator, "

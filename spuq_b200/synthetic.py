@@ -80,7 +80,7 @@ def fd_values(a_nodal, valid):
 
 def _coefficient(n, k1, k2, amp, device, dtype=torch.float64):
     # the 1-D cosine factors are evaluated with numpy on the host (n + 2 values) so that every device and
-    # the oracle-side generator (oracle/synth.py) see bit-identical blocks; the outer product and the
+    # the numpy restatement used by the CPU-side checker see bit-identical blocks; the outer product and the
     # face averages are single IEEE operations and round the same everywhere
     x = np.linspace(0.0, 1.0, n + 2)
     cx = torch.from_numpy(np.cos(math.pi * k1 * x)).to(device=device, dtype=dtype)
