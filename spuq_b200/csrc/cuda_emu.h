@@ -17,6 +17,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
+#define __grid_constant__
 #define __launch_bounds__(...)
 
 struct dim3 {

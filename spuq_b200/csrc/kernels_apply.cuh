@@ -89,6 +89,68 @@ k_apply_ell(int64_t n_rows, int32_t L, int32_t K, const int32_t* __restrict__ el
 }
 
 // ---------------------------------------------------------------------------------------------
+// General sparse blocks, column-blocked ("design M" of kernels_tiled.cuh without the grid): the form
+// the SG operator takes on unstructured meshes (P1 FEM blocks of fem/fenics/fenics_operator.py:43-50
+// behind linalg/scipy_operator.py:29-40).
+//   * a CTA owns 128 rows and a block of 16 output columns whose accumulators stay in registers;
+//   * the block's terms are grouped by block matrix: the row's KW values of A_m (padded ELL copy,
+//     coalesced) are loaded ONCE per group and reused by every term of that matrix, the row's column
+//     indices once per CTA;
+//   * per term only the gather of the input column is left: KW loads of W through L1 per row.
+// Work items are ordered row block major, so the 62 column blocks that read the same rows of W run
+// close together in time (L2 reuse of W and of the A values).
+// ---------------------------------------------------------------------------------------------
+constexpr int ELLBLK_C = 16;
+
+template <int KW>
+__global__ void __launch_bounds__(128)
+k_apply_ellblk(int64_t n_rows, int32_t K, const int32_t* __restrict__ ell_cols,
+               const double* __restrict__ ell_vals, BlockView bv, const double* __restrict__ W, int64_t ldw,
+               double* __restrict__ Y, int64_t ldy, const double* gate) {
+    if (gate_closed(gate)) return;
+    const int64_t item = blockIdx.x;
+    const int32_t blk = (int32_t)(item % bv.nblk);
+    const int64_t row = (item / bv.nblk) * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    int32_t cols[KW];
+#pragma unroll
+    for (int k = 0; k < KW; ++k) cols[k] = k < K ? ell_cols[(int64_t)k * n_rows + row] : 0;
+    double acc[ELLBLK_C];
+#pragma unroll
+    for (int c = 0; c < ELLBLK_C; ++c) acc[c] = 0.0;
+    for (int32_t g = bv.bgrp[blk]; g < bv.bgrp[blk + 1]; ++g) {
+        double a[KW];
+        const double* ap = ell_vals + ((int64_t)bv.gmat[g] * K) * n_rows + row;
+#pragma unroll
+        for (int k = 0; k < KW; ++k) a[k] = k < K ? ap[(int64_t)k * n_rows] : 0.0;
+        for (int32_t t = bv.gterm[g]; t < bv.gterm[g + 1]; ++t) {
+            const double* w = W + (int64_t)bv.tcol[t] * ldw;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < KW; k += 2) {
+                s0 = fma(a[k], w[cols[k]], s0);
+                if (k + 1 < KW) s1 = fma(a[k + 1], w[cols[k + 1]], s1);
+            }
+            const double v = bv.tcoef[t] * (s0 + s1);
+#define SPUQ_ACC_CASE(k) case k: acc[k] += v; break;
+            switch (bv.tacc[t]) {
+                SPUQ_ACC_CASE(0) SPUQ_ACC_CASE(1) SPUQ_ACC_CASE(2) SPUQ_ACC_CASE(3)
+                SPUQ_ACC_CASE(4) SPUQ_ACC_CASE(5) SPUQ_ACC_CASE(6) SPUQ_ACC_CASE(7)
+                SPUQ_ACC_CASE(8) SPUQ_ACC_CASE(9) SPUQ_ACC_CASE(10) SPUQ_ACC_CASE(11)
+                SPUQ_ACC_CASE(12) SPUQ_ACC_CASE(13) SPUQ_ACC_CASE(14) SPUQ_ACC_CASE(15)
+                default: break;
+            }
+#undef SPUQ_ACC_CASE
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < ELLBLK_C; ++c) {
+        const int32_t col = bv.bcol[(int64_t)blk * ELLBLK_C + c];
+        if (col >= 0) Y[row + (int64_t)col * ldy] = acc[c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stencil, simple form: diagonal storage, one thread per PAIR of adjacent rows (128-bit loads of
 // the A diagonals and of the aligned W diagonals), one output column at a time.  This is the
 // reference point for the register-tiled kernel in kernels_tiled.cuh.

@@ -194,6 +194,7 @@ k_thomas_y(int32_t nx, int32_t ny, int32_t L, double oy, const double* __restric
 // ---- two-level strip partition: plan (host tables) and driver ---------------------------------------
 struct StripPlan {
     StripView sv{};
+    StripQ Q{};
     std::vector<void*> dev;               // device allocations
     int32_t cmax = 0;                     // tallest strip
     size_t smem_bytes = 0;
@@ -266,16 +267,16 @@ int strip_plan_build(spuq_sg_precond* p) {
     const double pi = 3.14159265358979323846;
     const double dxx = 0.5 * p->d, dyy = 0.5 * p->d, ox = p->ox, oy = p->oy;
     // strip height: two CTAs per SM when that still allows >= 12 rows, else one
-    const size_t fixed = sizeof(double) * ((size_t)STRIP_CMAX * STRIP_HP + (size_t)STRIP_CMAX * 64);
+    std::vector<int32_t> ystart, ylen, xstart, xlen;
+    partition_chunks(nx, 30, &xstart, &xlen);
+    const size_t fixed = sizeof(double) * (size_t)STRIP_CMAX * std::max<size_t>(xstart.size() - 1, 1);
     auto rows_for = [&](size_t budget) { return budget > fixed ? (int)((budget - fixed) / (sizeof(double) * (size_t)nx)) : 0; };
     int cap = std::min(STRIP_CMAX, rows_for(112 * 1024));
     if (cap < 12) cap = std::min(STRIP_CMAX, rows_for(224 * 1024));
     if (cap < 2) return SPUQ_OK;                          // grid too wide for shared memory: plain path
     StripPlan* sp = new StripPlan();
     StripView& sv = sp->sv;
-    std::vector<int32_t> ystart, ylen, xstart, xlen;
     partition_line(ny, cap, &ystart, &ylen);
-    partition_chunks(nx, 30, &xstart, &xlen);
     sv.nx = nx; sv.ny = ny; sv.ox = ox; sv.oy = oy;
     sv.P = (int32_t)ystart.size(); sv.q = sv.P - 1;
     sv.PX = (int32_t)xstart.size(); sv.qx = sv.PX - 1;
@@ -284,6 +285,9 @@ int strip_plan_build(spuq_sg_precond* p) {
     sv.ch[0] = ylen.front(); sv.ch[1] = ylen.back();     // heights h+1 (first strips) and h
     sv.xlen_cls_len[0] = xlen.front(); sv.xlen_cls_len[1] = xlen.back();
     sp->cmax = sv.ch[0];
+    sv.n_tall = 0;
+    for (size_t i = 0; i < ylen.size(); ++i) sv.n_tall += (ylen[i] == sv.ch[0]) ? 1 : 0;
+    if (sv.ch[0] == sv.ch[1]) sv.n_tall = sv.P;
     std::vector<int32_t> ycls(sv.P);
     for (int i = 0; i < sv.P; ++i) ycls[i] = ylen[i] == sv.ch[0] ? 0 : 1;
     sv.ystart = strip_upload(sp, ystart); sv.ycls = strip_upload(sp, ycls);
@@ -293,7 +297,8 @@ int strip_plan_build(spuq_sg_precond* p) {
     for (int cls = 0; cls < 2 && ok; ++cls) {
         const int c = sv.ch[cls];
         const int hp = (c + 1) / 2;
-        std::vector<double> qc((size_t)c * STRIP_HP, 0.0), ipx((size_t)c * cx), spk((size_t)2 * c * cx, 0.0),
+        double* qc = sp->Q.q[cls];
+        std::vector<double> ipx((size_t)c * cx), spk((size_t)2 * c * cx, 0.0),
             sip((size_t)c * std::max(qx, 1), 0.0), sof((size_t)c * std::max(qx, 1), 0.0);
         const double sc = std::sqrt(2.0 / (c + 1.0));
         for (int j = 0; j < c; ++j) {
@@ -324,9 +329,9 @@ int strip_plan_build(spuq_sg_precond* p) {
                 prev_piv = pvt; prev_off = E;
             }
         }
-        sv.qc[cls] = strip_upload(sp, qc); sv.ipivx[cls] = strip_upload(sp, ipx); sv.spike[cls] = strip_upload(sp, spk);
+        sv.ipivx[cls] = strip_upload(sp, ipx); sv.spike[cls] = strip_upload(sp, spk);
         sv.sx_ipiv[cls] = strip_upload(sp, sip); sv.sx_off[cls] = strip_upload(sp, sof);
-        ok = ok && sv.qc[cls] && sv.ipivx[cls] && sv.spike[cls] && sv.sx_ipiv[cls] && sv.sx_off[cls];
+        ok = ok && sv.ipivx[cls] && sv.spike[cls] && sv.sx_ipiv[cls] && sv.sx_off[cls];
     }
     // separator rows: per x-mode k a q x q tridiagonal system, stored in the order the row transform
     // delivers the modes (even | odd when the transform is split by parity)
@@ -354,7 +359,7 @@ int strip_plan_build(spuq_sg_precond* p) {
         sp->sy_ipiv = strip_upload(sp, ip); sp->sy_off = strip_upload(sp, of);
         ok = ok && sp->sy_ipiv && sp->sy_off;
     }
-    sp->smem_bytes = sizeof(double) * ((size_t)STRIP_CMAX * STRIP_HP + (size_t)STRIP_CMAX * std::max(qx, 1) + (size_t)sp->cmax * nx);
+    sp->smem_bytes = sizeof(double) * ((size_t)STRIP_CMAX * std::max(qx, 1) + (size_t)sp->cmax * nx);
     p->strip = sp;
     if (!ok) { strip_plan_destroy(p); return SPUQ_OK; }       // not fatal: the plain path still works
 #ifndef SPUQ_EMU
@@ -391,7 +396,7 @@ static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
     const dim3 grid((unsigned)((int64_t)L * sv.P)), block(STRIP_THREADS);
     const double* U = nullptr;
     if (q > 0) {
-        SPUQ_LAUNCH((k_strip<false>), grid, block, sp->smem_bytes, stream, sv, L, R, S, Gf, Gl, (const double*)nullptr, gate);
+        SPUQ_LAUNCH((k_strip<false>), grid, block, sp->smem_bytes, stream, sp->Q, sv, L, R, S, Gf, Gl, (const double*)nullptr, gate);
         const int64_t Mrows = (int64_t)L * q;
         const unsigned eb = (unsigned)std::min<int64_t>((Mrows * nx + 255) / 256, 1 << 20);
         SPUQ_LAUNCH(k_sep_assemble, dim3(eb), dim3(256), 0, stream, sv, L, R, Gf, Gl, Z, gate);
@@ -420,7 +425,7 @@ static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
             U = Z;
         }
     }
-    SPUQ_LAUNCH((k_strip<true>), grid, block, sp->smem_bytes, stream, sv, L, R, S, Gf, Gl, U, gate);
+    SPUQ_LAUNCH((k_strip<true>), grid, block, sp->smem_bytes, stream, sp->Q, sv, L, R, S, Gf, Gl, U, gate);
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }

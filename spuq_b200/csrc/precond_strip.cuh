@@ -48,18 +48,26 @@ struct StripView {
     int32_t PX, qx;                   // x-chunks per row, x-separators (= PX - 1)
     int32_t cxmax;                    // longest chunk
     double ox, oy;
-    const int32_t* ystart;            // P: first grid row of strip p
+    const int32_t* ystart;            // P: first grid row of strip p   (host-side / assembly kernel use)
     const int32_t* ycls;              // P: height class of strip p
+    int32_t n_tall;                   // the first n_tall strips have height ch[0] = ch[1] + 1 (or all ch[0])
     const int32_t* xstart;            // PX: first x of chunk ch
     const int32_t* xlen;              // PX
     int32_t ch[2];                    // heights of the two classes
     // per class: Q (c x HP, parity folded), x-direction tables per mode j
-    const double* qc[2];              // [c][HP]
     const double* ipivx[2];           // [c][cxmax]   reciprocal Thomas pivots of tridiag(ox, dxx + theta_j, ox)
     const double* spike[2];           // [2][c][cxmax] first spike (T_len^{-1} e_0) for the two chunk lengths
     const double* sx_ipiv[2];         // [c][qx]      x-separator system: reciprocal pivots
     const double* sx_off[2];          // [c][qx]      ... off-diagonal between separator i and i+1
     int32_t xlen_cls_len[2];          // chunk lengths of the two chunk classes
+};
+
+// The two y-transform matrices travel as a KERNEL PARAMETER (constant bank, 8 KB): every thread of a
+// warp reads the same entry at the same time, which the constant cache serves without touching the
+// shared-memory pipe (uniform 16-byte shared loads of the matrix were 60 % of that pipe's wavefronts in
+// the first version of this kernel, profiles/r2_precond_strip_notes.md).
+struct StripQ {
+    double q[2][STRIP_CMAX * STRIP_HP];     // [class][j * HP + i] = Q[j][i], i < ceil(c/2), 0 beyond
 };
 
 #ifdef SPUQ_EMU
@@ -92,28 +100,31 @@ __device__ __forceinline__ void strip_ytransform(const double* __restrict__ qc, 
             p[s] = 0.0; m[s] = 0.0;
         }
     }
-    for (int j = 0; j < c; j += 2) {            // even modes: symmetric part
-        const double2* q = reinterpret_cast<const double2*>(qc + j * STRIP_HP);     // 16-byte broadcast loads
-        double a0 = 0.0, a1 = 0.0;
+    // four output modes of one parity at a time: four independent DFMA chains, every mirror sum / difference
+    // is used four times from registers; the matrix entries are warp-uniform constant-bank loads
+    auto run = [&](const double (&f)[STRIP_HP], int j0) {
+        for (int j = j0; j < c; j += 8) {
+            const double* q0 = qc + j * STRIP_HP;
+            const int j1 = (j + 2 < c) ? 2 : 0, j2 = (j + 4 < c) ? 4 : 0, j3 = (j + 6 < c) ? 6 : 0;
+            const double* q1 = q0 + j1 * STRIP_HP;
+            const double* q2 = q0 + j2 * STRIP_HP;
+            const double* q3 = q0 + j3 * STRIP_HP;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-        for (int i = 0; i < STRIP_HP / 2; ++i) {
-            const double2 qq = q[i];
-            a0 = fma(qq.x, p[2 * i], a0);
-            a1 = fma(qq.y, p[2 * i + 1], a1);
+            for (int i = 0; i < STRIP_HP; ++i) {
+                a0 = fma(q0[i], f[i], a0);
+                a1 = fma(q1[i], f[i], a1);
+                a2 = fma(q2[i], f[i], a2);
+                a3 = fma(q3[i], f[i], a3);
+            }
+            emit(j, a0);
+            if (j1) emit(j + 2, a1);
+            if (j2) emit(j + 4, a2);
+            if (j3) emit(j + 6, a3);
         }
-        emit(j, a0 + a1);
-    }
-    for (int j = 1; j < c; j += 2) {            // odd modes: antisymmetric part
-        const double2* q = reinterpret_cast<const double2*>(qc + j * STRIP_HP);     // 16-byte broadcast loads
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-        for (int i = 0; i < STRIP_HP / 2; ++i) {
-            const double2 qq = q[i];
-            a0 = fma(qq.x, m[2 * i], a0);
-            a1 = fma(qq.y, m[2 * i + 1], a1);
-        }
-        emit(j, a0 + a1);
-    }
+    };
+    run(p, 0);          // even modes: symmetric part
+    run(m, 1);          // odd modes: antisymmetric part
 }
 
 // One strip of one slab column.  FINAL = false: Gf/Gl <- first / last row of A_strip^{-1} R_strip.
@@ -121,12 +132,12 @@ __device__ __forceinline__ void strip_ytransform(const double* __restrict__ qc, 
 // separator row below the strip is copied from U.
 template <bool FINAL>
 __global__ void __launch_bounds__(STRIP_THREADS, 2)
-k_strip(StripView sv, int32_t L, const double* __restrict__ R, double* __restrict__ S,
+k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, const double* __restrict__ R, double* __restrict__ S,
         double* __restrict__ Gf, double* __restrict__ Gl, const double* __restrict__ U, const double* gate) {
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
 #ifdef SPUQ_EMU
     if (threadIdx.x != 0) return;
-    std::vector<double> smem_store((size_t)STRIP_CMAX * sv.nx + STRIP_CMAX * STRIP_HP + STRIP_CMAX * (sv.qx + 1));
+    std::vector<double> smem_store((size_t)STRIP_CMAX * sv.nx + STRIP_CMAX * (sv.qx + 1));
     double* smem = smem_store.data();
 #else
     extern __shared__ __align__(16) double smem[];
@@ -135,22 +146,37 @@ k_strip(StripView sv, int32_t L, const double* __restrict__ R, double* __restric
     const int p = (int)(blockIdx.x % (unsigned)sv.P);
     const int64_t col = blockIdx.x / (unsigned)sv.P;
     if (col >= L) return;
-    const int cls = sv.ycls[p];
+    // class, height and first row from the parameters alone (no table look-up): warp-uniform values, so the
+    // transform-matrix addresses below are uniform too
+    const int cls = (p < sv.n_tall) ? 0 : 1;
     const int c = sv.ch[cls];
-    const int y0 = sv.ystart[p];
-    double* qc = smem;                                  // [c][HP]
-    double* sepv = qc + STRIP_CMAX * STRIP_HP;          // [c][qx]
+    const int y0 = (p < sv.n_tall) ? p * (sv.ch[0] + 1) : sv.n_tall * (sv.ch[0] + 1) + (p - sv.n_tall) * (sv.ch[1] + 1);
+    const double* qc = Q.q[cls];                        // [c][HP], constant bank
+    double* sepv = smem;                                // [c][qx]
     double* strip = sepv + STRIP_CMAX * (sv.qx > 0 ? sv.qx : 1);   // [c][nx]
     const int64_t N = (int64_t)nx * sv.ny;
     const double* src = R + col * N + (int64_t)y0 * nx;
 
     // ---- phase 0: strip and transform matrix into shared memory ------------------------------------
-    for (int i = STRIP_T0; i < c * STRIP_HP; i += STRIP_TS) qc[i] = sv.qc[cls][i];     // zero beyond ceil(c/2)
 #ifndef SPUQ_EMU
-    if (((c * nx) & 1) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(strip)) & 15) == 0) {
-        const double2* s2 = reinterpret_cast<const double2*>(src);
-        double2* d2 = reinterpret_cast<double2*>(strip);
-        for (int i = STRIP_T0; i < (c * nx) / 2; i += STRIP_TS) d2[i] = s2[i];
+    // the strip is c*nx contiguous doubles: one bulk copy (TMA) issued by one thread, no registers and no
+    // load instructions spent on it; the rest of the block waits on the mbarrier
+    __shared__ __align__(8) unsigned long long strip_bar;
+    const uint32_t bytes = (uint32_t)(c * nx) * 8u;
+    const bool bulk = (bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (bulk) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&strip_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(strip)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+        }
+        __syncthreads();                                     // barrier initialised before anyone waits on it
+        asm volatile(
+            "{\n.reg .pred P1;\nSTRIP_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n@P1 bra STRIP_DONE;\nbra STRIP_WAIT;\nSTRIP_DONE:\n}\n"
+            ::"r"(bar) : "memory");
     } else
 #endif
     for (int i = STRIP_T0; i < c * nx; i += STRIP_TS) strip[i] = src[i];

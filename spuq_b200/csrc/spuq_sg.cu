@@ -592,7 +592,26 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
         const int32_t cpc = p->cols_per_block > 0 ? p->cols_per_block : pick_cols_per_cta(p, row_blocks);
         const dim3 grid((unsigned)row_blocks, (unsigned)((p->L + cpc - 1) / cpc));
         SPUQ_REQUIRE(grid.y <= 65535u, "apply: too many column chunks (%u); raise cols_per_block", grid.y);
-        if (p->path == SPUQ_PATH_CSR) {
+        // column-blocked form (A values of a row in registers across the terms of a matrix) whenever the
+        // operator has expansion terms and the padded row fits the register budget; variant 1 keeps
+        // the one-column-at-a-time kernels (cross-check)
+        if (p->path == SPUQ_PATH_ELL && p->M > 0 && p->ell_K <= 16 && p->variant != 1) {
+            if (p->bv.bcol == nullptr || p->bv.C != ELLBLK_C) {
+                int rc = build_blocks(p, ELLBLK_C);
+                if (rc) return rc;
+            }
+            const int64_t items = row_blocks * p->bv.nblk;
+            SPUQ_REQUIRE(items < 0x7fffffffLL, "apply: too many work items (%lld)", (long long)items);
+            if (p->ell_K <= 8) {
+                SPUQ_LAUNCH((k_apply_ellblk<8>), dim3((unsigned)items), dim3(threads), 0, stream, p->n_rows, p->ell_K,
+                            p->ell_cols, p->ell_vals, p->bv, W, ldw, Y, ldy, gate);
+                p->kernel_name = "k_apply_ellblk<8>";
+            } else {
+                SPUQ_LAUNCH((k_apply_ellblk<16>), dim3((unsigned)items), dim3(threads), 0, stream, p->n_rows, p->ell_K,
+                            p->ell_cols, p->ell_vals, p->bv, W, ldw, Y, ldy, gate);
+                p->kernel_name = "k_apply_ellblk<16>";
+            }
+        } else if (p->path == SPUQ_PATH_CSR) {
             SPUQ_LAUNCH(k_apply_csr, grid, dim3(threads), 0, stream, p->n_rows, p->L, p->rowptr, p->colidx,
                         p->vals_ptrs_dev, tv, W, ldw, Y, ldy, cpc, gate);
             p->kernel_name = "k_apply_csr";

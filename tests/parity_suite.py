@@ -53,7 +53,9 @@ def check_apply_paths(n=12, M=4, p=2, kind="legendre", mu=0.0):
         Y, plan = product_apply(c, path)
         assert relerr(Y, c.Y) <= TOL, (path, relerr(Y, c.Y))
         seen.add(plan.kernel_name)
-    assert {"k_apply_csr", "k_apply_ell<8>"} <= seen
+    assert {"k_apply_csr", "k_apply_ellblk<8>"} <= seen
+    Y, plan = product_apply(c, _abi.PATH_ELL, (1, 0, 0, 0))          # one column at a time (cross-check kernel)
+    assert plan.kernel_name == "k_apply_ell<8>" and relerr(Y, c.Y) <= TOL
     for tune in [(1, 0, 0, 0), (2, 8, 2, 0), (2, 4, 2, 0), (2, 16, 2, 0), (2, 8, 1, 0), (2, 16, 1, 0), (2, 4, 4, 0),
                  (4, 1, 0, 0), (4, 2, 0, 0), (4, 1, 1, 0), (4, 2, 1, 0), (4, 3, 1, 0), (4, 2, 3, 0)]:
         Y, plan = product_apply(c, _abi.PATH_STENCIL, tune)
@@ -139,6 +141,29 @@ def check_apply_unstructured():
     assert plan.info()["path"] == "ell"
     with pytest.raises(_abi.SpuqError, match="not a 3x3-window grid stencil"):
         product_apply(c, _abi.PATH_STENCIL)
+    # the SG operator on an "unstructured" numbering: the grid blocks of a diffusion problem with the dofs
+    # renumbered tile by tile (oracle/synth.py), which the stencil recognition must reject; column-blocked
+    # general kernel (row widths 5 -> KW = 8) against the oracle, odd row count, beta0 != 0
+    from oracle import synth
+    n, M = 13, 5
+    idx = synthetic.anisotropic_indices(M, 7.0)
+    perm = synth.tile_permutation(n, 4)
+    mats = synth.permuted(synth.fd_matrices(n, M), perm)
+    from tests.cases import Case, oracle_rv
+    c = Case()
+    c.N, c.M, c.idx, c.mats = n * n, M, idx, mats
+    rng = np.random.RandomState(11)
+    c.W = rng.random_sample((c.N, idx.shape[0]))
+    c.rvs = synthetic.make_rvs("hermite", M, 0.5)
+    c.A, c.cf = oracle_operator(mats, [oracle_rv("hermite", 0.5)] * M)
+    c.w = oracle_multivector(idx, c.W)
+    c.Y = (c.A * c.w).to_slab()
+    Y, plan = product_apply(c)
+    assert plan.kernel_name == "k_apply_ellblk<8>" and relerr(Y, c.Y) <= TOL, (plan.kernel_name, relerr(Y, c.Y))
+    # wider rows (random sparse blocks, up to 16 entries per row): KW = 16
+    c2 = random_sparse_case(40, 3, synthetic.anisotropic_indices(3, 5.0), density=0.2, seed=9)
+    Y, plan = product_apply(c2, _abi.PATH_ELL)
+    assert relerr(Y, c2.Y) <= TOL, (plan.kernel_name, relerr(Y, c2.Y))
 
 
 def nine_point_case(nx, ny, M, idx, seed=3):
