@@ -47,6 +47,14 @@ CONFIGS = {
     "c2": dict(n=512, M=20, lam=("td", 20, 3), kind="legendre", mu=0.0),
     "c3": dict(n=1000, M=50, lam=("aniso", 50, 11.3), kind="hermite", mu=0.0),
     "c4": dict(n=500, M=30, lam=("prefix", 30, 3, 5000), kind="legendre", mu=0.0),
+    # config 3 on an "unstructured" numbering: the same blocks with the dofs renumbered tile by tile (16 x 16
+    # tiles, random order inside a tile), so that the stencil recognition rejects the pattern and the
+    # general sparse path (k_apply_ellblk) runs
+    "c3u": dict(n=1000, M=50, lam=("aniso", 50, 11.3), kind="hermite", mu=0.0, perm=16),
+    "c2u": dict(n=512, M=20, lam=("td", 20, 3), kind="legendre", mu=0.0, perm=16),
+    # config 3 in its natural (row-major) numbering but pushed through the general sparse path: what a mesh
+    # with a bandwidth-reducing numbering looks like to that kernel
+    "c3n": dict(n=1000, M=50, lam=("aniso", 50, 11.3), kind="hermite", mu=0.0, path="ell"),
     # c3 on a 256 x 256 grid: same Lambda and schedule, 15x less work -- for ncu captures only
     "c5t": dict(n=64, M=8, lam=("aniso", 8, 9.0), kind="hermite", mu=0.0),
     "c3t": dict(n=64, M=50, lam=("aniso", 50, 11.3), kind="hermite", mu=0.0),
@@ -63,8 +71,11 @@ def workload_name(key):
         ls = "anisotropic downward-closed Lambda (T=%s)" % lam[2]
     else:
         ls = "first %d indices of the degree-%d set" % (lam[3], lam[2])
-    return "%s: 2D diffusion %dx%d FD grid (N=%d), M=%d, %s, %s chaos" % (
-        key, c["n"], c["n"], c["n"] ** 2, c["M"], ls, c["kind"])
+    extra = ", dofs renumbered in random order inside %dx%d tiles (general sparse path)" % (c["perm"], c["perm"]) if c.get("perm") else ""
+    if c.get("path") == "ell":
+        extra = ", natural numbering forced through the general sparse path"
+    return "%s: 2D diffusion %dx%d FD grid (N=%d), M=%d, %s, %s chaos%s" % (
+        key, c["n"], c["n"], c["n"] ** 2, c["M"], ls, c["kind"], extra)
 
 
 def bench_config(key, N, L, M):
@@ -162,6 +173,8 @@ class CpuReference:
         idx = synth.index_set(cfg["lam"])
         self.L = L = idx.shape[0]
         mats = synth.fd_matrices(n, M)
+        if cfg.get("perm"):
+            mats = synth.permuted(mats, synth.tile_permutation(n, cfg["perm"]))
         pick = np.unique(np.linspace(0, L - 1, min(n_cols, L)).astype(int))
         rng = np.random.RandomState(seed)
         # input columns: the caller's slab (parity check against the GPU result) or seeded random data
@@ -249,9 +262,13 @@ def run_gpu(args):
             Wt.view(L, nyl, n)[:, -1, :] = 0.0
     else:
         rowptr, colidx, vals = synthetic.fd_blocks(n, M, device=dev)
+        if cfg.get("perm"):
+            rowptr, colidx, vals = synthetic.permute_blocks(rowptr, colidx, vals, synthetic.tile_permutation(n, cfg["perm"]))
         blocks = DeviceBlocks(rowptr, colidx, vals, (N, N))
         from spuq_b200.sharding import ShardedApply
-        sharded = ShardedApply(blocks, rvs, tables)             # world == 1: the whole operator
+        from spuq_b200 import _abi as _abi_mod
+        sharded = ShardedApply(blocks, rvs, tables,             # world == 1: the whole operator
+                               path=_abi_mod.PATH_ELL if cfg.get("path") == "ell" else _abi_mod.PATH_AUTO)
         A = sharded.op
         Lp = sharded.cols * world                               # columns padded for equal reduce-scatter shares
         Nloc = N
@@ -273,7 +290,9 @@ def run_gpu(args):
             dist.reduce_scatter_tensor(Yown, Yfull, op=dist.ReduceOp.SUM)
 
     def step():
-        comm_before()
+        if rows_mode:
+            sharded.apply(plan, Wt, Yfull[:L], overlap=not args.no_overlap)   # exchange overlapped with the interior tile rows
+            return
         plan.apply(Wt, Yfull[:L])
         comm_after()
 
@@ -294,11 +313,9 @@ def run_gpu(args):
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0.record()
     for k in range(args.steps):
-        comm_before()
         kev[k][0].record()
-        plan.apply(Wt, Yfull[:L])
+        step()
         kev[k][1].record()
-        comm_after()
     ev1.record()
     barrier()
     total_ms = ev0.elapsed_time(ev1)
@@ -309,7 +326,8 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, kernel_ms = float(t[0]), float(t[1])
     ms_per_step = total_ms / args.steps
-    launches = args.steps * plan.last_launches
+    per_step_launches = sharded.last_launches if rows_mode else plan.last_launches
+    launches = args.steps * per_step_launches
 
     # ---- e2e: host buffers through the public operator API, H2D + kernel + D2H every step -------
     e2e = None
@@ -343,8 +361,10 @@ def run_gpu(args):
                     ev_in[b].record(s_in)
                 cur.wait_event(ev_in[b])
                 if rows_mode:
-                    sharded.exchange_halos(Wdev[b])
-                y = A.apply(wv[b])                                # public API: MultiOperator.apply
+                    y = wv[b].like(torch.empty_like(Wdev[b]))
+                    sharded.apply(plan, Wdev[b], y.slab, overlap=not args.no_overlap)
+                else:
+                    y = A.apply(wv[b])                            # public API: MultiOperator.apply
                 ev_done[b].record(cur)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_done[b])
@@ -380,7 +400,7 @@ def run_gpu(args):
         e2e = {"value": N * L / (e2e_ms * 1e-3) / 1e9, "unit": "GDoF/s", "steps": e2e_steps,
                "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h_in.numel() * 8),
                "d2h_bytes_per_step": int(h_out.numel() * 8)}
-        launches += e2e_steps * plan.last_launches
+        launches += e2e_steps * per_step_launches
 
     # ---- inputs of the parity check: the few slab columns the sampled oracle apply reads, and the same
     # output columns of this run's result, gathered to rank 0 (rows mode: band by band)
@@ -436,7 +456,8 @@ def run_gpu(args):
         "dtype": "f64", "data": "synthetic",
         "config": bench_config(args.config, N, L, M),
         "parallelism": ("1 GPU" if world == 1 else
-                        ("grid rows sharded x%d, halo rows exchanged point-to-point (NCCL) every step" % world) if rows_mode
+                        ("grid rows sharded x%d, halo rows exchanged point-to-point (NCCL) every step%s" % (
+                            world, "" if args.no_overlap else ", overlapped with the tile rows that read no halo row")) if rows_mode
                         else ("M-sharded x%d + NCCL reduce-scatter over Lambda" % world)),
         "details": {"n_terms": info["n_terms"], "nnz_per_block": info["nnz"], "kernel": plan.kernel_name,
                     "path": info["path"], "host_numa_node_rank0": numa},
@@ -608,6 +629,7 @@ def main():
                     help="multi-GPU decomposition: grid rows + halo exchange (default) or expansion terms + reduce-scatter")
     ap.add_argument("--no-clocks", action="store_true", help="development: do not run the nvidia-smi clock sampler")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="rows mode: exchange the halo rows before the kernel instead of beside it")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pcg", action="store_true", help="skip the config-4 PCG solve appended to the 1-GPU line")
     ap.add_argument("--pcg-config", default="c4", choices=sorted(CONFIGS))

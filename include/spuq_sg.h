@@ -142,6 +142,18 @@ SPUQ_API int spuq_sg_plan_tune(spuq_sg_plan* plan, int32_t variant, int32_t cols
 SPUQ_API int spuq_sg_apply(spuq_sg_plan* plan, const double* W_dev, int64_t ldw,
                   double* Y_dev, int64_t ldy, void* stream);
 
+/* The same product restricted to a part of the OUTPUT grid rows, for callers that overlap a halo exchange
+ * with the bulk of the work (row-sharded slabs, spuq_b200.sharding.RowShardedApply): the first and the
+ * last grid row of the local slab are halo rows filled from the neighbouring ranks.
+ *   part 1  every output tile row whose stencil window reads neither halo row (may start before the
+ *           exchange has finished)
+ *   part 2  the remaining tile rows (after the exchange)
+ *   part 0  all rows (= spuq_sg_apply)
+ * Parts 1 and 2 together write every output row exactly once.  On kernel paths without a tile-row range
+ * part 1 does nothing and part 2 computes everything. */
+SPUQ_API int spuq_sg_apply_part(spuq_sg_plan* plan, const double* W_dev, int64_t ldw,
+                       double* Y_dev, int64_t ldy, int32_t part, void* stream);
+
 /* Number of kernels launched by the last spuq_sg_* call on this plan (for bench.py's
  * gpu_launches) and the name of the apply kernel. */
 SPUQ_API int spuq_sg_plan_last_launches(const spuq_sg_plan* plan);

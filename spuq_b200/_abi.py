@@ -53,6 +53,7 @@ SIGNATURES = {
     "spuq_sg_plan_info": (C.c_int, [_vp, _i32p, _i64p, _i64p, _i64p, _i64p]),
     "spuq_sg_plan_tune": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "spuq_sg_apply": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, _vp]),
+    "spuq_sg_apply_part": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, C.c_int32, _vp]),
     "spuq_sg_plan_last_launches": (C.c_int, [_vp]),
     "spuq_sg_plan_kernel_name": (C.c_char_p, [_vp]),
     "spuq_sg_reduce_scratch_bytes": (C.c_int64, []),

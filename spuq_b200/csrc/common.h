@@ -149,6 +149,9 @@ struct spuq_sg_plan {
     unsigned long long* d_work_counter = nullptr;
     std::vector<void*> sched_dev;                      // device arrays of the current schedule
 
+    // spuq_sg_apply_part: 0 = whole grid, 1 = tile rows that read no halo grid row, 2 = the others
+    int32_t part = 0;
+
     // tunables
     int32_t variant = 0, cols_per_block = 0, rows_per_thread = 0, ctas_per_sm = 0;
 

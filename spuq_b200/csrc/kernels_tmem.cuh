@@ -241,6 +241,7 @@ __global__ void __launch_bounds__((G_ == 1) ? 160 : 384, 1)
 k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapA,
              const SchedRec* __restrict__ recs, const int32_t* __restrict__ pcmd,
              const int32_t* __restrict__ blk_pcmd, int32_t nblk, int32_t s, int32_t ny, int32_t nty,
+             int32_t ty_off0, int32_t ty_cnt0, int32_t ty_off1,
              int64_t n_items, unsigned long long* __restrict__ work_counter,
              double* __restrict__ Y, int64_t ldy, const double* gate, int32_t debug_flags) {
     using Cfg = TmemCfg<K, NINE, G_>;
@@ -319,7 +320,11 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                     if (valid) {
                         blk = (int32_t)(item % (unsigned long long)nblk);
                         const int64_t tile = (int64_t)(item / (unsigned long long)nblk);
-                        P.yt = (int32_t)(tile % nty) * Cfg::TILE_Y;
+                        // tile rows of this launch: ty_cnt0 rows from ty_off0, the rest from ty_off1 (a launch
+                        // over all rows has ty_off0 = 0, ty_cnt0 = nty); spuq_sg_apply_part uses the two ranges
+                        // for the tile rows that touch the halo grid rows / for all the others
+                        const int32_t tr = (int32_t)(tile % nty);
+                        P.yt = (tr < ty_cnt0 ? ty_off0 + tr : ty_off1 + (tr - ty_cnt0)) * Cfg::TILE_Y;
                         P.xt = (int32_t)(tile / nty) * Cfg::TILE_X;
                     }
                     if (lane == 0) {

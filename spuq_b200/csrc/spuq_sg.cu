@@ -540,24 +540,34 @@ static int launch_tmem(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y,
         p->tmap_w_ptr = W; p->tmap_w_ld = ldw; p->tmap_w_rows = Cfg::WIN_ROWS;
     }
     auto kern = k_apply_tmem<K, NINE, G>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SPUQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_done = true;
-    }
+    // the attribute is per device: set it before every launch (cheap) instead of caching a process-wide flag
+    SPUQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const Schedule* sc = static_cast<const Schedule*>(p->sched_host);
     const int32_t ntx = (p->st.s + Cfg::TILE_X - 1) / Cfg::TILE_X;
-    const int32_t nty = (p->ny + Cfg::TILE_Y - 1) / Cfg::TILE_Y;
+    const int32_t nty_all = (p->ny + Cfg::TILE_Y - 1) / Cfg::TILE_Y;
+    // tile rows of this launch (spuq_sg_apply_part): a tile row t reads the grid rows t*TILE_Y - 1 ..
+    // t*TILE_Y + TILE_Y, so it touches a halo grid row (first / last row of the local grid) when t == 0 or
+    // t*TILE_Y + TILE_Y >= ny - 1
+    int32_t t_hi = (p->ny - 1 - Cfg::TILE_Y + Cfg::TILE_Y - 1) / Cfg::TILE_Y;      // first t with t*TY + TY >= ny - 1
+    t_hi = std::max(1, std::min(t_hi, nty_all));
+    int32_t off0 = 0, cnt0 = nty_all, off1 = 0, nty = nty_all;
+    if (p->part == 1) { off0 = 1; cnt0 = t_hi - 1; nty = cnt0; }                              // interior
+    else if (p->part == 2) { off0 = 0; cnt0 = 1; off1 = t_hi; nty = 1 + (nty_all - t_hi); }   // boundary
+    if (nty_all < 3 && p->part == 1) return SPUQ_OK;                  // nothing is interior
+    if (nty_all < 3 && p->part == 2) { off0 = 0; cnt0 = nty_all; nty = nty_all; }
+    if (nty <= 0) return SPUQ_OK;
     const int64_t items = (int64_t)ntx * nty * sc->nblk;
     const int64_t grid = std::min<int64_t>((items + Cfg::G - 1) / Cfg::G, (int64_t)p->n_sm);
-    SPUQ_CUDA_TRY(cudaMemsetAsync(p->d_work_counter, 0, sizeof(unsigned long long), stream));
+    // one counter per part: the interior and the boundary launch of one apply may be in flight together
+    unsigned long long* counter = p->d_work_counter + (p->part == 2 ? 1 : 0);
+    SPUQ_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
     static const int32_t debug_flags = std::getenv("SPUQ_KDEBUG") ? std::atoi(std::getenv("SPUQ_KDEBUG")) : 0;
     CUtensorMap mw, ma;
     std::memcpy(&mw, p->tmap_w, sizeof(mw));
     std::memcpy(&ma, p->tmap_a, sizeof(ma));
     kern<<<dim3((unsigned)grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream>>>(
         mw, ma, static_cast<const SchedRec*>(p->d_recs), p->d_pcmd, p->d_blk_pcmd, sc->nblk, p->st.s, p->ny, nty,
-        items, p->d_work_counter, Y, ldy, gate, debug_flags);
+        off0, cnt0, off1, items, counter, Y, ldy, gate, debug_flags);
     char name[80];
     snprintf(name, sizeof(name), "k_apply_tmem<K=%d,G=%d,%s>", K, G, NINE ? "9pt" : "5pt");
     p->kernel_name = name;
@@ -746,6 +756,33 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
 }
 
 }  // namespace spuq
+
+extern "C" int spuq_sg_apply_part(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t ldy,
+                                  int32_t part, void* stream) {
+    SPUQ_REQUIRE(p != nullptr, "apply_part: null plan");
+    SPUQ_REQUIRE(part >= 0 && part <= 2, "apply_part: part must be 0 (all), 1 (interior) or 2 (boundary)");
+    SPUQ_CUDA_TRY(cudaSetDevice(p->device));
+    if (part != 0) {
+        const bool aligned = (p->st.s % 2 == 0) && (ldw % 2 == 0) && (ldy % 2 == 0) &&
+                             (((uintptr_t)W | (uintptr_t)Y) & 15) == 0;
+        const bool tmem = p->path == SPUQ_PATH_STENCIL && aligned && p->n_slots > 0 && (p->variant == 4 || p->variant == 0);
+#ifdef SPUQ_EMU
+        const bool split = false;
+#else
+        const bool split = tmem;
+#endif
+        if (!split) {
+            // kernels without a tile-row range: the whole grid in the boundary call, which is the one the
+            // caller issues after the halo rows have arrived
+            if (part == 1) { p->last_launches = 0; return SPUQ_OK; }
+            part = 0;
+        }
+    }
+    p->part = part;
+    const int rc = apply_impl(p, W, ldw, Y, ldy, static_cast<cudaStream_t>(stream), nullptr);
+    p->part = 0;
+    return rc;
+}
 
 extern "C" int spuq_sg_apply(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t ldy,
                              void* stream) {

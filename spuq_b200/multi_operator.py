@@ -150,6 +150,14 @@ class SGPlan:
         _abi.check(_abi.lib().spuq_sg_apply(self.handle, _abi.ptr(W), self.n_cols, _abi.ptr(Y), self.n_rows,
                                             _abi.stream_ptr()), "apply")
 
+    def apply_part(self, W, Y, part):
+        """Part of the output grid rows (1: tile rows that read no halo row, 2: the rest, 0: all); see
+        ``spuq_sg_apply_part``."""
+        assert W.is_contiguous() and Y.is_contiguous()
+        assert tuple(W.shape) == (self.L, self.n_cols) and tuple(Y.shape) == (self.L, self.n_rows)
+        _abi.check(_abi.lib().spuq_sg_apply_part(self.handle, _abi.ptr(W), self.n_cols, _abi.ptr(Y), self.n_rows,
+                                                 int(part), _abi.stream_ptr()), "apply_part")
+
     @property
     def kernel_name(self):
         return _abi.lib().spuq_sg_plan_kernel_name(self.handle).decode()

@@ -114,6 +114,8 @@ class RowShardedApply:
         self.nyl = y1 - y0 + 2
         self.op = MultiOperator.from_blocks(blocks, rvs, path=path)
         self._bufs = None
+        self._side = None
+        self.last_launches = 0
 
     def plan_for(self, w):
         return self.op.plan_for(w)
@@ -144,9 +146,29 @@ class RowShardedApply:
         if self.rank < self.world - 1:
             W3[:, self.nyl - 1, :].copy_(r_dn)
 
-    def apply(self, plan, W, Y):
-        self.exchange_halos(W)
-        plan.apply(W, Y)
+    def apply(self, plan, W, Y, overlap=True):
+        """Y = A W on the local slab.  With ``overlap`` the halo exchange runs on a side stream while the
+        kernel already works on the tile rows that read no halo row (spuq_sg_apply_part 1); the tile rows
+        at the two ends follow once the halo rows have arrived (part 2)."""
+        if self.world == 1 or not overlap or W.device.type != "cuda":
+            self.exchange_halos(W)
+            plan.apply(W, Y)
+            self.last_launches = plan.last_launches
+            return Y
+        cur = torch.cuda.current_stream(W.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(W.device)
+            self._ev_ready, self._ev_halo = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_ready.record(cur)                      # W is complete on the current stream
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ev_ready)
+            self.exchange_halos(W)                      # enqueued FIRST: the NCCL kernel gets its SMs before
+            self._ev_halo.record(self._side)            # the persistent apply kernel fills the device
+        plan.apply_part(W, Y, 1)
+        n1 = plan.last_launches
+        cur.wait_event(self._ev_halo)
+        plan.apply_part(W, Y, 2)
+        self.last_launches = n1 + plan.last_launches
         return Y
 
 

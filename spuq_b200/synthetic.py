@@ -28,7 +28,7 @@ from .multiindex import MultiindexSet
 from .lambda_tables import sort_permutation
 from .random_variable import NormalRV, UniformRV
 
-__all__ = ["kl_frequencies", "kl_amplitudes", "fd_pattern", "fd_values", "fd_blocks",
+__all__ = ["kl_frequencies", "kl_amplitudes", "fd_pattern", "fd_values", "fd_blocks", "tile_permutation", "permute_blocks",
            "fd_blocks_rows", "fd_pattern_rect", "complete_order_indices", "anisotropic_indices", "truncated_complete_indices",
            "make_rvs", "blocks_to_scipy", "FDDiscretisation"]
 
@@ -137,6 +137,43 @@ def fd_pattern_rect(nx, ny, device="cpu"):
     rowptr = torch.zeros(N + 1, dtype=torch.int64, device=device)
     rowptr[1:] = torch.cumsum(counts, 0)
     return rowptr.to(torch.int32), cols[valid].to(torch.int32), valid
+
+
+def tile_permutation(n, tile=16, seed=4321):
+    """Renumbering of the n x n grid with the locality of an unstructured-mesh numbering but without the
+    stencil structure: tiles of tile x tile nodes in row-major tile order, the nodes of a tile in random
+    order.  perm[new] = old.  (Workload "c3u": the general sparse path on config-3 blocks.)"""
+    rng = np.random.RandomState(seed)
+    ids = np.arange(n * n).reshape(n, n)
+    out = []
+    for ty in range(0, n, tile):
+        for tx in range(0, n, tile):
+            blk = ids[ty:ty + tile, tx:tx + tile].ravel().copy()
+            rng.shuffle(blk)
+            out.append(blk)
+    return np.concatenate(out)
+
+
+def permute_blocks(rowptr, colidx, vals, perm):
+    """P A P^T of all blocks on their shared pattern (row / column new = old perm[new]), column indices
+    of a row ascending; runs where the tensors live (HBM for the benchmark sizes)."""
+    dev = rowptr.device
+    perm_t = torch.as_tensor(np.asarray(perm), dtype=torch.int64, device=dev)
+    N = perm_t.numel()
+    inv = torch.empty_like(perm_t)
+    inv[perm_t] = torch.arange(N, device=dev)
+    rp = rowptr.to(torch.int64)
+    counts = (rp[1:] - rp[:-1])[perm_t]
+    new_rp = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+    new_rp[1:] = torch.cumsum(counts, 0)
+    nnz = int(new_rp[-1])
+    new_row = torch.repeat_interleave(torch.arange(N, device=dev), counts)
+    within = torch.arange(nnz, device=dev) - new_rp[new_row]
+    eidx = rp[perm_t][new_row] + within                       # entry of the old matrix
+    new_col = inv[colidx.to(torch.int64)[eidx]]
+    order = torch.argsort(new_row * N + new_col)              # rows are contiguous: a global sort sorts every row
+    eidx = eidx[order]
+    return new_rp.to(torch.int32), new_col[order].to(torch.int32), vals[:, eidx].contiguous()
 
 
 def blocks_to_scipy(rowptr, colidx, vals, n_rows):

@@ -286,6 +286,42 @@ def test_full_size_config4_apply_and_pcg():
     assert float(torch.linalg.norm(r.slab)) <= 1e-9 * float(torch.linalg.norm(f.slab))
 
 
+def test_general_sparse_path_100k_rows():
+    """The SG operator on a renumbered grid (N = 102400 rows, 21 blocks, 287 indices): the pattern is no
+    stencil, so the column-blocked general kernel runs; sampled output columns against the oracle's apply
+    on the oracle's own permuted blocks; the one-column-at-a-time kernel as a second opinion."""
+    import spuq_b200 as sp
+    from oracle import synth
+    from oracle.sampled import SampledApply
+    from spuq_b200 import _abi, synthetic
+    from spuq_b200.multi_operator import DeviceBlocks
+    dev = _abi.device()
+    n, M = 320, 20
+    N = n * n
+    idx = synthetic.anisotropic_indices(M, 9.0)
+    L = idx.shape[0]
+    perm = synthetic.tile_permutation(n, 16)
+    rowptr, colidx, vals = synthetic.permute_blocks(*synthetic.fd_blocks(n, M, device=dev), perm)
+    A = sp.MultiOperator.from_blocks(DeviceBlocks(rowptr, colidx, vals, (N, N)), synthetic.make_rvs("hermite", M, 0.5))
+    g = torch.Generator(device=dev); g.manual_seed(99)
+    W = torch.rand((L, N), dtype=torch.float64, device=dev, generator=g)
+    w = sp.SlabMultiVector(idx, slab=W, _sorted=True)
+    plan = A.plan_for(w)
+    y = A.apply(w)
+    assert plan.kernel_name == "k_apply_ellblk<8>", plan.kernel_name
+    mats = synth.permuted(synth.fd_matrices(n, M), synth.tile_permutation(n, 16))
+    cols = [0, 1, 5, L // 2, L - 1]
+    ref, _ = SampledApply(mats, synth.index_set(("aniso", M, 9.0)), "hermite", 0.5, cols, lambda k: W[k].cpu().numpy()).run()
+    for k, r in ref.items():
+        err = np.linalg.norm(y.slab[k].cpu().numpy() - r) / np.linalg.norm(r)
+        assert err <= 1e-12, (k, err)
+    plan.tune(1, 0, 0, 0)
+    y2 = A.apply(w)
+    assert plan.kernel_name == "k_apply_ell<8>"
+    d = float(torch.linalg.norm(y2.slab - y.slab) / torch.linalg.norm(y.slab))
+    assert d <= 1e-13, d
+
+
 def test_parametric_samples():
     ps.check_parametric_samples()
 

@@ -41,6 +41,18 @@ def test_tile_permutation_is_a_permutation_and_breaks_the_stencil():
     assert offs.size > 9          # not a 3x3-window stencil any more
 
 
+def test_permuted_blocks_identical():
+    n, M = 12, 3
+    perm = synth.tile_permutation(n, 5)
+    assert np.array_equal(perm, synthetic.tile_permutation(n, 5))
+    ref = synth.permuted(synth.fd_matrices(n, M), perm)
+    rp, ci, v = synthetic.permute_blocks(*synthetic.fd_blocks(n, M), perm)
+    got = synthetic.blocks_to_scipy(rp, ci, v, n * n)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+        assert np.array_equal(a.data, b.data)
+
+
 @pytest.mark.parametrize("kind,mu", [("legendre", 0.0), ("hermite", 0.5)])
 def test_sampled_apply_equals_full_apply(kind, mu):
     idx = synthetic.complete_order_indices(4, 3)
