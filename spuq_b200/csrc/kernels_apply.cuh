@@ -102,6 +102,18 @@ k_apply_ell(int64_t n_rows, int32_t L, int32_t K, const int32_t* __restrict__ el
 // ---------------------------------------------------------------------------------------------
 constexpr int ELLBLK_C = 16;
 
+// acc[which] += v with a warp-uniform `which`: a jump into a table of 16 adds (a dynamically indexed
+// register array would live in local memory)
+__device__ __forceinline__ void ellblk_accumulate(double (&acc)[ELLBLK_C], int32_t which, double v) {
+    switch (which) {
+        case 0: acc[0] += v; break;   case 1: acc[1] += v; break;   case 2: acc[2] += v; break;   case 3: acc[3] += v; break;
+        case 4: acc[4] += v; break;   case 5: acc[5] += v; break;   case 6: acc[6] += v; break;   case 7: acc[7] += v; break;
+        case 8: acc[8] += v; break;   case 9: acc[9] += v; break;   case 10: acc[10] += v; break; case 11: acc[11] += v; break;
+        case 12: acc[12] += v; break; case 13: acc[13] += v; break; case 14: acc[14] += v; break; case 15: acc[15] += v; break;
+        default: break;
+    }
+}
+
 template <int KW>
 __global__ void __launch_bounds__(128)
 k_apply_ellblk(int64_t n_rows, int32_t K, const int32_t* __restrict__ ell_cols,
@@ -123,24 +135,28 @@ k_apply_ellblk(int64_t n_rows, int32_t K, const int32_t* __restrict__ ell_cols,
         const double* ap = ell_vals + ((int64_t)bv.gmat[g] * K) * n_rows + row;
 #pragma unroll
         for (int k = 0; k < KW; ++k) a[k] = k < K ? ap[(int64_t)k * n_rows] : 0.0;
-        for (int32_t t = bv.gterm[g]; t < bv.gterm[g + 1]; ++t) {
-            const double* w = W + (int64_t)bv.tcol[t] * ldw;
-            double s0 = 0.0, s1 = 0.0;
+        // two terms per trip: all 2 x KW gathers are issued before the first product, so that two input
+        // columns are in flight per warp (the gathers are the only latency on this path)
+        const int32_t t1 = bv.gterm[g + 1];
+        int32_t t = bv.gterm[g];
+        for (; t + 1 < t1; t += 2) {
+            const double* wa = W + (int64_t)bv.tcol[t] * ldw;
+            const double* wb = W + (int64_t)bv.tcol[t + 1] * ldw;
+            double ga[KW], gb[KW];
 #pragma unroll
-            for (int k = 0; k < KW; k += 2) {
-                s0 = fma(a[k], w[cols[k]], s0);
-                if (k + 1 < KW) s1 = fma(a[k + 1], w[cols[k + 1]], s1);
-            }
-            const double v = bv.tcoef[t] * (s0 + s1);
-#define SPUQ_ACC_CASE(k) case k: acc[k] += v; break;
-            switch (bv.tacc[t]) {
-                SPUQ_ACC_CASE(0) SPUQ_ACC_CASE(1) SPUQ_ACC_CASE(2) SPUQ_ACC_CASE(3)
-                SPUQ_ACC_CASE(4) SPUQ_ACC_CASE(5) SPUQ_ACC_CASE(6) SPUQ_ACC_CASE(7)
-                SPUQ_ACC_CASE(8) SPUQ_ACC_CASE(9) SPUQ_ACC_CASE(10) SPUQ_ACC_CASE(11)
-                SPUQ_ACC_CASE(12) SPUQ_ACC_CASE(13) SPUQ_ACC_CASE(14) SPUQ_ACC_CASE(15)
-                default: break;
-            }
-#undef SPUQ_ACC_CASE
+            for (int k = 0; k < KW; ++k) { ga[k] = wa[cols[k]]; gb[k] = wb[cols[k]]; }
+            double sa = 0.0, sb = 0.0;
+#pragma unroll
+            for (int k = 0; k < KW; ++k) { sa = fma(a[k], ga[k], sa); sb = fma(a[k], gb[k], sb); }
+            ellblk_accumulate(acc, bv.tacc[t], bv.tcoef[t] * sa);
+            ellblk_accumulate(acc, bv.tacc[t + 1], bv.tcoef[t + 1] * sb);
+        }
+        if (t < t1) {
+            const double* wa = W + (int64_t)bv.tcol[t] * ldw;
+            double sa = 0.0;
+#pragma unroll
+            for (int k = 0; k < KW; ++k) sa = fma(a[k], wa[cols[k]], sa);
+            ellblk_accumulate(acc, bv.tacc[t], bv.tcoef[t] * sa);
         }
     }
 #pragma unroll

@@ -197,6 +197,7 @@ struct StripPlan {
     StripQ Q{};
     std::vector<void*> dev;               // device allocations
     int32_t cmax = 0;                     // tallest strip
+    int32_t main_ct = 0;                  // height of the main strips when the kernel has a compile-time form for it
     size_t smem_bytes = 0;
     double* sy_ipiv = nullptr;            // [q][nx] separator system per x-mode (transform order of the GEMM path)
     double* sy_off = nullptr;
@@ -252,6 +253,16 @@ static T* strip_upload(StripPlan* sp, const std::vector<T>& h) {
     return static_cast<T*>(d);
 }
 
+#ifndef SPUQ_EMU
+template <typename F>
+static void strip_for_each_kernel(F f) {
+#define SPUQ_STRIP_K(ct) f((const void*)k_strip<false, ct>); f((const void*)k_strip<true, ct>);
+    SPUQ_STRIP_K(0) SPUQ_STRIP_K(8) SPUQ_STRIP_K(12) SPUQ_STRIP_K(16) SPUQ_STRIP_K(20) SPUQ_STRIP_K(24)
+    SPUQ_STRIP_K(26) SPUQ_STRIP_K(28) SPUQ_STRIP_K(32)
+#undef SPUQ_STRIP_K
+}
+#endif
+
 void strip_plan_destroy(spuq_sg_precond* p) {
     StripPlan* sp = static_cast<StripPlan*>(p->strip);
     if (!sp) return;
@@ -276,7 +287,23 @@ int strip_plan_build(spuq_sg_precond* p) {
     if (cap < 2) return SPUQ_OK;                          // grid too wide for shared memory: plain path
     StripPlan* sp = new StripPlan();
     StripView& sv = sp->sv;
-    partition_line(ny, cap, &ystart, &ylen);
+    // main strips of ONE height from the set the kernel is instantiated for (compile-time transform), plus a
+    // remainder strip of 1 .. 32 rows at the end (generic kernel)
+    {
+        static const int heights[] = {32, 28, 26, 24, 20, 16, 12, 8};
+        int cm = 0, nmain = 0, rem = 0;
+        for (int h : heights) {
+            if (h > cap) continue;
+            const int k = (ny - 1) / (h + 1), r = ny - k * (h + 1);
+            if (r >= 1 && r <= std::min(cap, STRIP_CMAX)) { cm = h; nmain = k; rem = r; break; }
+        }
+        if (cm == 0) partition_line(ny, cap, &ystart, &ylen);       // tiny grids: any heights, generic kernel
+        else {
+            int pos = 0;
+            for (int i = 0; i < nmain; ++i) { ystart.push_back(pos); ylen.push_back(cm); pos += cm + 1; }
+            ystart.push_back(pos); ylen.push_back(rem);
+        }
+    }
     sv.nx = nx; sv.ny = ny; sv.ox = ox; sv.oy = oy;
     sv.P = (int32_t)ystart.size(); sv.q = sv.P - 1;
     sv.PX = (int32_t)xstart.size(); sv.qx = sv.PX - 1;
@@ -284,7 +311,12 @@ int strip_plan_build(spuq_sg_precond* p) {
     sv.cxmax = *std::max_element(xlen.begin(), xlen.end());
     sv.ch[0] = ylen.front(); sv.ch[1] = ylen.back();     // heights h+1 (first strips) and h
     sv.xlen_cls_len[0] = xlen.front(); sv.xlen_cls_len[1] = xlen.back();
-    sp->cmax = sv.ch[0];
+    sp->cmax = std::max(sv.ch[0], sv.ch[1]);
+    {
+        static const int heights[] = {32, 28, 26, 24, 20, 16, 12, 8};
+        for (int h : heights) if (sv.ch[0] == h && ylen.size() > 1) sp->main_ct = h;
+        if (std::getenv("SPUQ_STRIP_GENERIC")) sp->main_ct = 0;        // A/B switch (development)
+    }
     sv.n_tall = 0;
     for (size_t i = 0; i < ylen.size(); ++i) sv.n_tall += (ylen[i] == sv.ch[0]) ? 1 : 0;
     if (sv.ch[0] == sv.ch[1]) sv.n_tall = sv.P;
@@ -363,18 +395,49 @@ int strip_plan_build(spuq_sg_precond* p) {
     p->strip = sp;
     if (!ok) { strip_plan_destroy(p); return SPUQ_OK; }       // not fatal: the plain path still works
 #ifndef SPUQ_EMU
-    if (cudaFuncSetAttribute(k_strip<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(k_strip<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem_bytes) != cudaSuccess) {
-        cudaGetLastError();
-        strip_plan_destroy(p);
-    } else {
+    bool attr_ok = true;
+    auto prep = [&](const void* fn) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem_bytes) != cudaSuccess) attr_ok = false;
         // two CTAs of ~110 KB per SM: ask for the largest shared-memory carve-out
-        cudaFuncSetAttribute(k_strip<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(k_strip<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaGetLastError();
-    }
+        cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    };
+    strip_for_each_kernel(prep);
+    if (!attr_ok) { cudaGetLastError(); strip_plan_destroy(p); }
+    cudaGetLastError();
 #endif
     return SPUQ_OK;
+}
+
+// launch k_strip<FINAL, CT> for the strips [p_off, p_off + p_cnt) of all L columns
+template <bool FINAL>
+static void strip_launch(int ct, const StripPlan* sp, int32_t L, int32_t p_off, int32_t p_cnt, const double* R, double* S,
+                         double* Gf, double* Gl, const double* U, cudaStream_t stream, const double* gate) {
+    if (p_cnt <= 0) return;
+    const dim3 grid((unsigned)((int64_t)L * p_cnt)), block(STRIP_THREADS);
+#define SPUQ_STRIP_L(c)                                                                                          \
+    case c: SPUQ_LAUNCH((k_strip<FINAL, c>), grid, block, sp->smem_bytes, stream, sp->Q, sp->sv, L, p_off, p_cnt, \
+                        R, S, Gf, Gl, U, gate); break;
+    switch (ct) {
+        SPUQ_STRIP_L(8) SPUQ_STRIP_L(12) SPUQ_STRIP_L(16) SPUQ_STRIP_L(20) SPUQ_STRIP_L(24) SPUQ_STRIP_L(26)
+        SPUQ_STRIP_L(28) SPUQ_STRIP_L(32)
+        default: SPUQ_LAUNCH((k_strip<FINAL, 0>), grid, block, sp->smem_bytes, stream, sp->Q, sp->sv, L, p_off, p_cnt,
+                             R, S, Gf, Gl, U, gate);
+    }
+#undef SPUQ_STRIP_L
+}
+
+// both passes over the strips: the main strips with the compile-time height, the rest generic
+template <bool FINAL>
+static void strip_pass(const StripPlan* sp, int32_t L, const double* R, double* S, double* Gf, double* Gl, const double* U,
+                       cudaStream_t stream, const double* gate) {
+    const StripView& sv = sp->sv;
+    const int main_ct = sp->main_ct;
+    if (main_ct > 0 && sv.n_tall > 0) {
+        strip_launch<FINAL>(main_ct, sp, L, 0, sv.n_tall, R, S, Gf, Gl, U, stream, gate);
+        strip_launch<FINAL>(0, sp, L, sv.n_tall, sv.P - sv.n_tall, R, S, Gf, Gl, U, stream, gate);
+    } else {
+        strip_launch<FINAL>(0, sp, L, 0, sv.P, R, S, Gf, Gl, U, stream, gate);
+    }
 }
 
 static int64_t strip_work_doubles(const StripPlan* sp, int32_t L) {
@@ -393,10 +456,9 @@ static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
     double* Gl = Gf + (int64_t)L * sv.P * nx;
     double* Z = Gl + (int64_t)L * sv.P * nx;
     double* Z2 = Z + (int64_t)L * q * nx;
-    const dim3 grid((unsigned)((int64_t)L * sv.P)), block(STRIP_THREADS);
     const double* U = nullptr;
     if (q > 0) {
-        SPUQ_LAUNCH((k_strip<false>), grid, block, sp->smem_bytes, stream, sp->Q, sv, L, R, S, Gf, Gl, (const double*)nullptr, gate);
+        strip_pass<false>(sp, L, R, S, Gf, Gl, nullptr, stream, gate);
         const int64_t Mrows = (int64_t)L * q;
         const unsigned eb = (unsigned)std::min<int64_t>((Mrows * nx + 255) / 256, 1 << 20);
         SPUQ_LAUNCH(k_sep_assemble, dim3(eb), dim3(256), 0, stream, sv, L, R, Gf, Gl, Z, gate);
@@ -425,7 +487,7 @@ static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
             U = Z;
         }
     }
-    SPUQ_LAUNCH((k_strip<true>), grid, block, sp->smem_bytes, stream, sp->Q, sv, L, R, S, Gf, Gl, U, gate);
+    strip_pass<true>(sp, L, R, S, Gf, Gl, U, stream, gate);
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }

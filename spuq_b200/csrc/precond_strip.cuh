@@ -127,12 +127,49 @@ __device__ __forceinline__ void strip_ytransform(const double* __restrict__ qc, 
     run(m, 1);          // odd modes: antisymmetric part
 }
 
+// The same transform for a strip height known at compile time (the main strips of a plan): both loops are
+// fully unrolled, so every matrix entry is an IMMEDIATE constant-bank operand of its DFMA -- no load
+// instruction at all -- and the chains of different modes interleave freely.
+template <int CT, typename Emit>
+__device__ __forceinline__ void strip_ytransform_ct(const StripQ& Q, const double* __restrict__ colx, int nx, Emit emit) {
+    constexpr int half = CT / 2, hp = (CT + 1) / 2;
+    double p[hp], m[hp];
+#pragma unroll
+    for (int s = 0; s < half; ++s) {
+        const double a = colx[(size_t)s * nx], b = colx[(size_t)(CT - 1 - s) * nx];
+        p[s] = a + b; m[s] = a - b;
+    }
+    if (CT & 1) { p[half] = colx[(size_t)half * nx]; m[half] = 0.0; }
+#pragma unroll
+    for (int j0 = 0; j0 < CT; j0 += 8) {         // groups of four modes per parity: bounded register use
+        double e[4], o[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { e[g] = 0.0; o[g] = 0.0; }
+#pragma unroll
+        for (int i = 0; i < hp; ++i) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (j0 + 2 * g < CT) e[g] = fma(Q.q[0][(j0 + 2 * g) * STRIP_HP + i], p[i], e[g]);
+                if (j0 + 2 * g + 1 < CT && i < half) o[g] = fma(Q.q[0][(j0 + 2 * g + 1) * STRIP_HP + i], m[i], o[g]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (j0 + 2 * g < CT) emit(j0 + 2 * g, e[g]);
+            if (j0 + 2 * g + 1 < CT) emit(j0 + 2 * g + 1, o[g]);
+        }
+    }
+}
+
 // One strip of one slab column.  FINAL = false: Gf/Gl <- first / last row of A_strip^{-1} R_strip.
 // FINAL = true: S_strip <- A_strip^{-1} (R_strip - oy * separator values on the adjacent rows), and the
 // separator row below the strip is copied from U.
-template <bool FINAL>
+// CT > 0: every strip of the launch has height CT (class 0); CT = 0: heights from the plan (any <= 32).
+// The launch covers strips p_off .. p_off + p_cnt - 1 of every column.
+template <bool FINAL, int CT>
 __global__ void __launch_bounds__(STRIP_THREADS, 2)
-k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, const double* __restrict__ R, double* __restrict__ S,
+k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off, int32_t p_cnt,
+        const double* __restrict__ R, double* __restrict__ S,
         double* __restrict__ Gf, double* __restrict__ Gl, const double* __restrict__ U, const double* gate) {
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
 #ifdef SPUQ_EMU
@@ -143,13 +180,13 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, const double*
     extern __shared__ __align__(16) double smem[];
 #endif
     const int nx = sv.nx;
-    const int p = (int)(blockIdx.x % (unsigned)sv.P);
-    const int64_t col = blockIdx.x / (unsigned)sv.P;
+    const int p = p_off + (int)(blockIdx.x % (unsigned)p_cnt);
+    const int64_t col = blockIdx.x / (unsigned)p_cnt;
     if (col >= L) return;
     // class, height and first row from the parameters alone (no table look-up): warp-uniform values, so the
     // transform-matrix addresses below are uniform too
-    const int cls = (p < sv.n_tall) ? 0 : 1;
-    const int c = sv.ch[cls];
+    const int cls = CT > 0 ? 0 : ((p < sv.n_tall) ? 0 : 1);
+    const int c = CT > 0 ? CT : sv.ch[cls];
     const int y0 = (p < sv.n_tall) ? p * (sv.ch[0] + 1) : sv.n_tall * (sv.ch[0] + 1) + (p - sv.n_tall) * (sv.ch[1] + 1);
     const double* qc = Q.q[cls];                        // [c][HP], constant bank
     double* sepv = smem;                                // [c][qx]
@@ -198,7 +235,9 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, const double*
 
     // ---- phase 1: sine transform along y, one thread per grid column -------------------------------
     for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
-        strip_ytransform(qc, strip + x, nx, c, [&](int j, double a) { strip[(size_t)j * nx + x] = a; });
+        auto put = [&](int j, double a) { strip[(size_t)j * nx + x] = a; };
+        if (CT > 0) strip_ytransform_ct<(CT > 0 ? CT : 1)>(Q, strip + x, nx, put);
+        else strip_ytransform(qc, strip + x, nx, c, put);
     }
     STRIP_SYNC();
 
@@ -270,7 +309,9 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, const double*
     if (FINAL) {
         double* dst = S + col * N + (int64_t)y0 * nx;
         for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
-            strip_ytransform(qc, strip + x, nx, c, [&](int j, double a) { dst[(size_t)j * nx + x] = a; });
+            auto put = [&](int j, double a) { dst[(size_t)j * nx + x] = a; };
+            if (CT > 0) strip_ytransform_ct<(CT > 0 ? CT : 1)>(Q, strip + x, nx, put);
+            else strip_ytransform(qc, strip + x, nx, c, put);
         }
     } else {
         double* gf = Gf + (col * sv.P + p) * nx;
