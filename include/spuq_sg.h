@@ -244,6 +244,28 @@ SPUQ_API int spuq_sg_precond_mean_fd_inverse(spuq_sg_precond* p, int64_t N, int3
 SPUQ_API int spuq_sg_precond_mean_fd_mode_order(const spuq_sg_precond* p, int32_t* order_host);
 SPUQ_API int spuq_sg_spike_correct(int32_t L, int32_t ny, int32_t nx, double* T_dev, const double* zl_dev,
                           const double* zr_dev, const double* sl_dev, const double* sr_dev, void* stream);
+/* The strip solver for a grid whose ROWS are sharded over ranks (spuq_b200.sharding, one rank per GPU).
+ * `bounds_host[world + 1]` are the global row boundaries; the handle belongs to the band of rank `rank`.
+ * The last row of every band but the last is a separator row, so the bands couple only through the
+ * separator system, which is solved redundantly on every rank from the gathered right-hand sides:
+ *     strip_forward   local strips, first / last rows of their solutions -> Gf, Gl [L][gf_ld][nx]
+ *     (caller)        the first-strip rows of Gf travel to the previous rank (slot gf_ld - 1 there)
+ *     strip_assemble  right-hand sides of the local separators -> rows first_sep .. of Z [q_glob][L][nx]
+ *     (caller)        all-gather of the separator rows
+ *     strip_schur     separator system of the whole grid, in place on Z (Z2: scratch of the same size)
+ *     strip_final     local strips with the separator values on their right-hand side -> S
+ * R and S are contiguous L x (n_loc * nx) slabs of the band's rows.  All kernels honour spuq_sg_set_gate. */
+SPUQ_API int spuq_sg_precond_mean_fd_rows(spuq_sg_precond** out, int device, int32_t nx, double d, double ox, double oy,
+                                 int32_t world, int32_t rank, const int32_t* bounds_host);
+SPUQ_API int spuq_sg_precond_strip_info(const spuq_sg_precond* p, int32_t* n_strips_loc, int32_t* q_loc, int32_t* q_glob,
+                               int32_t* first_sep, int32_t* gf_ld);
+SPUQ_API int spuq_sg_precond_strip_forward(spuq_sg_precond* p, int32_t L, const double* R_dev, double* Gf_dev, double* Gl_dev,
+                                  void* stream);
+SPUQ_API int spuq_sg_precond_strip_assemble(spuq_sg_precond* p, int32_t L, const double* R_dev, const double* Gf_dev,
+                                   const double* Gl_dev, double* Z_dev, void* stream);
+SPUQ_API int spuq_sg_precond_strip_schur(spuq_sg_precond* p, int32_t L, double* Z_dev, double* Z2_dev, void* stream);
+SPUQ_API int spuq_sg_precond_strip_final(spuq_sg_precond* p, int32_t L, const double* R_dev, const double* U_dev, double* S_dev,
+                                void* stream);
 SPUQ_API int spuq_sg_precond_destroy(spuq_sg_precond* p);
 /* workspace (bytes) precond_apply needs for an N x L slab */
 SPUQ_API int64_t spuq_sg_precond_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L);
@@ -265,6 +287,16 @@ SPUQ_API int spuq_sg_precond_apply(spuq_sg_precond* p, int64_t N, int32_t L, con
 SPUQ_API int spuq_sg_pcg_check_zeta(double* state_dev, int32_t pass, void* stream);   /* pcg.py:33-38 */
 SPUQ_API int spuq_sg_pcg_check_alpha(double* state_dev, void* stream);                /* pcg.py:41-45 */
 SPUQ_API int spuq_sg_pcg_rotate(double* state_dev, void* stream);                     /* zeta <- zeta_new */
+/* check_zeta that also records zeta of the pass in hist_dev[pass - 1] (device, may be NULL) */
+SPUQ_API int spuq_sg_pcg_check_zeta_hist(double* state_dev, int32_t pass, double* hist_dev, void* stream);
+/* state[dst] = state[src] while the solve is running: takes an all-reduced scalar over from a staging slot
+ * (slots 8..15 of the state are free for the caller) */
+SPUQ_API int spuq_sg_pcg_accept(double* state_dev, int32_t src, int32_t dst, void* stream);
+
+/* Conditional-execution scope for host-enqueued solver loops: while gate_dev is set for the calling thread,
+ * every kernel launched through spuq_sg_apply / _apply_part / _dot* / _axpy* / _xpay / _precond_apply and the
+ * strip phase calls is a no-op once *gate_dev != SPUQ_PCG_RUNNING (gate_dev = &state[4]).  NULL ends the scope. */
+SPUQ_API int spuq_sg_set_gate(const double* gate_dev);
 
 /* Whole solve on one GPU.  F_dev: right-hand side, W_dev: initial guess in, solution out (both
  * N x L contiguous).  work_dev: caller-owned, at least spuq_sg_pcg_work_bytes() bytes.

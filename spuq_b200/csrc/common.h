@@ -40,6 +40,12 @@ void set_error(const char* fmt, ...);
 
 int sm_count(int device);
 
+// Conditional-execution scope of the C ABI (spuq_sg_set_gate): while a gate word is set for the calling
+// thread, every kernel launched through an ABI entry point becomes a no-op once *gate != SPUQ_PCG_RUNNING.
+// This is how a host-enqueued solver loop (spuq_b200.sharding.RowShardedPCG) stays free of host round
+// trips: it enqueues whole passes and the device decides whether they still do anything.
+const double* abi_gate();
+
 // ---- device-side views handed to the kernels (plain structs, passed by value) ---------------
 
 // Per-column term lists: column mu of Y is  sum_t coef[t] * A_{mat[t]} * W[:, col[t]]

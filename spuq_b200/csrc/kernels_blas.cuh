@@ -296,6 +296,13 @@ __global__ void k_pcg_check_alpha(double* st) {
     else if (alpha < 0.0) st[4] = (double)SPUQ_PCG_NOT_PD;        // pcg.py:44-45
 }
 
+// st[dst] = st[src] while the solve is running: takes an all-reduced scalar over from its staging slot
+__global__ void k_pcg_accept(double* st, int32_t src, int32_t dst) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st[4] != (double)SPUQ_PCG_RUNNING) return;
+    st[dst] = st[src];
+}
+
 __global__ void k_pcg_rotate(double* st) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (st[4] != (double)SPUQ_PCG_RUNNING) return;

@@ -56,19 +56,19 @@ extern "C" int64_t spuq_sg_reduce_scratch_bytes(void) { return REDUCE_SCRATCH_BY
 
 extern "C" int spuq_sg_dot(int64_t n, const double* x, const double* y, double* out, void* scratch,
                            void* stream) {
-    return dot_impl(1, n, x, y, out, scratch, static_cast<cudaStream_t>(stream), nullptr);
+    return dot_impl(1, n, x, y, out, scratch, static_cast<cudaStream_t>(stream), abi_gate());
 }
 
 extern "C" int spuq_sg_dot2(int64_t n, const double* x, const double* y, double* out,
                             void* scratch, void* stream) {
-    return dot_impl(2, n, x, y, out, scratch, static_cast<cudaStream_t>(stream), nullptr);
+    return dot_impl(2, n, x, y, out, scratch, static_cast<cudaStream_t>(stream), abi_gate());
 }
 
 extern "C" int spuq_sg_axpy(int64_t n, double alpha, const double* num, const double* den,
                             const double* x, double* y, void* stream) {
     SPUQ_REQUIRE(n >= 0 && x && y, "axpy: null argument");
     SPUQ_LAUNCH(k_axpy, dim3(blas_grid(n, cur_sm_count(), 256)), dim3(256), 0,
-                static_cast<cudaStream_t>(stream), n, alpha, num, den, x, y, (const double*)nullptr);
+                static_cast<cudaStream_t>(stream), n, alpha, num, den, x, y, abi_gate());
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }
@@ -77,7 +77,7 @@ extern "C" int spuq_sg_axpy2(int64_t n, const double* num, const double* den, co
                              double* w, const double* z, double* rho, void* stream) {
     SPUQ_REQUIRE(n >= 0 && num && den && v && w && z && rho, "axpy2: null argument");
     SPUQ_LAUNCH(k_axpy2, dim3(blas_grid(n, cur_sm_count(), 256)), dim3(256), 0,
-                static_cast<cudaStream_t>(stream), n, num, den, v, w, z, rho, (const double*)nullptr);
+                static_cast<cudaStream_t>(stream), n, num, den, v, w, z, rho, abi_gate());
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }
@@ -86,7 +86,7 @@ extern "C" int spuq_sg_xpay(int64_t n, const double* num, const double* den, con
                             double* v, void* stream) {
     SPUQ_REQUIRE(n >= 0 && num && den && s && v, "xpay: null argument");
     SPUQ_LAUNCH(k_xpay, dim3(blas_grid(n, cur_sm_count(), 256)), dim3(256), 0,
-                static_cast<cudaStream_t>(stream), n, num, den, s, v, (const double*)nullptr);
+                static_cast<cudaStream_t>(stream), n, num, den, s, v, abi_gate());
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }
@@ -148,6 +148,19 @@ extern "C" int spuq_sg_pcg_check_zeta(double* st, int32_t pass, void* stream) {
 extern "C" int spuq_sg_pcg_check_alpha(double* st, void* stream) {
     SPUQ_REQUIRE(st, "pcg_check_alpha: null state");
     SPUQ_LAUNCH(k_pcg_check_alpha, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), st);
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+extern "C" int spuq_sg_pcg_check_zeta_hist(double* st, int32_t pass, double* hist_dev, void* stream) {
+    SPUQ_REQUIRE(st && pass >= 1, "pcg_check_zeta_hist: bad argument");
+    SPUQ_LAUNCH(k_pcg_check_zeta, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), st, pass, hist_dev);
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+extern "C" int spuq_sg_pcg_accept(double* st, int32_t src, int32_t dst, void* stream) {
+    SPUQ_REQUIRE(st && src >= 0 && dst >= 0 && src < SPUQ_PCG_STATE_DOUBLES && dst < SPUQ_PCG_STATE_DOUBLES,
+                 "pcg_accept: bad argument");
+    SPUQ_LAUNCH(k_pcg_accept, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), st, src, dst);
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }
@@ -220,7 +233,7 @@ int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
 
 extern "C" int spuq_sg_precond_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R,
                                      double* S, void* work, void* stream) {
-    return precond_apply_impl(p, N, L, R, S, work, static_cast<cudaStream_t>(stream), nullptr);
+    return precond_apply_impl(p, N, L, R, S, work, static_cast<cudaStream_t>(stream), abi_gate());
 }
 
 // ---- the solver -------------------------------------------------------------------------------------

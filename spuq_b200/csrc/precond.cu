@@ -165,6 +165,12 @@ k_mirror_merge(int64_t Mrows, int32_t n, double* __restrict__ X, const double* g
     }
 }
 
+__global__ void __launch_bounds__(256)
+k_copy_gated(int64_t n, const double* __restrict__ src, double* __restrict__ dst, const double* gate) {
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) dst[t] = src[t];
+}
+
 // Thomas solves along y, in place on X (L columns of ny x nx): one thread per (column, mode k),
 // lanes along k.  ipiv[y*nx + k] = reciprocal pivot of (T_y + lam_k I) at row y.
 __global__ void __launch_bounds__(128)
@@ -271,9 +277,30 @@ void strip_plan_destroy(spuq_sg_precond* p) {
     p->strip = nullptr;
 }
 
-int strip_plan_build(spuq_sg_precond* p) {
+// Strips of `nrows` grid rows: main strips of ONE height from the set the kernel is instantiated for
+// (compile-time transform), single separator rows between them, and a remainder strip of 1 .. cap rows at
+// the end (generic kernel).  Tiny grids: equal-as-possible strips of any height.
+static void choose_strips(int nrows, int cap, std::vector<int32_t>* ystart, std::vector<int32_t>* ylen) {
+    static const int heights[] = {32, 28, 26, 24, 20, 16, 12, 8};
+    ystart->clear(); ylen->clear();
+    int cm = 0, nmain = 0, rem = 0;
+    for (int h : heights) {
+        if (h > cap) continue;
+        const int k = (nrows - 1) / (h + 1), r = nrows - k * (h + 1);
+        if (r >= 1 && r <= std::min(cap, STRIP_CMAX)) { cm = h; nmain = k; rem = r; break; }
+    }
+    if (cm == 0) { partition_line(nrows, cap, ystart, ylen); return; }
+    int pos = 0;
+    for (int i = 0; i < nmain; ++i) { ystart->push_back(pos); ylen->push_back(cm); pos += cm + 1; }
+    ystart->push_back(pos); ylen->push_back(rem);
+}
+
+// ctx != null: the handle's grid is the band of rows [bounds[rank], bounds[rank+1]) of a grid whose rows are
+// sharded over `world` ranks; the last row of every band but the last is a separator (it couples the band to
+// the next one), and the separator system spans all bands.
+int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx) {
     const int32_t nx = p->nx, ny = p->ny;
-    if (ny < 2 || nx < 2) return SPUQ_OK;                 // 1-D: the plain path
+    if (ny < 2 || nx < 2) return ctx ? SPUQ_E_UNSUPPORTED : SPUQ_OK;      // 1-D: the plain path
     if (const char* e = std::getenv("SPUQ_PRECOND_PLAIN")) { if (e[0] == '1') return SPUQ_OK; }   // A/B switch (development)
     const double pi = 3.14159265358979323846;
     const double dxx = 0.5 * p->d, dyy = 0.5 * p->d, ox = p->ox, oy = p->oy;
@@ -287,25 +314,28 @@ int strip_plan_build(spuq_sg_precond* p) {
     if (cap < 2) return SPUQ_OK;                          // grid too wide for shared memory: plain path
     StripPlan* sp = new StripPlan();
     StripView& sv = sp->sv;
-    // main strips of ONE height from the set the kernel is instantiated for (compile-time transform), plus a
-    // remainder strip of 1 .. 32 rows at the end (generic kernel)
-    {
-        static const int heights[] = {32, 28, 26, 24, 20, 16, 12, 8};
-        int cm = 0, nmain = 0, rem = 0;
-        for (int h : heights) {
-            if (h > cap) continue;
-            const int k = (ny - 1) / (h + 1), r = ny - k * (h + 1);
-            if (r >= 1 && r <= std::min(cap, STRIP_CMAX)) { cm = h; nmain = k; rem = r; break; }
+    const int has_bottom = (ctx && ctx->rank < ctx->world - 1) ? 1 : 0;
+    choose_strips(ny - has_bottom, cap, &ystart, &ylen);
+    // all strips of all bands in global order (one band, this one, without a context)
+    std::vector<int32_t> gheights;
+    int32_t j0 = 0;
+    if (ctx) {
+        std::vector<int32_t> ys, yl;
+        for (int r = 0; r < ctx->world; ++r) {
+            const int nr = ctx->bounds[r + 1] - ctx->bounds[r] - (r < ctx->world - 1 ? 1 : 0);
+            if (nr < 1) { delete sp; set_error("precond_mean_fd_rows: rank %d owns fewer than two grid rows", r); return SPUQ_E_INVALID; }
+            choose_strips(nr, cap, &ys, &yl);
+            if (r == ctx->rank) j0 = (int32_t)gheights.size();
+            gheights.insert(gheights.end(), yl.begin(), yl.end());
         }
-        if (cm == 0) partition_line(ny, cap, &ystart, &ylen);       // tiny grids: any heights, generic kernel
-        else {
-            int pos = 0;
-            for (int i = 0; i < nmain; ++i) { ystart.push_back(pos); ylen.push_back(cm); pos += cm + 1; }
-            ystart.push_back(pos); ylen.push_back(rem);
-        }
+    } else {
+        gheights = ylen;
     }
     sv.nx = nx; sv.ny = ny; sv.ox = ox; sv.oy = oy;
-    sv.P = (int32_t)ystart.size(); sv.q = sv.P - 1;
+    sv.P = (int32_t)ystart.size(); sv.q = (int32_t)gheights.size() - 1;     // q: separators of the WHOLE grid
+    sv.q_loc = sv.P - 1 + has_bottom; sv.has_bottom = has_bottom; sv.u_above0 = j0 - 1;
+    sv.gf_ld = sv.P + has_bottom;
+    sv.u_js = nx; sv.u_cs = (int64_t)sv.q * nx;          // one-GPU layout; the phase entry points set their own
     sv.PX = (int32_t)xstart.size(); sv.qx = sv.PX - 1;
     if (sv.qx > 64) { delete sp; return SPUQ_OK; }
     sv.cxmax = *std::max_element(xlen.begin(), xlen.end());
@@ -370,16 +400,19 @@ int strip_plan_build(spuq_sg_precond* p) {
     if (ok && sv.q > 0) {
         const int q = sv.q, h = p->half;
         std::vector<double> ip((size_t)q * nx), of((size_t)q * nx);
-        std::vector<double> v[2];
+        std::vector<int32_t> distinct(gheights);
+        std::sort(distinct.begin(), distinct.end());
+        distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
+        std::vector<std::vector<double>> v(STRIP_CMAX + 2);
         for (int32_t c0 = 0; c0 < nx && ok; ++c0) {
             const int32_t k = h > 0 ? (c0 < h ? 2 * c0 : 2 * (c0 - h) + 1) : c0;
             const double bb = dyy + dxx + 2.0 * ox * std::cos((double)(k + 1) * pi / (nx + 1.0));
-            for (int cls = 0; cls < 2; ++cls) tri_first_column(sv.ch[cls], bb, oy, &v[cls]);
+            for (int32_t hh : distinct) tri_first_column(hh, bb, oy, &v[hh]);
             double prev_piv = 0.0, prev_off = 0.0;
             for (int j = 0; j < q; ++j) {
-                const int ca = ycls[j], cb = ycls[j + 1];
+                const int ca = gheights[j], cb = gheights[j + 1];
                 const double D = bb - oy * oy * (v[ca][0] + v[cb][0]);
-                const double E = -oy * oy * v[cb][sv.ch[cb] - 1];
+                const double E = -oy * oy * v[cb][cb - 1];
                 double pvt = D;
                 if (j > 0) pvt = D - prev_off * prev_off / prev_piv;
                 if (!(pvt != 0.0) || !std::isfinite(pvt)) ok = false;
@@ -410,17 +443,18 @@ int strip_plan_build(spuq_sg_precond* p) {
 
 // launch k_strip<FINAL, CT> for the strips [p_off, p_off + p_cnt) of all L columns
 template <bool FINAL>
-static void strip_launch(int ct, const StripPlan* sp, int32_t L, int32_t p_off, int32_t p_cnt, const double* R, double* S,
-                         double* Gf, double* Gl, const double* U, cudaStream_t stream, const double* gate) {
+static void strip_launch(int ct, const StripPlan* sp, const StripView& view, int32_t L, int32_t p_off, int32_t p_cnt,
+                         const double* R, double* S, double* Gf, double* Gl, const double* U, cudaStream_t stream,
+                         const double* gate) {
     if (p_cnt <= 0) return;
     const dim3 grid((unsigned)((int64_t)L * p_cnt)), block(STRIP_THREADS);
 #define SPUQ_STRIP_L(c)                                                                                          \
-    case c: SPUQ_LAUNCH((k_strip<FINAL, c>), grid, block, sp->smem_bytes, stream, sp->Q, sp->sv, L, p_off, p_cnt, \
+    case c: SPUQ_LAUNCH((k_strip<FINAL, c>), grid, block, sp->smem_bytes, stream, sp->Q, view, L, p_off, p_cnt, \
                         R, S, Gf, Gl, U, gate); break;
     switch (ct) {
         SPUQ_STRIP_L(8) SPUQ_STRIP_L(12) SPUQ_STRIP_L(16) SPUQ_STRIP_L(20) SPUQ_STRIP_L(24) SPUQ_STRIP_L(26)
         SPUQ_STRIP_L(28) SPUQ_STRIP_L(32)
-        default: SPUQ_LAUNCH((k_strip<FINAL, 0>), grid, block, sp->smem_bytes, stream, sp->Q, sp->sv, L, p_off, p_cnt,
+        default: SPUQ_LAUNCH((k_strip<FINAL, 0>), grid, block, sp->smem_bytes, stream, sp->Q, view, L, p_off, p_cnt,
                              R, S, Gf, Gl, U, gate);
     }
 #undef SPUQ_STRIP_L
@@ -428,20 +462,55 @@ static void strip_launch(int ct, const StripPlan* sp, int32_t L, int32_t p_off, 
 
 // both passes over the strips: the main strips with the compile-time height, the rest generic
 template <bool FINAL>
-static void strip_pass(const StripPlan* sp, int32_t L, const double* R, double* S, double* Gf, double* Gl, const double* U,
-                       cudaStream_t stream, const double* gate) {
-    const StripView& sv = sp->sv;
+static void strip_pass(const StripPlan* sp, const StripView& sv, int32_t L, const double* R, double* S, double* Gf, double* Gl,
+                       const double* U, cudaStream_t stream, const double* gate) {
     const int main_ct = sp->main_ct;
     if (main_ct > 0 && sv.n_tall > 0) {
-        strip_launch<FINAL>(main_ct, sp, L, 0, sv.n_tall, R, S, Gf, Gl, U, stream, gate);
-        strip_launch<FINAL>(0, sp, L, sv.n_tall, sv.P - sv.n_tall, R, S, Gf, Gl, U, stream, gate);
+        strip_launch<FINAL>(main_ct, sp, sv, L, 0, sv.n_tall, R, S, Gf, Gl, U, stream, gate);
+        strip_launch<FINAL>(0, sp, sv, L, sv.n_tall, sv.P - sv.n_tall, R, S, Gf, Gl, U, stream, gate);
     } else {
-        strip_launch<FINAL>(0, sp, L, 0, sv.P, R, S, Gf, Gl, U, stream, gate);
+        strip_launch<FINAL>(0, sp, sv, L, 0, sv.P, R, S, Gf, Gl, U, stream, gate);
     }
+}
+template <bool FINAL>
+static void strip_pass(const StripPlan* sp, int32_t L, const double* R, double* S, double* Gf, double* Gl, const double* U,
+                       cudaStream_t stream, const double* gate) {
+    strip_pass<FINAL>(sp, sp->sv, L, R, S, Gf, Gl, U, stream, gate);
 }
 
 static int64_t strip_work_doubles(const StripPlan* sp, int32_t L) {
     return (int64_t)L * sp->sv.nx * (2 * (int64_t)sp->sv.P + 2 * (int64_t)sp->sv.q);
+}
+
+// separator system in place on Z (layout of sv.u_js / u_cs, q rows of L columns); Z2: scratch of the same size.
+// Returns the buffer that holds the solution.
+static const double* strip_schur(spuq_sg_precond* p, const StripPlan* sp, const StripView& sv, int32_t L, double* Z, double* Z2,
+                                 cudaStream_t stream, const double* gate) {
+    const int32_t nx = sv.nx, q = sv.q;
+    const int64_t Mrows = (int64_t)L * q;
+    auto rowgemm = [&](const double* src, double* dst, int32_t nk, int32_t nc, const double* Q) {
+        const dim3 g((unsigned)((Mrows + GM - 1) / GM), (unsigned)((nc + GN - 1) / GN));
+        SPUQ_LAUNCH(k_rowgemm, g, dim3(G_THREADS), 0, stream, Mrows, nk, nc, src, nx, Q, dst, nx, gate);
+    };
+    const int64_t nthreads = (int64_t)L * nx;
+    const dim3 tg((unsigned)((nthreads + 127) / 128));
+    const int32_t h = p->half;
+    if (h > 0) {
+        const size_t hh = (size_t)h * h;
+        const unsigned mb = (unsigned)std::min<int64_t>((Mrows * h + 255) / 256, 1 << 20);
+        SPUQ_LAUNCH(k_mirror_split, dim3(mb), dim3(256), 0, stream, Mrows, nx, Z, Z2, gate);
+        rowgemm(Z2, Z, h, h, p->qsplit_dev);
+        rowgemm(Z2 + h, Z + h, h, h, p->qsplit_dev + hh);
+        SPUQ_LAUNCH(k_thomas_sep, tg, dim3(128), 0, stream, nx, q, L, sv.u_js, sv.u_cs, sp->sy_ipiv, sp->sy_off, Z, gate);
+        rowgemm(Z, Z2, h, h, p->qsplit_dev + 2 * hh);
+        rowgemm(Z + h, Z2 + h, h, h, p->qsplit_dev + 3 * hh);
+        SPUQ_LAUNCH(k_mirror_merge, dim3(mb), dim3(256), 0, stream, Mrows, nx, Z2, gate);
+        return Z2;
+    }
+    rowgemm(Z, Z2, nx, nx, p->q_dev);
+    SPUQ_LAUNCH(k_thomas_sep, tg, dim3(128), 0, stream, nx, q, L, sv.u_js, sv.u_cs, sp->sy_ipiv, sp->sy_off, Z2, gate);
+    rowgemm(Z2, Z, nx, nx, p->q_dev);
+    return Z;
 }
 
 static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
@@ -449,6 +518,7 @@ static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
     StripPlan* sp = static_cast<StripPlan*>(p->strip);
     const StripView& sv = sp->sv;
     const int32_t nx = sv.nx, q = sv.q;
+    SPUQ_REQUIRE(!sv.has_bottom && sv.u_above0 == -1, "precond_apply: this handle is a band of a row-sharded grid; use the strip phase calls");
     SPUQ_REQUIRE(N == (int64_t)nx * sv.ny, "precond_mean_fd: slab rows %lld != nx*ny", (long long)N);
     SPUQ_REQUIRE(work != nullptr || q == 0, "precond_mean_fd: workspace missing");
     SPUQ_REQUIRE((int64_t)L * sv.P < 0x7fffffffLL, "precond_mean_fd: too many strips for one launch");
@@ -459,33 +529,9 @@ static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
     const double* U = nullptr;
     if (q > 0) {
         strip_pass<false>(sp, L, R, S, Gf, Gl, nullptr, stream, gate);
-        const int64_t Mrows = (int64_t)L * q;
-        const unsigned eb = (unsigned)std::min<int64_t>((Mrows * nx + 255) / 256, 1 << 20);
+        const unsigned eb = (unsigned)std::min<int64_t>(((int64_t)L * q * nx + 255) / 256, 1 << 20);
         SPUQ_LAUNCH(k_sep_assemble, dim3(eb), dim3(256), 0, stream, sv, L, R, Gf, Gl, Z, gate);
-        auto rowgemm = [&](const double* src, double* dst, int32_t nk, int32_t nc, const double* Q) {
-            const dim3 g((unsigned)((Mrows + GM - 1) / GM), (unsigned)((nc + GN - 1) / GN));
-            SPUQ_LAUNCH(k_rowgemm, g, dim3(G_THREADS), 0, stream, Mrows, nk, nc, src, nx, Q, dst, nx, gate);
-        };
-        const int64_t nthreads = (int64_t)L * nx;
-        const dim3 tg((unsigned)((nthreads + 127) / 128));
-        const int32_t h = p->half;
-        if (h > 0) {
-            const size_t hh = (size_t)h * h;
-            const unsigned mb = (unsigned)std::min<int64_t>((Mrows * h + 255) / 256, 1 << 20);
-            SPUQ_LAUNCH(k_mirror_split, dim3(mb), dim3(256), 0, stream, Mrows, nx, Z, Z2, gate);
-            rowgemm(Z2, Z, h, h, p->qsplit_dev);
-            rowgemm(Z2 + h, Z + h, h, h, p->qsplit_dev + hh);
-            SPUQ_LAUNCH(k_thomas_sep, tg, dim3(128), 0, stream, nx, q, L, sp->sy_ipiv, sp->sy_off, Z, gate);
-            rowgemm(Z, Z2, h, h, p->qsplit_dev + 2 * hh);
-            rowgemm(Z + h, Z2 + h, h, h, p->qsplit_dev + 3 * hh);
-            SPUQ_LAUNCH(k_mirror_merge, dim3(mb), dim3(256), 0, stream, Mrows, nx, Z2, gate);
-            U = Z2;
-        } else {
-            rowgemm(Z, Z2, nx, nx, p->q_dev);
-            SPUQ_LAUNCH(k_thomas_sep, tg, dim3(128), 0, stream, nx, q, L, sp->sy_ipiv, sp->sy_off, Z2, gate);
-            rowgemm(Z2, Z, nx, nx, p->q_dev);
-            U = Z;
-        }
+        U = strip_schur(p, sp, sv, L, Z, Z2, stream, gate);
     }
     strip_pass<true>(sp, L, R, S, Gf, Gl, U, stream, gate);
     SPUQ_CUDA_TRY(cudaGetLastError());
@@ -719,7 +765,102 @@ extern "C" int spuq_sg_precond_mean_fd(spuq_sg_precond** out, int device, int32_
     }
     cudaMemcpy(p->q_dev, q.data(), sizeof(double) * q.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(p->piv_dev, piv.data(), sizeof(double) * piv.size(), cudaMemcpyHostToDevice);
-    strip_plan_build(p);
+    strip_plan_build(p, nullptr);
     *out = p;
+    return SPUQ_OK;
+}
+
+
+// ---- the strip solver in phases, for grids whose rows are sharded over ranks (spuq_b200.sharding) ----------
+// Layout of the separator arrays Z / U in these calls: [q_glob][L][nx] (separator-major), so that the block of
+// one rank's separators is contiguous and can be gathered as it is.
+static StripPlan* strip_of(spuq_sg_precond* p) {
+    return (p && p->kind == spuq_sg_precond::MEAN_FD) ? static_cast<StripPlan*>(p->strip) : nullptr;
+}
+static StripView rows_view(const StripPlan* sp, int32_t L) {
+    StripView v = sp->sv;
+    v.u_js = (int64_t)L * v.nx; v.u_cs = v.nx;
+    return v;
+}
+
+extern "C" int spuq_sg_precond_mean_fd_rows(spuq_sg_precond** out, int device, int32_t nx, double d, double ox, double oy,
+                                            int32_t world, int32_t rank, const int32_t* bounds_host) {
+    SPUQ_REQUIRE(out && bounds_host && world >= 1 && rank >= 0 && rank < world, "precond_mean_fd_rows: bad argument");
+    const int32_t n_loc = bounds_host[rank + 1] - bounds_host[rank];
+    SPUQ_REQUIRE(n_loc >= 2 && nx >= 2, "precond_mean_fd_rows: a band needs at least two grid rows and two columns");
+    SPUQ_CUDA_TRY(cudaSetDevice(device));
+    spuq_sg_precond* p = nullptr;
+    // the band's own handle (transform matrices of length nx for the separator system); its plain tables are
+    // those of an n_loc-row grid and are not used by the phase calls
+    int rc = spuq_sg_precond_mean_fd(&p, device, nx, n_loc, d, ox, oy);
+    if (rc) return rc;
+    strip_plan_destroy(p);
+    StripRowsCtx ctx{world, rank, bounds_host};
+    rc = strip_plan_build(p, &ctx);
+    if (rc || !p->strip) {
+        spuq_sg_precond_destroy(p);
+        if (!rc) set_error("precond_mean_fd_rows: the strip solver does not support this grid (nx = %d)", nx);
+        return rc ? rc : SPUQ_E_UNSUPPORTED;
+    }
+    *out = p;
+    return SPUQ_OK;
+}
+
+extern "C" int spuq_sg_precond_strip_info(const spuq_sg_precond* p, int32_t* n_strips_loc, int32_t* q_loc, int32_t* q_glob,
+                                          int32_t* first_sep, int32_t* gf_ld) {
+    const StripPlan* sp = strip_of(const_cast<spuq_sg_precond*>(p));
+    SPUQ_REQUIRE(sp, "precond_strip_info: the handle has no strip plan");
+    if (n_strips_loc) *n_strips_loc = sp->sv.P;
+    if (q_loc) *q_loc = sp->sv.q_loc;
+    if (q_glob) *q_glob = sp->sv.q;
+    if (first_sep) *first_sep = sp->sv.u_above0 + 1;
+    if (gf_ld) *gf_ld = sp->sv.gf_ld;
+    return SPUQ_OK;
+}
+
+// Gf / Gl [L][gf_ld][nx] <- first / last row of the local solution of every local strip
+extern "C" int spuq_sg_precond_strip_forward(spuq_sg_precond* p, int32_t L, const double* R, double* Gf, double* Gl, void* stream) {
+    StripPlan* sp = strip_of(p);
+    SPUQ_REQUIRE(sp && R && Gf && Gl && L >= 0, "precond_strip_forward: bad argument");
+    const StripView v = rows_view(sp, L);
+    strip_pass<false>(sp, v, L, R, nullptr, Gf, Gl, nullptr, static_cast<cudaStream_t>(stream), abi_gate());
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+// rows first_sep .. first_sep + q_loc - 1 of Z <- right-hand sides of the local separators (slot gf_ld - 1 of Gf
+// holds the first strip of the next rank when the band ends in a separator)
+extern "C" int spuq_sg_precond_strip_assemble(spuq_sg_precond* p, int32_t L, const double* R, const double* Gf, const double* Gl,
+                                              double* Z, void* stream) {
+    StripPlan* sp = strip_of(p);
+    SPUQ_REQUIRE(sp && R && Gf && Gl && Z && L >= 0, "precond_strip_assemble: bad argument");
+    const StripView v = rows_view(sp, L);
+    if (v.q_loc == 0 || L == 0) return SPUQ_OK;
+    const unsigned eb = (unsigned)std::min<int64_t>(((int64_t)L * v.q_loc * v.nx + 255) / 256, 1 << 20);
+    SPUQ_LAUNCH(k_sep_assemble, dim3(eb), dim3(256), 0, static_cast<cudaStream_t>(stream), v, L, R, Gf, Gl, Z, abi_gate());
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+// the separator system of the whole grid on Z [q_glob][L][nx]; the solution is left in Z (Z2: scratch, same size)
+extern "C" int spuq_sg_precond_strip_schur(spuq_sg_precond* p, int32_t L, double* Z, double* Z2, void* stream) {
+    StripPlan* sp = strip_of(p);
+    SPUQ_REQUIRE(sp && Z && Z2 && L >= 0, "precond_strip_schur: bad argument");
+    const StripView v = rows_view(sp, L);
+    if (v.q == 0 || L == 0) return SPUQ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double* U = strip_schur(p, sp, v, L, Z, Z2, st, abi_gate());
+    if (U != Z) {
+        const int64_t n = (int64_t)v.q * L * v.nx;
+        SPUQ_LAUNCH(k_copy_gated, dim3((unsigned)std::min<int64_t>((n + 255) / 256, 1 << 20)), dim3(256), 0, st, n, U, Z, abi_gate());
+    }
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+// S <- solution on the band's rows, given the separator values U [q_glob][L][nx] of the whole grid
+extern "C" int spuq_sg_precond_strip_final(spuq_sg_precond* p, int32_t L, const double* R, const double* U, double* S, void* stream) {
+    StripPlan* sp = strip_of(p);
+    SPUQ_REQUIRE(sp && R && S && L >= 0 && (U || sp->sv.q == 0), "precond_strip_final: bad argument");
+    const StripView v = rows_view(sp, L);
+    strip_pass<true>(sp, v, L, R, S, nullptr, nullptr, U, static_cast<cudaStream_t>(stream), abi_gate());
+    SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }

@@ -25,9 +25,13 @@ struct spuq_sg_precond {
 };
 
 namespace spuq {
+struct StripRowsCtx {            // the handle's grid is one band of a row-sharded grid
+    int32_t world, rank;
+    const int32_t* bounds;       // world + 1 global row boundaries
+};
 int mean_fd_destroy(spuq_sg_precond* p);
 // strip path (precond_strip.cuh / precond.cu)
-int strip_plan_build(spuq_sg_precond* p);
+int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx);
 void strip_plan_destroy(spuq_sg_precond* p);
 // general mean block through a sparse LU factorisation (precond_lu.cu)
 void lu_plan_destroy(spuq_sg_precond* p);

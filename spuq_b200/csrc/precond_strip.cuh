@@ -50,7 +50,13 @@ struct StripView {
     double ox, oy;
     const int32_t* ystart;            // P: first grid row of strip p   (host-side / assembly kernel use)
     const int32_t* ycls;              // P: height class of strip p
-    int32_t n_tall;                   // the first n_tall strips have height ch[0] = ch[1] + 1 (or all ch[0])
+    int32_t n_tall;                   // the first n_tall strips have height ch[0] (the main strips), the rest ch[1]
+    // separator values U(j, col, x) at U[j * u_js + col * u_cs + x].  One GPU: j = local separator, u_js = nx,
+    // u_cs = q * nx.  Row-sharded grid (every rank holds the separators of ALL ranks, j-major): the separator
+    // above the first local strip is number u_above0 (-1: none), the last local row is a separator of its own
+    // when has_bottom is set; Gf has gf_ld strip slots per column (one extra for the neighbour's first strip).
+    int64_t u_js, u_cs;
+    int32_t u_above0, has_bottom, gf_ld, q_loc;
     const int32_t* xstart;            // PX: first x of chunk ch
     const int32_t* xlen;              // PX
     int32_t ch[2];                    // heights of the two classes
@@ -220,15 +226,18 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
     if (FINAL) {
         STRIP_SYNC();
         const double oy = sv.oy;
+        const int ja = sv.u_above0 + p;                               // separator above / below this strip
+        const bool has_a = ja >= 0, has_b = (p < sv.P - 1) || sv.has_bottom;
+        const double* ua = U + (int64_t)ja * sv.u_js + col * sv.u_cs;
+        const double* ub = U + (int64_t)(ja + 1) * sv.u_js + col * sv.u_cs;
         for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
-            if (p > 0) strip[x] -= oy * U[(col * sv.q + (p - 1)) * nx + x];
-            if (p < sv.q) strip[(size_t)(c - 1) * nx + x] -= oy * U[(col * sv.q + p) * nx + x];
+            if (has_a) strip[x] -= oy * ua[x];
+            if (has_b) strip[(size_t)(c - 1) * nx + x] -= oy * ub[x];
         }
         // separator row below this strip
-        if (p < sv.q) {
+        if (has_b) {
             double* dst = S + col * N + (int64_t)(y0 + c) * nx;
-            const double* us = U + (col * sv.q + p) * nx;
-            for (int x = STRIP_T0; x < nx; x += STRIP_TS) dst[x] = us[x];
+            for (int x = STRIP_T0; x < nx; x += STRIP_TS) dst[x] = ub[x];
         }
     }
     STRIP_SYNC();
@@ -314,8 +323,8 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
             else strip_ytransform(qc, strip + x, nx, c, put);
         }
     } else {
-        double* gf = Gf + (col * sv.P + p) * nx;
-        double* gl = Gl + (col * sv.P + p) * nx;
+        double* gf = Gf + (col * sv.gf_ld + p) * nx;
+        double* gl = Gl + (col * sv.gf_ld + p) * nx;
         for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
             // rows 0 and c-1 of Q u: Q[0][j] and Q[c-1][j] = (-1)^j Q[0][j]
             double se = 0.0, so = 0.0;
@@ -330,46 +339,48 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
     }
 }
 
-// Z[col][j][x] = R[col][ysep_j][x] - oy * (Gl[col][j][x] + Gf[col][j+1][x])
+// Z(j0 + i, col, x) = R[col][ysep_i][x] - oy * (Gl[col][i][x] + Gf[col][i+1][x]) for the q_loc local separators
+// (i + 1 = gf_ld - 1 names the slot that holds the first strip of the NEXT rank); Z has the layout of U.
 __global__ void __launch_bounds__(256)
 k_sep_assemble(StripView sv, int32_t L, const double* __restrict__ R, const double* __restrict__ Gf,
                const double* __restrict__ Gl, double* __restrict__ Z, const double* gate) {
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
-    const int nx = sv.nx, q = sv.q;
+    const int nx = sv.nx, q = sv.q_loc;
     const int64_t total = (int64_t)L * q * nx;
     const int64_t N = (int64_t)nx * sv.ny;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int x = (int)(t % nx);
         const int64_t r = t / nx;
-        const int j = (int)(r % q);
+        const int i = (int)(r % q);
         const int64_t col = r / q;
-        const int ys = sv.ystart[j] + sv.ch[sv.ycls[j]];
-        Z[t] = R[col * N + (int64_t)ys * nx + x]
-               - sv.oy * (Gl[(col * sv.P + j) * nx + x] + Gf[(col * sv.P + j + 1) * nx + x]);
+        const int ys = sv.ystart[i] + sv.ch[sv.ycls[i]];
+        Z[(int64_t)(sv.u_above0 + 1 + i) * sv.u_js + col * sv.u_cs + x] =
+            R[col * N + (int64_t)ys * nx + x]
+            - sv.oy * (Gl[(col * sv.gf_ld + i) * nx + x] + Gf[(col * sv.gf_ld + i + 1) * nx + x]);
     }
 }
 
 // Tridiagonal solves of the separator system in the transformed domain, in place on X[col][j][k]:
 // one thread per (column, mode k), lanes along k.  ipiv[j*nx + k], off[j*nx + k] (coupling j <-> j+1).
 __global__ void __launch_bounds__(128)
-k_thomas_sep(int32_t nx, int32_t q, int32_t L, const double* __restrict__ ipiv, const double* __restrict__ off,
-             double* __restrict__ X, const double* gate) {
+k_thomas_sep(int32_t nx, int32_t q, int32_t L, int64_t js, int64_t cs, const double* __restrict__ ipiv,
+             const double* __restrict__ off, double* __restrict__ X, const double* gate) {
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)L * nx) return;
     const int32_t k = (int32_t)(t % nx);
     const int64_t col = t / nx;
-    double* x = X + col * (int64_t)nx * q + k;
+    double* x = X + col * cs + k;            // element (j, col, k) at j * js + col * cs + k
     double z = x[0];
     for (int32_t j = 1; j < q; ++j) {
-        z = x[(int64_t)j * nx] - off[(int64_t)(j - 1) * nx + k] * ipiv[(int64_t)(j - 1) * nx + k] * z;
-        x[(int64_t)j * nx] = z;
+        z = x[(int64_t)j * js] - off[(int64_t)(j - 1) * nx + k] * ipiv[(int64_t)(j - 1) * nx + k] * z;
+        x[(int64_t)j * js] = z;
     }
     double u = z * ipiv[(int64_t)(q - 1) * nx + k];
-    x[(int64_t)(q - 1) * nx] = u;
+    x[(int64_t)(q - 1) * js] = u;
     for (int32_t j = q - 2; j >= 0; --j) {
-        u = (x[(int64_t)j * nx] - off[(int64_t)j * nx + k] * u) * ipiv[(int64_t)j * nx + k];
-        x[(int64_t)j * nx] = u;
+        u = (x[(int64_t)j * js] - off[(int64_t)j * nx + k] * u) * ipiv[(int64_t)j * nx + k];
+        x[(int64_t)j * js] = u;
     }
 }
 

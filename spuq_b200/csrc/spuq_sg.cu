@@ -29,6 +29,9 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static thread_local const double* g_abi_gate = nullptr;
+const double* abi_gate() { return g_abi_gate; }
+
 int sm_count(int device) {
 #ifdef SPUQ_EMU
     (void)device;
@@ -779,7 +782,7 @@ extern "C" int spuq_sg_apply_part(spuq_sg_plan* p, const double* W, int64_t ldw,
         }
     }
     p->part = part;
-    const int rc = apply_impl(p, W, ldw, Y, ldy, static_cast<cudaStream_t>(stream), nullptr);
+    const int rc = apply_impl(p, W, ldw, Y, ldy, static_cast<cudaStream_t>(stream), abi_gate());
     p->part = 0;
     return rc;
 }
@@ -788,5 +791,10 @@ extern "C" int spuq_sg_apply(spuq_sg_plan* p, const double* W, int64_t ldw, doub
                              void* stream) {
     SPUQ_REQUIRE(p != nullptr, "apply: null plan");
     SPUQ_CUDA_TRY(cudaSetDevice(p->device));
-    return apply_impl(p, W, ldw, Y, ldy, static_cast<cudaStream_t>(stream), nullptr);
+    return apply_impl(p, W, ldw, Y, ldy, static_cast<cudaStream_t>(stream), abi_gate());
+}
+
+extern "C" int spuq_sg_set_gate(const double* gate_dev) {
+    g_abi_gate = gate_dev;
+    return SPUQ_OK;
 }

@@ -19,7 +19,7 @@ from .pcg import PCG_MESSAGES
 from . import _abi
 
 __all__ = ["shard_ranges", "padded_columns", "ShardedApply", "row_ranges", "RowShardedApply", "RowShardedPCG",
-           "PartitionedMeanSolver"]
+           "PartitionedMeanSolver", "StripRowsMeanSolver"]
 
 
 def shard_ranges(tables, M, world):
@@ -274,6 +274,95 @@ class PartitionedMeanSolver:
         return Sc
 
 
+class StripRowsMeanSolver:
+    """A_0^{-1} on ROW-sharded slabs with the strip solver of libspuq_sg (csrc/precond_strip.cuh): every
+    rank solves the strips of its own band in shared memory; the last row of every band but the last is a
+    separator row, and the separator system of the whole grid (a few per cent of the rows) is solved
+    redundantly on every rank after an all-gather of its right-hand sides.  Per call: one row of L x nx
+    doubles to the previous rank and one all-gather of the separator rows; no transposition of the slab,
+    no full-length transform of the bulk, no host synchronisation."""
+
+    def __init__(self, nx, ranges, rank, stencil, group=None):
+        d, ox, oy = stencil
+        self.nx, self.ranges, self.rank, self.group = int(nx), list(ranges), int(rank), group
+        self.world = len(self.ranges)
+        for (a0, a1), (b0, b1) in zip(self.ranges[:-1], self.ranges[1:]):
+            assert a1 == b0, "row ranges must be contiguous"
+        bounds = np.array([r0 for r0, _ in self.ranges] + [self.ranges[-1][1]], dtype=np.int32)
+        self.n_loc = int(bounds[rank + 1] - bounds[rank])
+        lib = _abi.lib()
+        handle = C.c_void_p()
+        _abi.check(lib.spuq_sg_precond_mean_fd_rows(C.byref(handle), _abi.device_index(), self.nx, float(d), float(ox),
+                                                    float(oy), self.world, self.rank, _abi.ptr(bounds)), "precond_mean_fd_rows")
+        self.handle = handle
+        vals = [C.c_int32() for _ in range(5)]
+        _abi.check(lib.spuq_sg_precond_strip_info(handle, *[C.byref(v) for v in vals]), "precond_strip_info")
+        self.P, self.q_loc, self.q_glob, self.first_sep, self.gf_ld = [int(v.value) for v in vals]
+        if self.world > 1:
+            info = [None] * self.world
+            dist.all_gather_object(info, (self.first_sep, self.q_loc), group=group)
+            self.sep_blocks = info                                  # (first separator, count) of every rank
+        else:
+            self.sep_blocks = [(self.first_sep, self.q_loc)]
+        self.q_max = max(c for _, c in self.sep_blocks)
+        self._bufs = None
+
+    def _buffers(self, L, like):
+        if self._bufs is None or self._bufs[0] != L:
+            mk = lambda *shape: torch.empty(shape, dtype=like.dtype, device=like.device)      # noqa: E731
+            self._bufs = (L, mk(L, self.gf_ld, self.nx), mk(L, self.gf_ld, self.nx),
+                          mk(max(self.q_glob, 1), L, self.nx), mk(max(self.q_glob, 1), L, self.nx),
+                          mk(self.world, max(self.q_max, 1), L, self.nx), mk(L, self.nx), mk(L, self.nx))
+        return self._bufs[1:]
+
+    def solve(self, Rc, Sc):
+        """Rc, Sc: contiguous L x (n_loc * nx) slabs of the owned rows; Sc = (A_0^{-1} R) restricted to them."""
+        lib = _abi.lib()
+        L = Rc.shape[0]
+        assert Rc.is_contiguous() and Sc.is_contiguous() and Rc.shape == (L, self.n_loc * self.nx) == Sc.shape
+        Gf, Gl, Z, Z2, gath, snd, rcv = self._buffers(L, Rc)
+        st = _abi.stream_ptr()
+        _abi.check(lib.spuq_sg_precond_strip_forward(self.handle, L, _abi.ptr(Rc), _abi.ptr(Gf), _abi.ptr(Gl), st), "strip_forward")
+        if self.world > 1:
+            ops = []
+            if self.rank > 0:
+                snd.copy_(Gf[:, 0, :])                              # first row of my first strip -> previous rank
+                ops.append(dist.P2POp(dist.isend, snd, self.rank - 1, self.group))
+            if self.rank < self.world - 1:
+                ops.append(dist.P2POp(dist.irecv, rcv, self.rank + 1, self.group))
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            if self.rank < self.world - 1:
+                Gf[:, self.gf_ld - 1, :].copy_(rcv)
+        if self.q_glob > 0:
+            _abi.check(lib.spuq_sg_precond_strip_assemble(self.handle, L, _abi.ptr(Rc), _abi.ptr(Gf), _abi.ptr(Gl), _abi.ptr(Z), st),
+                       "strip_assemble")
+            if self.world > 1:
+                mine = gath[self.rank]
+                if self.q_loc:
+                    mine[:self.q_loc].copy_(Z[self.first_sep:self.first_sep + self.q_loc])
+                if dist.get_backend(self.group) == "nccl":
+                    dist.all_gather_into_tensor(gath, mine.clone(), group=self.group)
+                else:
+                    parts = [torch.empty_like(mine) for _ in range(self.world)]
+                    dist.all_gather(parts, mine.clone(), group=self.group)
+                    for r_, part in enumerate(parts):
+                        gath[r_].copy_(part)
+                for r_, (f0, cnt) in enumerate(self.sep_blocks):
+                    if cnt and r_ != self.rank:
+                        Z[f0:f0 + cnt].copy_(gath[r_, :cnt])
+            _abi.check(lib.spuq_sg_precond_strip_schur(self.handle, L, _abi.ptr(Z), _abi.ptr(Z2), st), "strip_schur")
+        _abi.check(lib.spuq_sg_precond_strip_final(self.handle, L, _abi.ptr(Rc), _abi.ptr(Z), _abi.ptr(Sc), st), "strip_final")
+        return Sc
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _abi.lib().spuq_sg_precond_destroy(self.handle)
+        except Exception:
+            pass
+
+
 class RowShardedPCG:
     """``pcg`` (application/egsz/pcg.py:15-53) on row-sharded slabs.
 
@@ -289,7 +378,7 @@ class RowShardedPCG:
     The reference's four failure conditions are checked on the all-reduced scalars, so all ranks
     take the same branch."""
 
-    def __init__(self, sharded_apply, nx, ny, ranges, mean_stencil=None, mean_solver="partition"):
+    def __init__(self, sharded_apply, nx, ny, ranges, mean_stencil=None, mean_solver="strip"):
         self.A = sharded_apply
         self.group = sharded_apply.group
         self.world, self.rank = sharded_apply.world, sharded_apply.rank
@@ -300,8 +389,9 @@ class RowShardedPCG:
         self.mean_stencil = mean_stencil                 # (d, ox, oy) of the constant-coefficient mean block
         # "partition": tridiagonal partition method, the slab stays row-sharded (default);
         # "transpose": all-to-all to column shards and back around the single-GPU solver
-        if mean_solver not in ("partition", "transpose"):
-            raise ValueError("mean_solver must be 'partition' or 'transpose'")
+        # "strip" (default): the strip solver on every band + a gathered separator system (StripRowsMeanSolver)
+        if mean_solver not in ("strip", "partition", "transpose"):
+            raise ValueError("mean_solver must be 'strip', 'partition' or 'transpose'")
         self.mean_solver = mean_solver
         if min(r1 - r0 for r0, r1 in self.ranges) < 2:
             self.mean_solver = "transpose"
@@ -352,9 +442,15 @@ class RowShardedPCG:
             return S
         L = R.shape[0]
         dev = R.device
-        if self.mean_solver == "partition":
+        if self.mean_solver in ("partition", "strip"):
             if self._partition is None:
-                self._partition = PartitionedMeanSolver(self.nx, self.ny, self.ranges, self.rank, self.mean_stencil, self.group)
+                if self.mean_solver == "strip":
+                    try:
+                        self._partition = StripRowsMeanSolver(self.nx, self.ranges, self.rank, self.mean_stencil, self.group)
+                    except _abi.SpuqError:
+                        self.mean_solver = "partition"         # grid the strip solver does not take
+                if self._partition is None:
+                    self._partition = PartitionedMeanSolver(self.nx, self.ny, self.ranges, self.rank, self.mean_stencil, self.group)
             R3 = R.view(L, self.nyl, self.nx)
             Rc = R3[:, 1:-1, :].contiguous().view(L, -1)
             Sc = torch.empty_like(Rc)
@@ -398,10 +494,33 @@ class RowShardedPCG:
         return S
 
     # ---- the solver ----------------------------------------------------------------------------
-    def solve(self, plan, F, W0, eps=1e-4, maxiter=100):
-        """F, W0: local slabs (halo rows ignored).  Returns (W, zeta, numit) like ``pcg``; raises
-        the reference's exceptions."""
+    def solve(self, plan, F, W0, eps=1e-4, maxiter=100, poll_every=8):
+        """F, W0: local slabs (halo rows ignored).  Returns (W, zeta, numit) like ``pcg``; raises the
+        reference's exceptions.
+
+        The loop is enqueued by the host but decided on the device: zeta, alpha and the status word live in
+        a device state buffer, the inner products are all-reduced in place on it (NCCL on the stream), the
+        reference's branch conditions (pcg.py:33-45) are evaluated by the library's one-thread kernels, and
+        every kernel of a pass is a no-op once the status has left RUNNING (spuq_sg_set_gate).  The host
+        reads the status word once per ``poll_every`` passes."""
+        lib = _abi.lib()
         dev = F.device
+        n = F.numel()
+        st = torch.zeros(_abi.PCG_STATE_DOUBLES, dtype=torch.float64, device=dev)
+        st[4] = float(_abi.PCG_RUNNING)
+        st[6] = float(eps) ** 2
+        hist = torch.zeros(max(int(maxiter), 1), dtype=torch.float64, device=dev)
+        scratch = torch.zeros(int(lib.spuq_sg_reduce_scratch_bytes()) // 8 + 1, dtype=torch.float64, device=dev)
+        sp = lambda k: C.c_void_p(st.data_ptr() + 8 * k)          # noqa: E731  address of state word k
+        stream = _abi.stream_ptr
+
+        def dot_to(x, y, slot, stage):
+            """state[slot] = <x, y> summed over the ranks (staged in state[stage])."""
+            _abi.check(lib.spuq_sg_dot(n, _abi.ptr(x), _abi.ptr(y), sp(stage), _abi.ptr(scratch), stream()), "dot")
+            if self.world > 1:
+                dist.all_reduce(st[stage:stage + 1], op=dist.ReduceOp.SUM, group=self.group)
+            _abi.check(lib.spuq_sg_pcg_accept(_abi.ptr(st), stage, slot, stream()), "pcg_accept")
+
         W = W0.clone()
         self._zero_halos(W)
         rho = F.clone()
@@ -414,28 +533,38 @@ class RowShardedPCG:
         s = torch.empty_like(W)
         self.precondition(rho, s)                         # s = P rho           (:27)
         v = s.clone()                                     # v = s               (:28)
-        zeta = self._allreduce(_dot(rho, s), dev)         # zeta = <rho, s>     (:30)
-        self.last_history = []
-        for i in range(1, maxiter):                       # (:31)
-            self.last_history.append(zeta)
-            if zeta < 0:
-                raise Exception(PCG_MESSAGES[_abi.PCG_PRECOND_NOT_PD] % zeta)
-            if zeta <= eps ** 2:
-                self._zero_halos(W)
-                return W, zeta, i
-            self.A.apply(plan, v, z)                      # z = A v             (:40)
-            self._zero_halos(z)
-            alpha = self._allreduce(_dot(z, v), dev)      # (:41)
-            if alpha == 0:
-                raise Exception(PCG_MESSAGES[_abi.PCG_SINGULAR] % alpha)
-            if alpha < 0:
-                raise Exception(PCG_MESSAGES[_abi.PCG_NOT_PD] % alpha)
-            _axpy(zeta / alpha, v, W)                     # (:47)
-            _axpy(-zeta / alpha, z, rho)                  # (:48)
-            self.precondition(rho, s)                     # (:49)
-            zeta_new = self._allreduce(_dot(rho, s), dev)  # (:50)
-            _scal(zeta_new / zeta, v)                     # v = s + zeta_new / zeta * v   (:51)
-            _axpy(1.0, s, v)
-            self._zero_halos(v)
-            zeta = zeta_new
+        dot_to(rho, s, 0, 8)                              # zeta = <rho, s>     (:30)
+        lib.spuq_sg_set_gate(sp(4))
+        status, done = _abi.PCG_RUNNING, 1
+        try:
+            i = 1
+            while i < maxiter and status == _abi.PCG_RUNNING:
+                stop = min(maxiter, i + max(int(poll_every), 1))
+                for i in range(i, stop):                  # (:31)
+                    _abi.check(lib.spuq_sg_pcg_check_zeta_hist(_abi.ptr(st), i, _abi.ptr(hist), stream()), "check_zeta")   # :33-38
+                    self.A.apply(plan, v, z)              # z = A v             (:40)
+                    self._zero_halos(z)
+                    dot_to(z, v, 1, 9)                    # alpha = <z, v>      (:41)
+                    _abi.check(lib.spuq_sg_pcg_check_alpha(_abi.ptr(st), stream()), "check_alpha")                      # :42-45
+                    _abi.check(lib.spuq_sg_axpy2(n, sp(0), sp(1), _abi.ptr(v), _abi.ptr(W), _abi.ptr(z), _abi.ptr(rho),
+                                                 stream()), "axpy2")                                                   # :47-48
+                    self.precondition(rho, s)             # (:49)
+                    dot_to(rho, s, 2, 10)                 # zeta_new = <rho, s> (:50)
+                    _abi.check(lib.spuq_sg_xpay(n, sp(2), sp(0), _abi.ptr(s), _abi.ptr(v), stream()), "xpay")            # :51
+                    _abi.check(lib.spuq_sg_pcg_rotate(_abi.ptr(st), stream()), "rotate")
+                i = stop
+                h = st.cpu()                              # the one host read-back per poll_every passes
+                status, done = int(h[4]), int(h[5])
+        finally:
+            lib.spuq_sg_set_gate(None)
+        h = st.cpu()
+        zeta, alpha = float(h[0]), float(h[1])
+        self.last_history = hist[:done].cpu().tolist() if status != _abi.PCG_RUNNING else hist[:max(maxiter - 1, 0)].cpu().tolist()
+        if status == _abi.PCG_CONVERGED:
+            self._zero_halos(W)
+            return W, zeta, done
+        if status == _abi.PCG_PRECOND_NOT_PD:
+            raise Exception(PCG_MESSAGES[status] % zeta)
+        if status in (_abi.PCG_SINGULAR, _abi.PCG_NOT_PD):
+            raise Exception(PCG_MESSAGES[status] % alpha)
         raise Exception(PCG_MESSAGES[_abi.PCG_NOT_CONVERGED])

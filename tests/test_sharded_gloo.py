@@ -135,7 +135,7 @@ def _pcg_worker(rank, world, port, out_path, precond):
         plan = sh.plan_for(w)
         d = float(c.mats[0].diagonal()[0])
         solver = RowShardedPCG(sh, n, n, ranges, mean_stencil=(d, -1.0, -1.0) if precond.startswith("mean") else None,
-                               mean_solver="transpose" if precond == "mean-transpose" else "partition")
+                               mean_solver={"mean-transpose": "transpose", "mean-partition": "partition"}.get(precond, "strip"))
         X, zeta, it = solver.solve(plan, F, torch.zeros_like(F), eps=1e-9, maxiter=200)
         own = X.view(L, nyl, n)[:, 1:-1, :].contiguous()
         parts = [torch.empty_like(own) for _ in range(world)]
@@ -163,13 +163,56 @@ def _pcg_worker(rank, world, port, out_path, precond):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precond", ["mean", "mean-transpose", "identity"])
+@pytest.mark.parametrize("precond", ["mean", "mean-partition", "mean-transpose", "identity"])
 def test_row_sharded_pcg_two_ranks(tmp_path, emu, precond):
-    """PCG on row-sharded slabs (halo exchange for A, all-reduced scalars, mean preconditioner by the
-    tridiagonal partition method or through a transposition to column shards) against the oracle's
-    PCG on the global problem."""
+    """PCG on row-sharded slabs (halo exchange for A, scalars all-reduced in the device state, mean
+    preconditioner by the strip solver with a gathered separator system, by the tridiagonal partition method
+    or through a transposition to column shards) against the oracle's PCG on the global problem."""
     out = tmp_path / "res.txt"
     mp.spawn(_pcg_worker, args=(2, _free_port(), str(out), precond), nprocs=2, join=True)
     err, traj, it, it_o = [float(v) for v in out.read_text().split()]
     assert abs(it - it_o) <= 1, (it, it_o)
     assert traj <= 1e-9 and err <= 1e-8
+
+
+def _strip_rows_worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.sparse as sps
+        import scipy.sparse.linalg as spla
+        from spuq_b200 import _abi
+        from spuq_b200.sharding import StripRowsMeanSolver
+        _abi.use_library(conftest.EMU_LIB, "cpu")
+        worst = 0.0
+        for nx, ny, bounds, L in [(40, 75, [0, 30, 52, 75], 3), (33, 120, [0, 41, 80, 120], 2), (12, 9, [0, 3, 6, 9], 2)]:
+            ranges = list(zip(bounds[:-1], bounds[1:]))
+            T = lambda n, o, dd: sps.diags([o, dd, o], [-1, 0, 1], shape=(n, n))      # noqa: E731
+            A0 = sps.csr_matrix(sps.kron(sps.identity(ny), T(nx, -1.0, 2.0)) + sps.kron(T(ny, -1.0, 2.0), sps.identity(nx)))
+            rng = np.random.RandomState(17)
+            R = rng.random_sample((L, ny, nx))
+            solver = StripRowsMeanSolver(nx, ranges, rank, (4.0, -1.0, -1.0))
+            r0, r1 = ranges[rank]
+            Rc = torch.from_numpy(np.ascontiguousarray(R[:, r0:r1, :]).reshape(L, -1))
+            Sc = torch.empty_like(Rc)
+            for _ in range(2):                                     # second call: buffers reused
+                solver.solve(Rc, Sc)
+            lu = spla.splu(A0.tocsc())
+            ref = np.stack([lu.solve(R[k].reshape(-1)) for k in range(L)]).reshape(L, ny, nx)[:, r0:r1, :].reshape(L, -1)
+            worst = max(worst, float(np.max(np.abs(Sc.numpy() - ref)) / np.max(np.abs(ref))))
+        t = torch.tensor([worst], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            with open(out_path, "w") as f:
+                f.write("%r\n" % float(t[0]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_strip_rows_mean_solver_three_ranks(tmp_path, emu):
+    """The strip solver on row bands of three ranks (uneven bands, several strips per band, x-chunks with
+    separators, a band of three rows) against the global sparse direct solve."""
+    out = tmp_path / "err.txt"
+    mp.spawn(_strip_rows_worker, args=(3, _free_port(), str(out)), nprocs=3, join=True)
+    assert float(out.read_text()) <= 1e-12

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--eps", type=float, default=1e-10)
     ap.add_argument("--maxiter", type=int, default=200)
     ap.add_argument("--poll", type=int, default=8)
-    ap.add_argument("--mean-solver", default="partition", choices=["partition", "transpose"])
+    ap.add_argument("--mean-solver", default="strip", choices=["strip", "partition", "transpose"])
     args = ap.parse_args()
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         return main_sharded(args)
