@@ -301,7 +301,8 @@ SPUQ_API int spuq_sg_set_gate(const double* gate_dev);
 /* Whole solve on one GPU.  F_dev: right-hand side, W_dev: initial guess in, solution out (both
  * N x L contiguous).  work_dev: caller-owned, at least spuq_sg_pcg_work_bytes() bytes.
  * Returns (through host pointers) zeta, the pass index `numit` and the status; semantic of the
- * return triple as pcg.py:38.  `poll_every` passes are enqueued between two status read-backs
+ * return triple as pcg.py:38.  For the statuses SINGULAR and NOT_PD zeta_out receives alpha = <Av, v>, the
+ * value the reference prints in those messages (pcg.py:42-45).  `poll_every` passes are enqueued between two status read-backs
  * (no host round trip per iteration); zeta_hist_host (optional, maxiter doubles) receives zeta of
  * every executed pass for trajectory comparisons. */
 SPUQ_API int64_t spuq_sg_pcg_work_bytes(const spuq_sg_plan* A, const spuq_sg_precond* P);

@@ -256,7 +256,10 @@ extern "C" int spuq_sg_pcg(spuq_sg_plan* A, spuq_sg_precond* P, const double* F,
                            double* zeta_hist, void* stream_) {
     SPUQ_REQUIRE(A && P && F && Wv && work, "pcg: null argument");
     SPUQ_REQUIRE(A->n_rows == A->n_cols, "pcg: operator must be square");
-    SPUQ_REQUIRE(maxiter >= 1 && maxiter <= 4096, "pcg: maxiter must be in [1, 4096]");
+    SPUQ_REQUIRE(maxiter >= 1, "pcg: maxiter must be at least 1");
+    // the device-side zeta history has room for 4096 passes; longer solves keep iterating and simply
+    // stop recording (zeta_hist_host then holds the first 4096 entries)
+    const int32_t hist_cap = 4096;
     if (poll_every < 1) poll_every = 8;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SPUQ_CUDA_TRY(cudaSetDevice(A->device));
@@ -298,7 +301,7 @@ extern "C" int spuq_sg_pcg(spuq_sg_plan* A, spuq_sg_precond* P, const double* F,
     while (pass < maxiter && status == SPUQ_PCG_RUNNING) {
         const int32_t stop = std::min(maxiter, pass + poll_every);
         for (; pass < stop; ++pass) {
-            SPUQ_LAUNCH(k_pcg_check_zeta, dim3(1), dim3(1), 0, stream, st, pass, hist);      // :33-38
+            SPUQ_LAUNCH(k_pcg_check_zeta, dim3(1), dim3(1), 0, stream, st, pass, pass <= hist_cap ? hist : (double*)nullptr);   // :33-38
             if ((rc = apply_impl(A, v, N, z, N, stream, gate))) return rc;                   // :40
             if ((rc = dot_impl(1, n, z, v, st + 1, scratch, stream, gate))) return rc;       // :41
             SPUQ_LAUNCH(k_pcg_check_alpha, dim3(1), dim3(1), 0, stream, st);                  // :42-45
@@ -319,8 +322,9 @@ extern "C" int spuq_sg_pcg(spuq_sg_plan* A, spuq_sg_precond* P, const double* F,
     if (status == SPUQ_PCG_RUNNING) status = SPUQ_PCG_NOT_CONVERGED;     // pcg.py:53
     const int32_t numit = (int32_t)h_state[5];
     if (zeta_hist && numit > 0)
-        SPUQ_CUDA_TRY(cudaMemcpy(zeta_hist, hist, sizeof(double) * numit, cudaMemcpyDeviceToHost));
-    if (zeta_out) *zeta_out = h_state[0];
+        SPUQ_CUDA_TRY(cudaMemcpy(zeta_hist, hist, sizeof(double) * std::min(numit, hist_cap), cudaMemcpyDeviceToHost));
+    // the reference formats the singular / not-positive-definite messages with alpha (pcg.py:42-45)
+    if (zeta_out) *zeta_out = (status == SPUQ_PCG_SINGULAR || status == SPUQ_PCG_NOT_PD) ? h_state[1] : h_state[0];
     if (numit_out) *numit_out = numit;
     if (status_out) *status_out = status;
     A->last_launches = launches;

@@ -329,6 +329,8 @@ class MultiOperator(Operator):
     """Discrete SG operator on one shared spatial basis (EGSZ (2.6) generalised to spuq's
     orthonormal polynomials), applied by the B200 kernel."""
 
+    PLAN_CACHE = 2          # kernel plans kept alive (least recently used index sets are released)
+
     def __init__(self, coeff_field, assemble_0, assemble_m=None, domain=None, codomain=None,
                  m_range=None, include_mean=True, path=_abi.PATH_AUTO):
         if not isinstance(coeff_field, CoefficientField):
@@ -403,6 +405,8 @@ class MultiOperator(Operator):
             maxm = avail
         key = (w.index_array.shape, w.index_array.tobytes(), maxm, w.n)
         plan = self._plans.get(key)
+        if plan is not None:
+            self._plans[key] = self._plans.pop(key)                 # most recently used last
         if plan is None:
             blocks = self._device_blocks(w.spatial_basis, maxm)
             assert blocks.shape == (w.n, w.n), "spatial blocks do not match the vector dimension"
@@ -413,6 +417,12 @@ class MultiOperator(Operator):
             plan = SGPlan(blocks, len(w), tables, m_range, self._include_mean, self._path)
             plan.tables = tables
             self._plans[key] = plan
+            # a plan owns a private re-layout of all blocks (about 2 GB on config 3) and its schedule: an
+            # adaptive loop that grows Lambda every iteration must not keep one per index set.  Keep the
+            # last PLAN_CACHE sets (current + previous), release the rest now rather than at collection time.
+            while len(self._plans) > self.PLAN_CACHE:
+                old_key = next(iter(self._plans))
+                self._plans.pop(old_key).close()
         return plan
 
     # -- application ---------------------------------------------------------------------------
@@ -481,6 +491,7 @@ class PreconditioningOperator(Operator):
         slab_in = w if isinstance(w, SlabMultiVector) else SlabMultiVector.from_multivector(w)
         solver = self.slab_operator(slab_in)
         if isinstance(solver, CsrSlabOperator) and solver.plan.L != len(slab_in):
+            solver.plan.close()
             solver.plan = SGPlan(solver.blocks, len(slab_in))
         out = slab_in.like(torch.empty_like(slab_in.slab))
         solver.apply_slab(slab_in.slab, out.slab)

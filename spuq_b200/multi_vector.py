@@ -104,36 +104,6 @@ class MultiVector(Vector):
             mv[mi] = self[mi].copy()
         return mv
 
-    def insert_zero_columns(self, new_indices):
-        """Grow Lambda by several indices at once (``Marking.refine_y``, marking2.py:205-208): the new
-        columns are zero, indices already present are left alone (the reference would overwrite them
-        with zeros; a marking never proposes active indices), and the slab is re-laid-out in sorted
-        order with ONE gather on the device instead of one per index."""
-        fresh = []
-        for mi in new_indices:
-            if not isinstance(mi, Multiindex):
-                raise TypeError("MultiVector keys are Multiindex objects")
-            if mi not in self._pos and mi not in fresh:
-                fresh.append(mi)
-        if not fresh:
-            return
-        if self.slab is None:
-            raise ValueError("insert_zero_columns needs a vector that already has a basis")
-        self.on_modify()
-        n_old = len(self._keys)
-        width = max([self._index_array.shape[1] if self._index_array.size else 0, 1] + [len(mi) for mi in fresh])
-        old = as_index_array(self._index_array, width) if n_old else np.zeros((0, width), np.int32)
-        add = np.array([mi.padded(width) for mi in fresh], dtype=np.int32).reshape(len(fresh), width)
-        arr = np.vstack([old, add])
-        perm = sort_permutation(arr)
-        new_slab = torch.zeros((arr.shape[0], self._n), dtype=torch.float64, device=self.slab.device)
-        src = torch.as_tensor(perm.astype(np.int64), device=self.slab.device)
-        keep = src < n_old
-        if n_old:
-            new_slab[keep] = self.slab[src[keep]]
-        self.slab = new_slab
-        self._set_indices(np.ascontiguousarray(arr[perm]))
-
     def set_defaults(self, multiindex_set, init_vector):
         if not isinstance(multiindex_set, MultiindexSet) or not isinstance(init_vector, Vector):
             raise TypeError("set_defaults(MultiindexSet, Vector)")
@@ -503,6 +473,36 @@ class SlabMultiVector(MultiVector):
                 col.copy_(val.tensor)
         else:
             col.copy_(torch.from_numpy(np.ascontiguousarray(val.coeffs, dtype=np.float64)))
+
+    def insert_zero_columns(self, new_indices):
+        """Grow Lambda by several indices at once (``Marking.refine_y``, marking2.py:205-208): the new
+        columns are zero, indices already present are left alone (the reference would overwrite them
+        with zeros; a marking never proposes active indices), and the slab is re-laid-out in sorted
+        order with ONE gather on the device instead of one per index."""
+        fresh = []
+        for mi in new_indices:
+            if not isinstance(mi, Multiindex):
+                raise TypeError("MultiVector keys are Multiindex objects")
+            if mi not in self._pos and mi not in fresh:
+                fresh.append(mi)
+        if not fresh:
+            return
+        if self.slab is None:
+            raise ValueError("insert_zero_columns needs a vector that already has a basis")
+        self.on_modify()
+        n_old = len(self._keys)
+        width = max([self._index_array.shape[1] if self._index_array.size else 0, 1] + [len(mi) for mi in fresh])
+        old = as_index_array(self._index_array, width) if n_old else np.zeros((0, width), np.int32)
+        add = np.array([mi.padded(width) for mi in fresh], dtype=np.int32).reshape(len(fresh), width)
+        arr = np.vstack([old, add])
+        perm = sort_permutation(arr)
+        new_slab = torch.zeros((arr.shape[0], self._n), dtype=torch.float64, device=self.slab.device)
+        src = torch.as_tensor(perm.astype(np.int64), device=self.slab.device)
+        keep = src < n_old
+        if n_old:
+            new_slab[keep] = self.slab[src[keep]]
+        self.slab = new_slab
+        self._set_indices(np.ascontiguousarray(arr[perm]))
 
     def _insert(self, mi):
         """Grow Lambda by one index (Lambda growth between solves, marking2.py:205-208): the new

@@ -74,6 +74,7 @@ def _precond_for(P, slab):
             solver.set_columns(L)
             return _Precond(solver.handle, keep=solver)
         if solver.plan.L != L:
+            solver.plan.close()
             solver.plan = SGPlan(solver.blocks, L)
         return _Precond.from_plan(solver.plan, keep=solver)
     if isinstance(P, (_CsrLeaf,)):

@@ -65,8 +65,15 @@ def fd_case(n, M, idx, kind="legendre", mu=0.0, seed=1234, dense=False, with_ora
 
 
 def relerr(Y, Yref):
-    """max over columns of ||y - yref||_2 / ||yref||_2 (SURVEY.md 8d parity criterion)."""
-    return float(np.max(np.linalg.norm(Y - Yref, axis=0)) / np.linalg.norm(Yref))
+    """max over columns mu of ||y[mu] - yref[mu]||_2 / ||yref[mu]||_2: the per-column criterion (a column
+    whose reference is exactly zero must be reproduced as zero)."""
+    num = np.linalg.norm(Y - Yref, axis=0)
+    den = np.linalg.norm(Yref, axis=0)
+    ok = den > 0
+    worst = float(np.max(num[ok] / den[ok])) if ok.any() else 0.0
+    if (~ok).any() and float(np.max(num[~ok])) > 0.0:
+        return float("inf")
+    return worst
 
 
 def random_sparse_case(N, M, idx, density=0.05, seed=7, kind="hermite", mu=0.5):

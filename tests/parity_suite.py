@@ -653,6 +653,18 @@ def check_pcg_failures():
         sp.pcg(sp.MatrixOperator(np.eye(N)), x, sp.MultiplicationOperator(-1, basis), 0 * x)
     with pytest.raises(Exception, match="PCG did not converge"):
         sp.pcg(sp.MatrixOperator(np.diag([1.0, 10.0, 100.0, 1000.0])), x, I, 0 * x, eps=1e-14, maxiter=3)
+    # the messages carry the value the reference prints: alpha = <Av, v> for the matrix failures (pcg.py:42-45),
+    # zeta for the preconditioner failure (:33-36); same text as the oracle's exceptions
+    A2, x2 = np.diag([1.0, -2.0]), np.array([1.0, 1.0])
+    with pytest.raises(Exception) as e_o:
+        osg.pcg(olin.MatrixOperator(A2), olin.FlatVector(x2), olin.MultiplicationOperator(1, olin.CanonicalBasis(2)),
+                olin.FlatVector(0 * x2))
+    with pytest.raises(Exception) as e_p:
+        sp.pcg(sp.MatrixOperator(A2), sp.FlatVector(x2), sp.MultiplicationOperator(1, sp.CanonicalBasis(2)), sp.FlatVector(0 * x2))
+    assert str(e_p.value) == str(e_o.value) == "Matrix for PCG is not positive definite (-1.0)"
+    # maxiter beyond the device history (4096 passes) is accepted, as in the reference
+    xs, zeta, it = sp.pcg(sp.MatrixOperator(np.diag([1.0, 2.0, 3.0, 4.0])), x, I, 0 * x, eps=1e-10, maxiter=10000)
+    assert it <= 6 and np.allclose(xs.coeffs, 1.0 / np.array([1.0, 2.0, 3.0, 4.0]))
 
 
 def check_pcg_sg(n=8, M=3, p=2, kind="legendre", precond="jacobi", eps=1e-8, poll_every=3):
