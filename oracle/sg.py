@@ -363,6 +363,78 @@ def neighbour_combination(w, coeff_field, m):
     return out
 
 
+def supp(Lambda):
+    """Union of the supports of the indices of Lambda; multi_vector.py:24-26."""
+    return set.union(*[set(int(i) for i in np.flatnonzero(mu.as_array)) for mu in Lambda])
+
+
+def evaluate_upper_tail_bound(w, coeff_field, energynorm, ainfty, add_maxm=10):
+    """Upper tail bounds of EGSZ section 3.2; residual_estimator2.py:176-290 with the two FEM ingredients
+    supplied by the caller: ``energynorm(vec)`` (pde.energy_norm applied to w[mu], :207-211) and
+    ``ainfty(m)`` = ||a_m / a_mean||_inf (:181-205).  M = w.max_order + add_maxm (:271), capped at the
+    length of the coefficient field when that is finite (the reference's own commented-out variant, :270).
+    Returns (global_zeta, zeta, zeta_bar, eval_zeta_m) like the reference; note that LambdaBoundary
+    (:213-223) yields a boundary index once per neighbour it has in Lambda and :279 ADDS eval_zeta for
+    every yield."""
+    from collections import defaultdict
+    from math import sqrt
+
+    def LambdaBoundary(Lambda):
+        suppLambda = supp(Lambda)
+        for mu in Lambda:
+            for m in suppLambda:
+                mu1 = mu.inc(m)
+                if mu1 not in Lambda:
+                    yield mu1
+                mu2 = mu.dec(m)
+                if mu2 not in Lambda and mu2 is not None:
+                    yield mu2
+
+    def eval_zeta_bar(mu, suppLambda, normw, M):
+        zz = 0
+        for m in range(M):
+            if m in suppLambda:
+                continue
+            _, am_rv = coeff_field[m]
+            beta = am_rv.orth_polys.get_beta(mu[m])
+            zz += (beta[1] * ainfty(m)) ** 2
+        return normw[mu] * sqrt(zz)
+
+    def eval_zeta(mu, Lambda, normw, M=None, this_m=None):
+        z = 0
+        if this_m is None:
+            for m in range(M):
+                _, am_rv = coeff_field[m]
+                beta = am_rv.orth_polys.get_beta(mu[m])
+                a = ainfty(m)
+                mu1 = mu.inc(m)
+                if mu1 in Lambda:
+                    z += a * beta[1] * normw[mu1]
+                mu2 = mu.dec(m)
+                if mu2 in Lambda:
+                    z += a * beta[-1] * normw[mu2]
+            return z
+        m = this_m
+        _, am_rv = coeff_field[m]
+        beta = am_rv.orth_polys.get_beta(mu[m])
+        return ainfty(m) * beta[1] * normw[mu]
+
+    Lambda = w.active_indices()
+    suppLambda = supp(Lambda)
+    M = w.max_order + add_maxm
+    try:
+        M = min(M, len(coeff_field))
+    except TypeError:
+        pass
+    normw = {mu: energynorm(w[mu]) for mu in Lambda}
+    zeta = defaultdict(int)
+    for nu in LambdaBoundary(Lambda):
+        zeta[nu] += eval_zeta(nu, Lambda, normw, M)
+    zeta_bar = {mu: eval_zeta_bar(mu, suppLambda, normw, M) for mu in Lambda}
+    global_zeta = sqrt(sum(v ** 2 for v in zeta.values()) + sum(v ** 2 for v in zeta_bar.values()))
+    return global_zeta, zeta, zeta_bar, (lambda mu, m: eval_zeta(mu, Lambda, normw, M, m))
+
+
 def refine_y(w, new_mi):
     """Marking.refine_y, marking2.py:205-208: a zero vector for every new multi-index."""
     some = w[w.active_indices()[0]]

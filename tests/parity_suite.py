@@ -285,6 +285,44 @@ def check_apply_multiblock():
         assert relerr(total, c.Y) <= TOL
 
 
+def check_upper_tail_bound():
+    """evaluateUpperTailBound (residual_estimator2.py:176-290) on the slab against the oracle's restatement:
+    same boundary indices with the same multiplicities, zeta / zeta_bar / global_zeta to 1e-12."""
+    from spuq_b200.residual import evaluate_upper_tail_bound, lambda_boundary
+    for kind, mu_rv, T in (("hermite", 0.5, 6.0), ("legendre", 0.0, 7.5)):
+        M = 4
+        idx = synthetic.anisotropic_indices(M, T)
+        c = fd_case(8, M, idx, kind, mu_rv)
+        K0 = c.mats[0]
+        ainfty = lambda m: 0.9 / (m + 2.0) ** 2                       # noqa: E731
+        n_terms = M + 3                                               # a field longer than the vector's order
+        rv_o = c.orvs[0]
+        cf_o = osg.ListCoefficientField("mean", list(range(n_terms)), [rv_o] * n_terms)
+        energy_o = lambda v: float(np.sqrt(max(float(np.dot(v.coeffs, K0 @ v.coeffs)), 0.0)))      # noqa: E731
+        g_o, zeta_o, zbar_o, zm_o = osg.evaluate_upper_tail_bound(c.w, cf_o, energy_o, ainfty, add_maxm=2)
+        cf_p = sp.ListCoefficientField("mean", list(range(n_terms)), synthetic.make_rvs(kind, n_terms, mu_rv))
+        w = sp.SlabMultiVector.from_array(idx, c.W)
+        g_p, zeta_p, zbar_p, zm_p = evaluate_upper_tail_bound(w, cf_p, K0, ainfty, add_maxm=2)
+        width = max(len(k.as_array) for k in zeta_o) if zeta_o else 0
+        as_t = lambda k, wd: tuple(int(v) for v in np.pad(np.asarray(k.as_array), (0, max(0, wd - len(k.as_array)))))  # noqa: E731
+        wd = max(width, idx.shape[1], n_terms)
+        zo = {as_t(k, wd): v for k, v in zeta_o.items()}
+        zp = {as_t(k, wd): v for k, v in zeta_p.items()}
+        assert set(zo) == set(zp) and len(zo) > 0
+        for k in zo:
+            assert abs(zo[k] - zp[k]) <= 1e-12 * max(abs(zo[k]), 1e-300), (k, zo[k], zp[k])
+        bo = {as_t(k, wd): v for k, v in zbar_o.items()}
+        bp = {as_t(k, wd): v for k, v in zbar_p.items()}
+        assert set(bo) == set(bp)
+        for k in bo:
+            assert abs(bo[k] - bp[k]) <= 1e-12 * max(abs(bo[k]), 1e-300), (k, bo[k], bp[k])
+        assert abs(g_o - g_p) <= 1e-12 * g_o
+        mu_o = c.w.active_indices()[1]
+        assert abs(zm_o(mu_o, 0) - zm_p(sp.Multiindex(np.asarray(mu_o.as_array)), 0)) <= 1e-12 * abs(zm_o(mu_o, 0))
+        # multiplicities of the boundary generator
+        assert any(v > 1 for v in lambda_boundary(idx).values())
+
+
 def check_row_bands_manual_exchange(n=24, M=3, bands=((0, 7), (7, 16), (16, 24))):
     """The single-GPU kernel on row bands with halo rows, as RowShardedApply runs it, with all ranks
     simulated in one process (halo rows copied by hand): bands of odd and even height that are not

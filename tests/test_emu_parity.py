@@ -108,5 +108,9 @@ def test_neighbour_combination():
     ps.check_neighbour_combination()
 
 
+def test_upper_tail_bound():
+    ps.check_upper_tail_bound()
+
+
 def test_row_bands_manual_exchange():
     ps.check_row_bands_manual_exchange()

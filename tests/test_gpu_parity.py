@@ -338,6 +338,10 @@ def test_neighbour_combination():
     ps.check_neighbour_combination()
 
 
+def test_upper_tail_bound():
+    ps.check_upper_tail_bound()
+
+
 def test_row_bands_manual_exchange():
     ps.check_row_bands_manual_exchange()
     ps.check_row_bands_manual_exchange(n=128, M=3, bands=((0, 63), (63, 128)))       # 65 and 67 local rows, TMA-sized grid
