@@ -252,6 +252,7 @@ def run_gpu(args):
         rowptr, colidx, vals = synthetic.fd_blocks_rows(n, M, y0, y1, device=dev)
         blocks = DeviceBlocks(rowptr, colidx, vals, (Nloc, Nloc))
         sharded = RowShardedApply(blocks, rvs, n, y0, y1)
+        sharded.halo = args.halo
         A = sharded.op
         Lp = L
         Wt = torch.rand((L, Nloc), dtype=torch.float64, device=dev, generator=g)
@@ -291,7 +292,7 @@ def run_gpu(args):
 
     def step():
         if rows_mode:
-            sharded.apply(plan, Wt, Yfull[:L], overlap=not args.no_overlap)   # exchange overlapped with the interior tile rows
+            sharded.apply(plan, Wt, Yfull[:L], overlap=args.overlap)   # exchange overlapped with the interior tile rows
             return
         plan.apply(Wt, Yfull[:L])
         comm_after()
@@ -362,7 +363,7 @@ def run_gpu(args):
                 cur.wait_event(ev_in[b])
                 if rows_mode:
                     y = wv[b].like(torch.empty_like(Wdev[b]))
-                    sharded.apply(plan, Wdev[b], y.slab, overlap=not args.no_overlap)
+                    sharded.apply(plan, Wdev[b], y.slab, overlap=args.overlap)
                 else:
                     y = A.apply(wv[b])                            # public API: MultiOperator.apply
                 ev_done[b].record(cur)
@@ -456,8 +457,9 @@ def run_gpu(args):
         "dtype": "f64", "data": "synthetic",
         "config": bench_config(args.config, N, L, M),
         "parallelism": ("1 GPU" if world == 1 else
-                        ("grid rows sharded x%d, halo rows exchanged point-to-point (NCCL) every step%s" % (
-                            world, "" if args.no_overlap else ", overlapped with the tile rows that read no halo row")) if rows_mode
+                        ("grid rows sharded x%d, halo rows %s every step" % (
+                            world, "written into the neighbours' slabs (CUDA IPC peer copies + flags)" if args.halo == "peer"
+                            else "exchanged point-to-point (NCCL)" + (", overlapped with the interior tile rows" if args.overlap else ""))) if rows_mode
                         else ("M-sharded x%d + NCCL reduce-scatter over Lambda" % world)),
         "details": {"n_terms": info["n_terms"], "nnz_per_block": info["nnz"], "kernel": plan.kernel_name,
                     "path": info["path"], "host_numa_node_rank0": numa},
@@ -629,7 +631,10 @@ def main():
                     help="multi-GPU decomposition: grid rows + halo exchange (default) or expansion terms + reduce-scatter")
     ap.add_argument("--no-clocks", action="store_true", help="development: do not run the nvidia-smi clock sampler")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="rows mode: exchange the halo rows before the kernel instead of beside it")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="rows mode: halo rows written into the neighbours' memory through CUDA IPC (default) or sent with NCCL")
+    ap.add_argument("--overlap", action="store_true",
+                    help="rows mode with --halo nccl: run the exchange beside the tile rows that read no halo row")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pcg", action="store_true", help="skip the config-4 PCG solve appended to the 1-GPU line")
     ap.add_argument("--pcg-config", default="c4", choices=sorted(CONFIGS))

@@ -293,6 +293,18 @@ SPUQ_API int spuq_sg_pcg_check_zeta_hist(double* state_dev, int32_t pass, double
  * (slots 8..15 of the state are free for the caller) */
 SPUQ_API int spuq_sg_pcg_accept(double* state_dev, int32_t src, int32_t dst, void* stream);
 
+/* Peer-memory halo exchange (row-sharded slabs on the GPUs of one NVSwitch box): a rank copies its boundary
+ * grid rows straight into the halo rows of its neighbours' slabs, which it has mapped through CUDA IPC,
+ * with the copy engines (no kernel, no staging buffer), and signals with a sequence number written after
+ * the copy on the same stream; the neighbour's stream waits for that number before its apply kernel.
+ *   copy2d_async     cudaMemcpy2DAsync with cudaMemcpyDefault (either side may be peer memory)
+ *   flag_wait_geq    the stream waits until *flag_dev >= value (one polling thread, ahead of the kernel)
+ *   enable_peer_access  cudaDeviceEnablePeerAccess, idempotent */
+SPUQ_API int spuq_sg_copy2d_async(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width_bytes,
+                         int64_t height, void* stream);
+SPUQ_API int spuq_sg_flag_wait_geq(const int64_t* flag_dev, int64_t value, void* stream);
+SPUQ_API int spuq_sg_enable_peer_access(int device, int peer_device);
+
 /* Conditional-execution scope for host-enqueued solver loops: while gate_dev is set for the calling thread,
  * every kernel launched through spuq_sg_apply / _apply_part / _dot* / _axpy* / _xpay / _precond_apply and the
  * strip phase calls is a no-op once *gate_dev != SPUQ_PCG_RUNNING (gate_dev = &state[4]).  NULL ends the scope. */

@@ -794,6 +794,54 @@ extern "C" int spuq_sg_apply(spuq_sg_plan* p, const double* W, int64_t ldw, doub
     return apply_impl(p, W, ldw, Y, ldy, static_cast<cudaStream_t>(stream), abi_gate());
 }
 
+// ---- peer-memory halo exchange helpers (spuq_b200.sharding.PeerHaloExchange) -----------------------
+#ifndef SPUQ_EMU
+__global__ void k_flag_wait_geq(const volatile long long* flag, long long value) {
+    while (*flag < value) __nanosleep(200);
+}
+#else
+void k_flag_wait_geq(const volatile long long*, long long) {}
+#endif
+
+extern "C" int spuq_sg_copy2d_async(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width_bytes,
+                                    int64_t height, void* stream) {
+    SPUQ_REQUIRE(dst && src && width_bytes >= 0 && height >= 0 && dpitch >= width_bytes && spitch >= width_bytes,
+                 "copy2d_async: bad argument");
+    if (width_bytes == 0 || height == 0) return SPUQ_OK;
+#ifdef SPUQ_EMU
+    for (int64_t r = 0; r < height; ++r)
+        std::memcpy(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, (size_t)width_bytes);
+#else
+    SPUQ_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width_bytes, (size_t)height,
+                                    cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+#endif
+    return SPUQ_OK;
+}
+
+extern "C" int spuq_sg_flag_wait_geq(const int64_t* flag_dev, int64_t value, void* stream) {
+    SPUQ_REQUIRE(flag_dev != nullptr, "flag_wait_geq: null flag");
+    SPUQ_LAUNCH(k_flag_wait_geq, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream),
+                reinterpret_cast<const volatile long long*>(flag_dev), (long long)value);
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+}
+
+extern "C" int spuq_sg_enable_peer_access(int device, int peer_device) {
+#ifndef SPUQ_EMU
+    SPUQ_CUDA_TRY(cudaSetDevice(device));
+    int can = 0;
+    SPUQ_CUDA_TRY(cudaDeviceCanAccessPeer(&can, device, peer_device));
+    SPUQ_REQUIRE(can, "enable_peer_access: device %d cannot access device %d", device, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        set_error("cudaDeviceEnablePeerAccess(%d) failed: %s", peer_device, cudaGetErrorString(e));
+        return SPUQ_E_CUDA;
+    }
+    cudaGetLastError();
+#endif
+    return SPUQ_OK;
+}
+
 extern "C" int spuq_sg_set_gate(const double* gate_dev) {
     g_abi_gate = gate_dev;
     return SPUQ_OK;

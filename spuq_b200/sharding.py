@@ -94,6 +94,108 @@ def row_ranges(ny, world, align=8):
     return [(min(r * per, ny), min((r + 1) * per, ny)) for r in range(world)]
 
 
+class PeerHaloExchange:
+    """Halo rows of row-sharded slabs written straight into the neighbours' memory (one NVSwitch box).
+
+    Every rank maps its neighbours' slabs through CUDA IPC (torch's storage sharing) and, per exchange,
+    enqueues on its own stream: two 2-D copies (its first / last owned grid row of all columns -> the
+    neighbour's halo row; copy engines over NVLink, no kernel, no staging), a sequence number written
+    behind each copy into the neighbour's flag word, and a wait for the two numbers the neighbours write
+    into its own flags.  A second pair of flags tells a writer that the reader's kernel is done with the
+    previous contents of the halo row.  No NCCL call, no host synchronisation; the exchange costs two
+    DMA transfers instead of six staging kernels and a send/receive kernel.
+
+    flags (int64, per rank): [0] top halo written by the rank above, [1] bottom halo written by the rank
+    below, [2] the rank above has consumed what I wrote into its bottom halo, [3] same for the rank below."""
+
+    SEQ = 1 << 20
+
+    def __init__(self, rank, world, device, group=None):
+        self.rank, self.world, self.group, self.device = rank, world, group, device
+        self.flags = torch.zeros(4, dtype=torch.int64, device=device)
+        self.seq = torch.arange(self.SEQ, dtype=torch.int64, device=device)
+        self.step = 0
+        self._slabs = {}
+        self._keep = []
+        handles = [None] * world
+        dist.all_gather_object(handles, (device.index, self.flags.untyped_storage()._share_cuda_()), group=group)
+        self.peer_dev = {}
+        self.peer_flags = {}
+        lib = _abi.lib()
+        for r in (rank - 1, rank + 1):
+            if 0 <= r < world:
+                dev_r, h = handles[r]
+                _abi.check(lib.spuq_sg_enable_peer_access(device.index, dev_r), "enable_peer_access")
+                self.peer_dev[r] = dev_r
+                self.peer_flags[r] = self._open(h, torch.int64, (4,))
+
+    def _open(self, handle, dtype, shape):
+        st = torch.UntypedStorage._new_shared_cuda(*handle)
+        self._keep.append(st)
+        t = torch.empty(0, dtype=dtype, device=st.device)
+        t.set_(st, 0, shape)                   # the shared storage starts where the sender's storage starts
+        return t
+
+    def _peers_of(self, W, nyl, nx):
+        """Neighbours' views of the slab that corresponds to W (registered collectively on first use)."""
+        key = (W.data_ptr(), tuple(W.shape))
+        if key not in self._slabs:
+            L = W.shape[0]
+            stor = W.untyped_storage()
+            off = W.storage_offset()
+            info = [None] * self.world
+            dist.all_gather_object(info, (stor._share_cuda_(), off, L, nyl), group=self.group)
+            peers = {}
+            for r in (self.rank - 1, self.rank + 1):
+                if 0 <= r < self.world:
+                    h, off_r, L_r, nyl_r = info[r]
+                    assert L_r == L
+                    st = torch.UntypedStorage._new_shared_cuda(*h)
+                    self._keep.append(st)
+                    base = torch.empty(0, dtype=W.dtype, device=st.device)
+                    base.set_(st, off_r, (L, nyl_r * nx))
+                    peers[r] = (base, nyl_r)
+            self._slabs[key] = peers
+        return self._slabs[key]
+
+    def exchange(self, W, nyl, nx, stream):
+        """Enqueue the exchange of the halo rows of W (L x nyl*nx) on `stream`; returns after enqueueing."""
+        lib = _abi.lib()
+        peers = self._peers_of(W, nyl, nx)
+        self.step += 1
+        k = self.step
+        assert k < self.SEQ, "sequence numbers exhausted"
+        L = W.shape[0]
+        row = nx * 8
+        my_pitch = nyl * row
+        fl = self.flags.data_ptr()
+        up, dn = self.rank - 1, self.rank + 1
+        for r, src_row, consumed_slot, written_slot in ((up, 1, 2, 1), (dn, nyl - 2, 3, 0)):
+            if r not in peers:
+                continue
+            base, nyl_r = peers[r]
+            dst_row = nyl_r - 1 if r == up else 0
+            # the neighbour's kernel of the previous exchange is done with the halo row I am about to overwrite
+            _abi.check(lib.spuq_sg_flag_wait_geq(C.c_void_p(fl + 8 * consumed_slot), k - 1, stream), "flag_wait")
+            _abi.check(lib.spuq_sg_copy2d_async(C.c_void_p(base.data_ptr() + dst_row * row), nyl_r * row,
+                                                C.c_void_p(W.data_ptr() + src_row * row), my_pitch, row, L, stream), "copy2d")
+            _abi.check(lib.spuq_sg_copy2d_async(C.c_void_p(self.peer_flags[r].data_ptr() + 8 * written_slot), 8,
+                                                C.c_void_p(self.seq.data_ptr() + 8 * k), 8, 8, 1, stream), "flag_write")
+        if up in peers:
+            _abi.check(lib.spuq_sg_flag_wait_geq(C.c_void_p(fl + 0), k, stream), "flag_wait")
+        if dn in peers:
+            _abi.check(lib.spuq_sg_flag_wait_geq(C.c_void_p(fl + 8), k, stream), "flag_wait")
+
+    def consumed(self, stream):
+        """After the kernel that read the halo rows: tell both neighbours they may overwrite them."""
+        lib = _abi.lib()
+        k = self.step
+        for r, slot in ((self.rank - 1, 3), (self.rank + 1, 2)):
+            if r in self.peer_flags:
+                _abi.check(lib.spuq_sg_copy2d_async(C.c_void_p(self.peer_flags[r].data_ptr() + 8 * slot), 8,
+                                                    C.c_void_p(self.seq.data_ptr() + 8 * k), 8, 8, 1, stream), "flag_write")
+
+
 class RowShardedApply:
     """The SG operator with the SPATIAL rows sharded over the ranks (axis 3).
 
@@ -115,6 +217,8 @@ class RowShardedApply:
         self.op = MultiOperator.from_blocks(blocks, rvs, path=path)
         self._bufs = None
         self._side = None
+        self._peer = None
+        self.halo = "auto"               # "peer": CUDA-IPC copies; "nccl": send/recv; "auto": peer on NCCL groups
         self.last_launches = 0
 
     def plan_for(self, w):
@@ -146,10 +250,30 @@ class RowShardedApply:
         if self.rank < self.world - 1:
             W3[:, self.nyl - 1, :].copy_(r_dn)
 
-    def apply(self, plan, W, Y, overlap=True):
-        """Y = A W on the local slab.  With ``overlap`` the halo exchange runs on a side stream while the
-        kernel already works on the tile rows that read no halo row (spuq_sg_apply_part 1); the tile rows
-        at the two ends follow once the halo rows have arrived (part 2)."""
+    def _use_peer(self, W):
+        if self.world == 1 or W.device.type != "cuda" or self.halo == "nccl":
+            return False
+        if self.halo == "peer":
+            return True
+        return dist.get_backend(self.group) == "nccl"
+
+    def apply(self, plan, W, Y, overlap=False):
+        """Y = A W on the local slab.
+
+        Default on the GPUs of one box: the halo rows are written straight into the neighbours' slabs
+        (PeerHaloExchange: two DMA copies per neighbour and a flag), then ONE kernel launch.  With
+        ``halo = "nccl"`` the rows travel by NCCL send/recv through staging buffers; ``overlap`` then runs
+        that exchange on a side stream while the kernel already works on the tile rows that read no halo
+        row (spuq_sg_apply_part 1) and finishes the tile rows at the two ends afterwards (part 2)."""
+        if self._use_peer(W):
+            if self._peer is None:
+                self._peer = PeerHaloExchange(self.rank, self.world, W.device, self.group)
+            st = _abi.stream_ptr()
+            self._peer.exchange(W, self.nyl, self.nx, st)
+            plan.apply(W, Y)
+            self._peer.consumed(st)
+            self.last_launches = plan.last_launches
+            return Y
         if self.world == 1 or not overlap or W.device.type != "cuda":
             self.exchange_halos(W)
             plan.apply(W, Y)
