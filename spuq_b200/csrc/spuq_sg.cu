@@ -803,6 +803,91 @@ __global__ void k_flag_wait_geq(const volatile long long* flag, long long value)
 void k_flag_wait_geq(const volatile long long*, long long) {}
 #endif
 
+// One launch per exchange: wait until both neighbours are done with the halo rows of the previous exchange,
+// store this rank's first / last owned grid row of every column straight into the neighbours' halo rows
+// (coalesced 16-byte stores over NVLink), and -- last CTA to finish, after a system-wide fence -- publish
+// the sequence number in the neighbours' flag words.
+//   my_flags: [0] top halo written, [1] bottom halo written, [2] rank above consumed, [3] rank below consumed
+#ifndef SPUQ_EMU
+__global__ void __launch_bounds__(256)
+k_halo_push(const double* __restrict__ W, int32_t L, int32_t nyl, int32_t nx,
+            double* __restrict__ up_slab, int32_t up_nyl, double* __restrict__ dn_slab, int32_t dn_nyl,
+            const volatile long long* my_flags, volatile long long* up_flags, volatile long long* dn_flags,
+            long long seq, unsigned int* ticket) {
+    if (threadIdx.x == 0) {
+        if (up_slab) while (my_flags[2] < seq - 1) __nanosleep(100);
+        if (dn_slab) while (my_flags[3] < seq - 1) __nanosleep(100);
+    }
+    __syncthreads();
+    const int64_t row2 = nx / 2;                       // double2 per grid row (nx even)
+    const int64_t total = (int64_t)L * row2;
+    const double2* src = reinterpret_cast<const double2*>(W);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t col = t / row2, x2 = t - col * row2;
+        if (up_slab)      // my first owned row (local row 1) -> bottom halo row of the rank above
+            reinterpret_cast<double2*>(up_slab)[(col * up_nyl + (up_nyl - 1)) * row2 + x2] = src[(col * nyl + 1) * row2 + x2];
+        if (dn_slab)      // my last owned row (local row nyl - 2) -> top halo row of the rank below
+            reinterpret_cast<double2*>(dn_slab)[(col * dn_nyl) * row2 + x2] = src[(col * nyl + (nyl - 2)) * row2 + x2];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(ticket, 1u);
+        if (done == gridDim.x - 1) {
+            __threadfence_system();
+            if (up_flags) up_flags[1] = seq;           // I wrote the BOTTOM halo of the rank above
+            if (dn_flags) dn_flags[0] = seq;           // ... and the TOP halo of the rank below
+            *ticket = 0u;
+        }
+    }
+}
+__global__ void k_halo_wait(const volatile long long* my_flags, int has_up, int has_dn, long long seq) {
+    if (has_up) while (my_flags[0] < seq) __nanosleep(100);
+    if (has_dn) while (my_flags[1] < seq) __nanosleep(100);
+}
+__global__ void k_halo_done(volatile long long* up_flags, volatile long long* dn_flags, long long seq) {
+    __threadfence_system();
+    if (up_flags) up_flags[3] = seq;                   // seen from above I am the rank below
+    if (dn_flags) dn_flags[2] = seq;
+}
+#endif
+
+extern "C" int spuq_sg_halo_push(const double* W, int32_t L, int32_t nyl, int32_t nx, double* up_slab, int32_t up_nyl,
+                                 double* dn_slab, int32_t dn_nyl, const int64_t* my_flags, int64_t* up_flags,
+                                 int64_t* dn_flags, int64_t seq, void* ticket_dev, void* stream) {
+    SPUQ_REQUIRE(W && my_flags && ticket_dev && L >= 0 && nyl >= 3 && nx >= 2 && nx % 2 == 0, "halo_push: bad argument");
+#ifdef SPUQ_EMU
+    set_error("halo_push: peer-memory exchange needs CUDA devices");
+    return SPUQ_E_UNSUPPORTED;
+#else
+    const int64_t total = (int64_t)L * (nx / 2);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 64));
+    k_halo_push<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        W, L, nyl, nx, up_slab, up_nyl, dn_slab, dn_nyl, reinterpret_cast<const volatile long long*>(my_flags),
+        reinterpret_cast<volatile long long*>(up_flags), reinterpret_cast<volatile long long*>(dn_flags), (long long)seq,
+        static_cast<unsigned int*>(ticket_dev));
+    SPUQ_CUDA_TRY(cudaGetLastError());
+    return SPUQ_OK;
+#endif
+}
+extern "C" int spuq_sg_halo_wait(const int64_t* my_flags, int has_up, int has_dn, int64_t seq, void* stream) {
+    SPUQ_REQUIRE(my_flags != nullptr, "halo_wait: null flags");
+#ifndef SPUQ_EMU
+    k_halo_wait<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const volatile long long*>(my_flags), has_up, has_dn,
+                                                               (long long)seq);
+    SPUQ_CUDA_TRY(cudaGetLastError());
+#endif
+    return SPUQ_OK;
+}
+extern "C" int spuq_sg_halo_done(int64_t* up_flags, int64_t* dn_flags, int64_t seq, void* stream) {
+#ifndef SPUQ_EMU
+    k_halo_done<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<volatile long long*>(up_flags),
+                                                               reinterpret_cast<volatile long long*>(dn_flags), (long long)seq);
+    SPUQ_CUDA_TRY(cudaGetLastError());
+#endif
+    return SPUQ_OK;
+}
+
 extern "C" int spuq_sg_copy2d_async(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width_bytes,
                                     int64_t height, void* stream) {
     SPUQ_REQUIRE(dst && src && width_bytes >= 0 && height >= 0 && dpitch >= width_bytes && spitch >= width_bytes,

@@ -98,22 +98,21 @@ class PeerHaloExchange:
     """Halo rows of row-sharded slabs written straight into the neighbours' memory (one NVSwitch box).
 
     Every rank maps its neighbours' slabs through CUDA IPC (torch's storage sharing) and, per exchange,
-    enqueues on its own stream: two 2-D copies (its first / last owned grid row of all columns -> the
-    neighbour's halo row; copy engines over NVLink, no kernel, no staging), a sequence number written
-    behind each copy into the neighbour's flag word, and a wait for the two numbers the neighbours write
-    into its own flags.  A second pair of flags tells a writer that the reader's kernel is done with the
-    previous contents of the halo row.  No NCCL call, no host synchronisation; the exchange costs two
-    DMA transfers instead of six staging kernels and a send/receive kernel.
+    enqueues on its own stream ONE small kernel that stores its first / last owned grid row of all columns
+    into the neighbours' halo rows (coalesced stores over NVLink, no staging buffer) and then publishes a
+    sequence number in the neighbours' flag words, followed by a one-thread wait for the two numbers the
+    neighbours publish in its own flags.  A second pair of flags tells a writer that the reader's kernel is
+    done with the previous contents of the halo row.  No NCCL call, no host synchronisation: three tiny
+    launches instead of six staging copies and a send/receive kernel.  (A first version used two
+    cudaMemcpy2DAsync per exchange: ~1000 rows of 8 KB at a 4 MB pitch cost the copy engine 1 ms.)
 
     flags (int64, per rank): [0] top halo written by the rank above, [1] bottom halo written by the rank
     below, [2] the rank above has consumed what I wrote into its bottom halo, [3] same for the rank below."""
 
-    SEQ = 1 << 20
-
     def __init__(self, rank, world, device, group=None):
         self.rank, self.world, self.group, self.device = rank, world, group, device
         self.flags = torch.zeros(4, dtype=torch.int64, device=device)
-        self.seq = torch.arange(self.SEQ, dtype=torch.int64, device=device)
+        self.ticket = torch.zeros(2, dtype=torch.int32, device=device)
         self.step = 0
         self._slabs = {}
         self._keep = []
@@ -164,36 +163,21 @@ class PeerHaloExchange:
         peers = self._peers_of(W, nyl, nx)
         self.step += 1
         k = self.step
-        assert k < self.SEQ, "sequence numbers exhausted"
-        L = W.shape[0]
-        row = nx * 8
-        my_pitch = nyl * row
-        fl = self.flags.data_ptr()
         up, dn = self.rank - 1, self.rank + 1
-        for r, src_row, consumed_slot, written_slot in ((up, 1, 2, 1), (dn, nyl - 2, 3, 0)):
-            if r not in peers:
-                continue
-            base, nyl_r = peers[r]
-            dst_row = nyl_r - 1 if r == up else 0
-            # the neighbour's kernel of the previous exchange is done with the halo row I am about to overwrite
-            _abi.check(lib.spuq_sg_flag_wait_geq(C.c_void_p(fl + 8 * consumed_slot), k - 1, stream), "flag_wait")
-            _abi.check(lib.spuq_sg_copy2d_async(C.c_void_p(base.data_ptr() + dst_row * row), nyl_r * row,
-                                                C.c_void_p(W.data_ptr() + src_row * row), my_pitch, row, L, stream), "copy2d")
-            _abi.check(lib.spuq_sg_copy2d_async(C.c_void_p(self.peer_flags[r].data_ptr() + 8 * written_slot), 8,
-                                                C.c_void_p(self.seq.data_ptr() + 8 * k), 8, 8, 1, stream), "flag_write")
-        if up in peers:
-            _abi.check(lib.spuq_sg_flag_wait_geq(C.c_void_p(fl + 0), k, stream), "flag_wait")
-        if dn in peers:
-            _abi.check(lib.spuq_sg_flag_wait_geq(C.c_void_p(fl + 8), k, stream), "flag_wait")
+        up_slab, up_nyl = (_abi.ptr(peers[up][0]), peers[up][1]) if up in peers else (None, 0)
+        dn_slab, dn_nyl = (_abi.ptr(peers[dn][0]), peers[dn][1]) if dn in peers else (None, 0)
+        up_fl = _abi.ptr(self.peer_flags[up]) if up in peers else None
+        dn_fl = _abi.ptr(self.peer_flags[dn]) if dn in peers else None
+        _abi.check(lib.spuq_sg_halo_push(_abi.ptr(W), W.shape[0], nyl, nx, up_slab, up_nyl, dn_slab, dn_nyl,
+                                         _abi.ptr(self.flags), up_fl, dn_fl, k, _abi.ptr(self.ticket), stream), "halo_push")
+        _abi.check(lib.spuq_sg_halo_wait(_abi.ptr(self.flags), int(up in peers), int(dn in peers), k, stream), "halo_wait")
 
     def consumed(self, stream):
         """After the kernel that read the halo rows: tell both neighbours they may overwrite them."""
-        lib = _abi.lib()
-        k = self.step
-        for r, slot in ((self.rank - 1, 3), (self.rank + 1, 2)):
-            if r in self.peer_flags:
-                _abi.check(lib.spuq_sg_copy2d_async(C.c_void_p(self.peer_flags[r].data_ptr() + 8 * slot), 8,
-                                                    C.c_void_p(self.seq.data_ptr() + 8 * k), 8, 8, 1, stream), "flag_write")
+        up, dn = self.rank - 1, self.rank + 1
+        _abi.check(_abi.lib().spuq_sg_halo_done(_abi.ptr(self.peer_flags[up]) if up in self.peer_flags else None,
+                                                _abi.ptr(self.peer_flags[dn]) if dn in self.peer_flags else None,
+                                                self.step, stream), "halo_done")
 
 
 class RowShardedApply:
@@ -398,15 +382,38 @@ class PartitionedMeanSolver:
         return Sc
 
 
+def _all_to_all(send, recv, rank, group):
+    """send[q] -> rank q, recv[q] <- rank q (lists of contiguous tensors, possibly empty)."""
+    world = len(send)
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(recv, send, group=group)
+        return
+    ops = []
+    for q in range(world):
+        if q == rank:
+            recv[q].copy_(send[q])
+            continue
+        if send[q].numel():
+            ops.append(dist.P2POp(dist.isend, send[q], q, group))
+        if recv[q].numel():
+            ops.append(dist.P2POp(dist.irecv, recv[q], q, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
 class StripRowsMeanSolver:
     """A_0^{-1} on ROW-sharded slabs with the strip solver of libspuq_sg (csrc/precond_strip.cuh): every
     rank solves the strips of its own band in shared memory; the last row of every band but the last is a
     separator row, and the separator system of the whole grid (a few per cent of the rows) is solved
-    redundantly on every rank after an all-gather of its right-hand sides.  Per call: one row of L x nx
-    doubles to the previous rank and one all-gather of the separator rows; no transposition of the slab,
-    no full-length transform of the bulk, no host synchronisation."""
+    with its COLUMNS sharded over the ranks: an all-to-all moves the right-hand sides of the separator rows
+    (every rank receives all separators of |Lambda| / world columns), every rank solves its share, and a
+    second all-to-all returns to each rank the separator values next to its own strips.  Per call: one row
+    of L x nx doubles to the previous rank and two all-to-alls of a few separator rows; no transposition of
+    the slab, no full-length transform of the bulk, no host synchronisation.  ``schur="gather"`` solves the
+    whole separator system redundantly on every rank instead (one all-gather)."""
 
-    def __init__(self, nx, ranges, rank, stencil, group=None):
+    def __init__(self, nx, ranges, rank, stencil, group=None, schur="sharded"):
         d, ox, oy = stencil
         self.nx, self.ranges, self.rank, self.group = int(nx), list(ranges), int(rank), group
         self.world = len(self.ranges)
@@ -429,6 +436,9 @@ class StripRowsMeanSolver:
         else:
             self.sep_blocks = [(self.first_sep, self.q_loc)]
         self.q_max = max(c for _, c in self.sep_blocks)
+        self.schur = schur if self.world > 1 else "gather"
+        # separator rows a rank needs for its final pass: the one above its first strip and its own
+        self.need = [(max(f0 - 1, 0), f0 + cnt) for f0, cnt in self.sep_blocks]
         self._bufs = None
 
     def _buffers(self, L, like):
@@ -458,9 +468,16 @@ class StripRowsMeanSolver:
                 req.wait()
             if self.rank < self.world - 1:
                 Gf[:, self.gf_ld - 1, :].copy_(rcv)
+        U_ptr = _abi.ptr(Z)
         if self.q_glob > 0:
             _abi.check(lib.spuq_sg_precond_strip_assemble(self.handle, L, _abi.ptr(Rc), _abi.ptr(Gf), _abi.ptr(Gl), _abi.ptr(Z), st),
                        "strip_assemble")
+        if self.q_glob > 0 and self.schur == "sharded":
+            U_loc, a_me = self._schur_sharded(Z, L)
+            # strip_final indexes separators globally: shift the base so that row a_me of U is U_loc[0]
+            U_ptr = C.c_void_p(U_loc.data_ptr() - a_me * L * self.nx * 8)
+            self._u_keep = U_loc
+        elif self.q_glob > 0:
             if self.world > 1:
                 mine = gath[self.rank]
                 if self.q_loc:
@@ -476,8 +493,36 @@ class StripRowsMeanSolver:
                     if cnt and r_ != self.rank:
                         Z[f0:f0 + cnt].copy_(gath[r_, :cnt])
             _abi.check(lib.spuq_sg_precond_strip_schur(self.handle, L, _abi.ptr(Z), _abi.ptr(Z2), st), "strip_schur")
-        _abi.check(lib.spuq_sg_precond_strip_final(self.handle, L, _abi.ptr(Rc), _abi.ptr(Z), _abi.ptr(Sc), st), "strip_final")
+        _abi.check(lib.spuq_sg_precond_strip_final(self.handle, L, _abi.ptr(Rc), U_ptr, _abi.ptr(Sc), st), "strip_final")
         return Sc
+
+    def _schur_sharded(self, Z, L):
+        """Separator system with the columns sharded over the ranks.  Z [q_glob][L][nx] holds this rank's rows;
+        returns (U_loc [rows][L][nx], global index of its first row) with the rows this rank's strips touch."""
+        lib = _abi.lib()
+        world, nx, rank = self.world, self.nx, self.rank
+        Lc = -(-L // world)
+        Lp = Lc * world
+        f0, cnt = self.sep_blocks[rank]
+        mk = lambda *shape: torch.empty(shape, dtype=Z.dtype, device=Z.device)      # noqa: E731
+        mine = Z[f0:f0 + cnt]
+        if Lp != L:
+            pad = torch.zeros((cnt, Lp, nx), dtype=Z.dtype, device=Z.device)
+            pad[:, :L, :] = mine
+            mine = pad
+        send = list(mine.view(cnt, world, Lc, nx).permute(1, 0, 2, 3).contiguous().unbind(0))      # [world] x [cnt][Lc][nx]
+        Zc = mk(max(self.q_glob, 1), Lc, nx)
+        recv = [Zc[g0:g0 + c] for g0, c in self.sep_blocks]                       # contiguous row blocks, rank order
+        _all_to_all(send, recv, rank, self.group)
+        Z2 = mk(max(self.q_glob, 1), Lc, nx)
+        _abi.check(lib.spuq_sg_precond_strip_schur(self.handle, Lc, _abi.ptr(Zc), _abi.ptr(Z2), _abi.stream_ptr()), "strip_schur")
+        a_me, b_me = self.need[rank]
+        back = [Zc[a:b].contiguous() for a, b in self.need]
+        got = mk(world, max(b_me - a_me, 1), Lc, nx)
+        _all_to_all(back, [got[q][:b_me - a_me] for q in range(world)], rank, self.group)
+        U_loc = got[:, :b_me - a_me].permute(1, 0, 2, 3).reshape(b_me - a_me, Lp, nx)
+        U_loc = U_loc[:, :L, :].contiguous() if Lp != L else U_loc.contiguous()
+        return U_loc, a_me
 
     def __del__(self):
         try:

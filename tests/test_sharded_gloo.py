@@ -192,15 +192,16 @@ def _strip_rows_worker(rank, world, port, out_path):
             A0 = sps.csr_matrix(sps.kron(sps.identity(ny), T(nx, -1.0, 2.0)) + sps.kron(T(ny, -1.0, 2.0), sps.identity(nx)))
             rng = np.random.RandomState(17)
             R = rng.random_sample((L, ny, nx))
-            solver = StripRowsMeanSolver(nx, ranges, rank, (4.0, -1.0, -1.0))
             r0, r1 = ranges[rank]
             Rc = torch.from_numpy(np.ascontiguousarray(R[:, r0:r1, :]).reshape(L, -1))
-            Sc = torch.empty_like(Rc)
-            for _ in range(2):                                     # second call: buffers reused
-                solver.solve(Rc, Sc)
             lu = spla.splu(A0.tocsc())
             ref = np.stack([lu.solve(R[k].reshape(-1)) for k in range(L)]).reshape(L, ny, nx)[:, r0:r1, :].reshape(L, -1)
-            worst = max(worst, float(np.max(np.abs(Sc.numpy() - ref)) / np.max(np.abs(ref))))
+            for schur in ("sharded", "gather"):                    # separator system by column shards / redundantly
+                solver = StripRowsMeanSolver(nx, ranges, rank, (4.0, -1.0, -1.0), schur=schur)
+                Sc = torch.empty_like(Rc)
+                for _ in range(2):                                 # second call: buffers reused
+                    solver.solve(Rc, Sc)
+                worst = max(worst, float(np.max(np.abs(Sc.numpy() - ref)) / np.max(np.abs(ref))))
         t = torch.tensor([worst], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
