@@ -435,6 +435,16 @@ def evaluate_upper_tail_bound(w, coeff_field, energynorm, ainfty, add_maxm=10):
     return global_zeta, zeta, zeta_bar, (lambda mu, m: eval_zeta(mu, Lambda, normw, M, m))
 
 
+def refine_multivector(w, cell_ids=None):
+    """MultiVectorSharedBasis.refine, multi_vector.py:474-479: every vector prolongated onto the refined
+    (shared) basis."""
+    _, prolongate, _ = w[w.active_indices()[0]].basis.refine(cell_ids)
+    mv = MultiVector()
+    for mi in w.keys():
+        mv[mi] = prolongate(w[mi])
+    return mv
+
+
 def refine_y(w, new_mi):
     """Marking.refine_y, marking2.py:205-208: a zero vector for every new multi-index."""
     some = w[w.active_indices()[0]]

@@ -103,3 +103,59 @@ class LambdaTables:
 
     def key(self):
         return (self.index_array.shape, self.index_array.tobytes(), self.maxm)
+
+    def grown(self, indices, rvs, maxm=None):
+        """Tables of the set ``indices`` (a superset of this one) by UPDATING the neighbour tables instead
+        of looking every (mu, m) up again: the positions of the old entries are shifted to their places in
+        the new sorted order, and only the links of the added indices are looked up (``mu +- e_m`` of an
+        added mu, both directions).  Bit-identical to ``LambdaTables(indices, rvs, maxm)``; returns None when
+        the update does not apply (not a superset, or the number of terms changes), the caller then
+        rebuilds."""
+        arr = as_index_array(indices)
+        if arr.shape[0] < self.L:
+            return None
+        width = max(arr.shape[1], self.index_array.shape[1])
+        arr = as_index_array(arr, width)
+        old = as_index_array(self.index_array, width)
+        perm = sort_permutation(arr)
+        srt = np.ascontiguousarray(arr[perm])
+        pos = {tuple(int(v) for v in r): k for k, r in enumerate(srt)}
+        try:
+            newpos = np.array([pos[tuple(int(v) for v in r)] for r in old], dtype=np.int64)
+        except KeyError:
+            return None                                              # an old index is missing: not a superset
+        used = srt.any(axis=0)
+        max_order = int(np.flatnonzero(used).max()) + 1 if used.any() else 0
+        new_maxm = int(min(max_order if maxm is None else maxm, max_order))
+        if new_maxm != self.maxm or max_order != self.max_order:
+            return None
+        L = srt.shape[0]
+        out = object.__new__(LambdaTables)
+        out.perm, out.index_array, out.L = perm, srt, L
+        out.max_order, out.maxm = max_order, new_maxm
+        up = np.full((new_maxm, L), -1, dtype=np.int32)
+        dn = np.full((new_maxm, L), -1, dtype=np.int32)
+        shift = np.concatenate([newpos, [-1]]).astype(np.int32)       # old position -> new position, -1 -> -1
+        up[:, newpos] = shift[self.nbr_up]
+        dn[:, newpos] = shift[self.nbr_dn]
+        is_old = np.zeros(L, dtype=bool)
+        is_old[newpos] = True
+        for k in np.flatnonzero(~is_old):                             # links of the added indices only
+            t = [int(v) for v in srt[k]]
+            for m in range(new_maxm):
+                t[m] += 1
+                j = pos.get(tuple(t))
+                if j is not None:
+                    up[m, k] = j
+                    dn[m, j] = k
+                t[m] -= 2
+                if t[m] >= 0:
+                    j = pos.get(tuple(t))
+                    if j is not None:
+                        dn[m, k] = j
+                        up[m, j] = k
+                t[m] += 1
+        out.nbr_up, out.nbr_dn = up, dn
+        core = np.ascontiguousarray(srt[:, :max(new_maxm, 0)])
+        out.beta_up, out.beta_dn, out.beta_0 = beta_tables(core, rvs, new_maxm)
+        return out

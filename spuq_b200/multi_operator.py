@@ -410,7 +410,14 @@ class MultiOperator(Operator):
         if plan is None:
             blocks = self._device_blocks(w.spatial_basis, maxm)
             assert blocks.shape == (w.n, w.n), "spatial blocks do not match the vector dimension"
-            tables = LambdaTables(w.index_array, [self._rv(m) for m in range(maxm)], maxm)
+            rvs = [self._rv(m) for m in range(maxm)]
+            tables = None
+            if self._plans:                                      # Lambda usually GROWS between solves
+                last = next(reversed(self._plans.values()))
+                if getattr(last, "tables", None) is not None and last.tables.L < len(w):
+                    tables = last.tables.grown(w.index_array, rvs, maxm)
+            if tables is None:
+                tables = LambdaTables(w.index_array, rvs, maxm)
             m_range = self._m_range
             if m_range is not None:
                 m_range = (min(m_range[0], tables.maxm), min(m_range[1], tables.maxm))

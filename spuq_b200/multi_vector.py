@@ -187,6 +187,14 @@ class MultiVectorSharedBasis(MultiVector):
             assert val.basis == self[self.active_indices()[0]].basis
         super().__setitem__(mi, val)
 
+    def refine(self, cell_ids=None):
+        """Every vector prolongated onto the refined basis (multi_vector.py:474-479)."""
+        _, prolongate, _ = self[self.active_indices()[0]].basis.refine(cell_ids)
+        mv = type(self)()
+        for mi in self.keys():
+            mv[mi] = prolongate(self[mi])
+        return mv
+
 
 # ---- device helpers ------------------------------------------------------------------------------
 _scratch = {}
@@ -503,6 +511,33 @@ class SlabMultiVector(MultiVector):
             new_slab[keep] = self.slab[src[keep]]
         self.slab = new_slab
         self._set_indices(np.ascontiguousarray(arr[perm]))
+
+    def refine(self, cell_ids=None):
+        """``MultiVectorSharedBasis.refine`` (multi_vector.py:474-479) on the slab: the shared basis is refined
+        once and its prolongation applied to ALL columns in one launch (a rectangular sparse matrix times
+        the slab) instead of once per multi-index.  The basis' ``refine`` must return the reference's
+        triple (new_basis, prolongate, restrict); a ``prolongate`` that can state its matrix (``as_csr`` /
+        ``as_matrix``) runs on the device, any other callable column by column on the host."""
+        new_basis, prolongate, _ = self.spatial_basis.refine(cell_ids)
+        mat = None
+        if hasattr(prolongate, "as_csr"):
+            mat = prolongate.as_csr()
+        elif hasattr(prolongate, "as_matrix"):
+            import scipy.sparse as sps
+            m = prolongate.as_matrix()
+            mat = sps.csr_matrix(m if sps.issparse(m) else np.asarray(m, dtype=np.float64))
+        if mat is not None:
+            from .multi_operator import CsrSlabOperator
+            op = CsrSlabOperator(mat, len(self))
+            fine = torch.empty((len(self), mat.shape[0]), dtype=torch.float64, device=self.slab.device)
+            op.apply_slab(self.slab, fine)
+            op.plan.close()
+            out = type(self)(self._index_array, n=mat.shape[0], basis=new_basis, slab=fine, _sorted=True)
+            return out
+        mv = MultiVectorSharedBasis()
+        for mi in self.keys():
+            mv[mi] = prolongate(self[mi])
+        return type(self).from_multivector(mv)
 
     def _insert(self, mi):
         """Grow Lambda by one index (Lambda growth between solves, marking2.py:205-208): the new

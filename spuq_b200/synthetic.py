@@ -30,7 +30,7 @@ from .random_variable import NormalRV, UniformRV
 
 __all__ = ["kl_frequencies", "kl_amplitudes", "fd_pattern", "fd_values", "fd_blocks", "tile_permutation", "permute_blocks",
            "fd_blocks_rows", "fd_pattern_rect", "complete_order_indices", "anisotropic_indices", "truncated_complete_indices",
-           "make_rvs", "blocks_to_scipy", "FDDiscretisation"]
+           "make_rvs", "blocks_to_scipy", "FDDiscretisation", "GridBasis", "GridProlongation"]
 
 
 def kl_frequencies(M):
@@ -321,3 +321,56 @@ class FDDiscretisation:
     @property
     def l2_weight(self):
         return self.h ** 2
+
+
+class GridProlongation:
+    """Bilinear interpolation from the n x n interior grid to the (2n+1) x (2n+1) one (homogeneous Dirichlet
+    boundary): the ``prolongate`` callable a basis' ``refine`` returns in the reference
+    (fem/fenics/fenics_basis.py), here with a matrix the slab path can apply to all columns at once."""
+
+    def __init__(self, coarse, fine):
+        self.coarse, self.fine = coarse, fine
+        n, nf = coarse.n, fine.n
+        one = sps.lil_matrix((nf, n))
+        for i in range(n):
+            one[2 * i + 1, i] = 1.0
+            one[2 * i, i] = 0.5
+            one[2 * i + 2, i] = 0.5
+        one = sps.csr_matrix(one)
+        self._mat = sps.csr_matrix(sps.kron(one, one))          # rows iy*nf + ix, columns jy*n + jx
+
+    def as_csr(self):
+        return self._mat
+
+    def __call__(self, vec):
+        return type(vec)(self._mat @ np.asarray(vec.coeffs, dtype=np.float64), self.fine)
+
+
+class GridBasis:
+    """Nodal basis of the n x n interior grid (stand-in for the reference's FEniCSBasis as far as
+    ``MultiVectorSharedBasis.refine`` needs it): ``refine(cell_ids)`` -> (new_basis, prolongate, restrict)
+    with uniform refinement (cell_ids are ignored: every cell is halved)."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    @property
+    def dim(self):
+        return self.n * self.n
+
+    def __eq__(self, other):
+        return type(self) is type(other) and self.n == other.n
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    def copy(self):
+        return GridBasis(self.n)
+
+    def refine(self, cell_ids=None):
+        fine = GridBasis(2 * self.n + 1)
+        P = GridProlongation(self, fine)
+        R = P.as_csr().T.tocsr() * 0.25
+        return fine, P, (lambda vec: type(vec)(R @ np.asarray(vec.coeffs, dtype=np.float64), self))

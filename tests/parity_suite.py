@@ -285,6 +285,61 @@ def check_apply_multiblock():
         assert relerr(total, c.Y) <= TOL
 
 
+def check_refine_and_table_growth():
+    """f3: (i) MultiVectorSharedBasis.refine on the slab (one rectangular sparse product for all columns)
+    against the oracle's per-index prolongation; (ii) the neighbour tables of a grown Lambda obtained by
+    updating the old ones, bit-identical to a rebuild and to the oracle's look-ups."""
+    from spuq_b200.lambda_tables import LambdaTables
+    n, M = 7, 3
+    idx = synthetic.anisotropic_indices(M, 6.0)
+    rng = np.random.RandomState(4)
+    W = rng.random_sample((n * n, idx.shape[0]))
+    basis = synthetic.GridBasis(n)
+    w = sp.SlabMultiVector.from_array(idx, W, basis=basis)
+    fine = w.refine()
+    assert isinstance(fine, sp.SlabMultiVector) and fine.spatial_basis == synthetic.GridBasis(2 * n + 1)
+    w_o = oracle_multivector(idx, W, basis=basis)                  # the oracle works on the same basis object
+    fine_o = osg.refine_multivector(w_o)
+    assert np.max(np.abs(fine.to_array() - fine_o.to_slab())) <= 1e-15
+    assert fine.active_indices() == [sp.Multiindex(np.asarray(m.as_array)) for m in fine_o.active_indices()]
+    host = w.to_multivector(sp.MultiVectorSharedBasis).refine()     # host container: per-index path
+    assert np.max(np.abs(sp.SlabMultiVector.from_multivector(host).to_array() - fine_o.to_slab())) <= 1e-15
+    # (ii) growth: add the forward neighbours of a few indices, one of them twice, some already active
+    rvs = synthetic.make_rvs("hermite", M, 0.5)
+    t0 = LambdaTables(idx, rvs)
+    have = {tuple(r) for r in idx.tolist()}
+    add = []
+    for r in idx[::3]:
+        for m in range(M):
+            c = list(r); c[m] += 1
+            if tuple(c) not in have:
+                have.add(tuple(c)); add.append(c)
+    assert len(add) >= 3
+    grown_idx = np.vstack([idx, np.array(add, dtype=np.int32)])
+    t1 = t0.grown(grown_idx, rvs)
+    ref = LambdaTables(grown_idx, rvs)
+    assert t1 is not None
+    for name in ("index_array", "nbr_up", "nbr_dn", "beta_up", "beta_dn", "beta_0", "perm"):
+        assert np.array_equal(getattr(t1, name), getattr(ref, name)), name
+    Lam = sorted(omi.Multiindex(np.asarray(r, dtype=np.int64)) for r in grown_idx)
+    up_o, dn_o = osg.neighbour_tables(Lam, ref.maxm)
+    assert np.array_equal(t1.nbr_up, up_o) and np.array_equal(t1.nbr_dn, dn_o)
+    assert t0.grown(idx[1:], rvs) is None                           # not a superset -> rebuild
+    # through the operator: a plan for the grown vector after one for the original (uses the update)
+    c = fd_case(n, M, idx, "hermite", 0.5)
+    A = sp.MultiOperator.from_blocks(device_blocks(c), c.rvs)
+    ws = sp.SlabMultiVector.from_array(idx, c.W)
+    A.apply(ws)
+    sp.Marking.refine_y(ws, [sp.Multiindex(np.asarray(a)) for a in add])
+    y = A.apply(ws)
+    cg = fd_case(n, M, np.ascontiguousarray(ref.index_array), "hermite", 0.5, with_oracle=False)
+    Wg = ws.to_array()
+    wg_o = oracle_multivector(ref.index_array, Wg)
+    A_o, _ = oracle_operator(c.mats, c.orvs)
+    Yg = (A_o * wg_o).to_slab()
+    assert relerr(y.to_array()[:, np.linalg.norm(Yg, axis=0) > 0], Yg[:, np.linalg.norm(Yg, axis=0) > 0]) <= TOL
+
+
 def check_upper_tail_bound():
     """evaluateUpperTailBound (residual_estimator2.py:176-290) on the slab against the oracle's restatement:
     same boundary indices with the same multiplicities, zeta / zeta_bar / global_zeta to 1e-12."""

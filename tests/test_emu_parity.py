@@ -112,5 +112,9 @@ def test_upper_tail_bound():
     ps.check_upper_tail_bound()
 
 
+def test_refine_and_table_growth():
+    ps.check_refine_and_table_growth()
+
+
 def test_row_bands_manual_exchange():
     ps.check_row_bands_manual_exchange()

@@ -342,6 +342,10 @@ def test_upper_tail_bound():
     ps.check_upper_tail_bound()
 
 
+def test_refine_and_table_growth():
+    ps.check_refine_and_table_growth()
+
+
 def test_row_bands_manual_exchange():
     ps.check_row_bands_manual_exchange()
     ps.check_row_bands_manual_exchange(n=128, M=3, bands=((0, 63), (63, 128)))       # 65 and 67 local rows, TMA-sized grid
