@@ -315,6 +315,13 @@ SPUQ_API int spuq_sg_copy2d_async(void* dst, int64_t dpitch, const void* src, in
                          int64_t height, void* stream);
 SPUQ_API int spuq_sg_flag_wait_geq(const int64_t* flag_dev, int64_t value, void* stream);
 SPUQ_API int spuq_sg_enable_peer_access(int device, int peer_device);
+/* cudaIpcOpenMemHandle / cudaIpcCloseMemHandle with `device` current: maps an allocation another process
+ * exported (64-byte cudaIpcMemHandle_t) so that kernels of `device` can access it.  ipc_export: the handle of
+ * the allocation that contains ptr_dev (cudaMalloc'ed, e.g. a block of torch's caching allocator) and the
+ * byte offset of ptr_dev inside it. */
+SPUQ_API int spuq_sg_ipc_export(const void* ptr_dev, void* handle64_out_host, int64_t* offset_out_host);
+SPUQ_API int spuq_sg_ipc_open(int device, const void* handle64_host, void** ptr_out);
+SPUQ_API int spuq_sg_ipc_close(int device, void* ptr);
 
 /* Conditional-execution scope for host-enqueued solver loops: while gate_dev is set for the calling thread,
  * every kernel launched through spuq_sg_apply / _apply_part / _dot* / _axpy* / _xpay / _precond_apply and the

@@ -97,6 +97,9 @@ SIGNATURES = {
     "spuq_sg_copy2d_async": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, _vp]),
     "spuq_sg_flag_wait_geq": (C.c_int, [_vp, C.c_int64, _vp]),
     "spuq_sg_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),
+    "spuq_sg_ipc_export": (C.c_int, [_vp, C.c_char_p, _i64p]),
+    "spuq_sg_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(_vp)]),
+    "spuq_sg_ipc_close": (C.c_int, [C.c_int, _vp]),
     "spuq_sg_pcg_work_bytes": (C.c_int64, [_vp, _vp]),
     "spuq_sg_pcg": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, C.c_int32, C.c_int32, _vp,
                                _f64p, _i32p, _i32p, _vp, _vp]),

@@ -911,6 +911,58 @@ extern "C" int spuq_sg_flag_wait_geq(const int64_t* flag_dev, int64_t value, voi
     return SPUQ_OK;
 }
 
+// Map a peer's allocation (64-byte cudaIpcMemHandle_t exported by the process that owns it) into THIS device's
+// context, so that this device's kernels can store into it (a mapping made with the peer device current, as
+// torch's storage sharing does, is reachable by the copy engines only).
+// Export: the 64-byte IPC handle of the allocation that contains ptr, and ptr's byte offset inside it.
+extern "C" int spuq_sg_ipc_export(const void* ptr, void* handle64_out, int64_t* offset_out) {
+    SPUQ_REQUIRE(ptr && handle64_out && offset_out, "ipc_export: null argument");
+#ifdef SPUQ_EMU
+    set_error("ipc_export: needs CUDA devices");
+    return SPUQ_E_UNSUPPORTED;
+#else
+    typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static RangeFn range_fn = nullptr;
+    if (!range_fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            range_fn = reinterpret_cast<RangeFn>(f);
+    }
+    SPUQ_REQUIRE(range_fn != nullptr, "ipc_export: cuMemGetAddressRange entry point not available");
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    const CUresult r = range_fn(&base, &size, (CUdeviceptr)(uintptr_t)ptr);
+    SPUQ_REQUIRE(r == CUDA_SUCCESS, "ipc_export: cuMemGetAddressRange failed with CUresult %d", (int)r);
+    cudaIpcMemHandle_t h;
+    SPUQ_CUDA_TRY(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base)));
+    std::memcpy(handle64_out, &h, sizeof(h));
+    *offset_out = (int64_t)((uintptr_t)ptr - (uintptr_t)base);
+    return SPUQ_OK;
+#endif
+}
+
+extern "C" int spuq_sg_ipc_open(int device, const void* handle64, void** ptr_out) {
+    SPUQ_REQUIRE(handle64 && ptr_out, "ipc_open: null argument");
+#ifdef SPUQ_EMU
+    set_error("ipc_open: needs CUDA devices");
+    return SPUQ_E_UNSUPPORTED;
+#else
+    SPUQ_CUDA_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    SPUQ_CUDA_TRY(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return SPUQ_OK;
+#endif
+}
+extern "C" int spuq_sg_ipc_close(int device, void* ptr) {
+#ifndef SPUQ_EMU
+    if (ptr) { cudaSetDevice(device); cudaIpcCloseMemHandle(ptr); cudaGetLastError(); }
+#endif
+    return SPUQ_OK;
+}
+
 extern "C" int spuq_sg_enable_peer_access(int device, int peer_device) {
 #ifndef SPUQ_EMU
     SPUQ_CUDA_TRY(cudaSetDevice(device));

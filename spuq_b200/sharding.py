@@ -97,7 +97,8 @@ def row_ranges(ny, world, align=8):
 class PeerHaloExchange:
     """Halo rows of row-sharded slabs written straight into the neighbours' memory (one NVSwitch box).
 
-    Every rank maps its neighbours' slabs through CUDA IPC (torch's storage sharing) and, per exchange,
+    Every rank maps its neighbours' slabs into its own device context through CUDA IPC (handles exported and
+    opened by the library, with the accessing device current) and, per exchange,
     enqueues on its own stream ONE small kernel that stores its first / last owned grid row of all columns
     into the neighbours' halo rows (coalesced stores over NVLink, no staging buffer) and then publishes a
     sequence number in the neighbours' flag words, followed by a one-thread wait for the two numbers the
@@ -115,45 +116,47 @@ class PeerHaloExchange:
         self.ticket = torch.zeros(2, dtype=torch.int32, device=device)
         self.step = 0
         self._slabs = {}
-        self._keep = []
+        self._mapped = {}                      # exported handle -> base address in this device's context
         handles = [None] * world
-        dist.all_gather_object(handles, (device.index, self.flags.untyped_storage()._share_cuda_()), group=group)
-        self.peer_dev = {}
+        dist.all_gather_object(handles, (device.index, self._export(self.flags)), group=group)
         self.peer_flags = {}
         lib = _abi.lib()
         for r in (rank - 1, rank + 1):
             if 0 <= r < world:
                 dev_r, h = handles[r]
                 _abi.check(lib.spuq_sg_enable_peer_access(device.index, dev_r), "enable_peer_access")
-                self.peer_dev[r] = dev_r
-                self.peer_flags[r] = self._open(h, torch.int64, (4,))
+                self.peer_flags[r] = self._map(h)
 
-    def _open(self, handle, dtype, shape):
-        st = torch.UntypedStorage._new_shared_cuda(*handle)
-        self._keep.append(st)
-        t = torch.empty(0, dtype=dtype, device=st.device)
-        t.set_(st, 0, shape)                   # the shared storage starts where the sender's storage starts
-        return t
+    @staticmethod
+    def _export(t):
+        """(cudaIpcMemHandle bytes of the allocation that holds t, byte offset of t inside it)."""
+        buf = C.create_string_buffer(64)
+        off = C.c_int64()
+        _abi.check(_abi.lib().spuq_sg_ipc_export(_abi.ptr(t), buf, C.byref(off)), "ipc_export")
+        return (buf.raw, int(off.value))
+
+    def _map(self, exported):
+        """Device address (in this device's context) of a tensor another rank exported."""
+        handle, offset = exported
+        base = self._mapped.get(handle)
+        if base is None:
+            p = C.c_void_p()
+            _abi.check(_abi.lib().spuq_sg_ipc_open(self.device.index, handle, C.byref(p)), "ipc_open")
+            base = self._mapped[handle] = int(p.value)
+        return base + offset
 
     def _peers_of(self, W, nyl, nx):
-        """Neighbours' views of the slab that corresponds to W (registered collectively on first use)."""
+        """Neighbours' addresses of the slab that corresponds to W (registered collectively on first use)."""
         key = (W.data_ptr(), tuple(W.shape))
         if key not in self._slabs:
-            L = W.shape[0]
-            stor = W.untyped_storage()
-            off = W.storage_offset()
             info = [None] * self.world
-            dist.all_gather_object(info, (stor._share_cuda_(), off, L, nyl), group=self.group)
+            dist.all_gather_object(info, (self._export(W), W.shape[0], nyl), group=self.group)
             peers = {}
             for r in (self.rank - 1, self.rank + 1):
                 if 0 <= r < self.world:
-                    h, off_r, L_r, nyl_r = info[r]
-                    assert L_r == L
-                    st = torch.UntypedStorage._new_shared_cuda(*h)
-                    self._keep.append(st)
-                    base = torch.empty(0, dtype=W.dtype, device=st.device)
-                    base.set_(st, off_r, (L, nyl_r * nx))
-                    peers[r] = (base, nyl_r)
+                    exported, L_r, nyl_r = info[r]
+                    assert L_r == W.shape[0]
+                    peers[r] = (self._map(exported), nyl_r)
             self._slabs[key] = peers
         return self._slabs[key]
 
@@ -164,10 +167,10 @@ class PeerHaloExchange:
         self.step += 1
         k = self.step
         up, dn = self.rank - 1, self.rank + 1
-        up_slab, up_nyl = (_abi.ptr(peers[up][0]), peers[up][1]) if up in peers else (None, 0)
-        dn_slab, dn_nyl = (_abi.ptr(peers[dn][0]), peers[dn][1]) if dn in peers else (None, 0)
-        up_fl = _abi.ptr(self.peer_flags[up]) if up in peers else None
-        dn_fl = _abi.ptr(self.peer_flags[dn]) if dn in peers else None
+        up_slab, up_nyl = (C.c_void_p(peers[up][0]), peers[up][1]) if up in peers else (None, 0)
+        dn_slab, dn_nyl = (C.c_void_p(peers[dn][0]), peers[dn][1]) if dn in peers else (None, 0)
+        up_fl = C.c_void_p(self.peer_flags[up]) if up in peers else None
+        dn_fl = C.c_void_p(self.peer_flags[dn]) if dn in peers else None
         _abi.check(lib.spuq_sg_halo_push(_abi.ptr(W), W.shape[0], nyl, nx, up_slab, up_nyl, dn_slab, dn_nyl,
                                          _abi.ptr(self.flags), up_fl, dn_fl, k, _abi.ptr(self.ticket), stream), "halo_push")
         _abi.check(lib.spuq_sg_halo_wait(_abi.ptr(self.flags), int(up in peers), int(dn in peers), k, stream), "halo_wait")
@@ -175,8 +178,8 @@ class PeerHaloExchange:
     def consumed(self, stream):
         """After the kernel that read the halo rows: tell both neighbours they may overwrite them."""
         up, dn = self.rank - 1, self.rank + 1
-        _abi.check(_abi.lib().spuq_sg_halo_done(_abi.ptr(self.peer_flags[up]) if up in self.peer_flags else None,
-                                                _abi.ptr(self.peer_flags[dn]) if dn in self.peer_flags else None,
+        _abi.check(_abi.lib().spuq_sg_halo_done(C.c_void_p(self.peer_flags[up]) if up in self.peer_flags else None,
+                                                C.c_void_p(self.peer_flags[dn]) if dn in self.peer_flags else None,
                                                 self.step, stream), "halo_done")
 
 
