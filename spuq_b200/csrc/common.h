@@ -11,12 +11,15 @@
 #else
 #include <cuda_runtime.h>
 #define SPUQ_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+    do { ++spuq::launch_counter(); kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while (0)
 #endif
 
 #include "../../include/spuq_sg.h"
 
 namespace spuq {
+
+// kernels launched through SPUQ_LAUNCH by the calling thread (reporting: gpu_launches of bench.py)
+int& launch_counter();
 
 void set_error(const char* fmt, ...);
 

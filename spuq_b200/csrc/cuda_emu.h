@@ -68,5 +68,6 @@ static inline void emu_launch(dim3 grid, dim3 block, F&& body) {
         }
     }
 }
+namespace spuq { int& launch_counter(); }
 #define SPUQ_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    emu_launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
+    do { ++spuq::launch_counter(); emu_launch((grid), (block), [&]() { kernel(__VA_ARGS__); }); } while (0)

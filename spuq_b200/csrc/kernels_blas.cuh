@@ -16,6 +16,38 @@ constexpr int REDUCE_MAX_BLOCKS = 1024;
 // scratch layout: [0, 2*REDUCE_MAX_BLOCKS) doubles of partials, then one uint32 ticket
 constexpr int64_t REDUCE_SCRATCH_BYTES = 2 * REDUCE_MAX_BLOCKS * 8 + 64;
 
+// What the block that finishes a reduction does with the result besides storing it (PCG, pcg.py:41-51): the
+// reference's branch conditions are evaluated right where the scalar is produced, so a pass needs no
+// one-thread kernels between its big ones.
+//   DOT_EPI_ALPHA  st[1] = <z,v>; singular / not-positive-definite test                       (:41-45)
+//   DOT_EPI_ZETA   st[3] = zeta_new / zeta (the factor of the direction update, :51), zeta <- zeta_new, and
+//                  the convergence test of the NEXT pass (:33-38) with its history entry
+enum { DOT_EPI_NONE = 0, DOT_EPI_ALPHA = 1, DOT_EPI_ZETA = 2 };
+struct DotEpilogue {
+    int kind;
+    double* st;        // PCG state words
+    int32_t pass;      // DOT_EPI_ZETA: index of the pass that just ends (the test is that of pass + 1)
+    double* hist;      // zeta history (device) or null
+    int32_t hist_cap;
+};
+
+__device__ __forceinline__ void dot_epilogue(const DotEpilogue& e, double a) {
+    if (e.kind == DOT_EPI_ALPHA) {
+        e.st[1] = a;
+        if (a == 0.0) e.st[4] = (double)SPUQ_PCG_SINGULAR;
+        else if (a < 0.0) e.st[4] = (double)SPUQ_PCG_NOT_PD;
+    } else if (e.kind == DOT_EPI_ZETA) {
+        e.st[2] = a;
+        e.st[3] = a / e.st[0];
+        e.st[0] = a;
+        const int32_t next = e.pass + 1;
+        if (e.hist && next <= e.hist_cap) e.hist[next - 1] = a;
+        e.st[5] = (double)next;
+        if (a < 0.0) e.st[4] = (double)SPUQ_PCG_PRECOND_NOT_PD;
+        else if (a <= e.st[6]) e.st[4] = (double)SPUQ_PCG_CONVERGED;
+    }
+}
+
 #ifndef SPUQ_EMU
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -28,7 +60,7 @@ template <int NOUT>
 __global__ void __launch_bounds__(REDUCE_THREADS)
 k_dot(int64_t n, const double* __restrict__ x, const double* __restrict__ y,
       double* __restrict__ out, double* __restrict__ partials, unsigned int* ticket,
-      const double* gate) {
+      const double* gate, DotEpilogue epi) {
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
     double sxy = 0.0, sxx = 0.0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,6 +119,7 @@ k_dot(int64_t n, const double* __restrict__ x, const double* __restrict__ y,
         if (lane == 0) {
             out[0] = a;
             if (NOUT == 2) out[1] = b;
+            dot_epilogue(epi, a);
             *ticket = 0u;   // ready for the next reduction on this stream
         }
     }
@@ -94,13 +127,14 @@ k_dot(int64_t n, const double* __restrict__ x, const double* __restrict__ y,
 #else
 template <int NOUT>
 void k_dot(int64_t n, const double* x, const double* y, double* out, double*, unsigned int*,
-           const double* gate) {
+           const double* gate, DotEpilogue epi) {
     if (gate != nullptr && *gate != (double)SPUQ_PCG_RUNNING) return;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double sxy = 0.0, sxx = 0.0;
     for (int64_t i = 0; i < n; ++i) { sxy += x[i] * y[i]; sxx += x[i] * x[i]; }
     out[0] = sxy;
     if (NOUT == 2) out[1] = sxx;
+    dot_epilogue(epi, sxy);
 }
 #endif
 

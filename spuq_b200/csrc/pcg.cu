@@ -37,15 +37,16 @@ static int reduce_grid(int64_t n) {
 }
 
 int dot_impl(int nout, int64_t n, const double* x, const double* y, double* out, void* scratch,
-             cudaStream_t stream, const double* gate) {
+             cudaStream_t stream, const double* gate, const DotEpilogue* epi_in) {
+    const DotEpilogue epi = epi_in ? *epi_in : DotEpilogue{DOT_EPI_NONE, nullptr, 0, nullptr, 0};
     SPUQ_REQUIRE(n >= 0 && x && y && out && scratch, "dot: null argument");
     double* partials = static_cast<double*>(scratch);
     unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + 2 * REDUCE_MAX_BLOCKS);
     const int grid = reduce_grid(n);
     if (nout == 1)
-        SPUQ_LAUNCH((k_dot<1>), dim3(grid), dim3(REDUCE_THREADS), 0, stream, n, x, y, out, partials, ticket, gate);
+        SPUQ_LAUNCH((k_dot<1>), dim3(grid), dim3(REDUCE_THREADS), 0, stream, n, x, y, out, partials, ticket, gate, epi);
     else
-        SPUQ_LAUNCH((k_dot<2>), dim3(grid), dim3(REDUCE_THREADS), 0, stream, n, x, y, out, partials, ticket, gate);
+        SPUQ_LAUNCH((k_dot<2>), dim3(grid), dim3(REDUCE_THREADS), 0, stream, n, x, y, out, partials, ticket, gate, epi);
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }
@@ -209,6 +210,10 @@ int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
                        void* work, cudaStream_t stream, const double* gate) {
     SPUQ_REQUIRE(p && R && S, "precond_apply: null argument");
     const int64_t n = N * (int64_t)L;
+    struct Count {                       // kernels of this call, whatever path returns
+        spuq_sg_precond* p; int c0;
+        ~Count() { p->last_launches = std::max(launch_counter() - c0, p->kind == spuq_sg_precond::PLAN && p->plan ? p->plan->last_launches : 0); }
+    } count{p, launch_counter()};
     switch (p->kind) {
     case spuq_sg_precond::IDENTITY: {
         // S = scale * R  (MultiplicationOperator.apply, linalg/operator.py:471-472)
@@ -294,25 +299,31 @@ extern "C" int spuq_sg_pcg(spuq_sg_plan* A, spuq_sg_precond* P, const double* F,
     if ((rc = precond_apply_impl(P, N, L, rho, s, pwork, stream, nullptr))) return rc;
     SPUQ_CUDA_TRY(cudaMemcpyAsync(v, s, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
     if ((rc = dot_impl(1, n, rho, s, st + 0, scratch, stream, nullptr))) return rc;
-    launches += 5;
+    launches += 4 + A->last_launches + P->last_launches;
 
+    // A pass is five launches plus the preconditioner's: apply, <z,v> (+ the singular / not-PD test),
+    // the fused w / rho update, P rho, <rho,s> (+ zeta rotation, the factor of the direction update and the
+    // convergence test of the next pass), the direction update.  The first convergence test stands alone.
+    SPUQ_LAUNCH(k_pcg_check_zeta, dim3(1), dim3(1), 0, stream, st, 1, hist);                 // :33-38, pass 1
+    launches += 1;
     int32_t pass = 1;
     int status = SPUQ_PCG_RUNNING;
     while (pass < maxiter && status == SPUQ_PCG_RUNNING) {
         const int32_t stop = std::min(maxiter, pass + poll_every);
         for (; pass < stop; ++pass) {
-            SPUQ_LAUNCH(k_pcg_check_zeta, dim3(1), dim3(1), 0, stream, st, pass, pass <= hist_cap ? hist : (double*)nullptr);   // :33-38
             if ((rc = apply_impl(A, v, N, z, N, stream, gate))) return rc;                   // :40
-            if ((rc = dot_impl(1, n, z, v, st + 1, scratch, stream, gate))) return rc;       // :41
-            SPUQ_LAUNCH(k_pcg_check_alpha, dim3(1), dim3(1), 0, stream, st);                  // :42-45
+            const DotEpilogue ea{DOT_EPI_ALPHA, st, pass, nullptr, 0};
+            if ((rc = dot_impl(1, n, z, v, st + 8, scratch, stream, gate, &ea))) return rc;  // :41-45
             SPUQ_LAUNCH(k_axpy2, dim3(blas_grid(n, nsm, 256)), dim3(256), 0, stream, n, st + 0, st + 1,
                         v, Wv, z, rho, gate);                                                // :47-48
             if ((rc = precond_apply_impl(P, N, L, rho, s, pwork, stream, gate))) return rc;  // :49
-            if ((rc = dot_impl(1, n, rho, s, st + 2, scratch, stream, gate))) return rc;     // :50
-            SPUQ_LAUNCH(k_xpay, dim3(blas_grid(n, nsm, 256)), dim3(256), 0, stream, n, st + 2, st + 0,
+            // the last pass the loop may run (maxiter - 1) has no successor to test: the reference raises
+            // "did not converge" without looking at its zeta
+            const DotEpilogue ez{pass + 1 < maxiter ? DOT_EPI_ZETA : DOT_EPI_NONE, st, pass, hist, hist_cap};
+            if ((rc = dot_impl(1, n, rho, s, st + 9, scratch, stream, gate, &ez))) return rc;  // :50, :33-38
+            SPUQ_LAUNCH(k_xpay, dim3(blas_grid(n, nsm, 256)), dim3(256), 0, stream, n, st + 3, (const double*)nullptr,
                         s, v, gate);                                                         // :51
-            SPUQ_LAUNCH(k_pcg_rotate, dim3(1), dim3(1), 0, stream, st);
-            launches += 9;
+            launches += 5 + A->last_launches - 1 + P->last_launches;
         }
         SPUQ_CUDA_TRY(cudaGetLastError());
         SPUQ_CUDA_TRY(cudaMemcpyAsync(h_state, st, sizeof(h_state), cudaMemcpyDeviceToHost, stream));

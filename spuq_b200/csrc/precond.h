@@ -22,6 +22,7 @@ struct spuq_sg_precond {
     void* strip = nullptr;
     // SPARSE_LU: opaque spuq::LuPlan* (precond_lu.cu)
     void* lu = nullptr;
+    int last_launches = 0;           // kernels of the last spuq_sg_precond_apply / precond_apply_impl on this handle
 };
 
 namespace spuq {
@@ -43,6 +44,7 @@ int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, dou
                   cudaStream_t stream, const double* gate);
 int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S,
                        void* work, cudaStream_t stream, const double* gate);
+struct DotEpilogue;
 int dot_impl(int nout, int64_t n, const double* x, const double* y, double* out, void* scratch,
-             cudaStream_t stream, const double* gate);
+             cudaStream_t stream, const double* gate, const DotEpilogue* epi = nullptr);
 }

@@ -29,6 +29,8 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static thread_local int g_launch_counter = 0;
+int& launch_counter() { return g_launch_counter; }
 static thread_local const double* g_abi_gate = nullptr;
 const double* abi_gate() { return g_abi_gate; }
 
