@@ -540,6 +540,7 @@ def pcg_block(args, peak_gbs):
     x, zeta, it = sp.pcg(A, f, P, w0, eps=args.pcg_eps, maxiter=200, poll_every=8, history=hist)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    solve_launches = A.plan_for(x_true).last_launches          # kernels of the whole solve (spuq_sg_pcg counts them)
     err = float((x.slab - X).abs().max())
     passes = max(it - 1, 1)
 
@@ -559,7 +560,7 @@ def pcg_block(args, peak_gbs):
             "max_abs_error_vs_manufactured": err, "ms_apply": t_apply, "ms_precond": t_prec,
             "bytes_model_per_pass": model, "bytes_model_frac": model / (dt / passes) / 1e9 / peak_gbs,
             "preconditioner": "exact A_0^{-1} (strip partition, csrc/precond_strip.cuh)",
-            "gpu_launches": A.plan_for(x_true).last_launches}
+            "gpu_launches": solve_launches, "launches_per_pass": round((solve_launches - 20) / passes, 1)}
 
 
 def _ref_worker(ref, only, q):

@@ -19,6 +19,6 @@ from .pcg import pcg
 from .adaptive_solver import prepare_rhs, pcg_solve, error_norm
 from .sampling import compute_parametric_sample_solution, sample_solutions
 from .marking import Marking
-from .residual import neighbour_combination, column_energy_norms
+from .residual import neighbour_combination, column_energy_norms, lambda_boundary, evaluate_upper_tail_bound
 
 __version__ = "0.1.0"

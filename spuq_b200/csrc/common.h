@@ -87,6 +87,7 @@ struct BlockView {
     const int32_t* tcol;    // T
     const int32_t* tacc;    // T
     const double* tcoef;    // T
+    const void* trec;       // T packed 16-byte records {int32 col, int32 acc, double coef} (general sparse kernel)
 };
 
 }  // namespace spuq

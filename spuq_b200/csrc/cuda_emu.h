@@ -25,6 +25,11 @@ struct dim3 {
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 struct double2 { double x, y; };
+struct int4 { int x, y, z, w; };
+static inline double __hiloint2double(int hi, int lo) {
+    unsigned long long u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+    double d; std::memcpy(&d, &u, 8); return d;
+}
 static inline double2 make_double2(double a, double b) { return double2{a, b}; }
 
 extern thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;

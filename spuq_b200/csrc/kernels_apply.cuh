@@ -114,7 +114,21 @@ __device__ __forceinline__ void ellblk_accumulate(double (&acc)[ELLBLK_C], int32
     }
 }
 
-template <int KW>
+// one gathered operand: W_col[cols_k] with the address formed by ONE 32 x 32 -> 64 multiply-add (the compiler's
+// own code sign-extended the column index and spent a LEA pair per gather: 105 instructions per term)
+__device__ __forceinline__ double ellblk_gather(const double* wcol, int32_t col_k) {
+#ifdef SPUQ_EMU
+    return wcol[col_k];
+#else
+    double v;
+    asm("{\n.reg .u64 a;\nmad.wide.s32 a, %2, 8, %1;\nld.global.nc.f64 %0, [a];\n}\n" : "=d"(v) : "l"(wcol), "r"(col_k));
+    return v;
+#endif
+}
+
+// KW = padded row width held in registers; EXACT: every row has exactly KW stored entries slots (K == KW), so
+// no slot needs a guard
+template <int KW, bool EXACT>
 __global__ void __launch_bounds__(128)
 k_apply_ellblk(int64_t n_rows, int32_t K, const int32_t* __restrict__ ell_cols,
                const double* __restrict__ ell_vals, BlockView bv, const double* __restrict__ W, int64_t ldw,
@@ -125,38 +139,46 @@ k_apply_ellblk(int64_t n_rows, int32_t K, const int32_t* __restrict__ ell_cols,
     const int64_t row = (item / bv.nblk) * blockDim.x + threadIdx.x;
     if (row >= n_rows) return;
     int32_t cols[KW];
+    {
+        const int32_t* cp = ell_cols + row;
 #pragma unroll
-    for (int k = 0; k < KW; ++k) cols[k] = k < K ? ell_cols[(int64_t)k * n_rows + row] : 0;
+        for (int k = 0; k < KW; ++k) { cols[k] = (EXACT || k < K) ? *cp : 0; cp += n_rows; }
+    }
     double acc[ELLBLK_C];
 #pragma unroll
     for (int c = 0; c < ELLBLK_C; ++c) acc[c] = 0.0;
+    const int4* trec = reinterpret_cast<const int4*>(bv.trec);        // {col, acc, coef lo, coef hi} per term
     for (int32_t g = bv.bgrp[blk]; g < bv.bgrp[blk + 1]; ++g) {
         double a[KW];
-        const double* ap = ell_vals + ((int64_t)bv.gmat[g] * K) * n_rows + row;
+        {
+            const double* ap = ell_vals + ((int64_t)bv.gmat[g] * K) * n_rows + row;
 #pragma unroll
-        for (int k = 0; k < KW; ++k) a[k] = k < K ? ap[(int64_t)k * n_rows] : 0.0;
+            for (int k = 0; k < KW; ++k) { a[k] = (EXACT || k < K) ? *ap : 0.0; ap += n_rows; }
+        }
         // two terms per trip: all 2 x KW gathers are issued before the first product, so that two input
         // columns are in flight per warp (the gathers are the only latency on this path)
         const int32_t t1 = bv.gterm[g + 1];
         int32_t t = bv.gterm[g];
         for (; t + 1 < t1; t += 2) {
-            const double* wa = W + (int64_t)bv.tcol[t] * ldw;
-            const double* wb = W + (int64_t)bv.tcol[t + 1] * ldw;
+            const int4 ra = __ldg(trec + t), rb = __ldg(trec + t + 1);
+            const double* wa = W + (int64_t)ra.x * ldw;
+            const double* wb = W + (int64_t)rb.x * ldw;
             double ga[KW], gb[KW];
 #pragma unroll
-            for (int k = 0; k < KW; ++k) { ga[k] = wa[cols[k]]; gb[k] = wb[cols[k]]; }
+            for (int k = 0; k < KW; ++k) { ga[k] = ellblk_gather(wa, cols[k]); gb[k] = ellblk_gather(wb, cols[k]); }
             double sa = 0.0, sb = 0.0;
 #pragma unroll
             for (int k = 0; k < KW; ++k) { sa = fma(a[k], ga[k], sa); sb = fma(a[k], gb[k], sb); }
-            ellblk_accumulate(acc, bv.tacc[t], bv.tcoef[t] * sa);
-            ellblk_accumulate(acc, bv.tacc[t + 1], bv.tcoef[t + 1] * sb);
+            ellblk_accumulate(acc, ra.y, __hiloint2double(ra.w, ra.z) * sa);
+            ellblk_accumulate(acc, rb.y, __hiloint2double(rb.w, rb.z) * sb);
         }
         if (t < t1) {
-            const double* wa = W + (int64_t)bv.tcol[t] * ldw;
+            const int4 ra = __ldg(trec + t);
+            const double* wa = W + (int64_t)ra.x * ldw;
             double sa = 0.0;
 #pragma unroll
-            for (int k = 0; k < KW; ++k) sa = fma(a[k], wa[cols[k]], sa);
-            ellblk_accumulate(acc, bv.tacc[t], bv.tcoef[t] * sa);
+            for (int k = 0; k < KW; ++k) sa = fma(a[k], ellblk_gather(wa, cols[k]), sa);
+            ellblk_accumulate(acc, ra.y, __hiloint2double(ra.w, ra.z) * sa);
         }
     }
 #pragma unroll

@@ -339,6 +339,7 @@ int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx) {
     sv.PX = (int32_t)xstart.size(); sv.qx = sv.PX - 1;
     if (sv.qx > 64) { delete sp; return SPUQ_OK; }
     sv.cxmax = *std::max_element(xlen.begin(), xlen.end());
+    if (sv.cxmax > STRIP_CX) { delete sp; return ctx ? SPUQ_E_UNSUPPORTED : SPUQ_OK; }
     sv.ch[0] = ylen.front(); sv.ch[1] = ylen.back();     // heights h+1 (first strips) and h
     sv.xlen_cls_len[0] = xlen.front(); sv.xlen_cls_len[1] = xlen.back();
     sp->cmax = std::max(sv.ch[0], sv.ch[1]);

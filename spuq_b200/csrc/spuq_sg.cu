@@ -184,6 +184,11 @@ static int build_blocks(spuq_sg_plan* p, int32_t C) {
     p->bv = BlockView{};
     int rc;
     int32_t *d_bcol, *d_bgrp, *d_gmat, *d_gterm, *d_tcol, *d_tacc; double* d_tcoef;
+    struct TRec { int32_t col, acc; double coef; };
+    static_assert(sizeof(TRec) == 16, "term record must be 16 bytes");
+    std::vector<TRec> trec(tcol.size());
+    for (size_t i = 0; i < tcol.size(); ++i) trec[i] = TRec{tcol[i], tacc[i], tcoef[i]};
+    TRec* d_trec;
     const size_t first = p->owned_dev.size();
     if ((rc = dev_upload(p, bcol, &d_bcol))) return rc;
     if ((rc = dev_upload(p, bgrp, &d_bgrp))) return rc;
@@ -192,11 +197,12 @@ static int build_blocks(spuq_sg_plan* p, int32_t C) {
     if ((rc = dev_upload(p, tcol, &d_tcol))) return rc;
     if ((rc = dev_upload(p, tacc, &d_tacc))) return rc;
     if ((rc = dev_upload(p, tcoef, &d_tcoef))) return rc;
+    if ((rc = dev_upload(p, trec, &d_trec))) return rc;
     p->block_dev.assign(p->owned_dev.begin() + first, p->owned_dev.end());
     p->owned_dev.resize(first);
     p->bv.C = C; p->bv.nblk = nblk;
     p->bv.bcol = d_bcol; p->bv.bgrp = d_bgrp; p->bv.gmat = d_gmat; p->bv.gterm = d_gterm;
-    p->bv.tcol = d_tcol; p->bv.tacc = d_tacc; p->bv.tcoef = d_tcoef;
+    p->bv.tcol = d_tcol; p->bv.tacc = d_tacc; p->bv.tcoef = d_tcoef; p->bv.trec = d_trec;
     return SPUQ_OK;
 }
 
@@ -617,15 +623,22 @@ int apply_impl(spuq_sg_plan* p, const double* W, int64_t ldw, double* Y, int64_t
             }
             const int64_t items = row_blocks * p->bv.nblk;
             SPUQ_REQUIRE(items < 0x7fffffffLL, "apply: too many work items (%lld)", (long long)items);
-            if (p->ell_K <= 8) {
-                SPUQ_LAUNCH((k_apply_ellblk<8>), dim3((unsigned)items), dim3(threads), 0, stream, p->n_rows, p->ell_K,
-                            p->ell_cols, p->ell_vals, p->bv, W, ldw, Y, ldy, gate);
-                p->kernel_name = "k_apply_ellblk<8>";
-            } else {
-                SPUQ_LAUNCH((k_apply_ellblk<16>), dim3((unsigned)items), dim3(threads), 0, stream, p->n_rows, p->ell_K,
-                            p->ell_cols, p->ell_vals, p->bv, W, ldw, Y, ldy, gate);
-                p->kernel_name = "k_apply_ellblk<16>";
-            }
+            char name[64];
+            bool done = false;
+#define SPUQ_ELLBLK(kw)                                                                                              \
+    if (!done && p->ell_K <= kw) {                                                                                   \
+        if (p->ell_K == kw)                                                                                          \
+            SPUQ_LAUNCH((k_apply_ellblk<kw, true>), dim3((unsigned)items), dim3(threads), 0, stream, p->n_rows,      \
+                        p->ell_K, p->ell_cols, p->ell_vals, p->bv, W, ldw, Y, ldy, gate);                            \
+        else                                                                                                         \
+            SPUQ_LAUNCH((k_apply_ellblk<kw, false>), dim3((unsigned)items), dim3(threads), 0, stream, p->n_rows,     \
+                        p->ell_K, p->ell_cols, p->ell_vals, p->bv, W, ldw, Y, ldy, gate);                            \
+        snprintf(name, sizeof(name), "k_apply_ellblk<%d>", kw);                                                      \
+        done = true;                                                                                                 \
+    }
+            SPUQ_ELLBLK(3) SPUQ_ELLBLK(5) SPUQ_ELLBLK(7) SPUQ_ELLBLK(9) SPUQ_ELLBLK(12) SPUQ_ELLBLK(16)
+#undef SPUQ_ELLBLK
+            p->kernel_name = name;
         } else if (p->path == SPUQ_PATH_CSR) {
             SPUQ_LAUNCH(k_apply_csr, grid, dim3(threads), 0, stream, p->n_rows, p->L, p->rowptr, p->colidx,
                         p->vals_ptrs_dev, tv, W, ldw, Y, ldy, cpc, gate);

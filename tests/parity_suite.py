@@ -53,7 +53,7 @@ def check_apply_paths(n=12, M=4, p=2, kind="legendre", mu=0.0):
         Y, plan = product_apply(c, path)
         assert relerr(Y, c.Y) <= TOL, (path, relerr(Y, c.Y))
         seen.add(plan.kernel_name)
-    assert {"k_apply_csr", "k_apply_ellblk<8>"} <= seen
+    assert {"k_apply_csr", "k_apply_ellblk<5>"} <= seen
     Y, plan = product_apply(c, _abi.PATH_ELL, (1, 0, 0, 0))          # one column at a time (cross-check kernel)
     assert plan.kernel_name == "k_apply_ell<8>" and relerr(Y, c.Y) <= TOL
     for tune in [(1, 0, 0, 0), (2, 8, 2, 0), (2, 4, 2, 0), (2, 16, 2, 0), (2, 8, 1, 0), (2, 16, 1, 0), (2, 4, 4, 0),
@@ -159,7 +159,7 @@ def check_apply_unstructured():
     c.w = oracle_multivector(idx, c.W)
     c.Y = (c.A * c.w).to_slab()
     Y, plan = product_apply(c)
-    assert plan.kernel_name == "k_apply_ellblk<8>" and relerr(Y, c.Y) <= TOL, (plan.kernel_name, relerr(Y, c.Y))
+    assert plan.kernel_name == "k_apply_ellblk<5>" and relerr(Y, c.Y) <= TOL, (plan.kernel_name, relerr(Y, c.Y))
     # wider rows (random sparse blocks, up to 16 entries per row): KW = 16
     c2 = random_sparse_case(40, 3, synthetic.anisotropic_indices(3, 5.0), density=0.2, seed=9)
     Y, plan = product_apply(c2, _abi.PATH_ELL)

@@ -308,7 +308,7 @@ def test_general_sparse_path_100k_rows():
     w = sp.SlabMultiVector(idx, slab=W, _sorted=True)
     plan = A.plan_for(w)
     y = A.apply(w)
-    assert plan.kernel_name == "k_apply_ellblk<8>", plan.kernel_name
+    assert plan.kernel_name == "k_apply_ellblk<5>", plan.kernel_name
     mats = synth.permuted(synth.fd_matrices(n, M), synth.tile_permutation(n, 16))
     cols = [0, 1, 5, L // 2, L - 1]
     ref, _ = SampledApply(mats, synth.index_set(("aniso", M, 9.0)), "hermite", 0.5, cols, lambda k: W[k].cpu().numpy()).run()
