@@ -11,7 +11,7 @@ for c in c3u c3n c2 c4; do
 import json; d=json.loads(open('$O/r2_bench_$c.json').read().strip().splitlines()[-1]); print('$c', round(d['value'],1), round(d['ms_per_step'],3), round(d['roofline']['frac'],3), d['parity_relerr'], d['details']['kernel'])"
 done
 # launch list of the bench command (kernel share of the step) and of one config-4 solve
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-pcg > $O/r2_ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 400 --csv --log-file $O/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-pcg > $O/r2_ncu_launches.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $O/r2_pcg_c4_launches.csv python tools/pcg_bench.py --config c4 > $O/r2_ncu_pcg.log 2>&1
 python - <<'PY'
 import csv, collections
@@ -34,6 +34,6 @@ ncu --set full --clock-control none --import-source on -k regex:k_apply_tmem -s 
 python tools/ncu_to_json.py $O/r2_c3_apply_tmem.ncu-rep $O/r2_c3_apply_tmem_ncu_full.json $O/r2_traffic.json "c3|k_apply_tmem<K=2,G=2,5pt>" "profiles/r2_c3_apply_tmem_ncu_full.json (ncu --set full --clock-control none, one launch of bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-pcg)" > /dev/null
 ncu --set full --clock-control none --import-source on -k regex:k_strip -c 4 -f -o $O/r2_strip python tools/precond_bench.py --nx 500 --ny 500 --L 600 --reps 1 > $O/r2_ncu_full_strip.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_apply_ellblk -s 3 -c 1 -f -o $O/r2_c3n_ellblk python bench.py --config c3n --steps 1 --warmup 3 --no-e2e --no-cpu --no-pcg > $O/r2_ncu_full_c3n.log 2>&1
-python tools/ncu_to_json.py $O/r2_c3n_ellblk.ncu-rep $O/r2_c3n_ellblk_ncu_full.json $O/r2_traffic.json "c3n|k_apply_ellblk<8>" "profiles/r2_c3n_ellblk_ncu_full.json (ncu --set full, one launch of bench.py --config c3n)" > /dev/null
+python tools/ncu_to_json.py $O/r2_c3n_ellblk.ncu-rep $O/r2_c3n_ellblk_ncu_full.json $O/r2_traffic.json "c3n|k_apply_ellblk<5>" "profiles/r2_c3n_ellblk_ncu_full.json (ncu --set full, one launch of bench.py --config c3n)" > /dev/null
 for s in "500 500 5000" "512 512 1771" "1000 1000 988"; do set -- $s; python tools/precond_bench.py --nx $1 --ny $2 --L $3; done > $O/r2_precond_bench.json 2>/dev/null; cat $O/r2_precond_bench.json
 ls -la $O | tail -30
