@@ -94,6 +94,10 @@ def row_ranges(ny, world, align=8):
     return [(min(r * per, ny), min((r + 1) * per, ny)) for r in range(world)]
 
 
+class PeerUnavailable(RuntimeError):
+    """Raised on ALL ranks (the decision is taken on gathered data) when some rank cannot export or map a slab."""
+
+
 class PeerHaloExchange:
     """Halo rows of row-sharded slabs written straight into the neighbours' memory (one NVSwitch box).
 
@@ -118,14 +122,34 @@ class PeerHaloExchange:
         self._slabs = {}
         self._mapped = {}                      # exported handle -> base address in this device's context
         handles = [None] * world
-        dist.all_gather_object(handles, (device.index, self._export(self.flags)), group=group)
+        dist.all_gather_object(handles, (device.index, self._try_export(self.flags)), group=group)
+        if any(h is None for _, h in handles):
+            raise PeerUnavailable("a rank could not export its flag words through CUDA IPC")
         self.peer_flags = {}
         lib = _abi.lib()
-        for r in (rank - 1, rank + 1):
-            if 0 <= r < world:
-                dev_r, h = handles[r]
-                _abi.check(lib.spuq_sg_enable_peer_access(device.index, dev_r), "enable_peer_access")
-                self.peer_flags[r] = self._map(h)
+        err = None
+        try:
+            for r in (rank - 1, rank + 1):
+                if 0 <= r < world:
+                    dev_r, h = handles[r]
+                    _abi.check(lib.spuq_sg_enable_peer_access(device.index, dev_r), "enable_peer_access")
+                    self.peer_flags[r] = self._map(h)
+        except _abi.SpuqError as e:
+            err = e
+        self._agree(err is None, "a rank could not map its neighbours' flag words (%r)" % (err,))
+
+    def _agree(self, ok, what):
+        """Collective: all ranks continue only if all of them succeeded."""
+        oks = [None] * self.world
+        dist.all_gather_object(oks, bool(ok), group=self.group)
+        if not all(oks):
+            raise PeerUnavailable(what)
+
+    def _try_export(self, t):
+        try:
+            return self._export(t)
+        except _abi.SpuqError:
+            return None
 
     @staticmethod
     def _export(t):
@@ -150,13 +174,19 @@ class PeerHaloExchange:
         key = (W.data_ptr(), tuple(W.shape))
         if key not in self._slabs:
             info = [None] * self.world
-            dist.all_gather_object(info, (self._export(W), W.shape[0], nyl), group=self.group)
-            peers = {}
-            for r in (self.rank - 1, self.rank + 1):
-                if 0 <= r < self.world:
-                    exported, L_r, nyl_r = info[r]
-                    assert L_r == W.shape[0]
-                    peers[r] = (self._map(exported), nyl_r)
+            dist.all_gather_object(info, (self._try_export(W), W.shape[0], nyl), group=self.group)
+            if any(e is None for e, _, _ in info):
+                raise PeerUnavailable("a rank could not export its slab through CUDA IPC")
+            peers, err = {}, None
+            try:
+                for r in (self.rank - 1, self.rank + 1):
+                    if 0 <= r < self.world:
+                        exported, L_r, nyl_r = info[r]
+                        assert L_r == W.shape[0]
+                        peers[r] = (self._map(exported), nyl_r)
+            except _abi.SpuqError as e:
+                err = e
+            self._agree(err is None, "a rank could not map a neighbour's slab (%r)" % (err,))
             self._slabs[key] = peers
         return self._slabs[key]
 
@@ -253,14 +283,22 @@ class RowShardedApply:
         that exchange on a side stream while the kernel already works on the tile rows that read no halo
         row (spuq_sg_apply_part 1) and finishes the tile rows at the two ends afterwards (part 2)."""
         if self._use_peer(W):
-            if self._peer is None:
-                self._peer = PeerHaloExchange(self.rank, self.world, W.device, self.group)
-            st = _abi.stream_ptr()
-            self._peer.exchange(W, self.nyl, self.nx, st)
-            plan.apply(W, Y)
-            self._peer.consumed(st)
-            self.last_launches = plan.last_launches + 3        # + push, wait, done (one small kernel each)
-            return Y
+            # set-up and the registration of a new slab are collective and fail on ALL ranks together
+            # (PeerUnavailable: no CUDA IPC between the processes, no peer access): fall back to NCCL
+            try:
+                if self._peer is None:
+                    self._peer = PeerHaloExchange(self.rank, self.world, W.device, self.group)
+                st = _abi.stream_ptr()
+                self._peer.exchange(W, self.nyl, self.nx, st)
+            except PeerUnavailable as e:
+                if self.halo == "peer":
+                    raise
+                self._peer_error, self.halo = repr(e), "nccl"
+            else:
+                plan.apply(W, Y)
+                self._peer.consumed(st)
+                self.last_launches = plan.last_launches + 3        # + push, wait, done (one small kernel each)
+                return Y
         if self.world == 1 or not overlap or W.device.type != "cuda":
             self.exchange_halos(W)
             plan.apply(W, Y)
