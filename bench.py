@@ -427,6 +427,16 @@ def run_gpu(args):
             return {k: full[i] for i, k in enumerate(cols)}
         parity_in = (ncols, gather_cols(Wt, touched), gather_cols(Yfull[:L], pick))
 
+    # ---- row-sharded PCG of config 4 on the same ranks (all ranks take part; rank 0 reports it) ----------------
+    kernel_name = plan.kernel_name
+    pcg_rows = None
+    if rows_mode and not args.no_pcg:
+        # the apply slabs go back to torch's caching allocator (NOT to the driver: the neighbours still hold
+        # IPC mappings of them), the solve below allocates its own
+        barrier()
+        Wt = Yfull = w = plan = A = sharded = blocks = vals = Wdev = wv = h_in = h_out = y = None
+        pcg_rows = pcg_block_rows(args, world, rank, dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -439,7 +449,7 @@ def run_gpu(args):
     for name in ("r2_traffic.json", "r1_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
-                tr = json.load(f).get("%s|%s" % (args.config, plan.kernel_name))
+                tr = json.load(f).get("%s|%s" % (args.config, kernel_name))
             if tr and world == 1:
                 traffic = tr["dram_bytes"]
                 traffic_src = ("profiles/%s: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on "
@@ -461,7 +471,7 @@ def run_gpu(args):
                             world, "written into the neighbours' slabs (CUDA IPC peer copies + flags)" if args.halo == "peer"
                             else "exchanged point-to-point (NCCL)" + (", overlapped with the interior tile rows" if args.overlap else ""))) if rows_mode
                         else ("M-sharded x%d + NCCL reduce-scatter over Lambda" % world)),
-        "details": {"n_terms": info["n_terms"], "nnz_per_block": info["nnz"], "kernel": plan.kernel_name,
+        "details": {"n_terms": info["n_terms"], "nnz_per_block": info["nnz"], "kernel": kernel_name,
                     "path": info["path"], "host_numa_node_rank0": numa},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -490,14 +500,14 @@ def run_gpu(args):
                                              "MultiOperator.apply (cached scipy CSR leaves, one SpMV per (mu, m)); "
                                              "%.1f s; per-column cost is independent of the other columns" % (ref.n_cols, L, secs),
                                    "host_cpus": os.cpu_count()}
+    if pcg_rows is not None:
+        out["pcg"] = pcg_rows
     if world == 1 and not args.no_pcg:
         # free the apply benchmark's slabs before the solve (config 4 needs ~9 slabs of 10 GB)
-        del Wt, Yfull, w, plan, A, sharded, blocks, vals
-        if not args.no_e2e:
-            del Wdev, wv, h_in, h_out
-        import gc
-        gc.collect()
-        torch.cuda.empty_cache()
+        # the apply slabs go back to torch's caching allocator (NOT to the driver: the neighbours still hold
+        # IPC mappings of them), the solve below allocates its own
+        barrier()
+        Wt = Yfull = w = plan = A = sharded = blocks = vals = Wdev = wv = h_in = h_out = y = None
         out["pcg"] = pcg_block(args, peak)
     print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:
@@ -561,6 +571,58 @@ def pcg_block(args, peak_gbs):
             "bytes_model_per_pass": model, "bytes_model_frac": model / (dt / passes) / 1e9 / peak_gbs,
             "preconditioner": "exact A_0^{-1} (strip partition, csrc/precond_strip.cuh)",
             "gpu_launches": solve_launches, "launches_per_pass": round((solve_launches - 20) / passes, 1)}
+
+
+def pcg_block_rows(args, world, rank, dev):
+    """The config-4 solve with the grid rows sharded over the ranks (spuq_b200.sharding.RowShardedPCG): halo rows
+    written into the neighbours' memory, scalars all-reduced in the device state, strip solver on every band with
+    the separator system column-sharded.  Manufactured solution per band (seeded per rank), f = A x*, w0 = 0."""
+    import torch
+    import torch.distributed as dist
+    import spuq_b200 as sp
+    from spuq_b200 import synthetic
+    from spuq_b200.multi_operator import DeviceBlocks
+    from spuq_b200.sharding import RowShardedApply, RowShardedPCG, row_ranges
+    key = args.pcg_config
+    cfg = CONFIGS[key]
+    n, M = cfg["n"], cfg["M"]
+    idx = index_set(cfg)
+    L = idx.shape[0]
+    rvs = synthetic.make_rvs(cfg["kind"], M, cfg["mu"])
+    ranges = row_ranges(n, world, align=1)
+    y0, y1 = ranges[rank]
+    nyl = y1 - y0 + 2
+    rowptr, colidx, vals = synthetic.fd_blocks_rows(n, M, y0, y1, device=dev)
+    sh = RowShardedApply(DeviceBlocks(rowptr, colidx, vals, (nyl * n, nyl * n)), rvs, n, y0, y1)
+    sh.halo = args.halo
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    X = torch.zeros((L, nyl, n), dtype=torch.float64, device=dev)
+    X[:, 1:-1, :] = torch.rand((L, y1 - y0, n), dtype=torch.float64, device=dev, generator=g)
+    X = X.view(L, nyl * n)
+    w = sp.SlabMultiVector(idx, slab=X, _sorted=True)
+    plan = sh.plan_for(w)
+    F = torch.empty_like(X)
+    sh.apply(plan, X.clone(), F)
+    solver = RowShardedPCG(sh, n, n, ranges, mean_stencil=(4.0, -1.0, -1.0))
+    solver._zero_halos(F)
+    tmp = torch.empty_like(F)
+    solver.precondition(F, tmp)                        # set-up of the solver outside the timed solve
+    del tmp
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Xs, zeta, it = solver.solve(plan, F, torch.zeros_like(F), eps=args.pcg_eps, maxiter=200)
+    torch.cuda.synchronize(); dist.barrier()
+    dt = time.perf_counter() - t0
+    err = (Xs.view(L, nyl, n)[:, 1:-1, :] - X.view(L, nyl, n)[:, 1:-1, :]).abs().max().reshape(1)
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt[0])
+    passes = max(it - 1, 1)
+    return {"workload": workload_name(key), "eps": args.pcg_eps, "numit": it, "zeta": zeta, "seconds": dt,
+            "ms_per_pass": dt / passes * 1e3, "gdof_per_s_per_pass": n * n * L * passes / dt / 1e9,
+            "max_abs_error_vs_manufactured": float(err[0]),
+            "sharding": "grid rows x%d; preconditioner: exact A_0^{-1}, %s" % (world, solver.mean_solver)}
 
 
 def _ref_worker(ref, only, q):
