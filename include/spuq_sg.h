@@ -254,21 +254,26 @@ SPUQ_API int spuq_sg_spike_correct(int32_t L, int32_t ny, int32_t nx, double* T_
  *     (caller)        all-gather of the separator rows
  *     strip_schur     separator system of the whole grid, in place on Z (Z2: scratch of the same size)
  *     strip_final     local strips with the separator values on their right-hand side -> S
- * R and S are contiguous L x (n_loc * nx) slabs of the band's rows.  All kernels honour spuq_sg_set_gate. */
+ * R and S point at the band's first row of column 0; ld = column stride in doubles (0: n_loc * nx, the band
+ * stored on its own; larger: the band inside a halo-padded slab, no copy needed).  strip_final with
+ * dot_out_dev != NULL also leaves <R, S> over the band in dot_out_dev[0] (same kernel, no extra slab pass).
+ * All kernels honour spuq_sg_set_gate. */
 SPUQ_API int spuq_sg_precond_mean_fd_rows(spuq_sg_precond** out, int device, int32_t nx, double d, double ox, double oy,
                                  int32_t world, int32_t rank, const int32_t* bounds_host);
 SPUQ_API int spuq_sg_precond_strip_info(const spuq_sg_precond* p, int32_t* n_strips_loc, int32_t* q_loc, int32_t* q_glob,
                                int32_t* first_sep, int32_t* gf_ld);
-SPUQ_API int spuq_sg_precond_strip_forward(spuq_sg_precond* p, int32_t L, const double* R_dev, double* Gf_dev, double* Gl_dev,
-                                  void* stream);
-SPUQ_API int spuq_sg_precond_strip_assemble(spuq_sg_precond* p, int32_t L, const double* R_dev, const double* Gf_dev,
+SPUQ_API int spuq_sg_precond_strip_forward(spuq_sg_precond* p, int32_t L, const double* R_dev, int64_t ld, double* Gf_dev,
+                                  double* Gl_dev, void* stream);
+SPUQ_API int spuq_sg_precond_strip_assemble(spuq_sg_precond* p, int32_t L, const double* R_dev, int64_t ld, const double* Gf_dev,
                                    const double* Gl_dev, double* Z_dev, void* stream);
 SPUQ_API int spuq_sg_precond_strip_schur(spuq_sg_precond* p, int32_t L, double* Z_dev, double* Z2_dev, void* stream);
 SPUQ_API int spuq_sg_precond_strip_final(spuq_sg_precond* p, int32_t L, const double* R_dev, const double* U_dev, double* S_dev,
-                                void* stream);
+                                int64_t ld, double* dot_out_dev, void* stream);
 SPUQ_API int spuq_sg_precond_destroy(spuq_sg_precond* p);
 /* workspace (bytes) precond_apply needs for an N x L slab */
 SPUQ_API int64_t spuq_sg_precond_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L);
+/* kernels the last spuq_sg_precond_apply on this handle launched (bench.py's gpu_launches, the launch-count tests) */
+SPUQ_API int spuq_sg_precond_last_launches(const spuq_sg_precond* p);
 /* S = P R on N x L contiguous slabs */
 SPUQ_API int spuq_sg_precond_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R_dev,
                           double* S_dev, void* work_dev, void* stream);

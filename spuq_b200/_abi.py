@@ -77,12 +77,13 @@ SIGNATURES = {
     "spuq_sg_precond_mean_fd_rows": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int32, C.c_double, C.c_double, C.c_double,
                                                 C.c_int32, C.c_int32, _vp]),
     "spuq_sg_precond_strip_info": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p, _i32p]),
-    "spuq_sg_precond_strip_forward": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp]),
-    "spuq_sg_precond_strip_assemble": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "spuq_sg_precond_strip_forward": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _vp, _vp, _vp]),
+    "spuq_sg_precond_strip_assemble": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "spuq_sg_precond_strip_schur": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp]),
-    "spuq_sg_precond_strip_final": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp]),
+    "spuq_sg_precond_strip_final": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_int64, _vp, _vp]),
     "spuq_sg_precond_destroy": (C.c_int, [_vp]),
     "spuq_sg_precond_work_bytes": (C.c_int64, [_vp, C.c_int64, C.c_int32]),
+    "spuq_sg_precond_last_launches": (C.c_int, [_vp]),
     "spuq_sg_precond_apply": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp]),
     "spuq_sg_pcg_check_zeta": (C.c_int, [_vp, C.c_int32, _vp]),
     "spuq_sg_pcg_check_alpha": (C.c_int, [_vp, _vp]),

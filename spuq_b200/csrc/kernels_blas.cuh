@@ -8,6 +8,7 @@
 // the last block to finish (atomic ticket) adds the partials in index order with one warp.
 #pragma once
 #include "common.h"
+#include "reduce_common.cuh"
 
 namespace spuq {
 
@@ -16,45 +17,7 @@ constexpr int REDUCE_MAX_BLOCKS = 1024;
 // scratch layout: [0, 2*REDUCE_MAX_BLOCKS) doubles of partials, then one uint32 ticket
 constexpr int64_t REDUCE_SCRATCH_BYTES = 2 * REDUCE_MAX_BLOCKS * 8 + 64;
 
-// What the block that finishes a reduction does with the result besides storing it (PCG, pcg.py:41-51): the
-// reference's branch conditions are evaluated right where the scalar is produced, so a pass needs no
-// one-thread kernels between its big ones.
-//   DOT_EPI_ALPHA  st[1] = <z,v>; singular / not-positive-definite test                       (:41-45)
-//   DOT_EPI_ZETA   st[3] = zeta_new / zeta (the factor of the direction update, :51), zeta <- zeta_new, and
-//                  the convergence test of the NEXT pass (:33-38) with its history entry
-enum { DOT_EPI_NONE = 0, DOT_EPI_ALPHA = 1, DOT_EPI_ZETA = 2 };
-struct DotEpilogue {
-    int kind;
-    double* st;        // PCG state words
-    int32_t pass;      // DOT_EPI_ZETA: index of the pass that just ends (the test is that of pass + 1)
-    double* hist;      // zeta history (device) or null
-    int32_t hist_cap;
-};
-
-__device__ __forceinline__ void dot_epilogue(const DotEpilogue& e, double a) {
-    if (e.kind == DOT_EPI_ALPHA) {
-        e.st[1] = a;
-        if (a == 0.0) e.st[4] = (double)SPUQ_PCG_SINGULAR;
-        else if (a < 0.0) e.st[4] = (double)SPUQ_PCG_NOT_PD;
-    } else if (e.kind == DOT_EPI_ZETA) {
-        e.st[2] = a;
-        e.st[3] = a / e.st[0];
-        e.st[0] = a;
-        const int32_t next = e.pass + 1;
-        if (e.hist && next <= e.hist_cap) e.hist[next - 1] = a;
-        e.st[5] = (double)next;
-        if (a < 0.0) e.st[4] = (double)SPUQ_PCG_PRECOND_NOT_PD;
-        else if (a <= e.st[6]) e.st[4] = (double)SPUQ_PCG_CONVERGED;
-    }
-}
-
 #ifndef SPUQ_EMU
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 // NOUT = 1: out[0] = <x,y>;  NOUT = 2: out[0] = <x,y>, out[1] = <x,x>
 template <int NOUT>
 __global__ void __launch_bounds__(REDUCE_THREADS)

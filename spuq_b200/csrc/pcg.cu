@@ -198,6 +198,8 @@ extern "C" int spuq_sg_precond_destroy(spuq_sg_precond* p) {
     return SPUQ_OK;
 }
 
+extern "C" int spuq_sg_precond_last_launches(const spuq_sg_precond* p) { return p ? p->last_launches : 0; }
+
 extern "C" int64_t spuq_sg_precond_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L) {
     if (!p) return 0;
     if (p->kind == spuq_sg_precond::MEAN_FD) return mean_fd_work_bytes(p, N, L);
@@ -207,7 +209,7 @@ extern "C" int64_t spuq_sg_precond_work_bytes(const spuq_sg_precond* p, int64_t 
 
 namespace spuq {
 int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S,
-                       void* work, cudaStream_t stream, const double* gate) {
+                       void* work, cudaStream_t stream, const double* gate, FusedDot* fd) {
     SPUQ_REQUIRE(p && R && S, "precond_apply: null argument");
     const int64_t n = N * (int64_t)L;
     struct Count {                       // kernels of this call, whatever path returns
@@ -228,7 +230,7 @@ int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
         SPUQ_REQUIRE(p->plan->n_rows == N && p->plan->L == L, "precond_apply: plan shape mismatch");
         return apply_impl(p->plan, R, N, S, N, stream, gate);
     case spuq_sg_precond::MEAN_FD:
-        return mean_fd_apply(p, N, L, R, S, work, stream, gate);
+        return mean_fd_apply(p, N, L, R, S, work, stream, gate, fd);
     case spuq_sg_precond::SPARSE_LU:
         return lu_apply(p, N, L, R, S, work, stream, gate);
     }
@@ -316,11 +318,16 @@ extern "C" int spuq_sg_pcg(spuq_sg_plan* A, spuq_sg_precond* P, const double* F,
             if ((rc = dot_impl(1, n, z, v, st + 8, scratch, stream, gate, &ea))) return rc;  // :41-45
             SPUQ_LAUNCH(k_axpy2, dim3(blas_grid(n, nsm, 256)), dim3(256), 0, stream, n, st + 0, st + 1,
                         v, Wv, z, rho, gate);                                                // :47-48
-            if ((rc = precond_apply_impl(P, N, L, rho, s, pwork, stream, gate))) return rc;  // :49
             // the last pass the loop may run (maxiter - 1) has no successor to test: the reference raises
             // "did not converge" without looking at its zeta
             const DotEpilogue ez{pass + 1 < maxiter ? DOT_EPI_ZETA : DOT_EPI_NONE, st, pass, hist, hist_cap};
-            if ((rc = dot_impl(1, n, rho, s, st + 9, scratch, stream, gate, &ez))) return rc;  // :50, :33-38
+            FusedDot fd{&ez, st + 9, false};
+            if ((rc = precond_apply_impl(P, N, L, rho, s, pwork, stream, gate, &fd))) return rc;  // :49
+            if (!fd.done) {
+                if ((rc = dot_impl(1, n, rho, s, st + 9, scratch, stream, gate, &ez))) return rc;  // :50, :33-38
+            } else {
+                launches -= 1;                                                                   // <rho, s> came with P rho
+            }
             SPUQ_LAUNCH(k_xpay, dim3(blas_grid(n, nsm, 256)), dim3(256), 0, stream, n, st + 3, (const double*)nullptr,
                         s, v, gate);                                                         // :51
             launches += 5 + A->last_launches - 1 + P->last_launches;

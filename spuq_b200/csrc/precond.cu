@@ -207,6 +207,10 @@ struct StripPlan {
     size_t smem_bytes = 0;
     double* sy_ipiv = nullptr;            // [q][nx] separator system per x-mode (transform order of the GEMM path)
     double* sy_off = nullptr;
+    double* partials = nullptr;           // fused-dot partials of the phase entry points (grown on demand)
+    int64_t partials_cap = 0;
+    unsigned int* ticket = nullptr;       // completion counter of the fused <R, S> (zero between launches)
+    size_t schur_smem = 0;                // > 0: the separator system runs as k_schur_fused with this much shared memory
 };
 
 // first column of (tridiag(o, b, o) of size n)^{-1}
@@ -266,6 +270,12 @@ static void strip_for_each_kernel(F f) {
     SPUQ_STRIP_K(0) SPUQ_STRIP_K(8) SPUQ_STRIP_K(12) SPUQ_STRIP_K(16) SPUQ_STRIP_K(20) SPUQ_STRIP_K(24)
     SPUQ_STRIP_K(26) SPUQ_STRIP_K(28) SPUQ_STRIP_K(32)
 #undef SPUQ_STRIP_K
+}
+template <typename F>
+static void schur_for_each_kernel(F f) {
+    f((const void*)k_schur_fused<4>); f((const void*)k_schur_fused<8>); f((const void*)k_schur_fused<12>);
+    f((const void*)k_schur_fused<16>); f((const void*)k_schur_fused<20>); f((const void*)k_schur_fused<24>);
+    f((const void*)k_schur_fused<28>); f((const void*)k_schur_fused<32>);
 }
 #endif
 
@@ -331,7 +341,7 @@ int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx) {
     } else {
         gheights = ylen;
     }
-    sv.nx = nx; sv.ny = ny; sv.ox = ox; sv.oy = oy;
+    sv.nx = nx; sv.ny = ny; sv.ld = (int64_t)nx * ny; sv.ox = ox; sv.oy = oy;
     sv.P = (int32_t)ystart.size(); sv.q = (int32_t)gheights.size() - 1;     // q: separators of the WHOLE grid
     sv.q_loc = sv.P - 1 + has_bottom; sv.has_bottom = has_bottom; sv.u_above0 = j0 - 1;
     sv.gf_ld = sv.P + has_bottom;
@@ -353,6 +363,7 @@ int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx) {
     if (sv.ch[0] == sv.ch[1]) sv.n_tall = sv.P;
     std::vector<int32_t> ycls(sv.P);
     for (int i = 0; i < sv.P; ++i) ycls[i] = ylen[i] == sv.ch[0] ? 0 : 1;
+    sp->ticket = strip_upload(sp, std::vector<unsigned int>(4, 0u));
     sv.ystart = strip_upload(sp, ystart); sv.ycls = strip_upload(sp, ycls);
     sv.xstart = strip_upload(sp, xstart); sv.xlen = strip_upload(sp, xlen);
     bool ok = sv.ystart && sv.ycls && sv.xstart && sv.xlen;
@@ -436,9 +447,26 @@ int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx) {
         cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     };
     strip_for_each_kernel(prep);
-    if (!attr_ok) { cudaGetLastError(); strip_plan_destroy(p); }
+    if (!attr_ok) { cudaGetLastError(); strip_plan_destroy(p); return SPUQ_OK; }
     cudaGetLastError();
 #endif
+    // the separator system in one kernel when a column's separator rows fit shared memory
+    {
+        const int32_t h = p->half;
+        const size_t need = sizeof(double) * (size_t)sv.q * 2 * (size_t)((h + 1) & ~1);
+        const char* e = std::getenv("SPUQ_SCHUR_PLAIN");                   // A/B switch (development)
+        if (h > 0 && nx == 2 * h && nx <= SCHUR_THREADS && sv.q >= 1 && sv.q <= SCHUR_RMAX && need <= 200 * 1024 &&
+            !(e && e[0] == '1')) {
+            sp->schur_smem = need;
+#ifndef SPUQ_EMU
+            bool s_ok = true;
+            schur_for_each_kernel([&](const void* fn) {
+                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) s_ok = false;
+            });
+            if (!s_ok) { cudaGetLastError(); sp->schur_smem = 0; }
+#endif
+        }
+    }
     return SPUQ_OK;
 }
 
@@ -446,47 +474,62 @@ int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx) {
 template <bool FINAL>
 static void strip_launch(int ct, const StripPlan* sp, const StripView& view, int32_t L, int32_t p_off, int32_t p_cnt,
                          const double* R, double* S, double* Gf, double* Gl, const double* U, cudaStream_t stream,
-                         const double* gate) {
+                         const double* gate, const StripDot& dot) {
     if (p_cnt <= 0) return;
     const dim3 grid((unsigned)((int64_t)L * p_cnt)), block(STRIP_THREADS);
 #define SPUQ_STRIP_L(c)                                                                                          \
     case c: SPUQ_LAUNCH((k_strip<FINAL, c>), grid, block, sp->smem_bytes, stream, sp->Q, view, L, p_off, p_cnt, \
-                        R, S, Gf, Gl, U, gate); break;
+                        R, S, Gf, Gl, U, gate, dot); break;
     switch (ct) {
         SPUQ_STRIP_L(8) SPUQ_STRIP_L(12) SPUQ_STRIP_L(16) SPUQ_STRIP_L(20) SPUQ_STRIP_L(24) SPUQ_STRIP_L(26)
         SPUQ_STRIP_L(28) SPUQ_STRIP_L(32)
         default: SPUQ_LAUNCH((k_strip<FINAL, 0>), grid, block, sp->smem_bytes, stream, sp->Q, view, L, p_off, p_cnt,
-                             R, S, Gf, Gl, U, gate);
+                             R, S, Gf, Gl, U, gate, dot);
     }
 #undef SPUQ_STRIP_L
 }
 
-// both passes over the strips: the main strips with the compile-time height, the rest generic
+// one pass over all strips of all columns: ONE launch (the kernel of the main strips' height also takes the
+// remainder strip through its generic branch)
 template <bool FINAL>
 static void strip_pass(const StripPlan* sp, const StripView& sv, int32_t L, const double* R, double* S, double* Gf, double* Gl,
-                       const double* U, cudaStream_t stream, const double* gate) {
-    const int main_ct = sp->main_ct;
-    if (main_ct > 0 && sv.n_tall > 0) {
-        strip_launch<FINAL>(main_ct, sp, sv, L, 0, sv.n_tall, R, S, Gf, Gl, U, stream, gate);
-        strip_launch<FINAL>(0, sp, sv, L, sv.n_tall, sv.P - sv.n_tall, R, S, Gf, Gl, U, stream, gate);
-    } else {
-        strip_launch<FINAL>(0, sp, sv, L, 0, sv.P, R, S, Gf, Gl, U, stream, gate);
-    }
+                       const double* U, cudaStream_t stream, const double* gate, const StripDot& dot = StripDot{}) {
+    strip_launch<FINAL>(sv.n_tall > 0 ? sp->main_ct : 0, sp, sv, L, 0, sv.P, R, S, Gf, Gl, U, stream, gate, dot);
 }
 template <bool FINAL>
 static void strip_pass(const StripPlan* sp, int32_t L, const double* R, double* S, double* Gf, double* Gl, const double* U,
-                       cudaStream_t stream, const double* gate) {
-    strip_pass<FINAL>(sp, sp->sv, L, R, S, Gf, Gl, U, stream, gate);
+                       cudaStream_t stream, const double* gate, const StripDot& dot = StripDot{}) {
+    strip_pass<FINAL>(sp, sp->sv, L, R, S, Gf, Gl, U, stream, gate, dot);
 }
 
 static int64_t strip_work_doubles(const StripPlan* sp, int32_t L) {
-    return (int64_t)L * sp->sv.nx * (2 * (int64_t)sp->sv.P + 2 * (int64_t)sp->sv.q);
+    // first / last rows of every strip, separator rows twice, one partial of the fused dot product per strip
+    return (int64_t)L * sp->sv.nx * (2 * (int64_t)sp->sv.P + 2 * (int64_t)sp->sv.q) + (int64_t)L * sp->sv.P + 8;
 }
 
 // separator system in place on Z (layout of sv.u_js / u_cs, q rows of L columns); Z2: scratch of the same size.
-// Returns the buffer that holds the solution.
+// R != null: the right-hand side is assembled from R, Gf, Gl first (one-GPU strips).  Returns the buffer that
+// holds the solution.
 static const double* strip_schur(spuq_sg_precond* p, const StripPlan* sp, const StripView& sv, int32_t L, double* Z, double* Z2,
-                                 cudaStream_t stream, const double* gate) {
+                                 cudaStream_t stream, const double* gate, const double* R = nullptr,
+                                 const double* Gf = nullptr, const double* Gl = nullptr) {
+    if (sp->schur_smem > 0) {
+        const dim3 grid((unsigned)L), block(SCHUR_THREADS);
+        const int rt = (sv.q + 3) / 4 * 4;
+#define SPUQ_SCHUR_L(r)                                                                                           \
+    case r: SPUQ_LAUNCH(k_schur_fused<r>, grid, block, sp->schur_smem, stream, sv, L, p->half, R != nullptr ? 1 : 0, \
+                        R, Gf, Gl, Z, p->qsplit_dev, sp->sy_ipiv, sp->sy_off, gate); break;
+        switch (rt) {
+            SPUQ_SCHUR_L(4) SPUQ_SCHUR_L(8) SPUQ_SCHUR_L(12) SPUQ_SCHUR_L(16) SPUQ_SCHUR_L(20) SPUQ_SCHUR_L(24)
+            SPUQ_SCHUR_L(28) SPUQ_SCHUR_L(32)
+        }
+#undef SPUQ_SCHUR_L
+        return Z;
+    }
+    if (R != nullptr) {
+        const unsigned eb = (unsigned)std::min<int64_t>(((int64_t)L * sv.q * sv.nx + 255) / 256, 1 << 20);
+        SPUQ_LAUNCH(k_sep_assemble, dim3(eb), dim3(256), 0, stream, sv, L, R, Gf, Gl, Z, gate);
+    }
     const int32_t nx = sv.nx, q = sv.q;
     const int64_t Mrows = (int64_t)L * q;
     auto rowgemm = [&](const double* src, double* dst, int32_t nk, int32_t nc, const double* Q) {
@@ -515,7 +558,7 @@ static const double* strip_schur(spuq_sg_precond* p, const StripPlan* sp, const 
 }
 
 static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
-                       cudaStream_t stream, const double* gate) {
+                       cudaStream_t stream, const double* gate, FusedDot* fd) {
     StripPlan* sp = static_cast<StripPlan*>(p->strip);
     const StripView& sv = sp->sv;
     const int32_t nx = sv.nx, q = sv.q;
@@ -530,11 +573,17 @@ static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
     const double* U = nullptr;
     if (q > 0) {
         strip_pass<false>(sp, L, R, S, Gf, Gl, nullptr, stream, gate);
-        const unsigned eb = (unsigned)std::min<int64_t>(((int64_t)L * q * nx + 255) / 256, 1 << 20);
-        SPUQ_LAUNCH(k_sep_assemble, dim3(eb), dim3(256), 0, stream, sv, L, R, Gf, Gl, Z, gate);
-        U = strip_schur(p, sp, sv, L, Z, Z2, stream, gate);
+        U = strip_schur(p, sp, sv, L, Z, Z2, stream, gate, R, Gf, Gl);
     }
-    strip_pass<true>(sp, L, R, S, Gf, Gl, U, stream, gate);
+    StripDot dot{};
+    if (fd != nullptr && sp->ticket != nullptr && work != nullptr) {
+        dot.partials = Z2 + (int64_t)L * q * nx;
+        dot.ticket = sp->ticket;
+        dot.out = fd->out;
+        dot.epi = *fd->epi;
+        fd->done = true;
+    }
+    strip_pass<true>(sp, L, R, S, Gf, Gl, U, stream, gate, dot);
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }
@@ -559,9 +608,9 @@ int64_t mean_fd_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L) {
 }
 
 int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
-                  cudaStream_t stream, const double* gate) {
+                  cudaStream_t stream, const double* gate, FusedDot* fd) {
     SPUQ_REQUIRE(N == (int64_t)p->nx * p->ny, "precond_mean_fd: slab rows %lld != nx*ny", (long long)N);
-    if (p->strip) return strip_apply(p, N, L, R, S, work, stream, gate);
+    if (p->strip) return strip_apply(p, N, L, R, S, work, stream, gate, fd);
     SPUQ_REQUIRE(work != nullptr, "precond_mean_fd: workspace missing");
     double* T = static_cast<double*>(work);
     const int64_t Mrows = (int64_t)L * p->ny;
@@ -778,9 +827,10 @@ extern "C" int spuq_sg_precond_mean_fd(spuq_sg_precond** out, int device, int32_
 static StripPlan* strip_of(spuq_sg_precond* p) {
     return (p && p->kind == spuq_sg_precond::MEAN_FD) ? static_cast<StripPlan*>(p->strip) : nullptr;
 }
-static StripView rows_view(const StripPlan* sp, int32_t L) {
+static StripView rows_view(const StripPlan* sp, int32_t L, int64_t ld = 0) {
     StripView v = sp->sv;
     v.u_js = (int64_t)L * v.nx; v.u_cs = v.nx;
+    if (ld > 0) v.ld = ld;
     return v;
 }
 
@@ -819,22 +869,27 @@ extern "C" int spuq_sg_precond_strip_info(const spuq_sg_precond* p, int32_t* n_s
     return SPUQ_OK;
 }
 
-// Gf / Gl [L][gf_ld][nx] <- first / last row of the local solution of every local strip
-extern "C" int spuq_sg_precond_strip_forward(spuq_sg_precond* p, int32_t L, const double* R, double* Gf, double* Gl, void* stream) {
+// Gf / Gl [L][gf_ld][nx] <- first / last row of the local solution of every local strip.
+// ld (here and below): column stride of R / S in doubles, 0 = nx * (rows of the band); R / S point at the
+// band's first row of column 0, so a band inside a halo-padded slab needs no copy.
+extern "C" int spuq_sg_precond_strip_forward(spuq_sg_precond* p, int32_t L, const double* R, int64_t ld, double* Gf, double* Gl,
+                                             void* stream) {
     StripPlan* sp = strip_of(p);
     SPUQ_REQUIRE(sp && R && Gf && Gl && L >= 0, "precond_strip_forward: bad argument");
-    const StripView v = rows_view(sp, L);
+    SPUQ_REQUIRE(ld == 0 || ld >= (int64_t)sp->sv.nx * sp->sv.ny, "precond_strip_forward: column stride shorter than the band");
+    const StripView v = rows_view(sp, L, ld);
     strip_pass<false>(sp, v, L, R, nullptr, Gf, Gl, nullptr, static_cast<cudaStream_t>(stream), abi_gate());
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }
 // rows first_sep .. first_sep + q_loc - 1 of Z <- right-hand sides of the local separators (slot gf_ld - 1 of Gf
 // holds the first strip of the next rank when the band ends in a separator)
-extern "C" int spuq_sg_precond_strip_assemble(spuq_sg_precond* p, int32_t L, const double* R, const double* Gf, const double* Gl,
-                                              double* Z, void* stream) {
+extern "C" int spuq_sg_precond_strip_assemble(spuq_sg_precond* p, int32_t L, const double* R, int64_t ld, const double* Gf,
+                                              const double* Gl, double* Z, void* stream) {
     StripPlan* sp = strip_of(p);
     SPUQ_REQUIRE(sp && R && Gf && Gl && Z && L >= 0, "precond_strip_assemble: bad argument");
-    const StripView v = rows_view(sp, L);
+    SPUQ_REQUIRE(ld == 0 || ld >= (int64_t)sp->sv.nx * sp->sv.ny, "precond_strip_assemble: column stride shorter than the band");
+    const StripView v = rows_view(sp, L, ld);
     if (v.q_loc == 0 || L == 0) return SPUQ_OK;
     const unsigned eb = (unsigned)std::min<int64_t>(((int64_t)L * v.q_loc * v.nx + 255) / 256, 1 << 20);
     SPUQ_LAUNCH(k_sep_assemble, dim3(eb), dim3(256), 0, static_cast<cudaStream_t>(stream), v, L, R, Gf, Gl, Z, abi_gate());
@@ -856,12 +911,31 @@ extern "C" int spuq_sg_precond_strip_schur(spuq_sg_precond* p, int32_t L, double
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }
-// S <- solution on the band's rows, given the separator values U [q_glob][L][nx] of the whole grid
-extern "C" int spuq_sg_precond_strip_final(spuq_sg_precond* p, int32_t L, const double* R, const double* U, double* S, void* stream) {
+// S <- solution on the band's rows, given the separator values U [q_glob][L][nx] of the whole grid.
+// dot_out != null: dot_out[0] <- <R, S> over the band (device scalar), produced by the same kernel.
+extern "C" int spuq_sg_precond_strip_final(spuq_sg_precond* p, int32_t L, const double* R, const double* U, double* S, int64_t ld,
+                                           double* dot_out, void* stream) {
     StripPlan* sp = strip_of(p);
     SPUQ_REQUIRE(sp && R && S && L >= 0 && (U || sp->sv.q == 0), "precond_strip_final: bad argument");
-    const StripView v = rows_view(sp, L);
-    strip_pass<true>(sp, v, L, R, S, nullptr, nullptr, U, static_cast<cudaStream_t>(stream), abi_gate());
+    SPUQ_REQUIRE(ld == 0 || ld >= (int64_t)sp->sv.nx * sp->sv.ny, "precond_strip_final: column stride shorter than the band");
+    const StripView v = rows_view(sp, L, ld);
+    StripDot dot{};
+    if (dot_out != nullptr) {
+        const int64_t need = (int64_t)L * v.P + 8;
+        if (sp->partials_cap < need) {                       // grows once per column count
+            SPUQ_CUDA_TRY(cudaSetDevice(p->device));
+            void* d = nullptr;
+            SPUQ_CUDA_TRY(cudaMalloc(&d, sizeof(double) * need));
+            sp->dev.push_back(d);                            // the old buffer (if any) is freed with the plan: a launch may still read it
+            sp->partials = static_cast<double*>(d);
+            sp->partials_cap = need;
+        }
+        dot.partials = sp->partials;
+        dot.ticket = sp->ticket;
+        dot.out = dot_out;
+        dot.epi = DotEpilogue{DOT_EPI_NONE, nullptr, 0, nullptr, 0};
+    }
+    strip_pass<true>(sp, v, L, R, S, nullptr, nullptr, U, static_cast<cudaStream_t>(stream), abi_gate(), dot);
     SPUQ_CUDA_TRY(cudaGetLastError());
     return SPUQ_OK;
 }

@@ -40,11 +40,19 @@ int64_t lu_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L);
 int lu_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work, cudaStream_t stream,
              const double* gate);
 int64_t mean_fd_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L);
-int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
-                  cudaStream_t stream, const double* gate);
-int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S,
-                       void* work, cudaStream_t stream, const double* gate);
 struct DotEpilogue;
+// A caller that needs <R, S> right after S = P R (pcg.py:49-50) offers the reduction to the preconditioner:
+// a path that can produce it while it writes S (the strip solver's final pass) sets `done`; otherwise the
+// caller launches its own dot product.
+struct FusedDot {
+    const DotEpilogue* epi;
+    double* out;
+    bool done;
+};
+int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
+                  cudaStream_t stream, const double* gate, FusedDot* fd = nullptr);
+int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S,
+                       void* work, cudaStream_t stream, const double* gate, FusedDot* fd = nullptr);
 int dot_impl(int nout, int64_t n, const double* x, const double* y, double* out, void* scratch,
              cudaStream_t stream, const double* gate, const DotEpilogue* epi = nullptr);
 }

@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "common.h"
+#include "reduce_common.cuh"
 #include "precond.h"
 
 namespace spuq {
@@ -46,6 +47,7 @@ constexpr int STRIP_CX = 32;          // longest x-chunk (registers of the chunk
 // Device view of the strip plan (passed by value).
 struct StripView {
     int32_t nx, ny, P, q;             // P strips, q = P - 1 separator rows
+    int64_t ld;                       // column stride of R and S in doubles (nx * ny, or more: a band inside a halo-padded slab)
     int32_t PX, qx;                   // x-chunks per row, x-separators (= PX - 1)
     int32_t cxmax;                    // longest chunk
     double ox, oy;
@@ -171,13 +173,69 @@ __device__ __forceinline__ void strip_ytransform_ct(const StripQ& Q, const doubl
 // One strip of one slab column.  FINAL = false: Gf/Gl <- first / last row of A_strip^{-1} R_strip.
 // FINAL = true: S_strip <- A_strip^{-1} (R_strip - oy * separator values on the adjacent rows), and the
 // separator row below the strip is copied from U.
-// CT > 0: every strip of the launch has height CT (class 0); CT = 0: heights from the plan (any <= 32).
+// CT > 0: the main strips (the first n_tall of a column, class 0) have height CT and take the compile-time
+// transform, the remainder strip goes through the generic code of the same kernel (block-uniform branch), so a
+// pass over the grid is ONE launch; CT = 0: all heights from the plan (any <= 32).
 // The launch covers strips p_off .. p_off + p_cnt - 1 of every column.
+// dot.partials != null (FINAL only): the kernel also leaves <R, S> in dot.out -- every CTA one partial (the
+// strip's right-hand side is read a second time, from L2 as a rule: it was loaded by this CTA a few microseconds
+// earlier), the last CTA to finish adds them in index order and runs the PCG epilogue of k_dot.
+struct StripDot {
+    double* partials;          // one per CTA of the launch; null: no dot
+    unsigned int* ticket;      // zero before the launch, reset by the last CTA
+    double* out;
+    DotEpilogue epi;
+};
+
+// Sum of `v` over the CTA -> dot.partials[blockIdx.x]; the last CTA of the launch adds all partials in index
+// order (fixed order: the result does not depend on the scheduling), stores the sum and runs the epilogue.
+__device__ __forceinline__ void strip_dot_finish(const StripDot& dot, double v) {
+#ifdef SPUQ_EMU
+    // one emulated thread per block, blocks in order: the running sum lives in partials[0]
+    if (blockIdx.x == 0) dot.partials[0] = 0.0;
+    dot.partials[0] += v;
+    if (blockIdx.x == gridDim.x - 1) { dot.out[0] = dot.partials[0]; dot_epilogue(dot.epi, dot.partials[0]); }
+#else
+    __shared__ double sh[STRIP_THREADS / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < STRIP_THREADS / 32; ++w) a += sh[w];
+        dot.partials[blockIdx.x] = a;
+        __threadfence();
+        is_last = atomicAdd(dot.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double a = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += STRIP_THREADS) a += __ldcg(dot.partials + i);
+    a = warp_sum(a);
+    __syncthreads();
+    if (lane == 0) sh[wid] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < STRIP_THREADS / 32; ++w) t += sh[w];
+        dot.out[0] = t;
+        dot_epilogue(dot.epi, t);
+        *dot.ticket = 0u;
+    }
+#endif
+}
+
 template <bool FINAL, int CT>
 __global__ void __launch_bounds__(STRIP_THREADS, 2)
 k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off, int32_t p_cnt,
         const double* __restrict__ R, double* __restrict__ S,
-        double* __restrict__ Gf, double* __restrict__ Gl, const double* __restrict__ U, const double* gate) {
+        double* __restrict__ Gf, double* __restrict__ Gl, const double* __restrict__ U, const double* gate,
+        StripDot dot) {
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
 #ifdef SPUQ_EMU
     if (threadIdx.x != 0) return;
@@ -192,14 +250,17 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
     if (col >= L) return;
     // class, height and first row from the parameters alone (no table look-up): warp-uniform values, so the
     // transform-matrix addresses below are uniform too
-    const int cls = CT > 0 ? 0 : ((p < sv.n_tall) ? 0 : 1);
-    const int c = CT > 0 ? CT : sv.ch[cls];
+    const bool tall = p < sv.n_tall;
+    const bool ct_path = CT > 0 && tall;                // block-uniform
+    const int cls = tall ? 0 : 1;
+    const int c = ct_path ? CT : sv.ch[cls];
     const int y0 = (p < sv.n_tall) ? p * (sv.ch[0] + 1) : sv.n_tall * (sv.ch[0] + 1) + (p - sv.n_tall) * (sv.ch[1] + 1);
     const double* qc = Q.q[cls];                        // [c][HP], constant bank
     double* sepv = smem;                                // [c][qx]
     double* strip = sepv + STRIP_CMAX * (sv.qx > 0 ? sv.qx : 1);   // [c][nx]
-    const int64_t N = (int64_t)nx * sv.ny;
+    const int64_t N = sv.ld;
     const double* src = R + col * N + (int64_t)y0 * nx;
+    double dsep = 0.0;                                  // <R, S> on the separator row below the strip (FINAL, dot)
 
     // ---- phase 0: strip and transform matrix into shared memory ------------------------------------
 #ifndef SPUQ_EMU
@@ -238,7 +299,13 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
         // separator row below this strip
         if (has_b) {
             double* dst = S + col * N + (int64_t)(y0 + c) * nx;
-            for (int x = STRIP_T0; x < nx; x += STRIP_TS) dst[x] = ub[x];
+            const double* rs = R + col * N + (int64_t)(y0 + c) * nx;
+            const bool with_dot = dot.partials != nullptr;
+            for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
+                const double u = ub[x];
+                if (with_dot) dsep = fma(u, rs[x], dsep);
+                dst[x] = u;
+            }
         }
     }
     STRIP_SYNC();
@@ -246,7 +313,7 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
     // ---- phase 1: sine transform along y, one thread per grid column -------------------------------
     for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
         auto put = [&](int j, double a) { strip[(size_t)j * nx + x] = a; };
-        if (CT > 0) strip_ytransform_ct<(CT > 0 ? CT : 1)>(Q, strip + x, nx, put);
+        if (ct_path) strip_ytransform_ct<(CT > 0 ? CT : 1)>(Q, strip + x, nx, put);
         else strip_ytransform(qc, strip + x, nx, c, put);
     }
     STRIP_SYNC();
@@ -326,11 +393,17 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
     // ---- phase 3: transform back -------------------------------------------------------------------
     if (FINAL) {
         double* dst = S + col * N + (int64_t)y0 * nx;
+        const bool with_dot = dot.partials != nullptr;
+        double dsum = 0.0;
         for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
-            auto put = [&](int j, double a) { dst[(size_t)j * nx + x] = a; };
-            if (CT > 0) strip_ytransform_ct<(CT > 0 ? CT : 1)>(Q, strip + x, nx, put);
+            auto put = [&](int j, double a) {
+                if (with_dot) dsum = fma(a, src[(size_t)j * nx + x], dsum);      // before the store: R and S may alias
+                dst[(size_t)j * nx + x] = a;
+            };
+            if (ct_path) strip_ytransform_ct<(CT > 0 ? CT : 1)>(Q, strip + x, nx, put);
             else strip_ytransform(qc, strip + x, nx, c, put);
         }
+        if (with_dot) strip_dot_finish(dot, dsum + dsep);
     } else {
         double* gf = Gf + (col * sv.gf_ld + p) * nx;
         double* gl = Gl + (col * sv.gf_ld + p) * nx;
@@ -356,7 +429,7 @@ k_sep_assemble(StripView sv, int32_t L, const double* __restrict__ R, const doub
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
     const int nx = sv.nx, q = sv.q_loc;
     const int64_t total = (int64_t)L * q * nx;
-    const int64_t N = (int64_t)nx * sv.ny;
+    const int64_t N = sv.ld;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int x = (int)(t % nx);
         const int64_t r = t / nx;
@@ -391,6 +464,140 @@ k_thomas_sep(int32_t nx, int32_t q, int32_t L, int64_t js, int64_t cs, const dou
         u = (x[(int64_t)j * js] - off[(int64_t)j * nx + k] * u) * ipiv[(int64_t)j * nx + k];
         x[(int64_t)j * js] = u;
     }
+}
+
+// ---- separator system in ONE kernel --------------------------------------------------------------------------
+// One CTA per slab column keeps the q separator rows of that column (q * nx doubles, 72 KB on configuration 4)
+// in shared memory from the right-hand side to the solution: mirror split, transform to the sine modes of
+// length nx, the q x q tridiagonal solve of every mode, transform back, mirror merge.  Thread t owns transform
+// column t (even modes first, then odd: the order of the sy_ipiv / sy_off tables) with its q accumulators in
+// registers, so the tridiagonal solve along the separators never leaves the register file; the only traffic
+// besides the q rows is the transform matrix (4 * (nx/2)^2 doubles per column, streamed from L2, coalesced
+// across the threads).  Replaces eight launches (assembly, split, four GEMMs, Thomas, merge) and the
+// Z <-> Z2 round trips; conditions: nx even, nx <= SCHUR_THREADS, q <= 32, q rows fit shared memory.
+constexpr int SCHUR_THREADS = 512;
+constexpr int SCHUR_RMAX = 32;
+
+// acc[r] = sum_i F[r][i] * Qm[i][c] for the rows r < q (F: shared memory, row pitch ps, 16-byte aligned rows)
+template <int RT>
+__device__ __forceinline__ void schur_half_product(const double* __restrict__ F, int ps, int h, int q,
+                                                   const double* __restrict__ Qm, int c, double* acc) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r] = 0.0;
+    int i = 0;
+#pragma unroll 4
+    for (; i + 1 < h; i += 2) {
+        const double q0 = __ldg(Qm + (size_t)i * h + c), q1 = __ldg(Qm + (size_t)(i + 1) * h + c);
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            if (r < q) {
+                const double2 f = *reinterpret_cast<const double2*>(F + (size_t)r * ps + i);
+                acc[r] = fma(f.x, q0, acc[r]);
+                acc[r] = fma(f.y, q1, acc[r]);
+            }
+        }
+    }
+    if (i < h) {
+        const double q0 = __ldg(Qm + (size_t)i * h + c);
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+            if (r < q) acc[r] = fma(F[(size_t)r * ps + i], q0, acc[r]);
+    }
+}
+
+// assemble != 0: the right-hand side is formed here from R, Gf, Gl (what k_sep_assemble writes; one-GPU layout of
+// the strips, u_above0 = -1); else it is read from Z.  The solution is written to Z (layout sv.u_js / sv.u_cs).
+template <int RT>
+__global__ void __launch_bounds__(SCHUR_THREADS, 1)
+k_schur_fused(StripView sv, int32_t L, int32_t h, int32_t assemble, const double* __restrict__ R,
+              const double* __restrict__ Gf, const double* __restrict__ Gl, double* __restrict__ Z,
+              const double* __restrict__ qsplit, const double* __restrict__ ipiv, const double* __restrict__ off,
+              const double* gate) {
+    if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
+    const int nx = sv.nx, q = sv.q;
+    const int hp2 = (h + 1) & ~1, ps = 2 * hp2;       // sums in [0, h), differences in [hp2, hp2 + h) of a row
+#ifdef SPUQ_EMU
+    if (threadIdx.x != 0) return;
+    std::vector<double> smem_store((size_t)q * ps), hold((size_t)(nx + 1) * RT);
+    double* buf = smem_store.data();
+    double* acc = nullptr;
+#define SCHUR_FOR_T for (int t = 0; (acc = &hold[(size_t)t * RT], t < nx); ++t)     // acc: the "registers" of emulated thread t
+#else
+    extern __shared__ __align__(16) double smem[];
+    double* buf = smem;
+    double acc[RT];
+    const int t = (int)threadIdx.x;                       // nx <= blockDim.x: one transform column per thread
+#define SCHUR_FOR_T if (t < nx)
+#endif
+    const int64_t col = blockIdx.x;
+    if (col >= L) return;
+    const int64_t N = sv.ld;
+    const size_t hh = (size_t)h * h;
+
+    // ---- right-hand side, split into mirror sums and differences ------------------------------------------
+    for (int e = STRIP_T0; e < q * h; e += STRIP_TS) {
+        const int j = e / h, i = e - j * h, i2 = nx - 1 - i;
+        double a, b;
+        if (assemble) {
+            const int ys = sv.ystart[j] + sv.ch[sv.ycls[j]];
+            const double* rr = R + col * N + (int64_t)ys * nx;
+            const double* gl = Gl + (col * sv.gf_ld + j) * nx;
+            const double* gf = Gf + (col * sv.gf_ld + j + 1) * nx;
+            a = rr[i] - sv.oy * (gl[i] + gf[i]);
+            b = rr[i2] - sv.oy * (gl[i2] + gf[i2]);
+        } else {
+            const double* z = Z + (int64_t)j * sv.u_js + col * sv.u_cs;
+            a = z[i]; b = z[i2];
+        }
+        buf[(size_t)j * ps + i] = a + b;
+        buf[(size_t)j * ps + hp2 + i] = a - b;
+    }
+    STRIP_SYNC();
+    // ---- to the modes, tridiagonal solve along the separators in registers -----------------------------------
+    SCHUR_FOR_T {
+        const int par = t >= h ? 1 : 0, c0 = t - par * h;
+        schur_half_product<RT>(buf + par * hp2, ps, h, q, qsplit + par * hh, c0, acc);
+        // the arithmetic of k_thomas_sep
+        double z = acc[0];
+#pragma unroll
+        for (int j = 1; j < RT; ++j)
+            if (j < q) { z = acc[j] - __ldg(off + (size_t)(j - 1) * nx + t) * __ldg(ipiv + (size_t)(j - 1) * nx + t) * z; acc[j] = z; }
+        double u = 0.0;
+#pragma unroll
+        for (int j = RT - 1; j >= 0; --j) {
+            if (j == q - 1) { u = acc[j] * __ldg(ipiv + (size_t)j * nx + t); acc[j] = u; }
+            else if (j < q - 1) { u = (acc[j] - __ldg(off + (size_t)j * nx + t) * u) * __ldg(ipiv + (size_t)j * nx + t); acc[j] = u; }
+        }
+    }
+    STRIP_SYNC();
+    SCHUR_FOR_T {
+        const int par = t >= h ? 1 : 0, c0 = t - par * h;
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+            if (r < q) buf[(size_t)r * ps + par * hp2 + c0] = acc[r];
+    }
+    STRIP_SYNC();
+    // ---- back to the grid -------------------------------------------------------------------------------------
+    SCHUR_FOR_T {
+        const int par = t >= h ? 1 : 0, c0 = t - par * h;
+        schur_half_product<RT>(buf + par * hp2, ps, h, q, qsplit + (2 + par) * hh, c0, acc);
+    }
+    STRIP_SYNC();
+    SCHUR_FOR_T {
+        const int par = t >= h ? 1 : 0, c0 = t - par * h;
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+            if (r < q) buf[(size_t)r * ps + par * hp2 + c0] = acc[r];
+    }
+    STRIP_SYNC();
+    for (int e = STRIP_T0; e < q * h; e += STRIP_TS) {
+        const int j = e / h, i = e - j * h;
+        const double pp = buf[(size_t)j * ps + i], mm = buf[(size_t)j * ps + hp2 + i];
+        double* z = Z + (int64_t)j * sv.u_js + col * sv.u_cs;
+        z[i] = pp + mm;
+        z[nx - 1 - i] = pp - mm;
+    }
+#undef SCHUR_FOR_T
 }
 
 }  // namespace spuq

@@ -490,14 +490,26 @@ class StripRowsMeanSolver:
                           mk(self.world, max(self.q_max, 1), L, self.nx), mk(L, self.nx), mk(L, self.nx))
         return self._bufs[1:]
 
-    def solve(self, Rc, Sc):
-        """Rc, Sc: contiguous L x (n_loc * nx) slabs of the owned rows; Sc = (A_0^{-1} R) restricted to them."""
+    def solve(self, Rc, Sc, dot_out=None):
+        """Sc = (A_0^{-1} R) restricted to the owned rows.  Rc, Sc: L x (n_loc * nx) slabs of the owned rows, or
+        L x n_loc x nx VIEWS of them inside halo-padded slabs (rows and grid columns contiguous, any column
+        stride): the kernels take the stride, nothing is copied.  ``dot_out`` (device scalar, one element):
+        receives <R, S> over the band, computed by the final strip pass itself."""
         lib = _abi.lib()
         L = Rc.shape[0]
-        assert Rc.is_contiguous() and Sc.is_contiguous() and Rc.shape == (L, self.n_loc * self.nx) == Sc.shape
+        ld = 0
+        for T in (Rc, Sc):
+            if T.dim() == 3:
+                assert T.shape == (L, self.n_loc, self.nx) and T.stride(2) == 1 and T.stride(1) == self.nx
+                ld = ld or int(T.stride(0))
+                assert ld == int(T.stride(0)), "R and S must share their column stride"
+            else:
+                assert T.is_contiguous() and T.shape == (L, self.n_loc * self.nx)
+        if ld:
+            assert Rc.dim() == 3 and Sc.dim() == 3, "R and S must both be views when one is"
         Gf, Gl, Z, Z2, gath, snd, rcv = self._buffers(L, Rc)
         st = _abi.stream_ptr()
-        _abi.check(lib.spuq_sg_precond_strip_forward(self.handle, L, _abi.ptr(Rc), _abi.ptr(Gf), _abi.ptr(Gl), st), "strip_forward")
+        _abi.check(lib.spuq_sg_precond_strip_forward(self.handle, L, _abi.ptr(Rc), ld, _abi.ptr(Gf), _abi.ptr(Gl), st), "strip_forward")
         if self.world > 1:
             ops = []
             if self.rank > 0:
@@ -511,7 +523,7 @@ class StripRowsMeanSolver:
                 Gf[:, self.gf_ld - 1, :].copy_(rcv)
         U_ptr = _abi.ptr(Z)
         if self.q_glob > 0:
-            _abi.check(lib.spuq_sg_precond_strip_assemble(self.handle, L, _abi.ptr(Rc), _abi.ptr(Gf), _abi.ptr(Gl), _abi.ptr(Z), st),
+            _abi.check(lib.spuq_sg_precond_strip_assemble(self.handle, L, _abi.ptr(Rc), ld, _abi.ptr(Gf), _abi.ptr(Gl), _abi.ptr(Z), st),
                        "strip_assemble")
         if self.q_glob > 0 and self.schur == "sharded":
             U_loc, a_me = self._schur_sharded(Z, L)
@@ -534,7 +546,8 @@ class StripRowsMeanSolver:
                     if cnt and r_ != self.rank:
                         Z[f0:f0 + cnt].copy_(gath[r_, :cnt])
             _abi.check(lib.spuq_sg_precond_strip_schur(self.handle, L, _abi.ptr(Z), _abi.ptr(Z2), st), "strip_schur")
-        _abi.check(lib.spuq_sg_precond_strip_final(self.handle, L, _abi.ptr(Rc), U_ptr, _abi.ptr(Sc), st), "strip_final")
+        _abi.check(lib.spuq_sg_precond_strip_final(self.handle, L, _abi.ptr(Rc), U_ptr, _abi.ptr(Sc), ld, _abi.ptr(dot_out), st),
+                   "strip_final")
         return Sc
 
     def _schur_sharded(self, Z, L):
@@ -644,12 +657,13 @@ class RowShardedPCG:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
 
-    def precondition(self, R, S):
-        """S = A_0^{-1} R on the owned rows (halo rows of S zero)."""
+    def precondition(self, R, S, dot_out=None):
+        """S = A_0^{-1} R on the owned rows (halo rows of S zero).  ``dot_out`` (device scalar): receives the
+        local <R, S> when the solver can produce it on the way (returns True then, else False / S)."""
         if self.mean_stencil is None:
             S.copy_(R)
             self._zero_halos(S)
-            return S
+            return False if dot_out is not None else S
         L = R.shape[0]
         dev = R.device
         if self.mean_solver in ("partition", "strip"):
@@ -662,14 +676,18 @@ class RowShardedPCG:
                 if self._partition is None:
                     self._partition = PartitionedMeanSolver(self.nx, self.ny, self.ranges, self.rank, self.mean_stencil, self.group)
             R3 = R.view(L, self.nyl, self.nx)
-            Rc = R3[:, 1:-1, :].contiguous().view(L, -1)
-            Sc = torch.empty_like(Rc)
-            self._partition.solve(Rc, Sc)
             S3 = S.view(L, self.nyl, self.nx)
             S3[:, 0, :].zero_()
             S3[:, self.nyl - 1, :].zero_()
+            if isinstance(self._partition, StripRowsMeanSolver):
+                # the strip kernels work on the band where it lies inside the halo-padded slabs
+                self._partition.solve(R3[:, 1:-1, :], S3[:, 1:-1, :], dot_out=dot_out)
+                return True if dot_out is not None else S
+            Rc = R3[:, 1:-1, :].contiguous().view(L, -1)
+            Sc = torch.empty_like(Rc)
+            self._partition.solve(Rc, Sc)
             S3[:, 1:-1, :].copy_(Sc.view(L, self.nyl - 2, self.nx))
-            return S
+            return False if dot_out is not None else S
         c0, c1 = self._col_range(self.rank, L)
         if self._solver is None:
             d, ox, oy = self.mean_stencil
@@ -682,7 +700,7 @@ class RowShardedPCG:
             self._solver.apply_slab(Rc, Sc)
             S3.zero_()
             S3[:, 1:-1, :].copy_(Sc.view(L, self.ny, self.nx))
-            return S
+            return False if dot_out is not None else S
         own = self.y1 - self.y0
         send = [R3[q0:q1, 1:-1, :].contiguous() for q0, q1 in (self._col_range(q, L) for q in range(self.world))]
         recv = [torch.empty((c1 - c0, r1 - r0, self.nx), dtype=R.dtype, device=dev) for r0, r1 in self.ranges]
@@ -701,7 +719,7 @@ class RowShardedPCG:
         for q, blk in enumerate(got):
             q0, q1 = self._col_range(q, L)
             S3[q0:q1, 1:-1, :].copy_(blk)
-        return S
+        return False if dot_out is not None else S
 
     # ---- the solver ----------------------------------------------------------------------------
     def solve(self, plan, F, W0, eps=1e-4, maxiter=100, poll_every=8):
@@ -758,8 +776,12 @@ class RowShardedPCG:
                     _abi.check(lib.spuq_sg_pcg_check_alpha(_abi.ptr(st), stream()), "check_alpha")                      # :42-45
                     _abi.check(lib.spuq_sg_axpy2(n, sp(0), sp(1), _abi.ptr(v), _abi.ptr(W), _abi.ptr(z), _abi.ptr(rho),
                                                  stream()), "axpy2")                                                   # :47-48
-                    self.precondition(rho, s)             # (:49)
-                    dot_to(rho, s, 2, 10)                 # zeta_new = <rho, s> (:50)
+                    if self.precondition(rho, s, dot_out=st[10:11]):      # (:49) with the local <rho, s> (:50)
+                        if self.world > 1:
+                            dist.all_reduce(st[10:11], op=dist.ReduceOp.SUM, group=self.group)
+                        _abi.check(lib.spuq_sg_pcg_accept(_abi.ptr(st), 10, 2, stream()), "pcg_accept")
+                    else:
+                        dot_to(rho, s, 2, 10)             # zeta_new = <rho, s> (:50)
                     _abi.check(lib.spuq_sg_xpay(n, sp(2), sp(0), _abi.ptr(s), _abi.ptr(v), stream()), "xpay")            # :51
                     _abi.check(lib.spuq_sg_pcg_rotate(_abi.ptr(st), stream()), "rotate")
                 i = stop

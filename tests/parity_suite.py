@@ -850,6 +850,10 @@ def check_mean_preconditioner():
         solver.apply_slab(Rt, Rt)                                   # in place (input and output alias)
         err = np.max(np.linalg.norm(Rt.cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1))
         assert err <= 1e-12, (nx, ny, err, "in place")
+        if (nx, ny) in ((70, 75), (64, 34), (100, 133)):
+            # strips + the separator system in ONE kernel: forward and final pass (main strips + remainder strip
+            # each) and k_schur_fused
+            assert _abi.lib().spuq_sg_precond_last_launches(solver.handle) <= 5, (nx, ny)
     with pytest.raises(_abi.SpuqError, match="constant-coefficient"):
         MeanSolveSlabOperator(sps.csr_matrix(sps.diags([np.arange(1.0, 10.0)], [0])), 1)
 
@@ -951,6 +955,11 @@ def check_pcg_sg_mean(n=12, M=3, p=2, eps=1e-10):
     assert np.max(np.abs(x.to_array() - x_o.to_slab())) <= 1e-8
     assert np.max(np.abs(x.to_array() - c.W)) <= 1e-7
     assert it <= 30                                       # mean-based preconditioning: few iterations
+    # a pass: apply, <z,v>, the w / rho update, strips forward, separator system, strips final (+ <rho,s>),
+    # the direction update -- seven launches (six when the grid is a single strip); the solve's count
+    # includes ~8 for the start-up
+    launches = A.plan_for(f).last_launches
+    assert launches <= 10 + 7 * it, (launches, it)
     # the preconditioner as a stand-alone operator: P * f, host containers too
     s = P * f
     lu_ref = (P_o * f_o).to_slab()

@@ -147,6 +147,7 @@ def test_mean_preconditioner():
 
 def test_pcg_sg_mean():
     ps.check_pcg_sg_mean()
+    ps.check_pcg_sg_mean(n=40, M=2, p=2)          # several strips: fused separator system and <rho,s>
 
 
 def test_sparse_lu_preconditioner():

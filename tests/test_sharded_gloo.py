@@ -202,6 +202,17 @@ def _strip_rows_worker(rank, world, port, out_path):
                 for _ in range(2):                                 # second call: buffers reused
                     solver.solve(Rc, Sc)
                 worst = max(worst, float(np.max(np.abs(Sc.numpy() - ref)) / np.max(np.abs(ref))))
+                # the band where it lies inside halo-padded slabs (no copy), with <R, S> from the final pass
+                n_loc = r1 - r0
+                Rp = torch.full((L, n_loc + 2, nx), 7.0, dtype=torch.float64)
+                Sp = torch.full((L, n_loc + 2, nx), -3.0, dtype=torch.float64)
+                Rp[:, 1:-1, :] = Rc.view(L, n_loc, nx)
+                d = torch.zeros(1, dtype=torch.float64)
+                solver.solve(Rp[:, 1:-1, :], Sp[:, 1:-1, :], dot_out=d)
+                worst = max(worst, float(np.max(np.abs(Sp[:, 1:-1, :].reshape(L, -1).numpy() - ref)) / np.max(np.abs(ref))))
+                assert float(Sp[:, 0, :].min()) == -3.0 == float(Sp[:, -1, :].max())       # halo rows untouched
+                dref = float(np.sum(Rc.numpy() * ref))
+                worst = max(worst, abs(float(d[0]) - dref) / abs(dref))
         t = torch.tensor([worst], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
