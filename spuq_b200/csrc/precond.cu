@@ -263,6 +263,13 @@ static T* strip_upload(StripPlan* sp, const std::vector<T>& h) {
     return static_cast<T*>(d);
 }
 
+// instantiated separator counts: two transform columns per thread up to SCHUR_R2MAX rows, one beyond
+#define SPUQ_SCHUR_FOR_EACH(X) X(4, 2) X(8, 2) X(12, 2) X(16, 2) X(18, 2) X(20, 2) X(22, 2) X(24, 2) X(28, 1) X(32, 1)
+static int schur_rows_for(int q) {
+    static const int rows[] = {4, 8, 12, 16, 18, 20, 22, 24, 28, 32};
+    for (int r : rows) if (q <= r) return r;
+    return 0;
+}
 #ifndef SPUQ_EMU
 template <typename F>
 static void strip_for_each_kernel(F f) {
@@ -273,9 +280,9 @@ static void strip_for_each_kernel(F f) {
 }
 template <typename F>
 static void schur_for_each_kernel(F f) {
-    f((const void*)k_schur_fused<4>); f((const void*)k_schur_fused<8>); f((const void*)k_schur_fused<12>);
-    f((const void*)k_schur_fused<16>); f((const void*)k_schur_fused<20>); f((const void*)k_schur_fused<24>);
-    f((const void*)k_schur_fused<28>); f((const void*)k_schur_fused<32>);
+#define SPUQ_SCHUR_K(r, c) f((const void*)k_schur_fused<r, c>);
+    SPUQ_SCHUR_FOR_EACH(SPUQ_SCHUR_K)
+#undef SPUQ_SCHUR_K
 }
 #endif
 
@@ -314,12 +321,22 @@ int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx) {
     if (const char* e = std::getenv("SPUQ_PRECOND_PLAIN")) { if (e[0] == '1') return SPUQ_OK; }   // A/B switch (development)
     const double pi = 3.14159265358979323846;
     const double dxx = 0.5 * p->d, dyy = 0.5 * p->d, ox = p->ox, oy = p->oy;
-    // strip height: two CTAs per SM when that still allows >= 12 rows, else one
+    // x-chunks: preferably chunks of 32 at a pitch of 33 when that makes 16 (or 32, ...) chunks per row: with the
+    // rows at a pitch that is a multiple of 16 doubles, the 16 lanes of a half-warp that sweep consecutive chunks
+    // then sit on 16 different bank pairs even when they straddle two rows (nx = 500, 512: 16 chunks).  Otherwise
+    // chunks of 30 at a pitch of 31 (odd: no conflicts inside a row).
     std::vector<int32_t> ystart, ylen, xstart, xlen;
-    partition_chunks(nx, 30, &xstart, &xlen);
-    const size_t fixed = sizeof(double) * (size_t)STRIP_CMAX * std::max<size_t>(xstart.size() - 1, 1);
-    auto rows_for = [&](size_t budget) { return budget > fixed ? (int)((budget - fixed) / (sizeof(double) * (size_t)nx)) : 0; };
-    int cap = std::min(STRIP_CMAX, rows_for(112 * 1024));
+    partition_chunks(nx, 32, &xstart, &xlen);
+    int32_t spitch = nx;
+    if (xstart.size() % 16 == 0 && !std::getenv("SPUQ_STRIP_PITCH31")) spitch = (nx + 15) / 16 * 16;
+    else partition_chunks(nx, 30, &xstart, &xlen);
+    const int qx_ = (int)xstart.size() - 1;
+    // strip height: two CTAs per SM when that still allows >= 12 rows, else one.  Per row of the strip: sp doubles
+    // and its x-separator values (odd pitch, see the kernel)
+    const size_t per_row = sizeof(double) * ((size_t)spitch + (size_t)(qx_ | 1));
+    auto rows_for = [&](size_t budget) { return (int)((budget - 64) / per_row); };
+    // 228 KB per SM, 1 KB reserved per CTA: two CTAs have 113 KB each
+    int cap = std::min(STRIP_CMAX, rows_for(113 * 1024));
     if (cap < 12) cap = std::min(STRIP_CMAX, rows_for(224 * 1024));
     if (cap < 2) return SPUQ_OK;                          // grid too wide for shared memory: plain path
     StripPlan* sp = new StripPlan();
@@ -341,13 +358,13 @@ int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx) {
     } else {
         gheights = ylen;
     }
-    sv.nx = nx; sv.ny = ny; sv.ld = (int64_t)nx * ny; sv.ox = ox; sv.oy = oy;
+    sv.nx = nx; sv.ny = ny; sv.sp = spitch; sv.ld = (int64_t)nx * ny; sv.ox = ox; sv.oy = oy;
     sv.P = (int32_t)ystart.size(); sv.q = (int32_t)gheights.size() - 1;     // q: separators of the WHOLE grid
     sv.q_loc = sv.P - 1 + has_bottom; sv.has_bottom = has_bottom; sv.u_above0 = j0 - 1;
     sv.gf_ld = sv.P + has_bottom;
     sv.u_js = nx; sv.u_cs = (int64_t)sv.q * nx;          // one-GPU layout; the phase entry points set their own
     sv.PX = (int32_t)xstart.size(); sv.qx = sv.PX - 1;
-    if (sv.qx > 64) { delete sp; return SPUQ_OK; }
+    if (sv.qx > STRIP_QXMAX) { delete sp; return SPUQ_OK; }
     sv.cxmax = *std::max_element(xlen.begin(), xlen.end());
     if (sv.cxmax > STRIP_CX) { delete sp; return ctx ? SPUQ_E_UNSUPPORTED : SPUQ_OK; }
     sv.ch[0] = ylen.front(); sv.ch[1] = ylen.back();     // heights h+1 (first strips) and h
@@ -436,7 +453,8 @@ int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx) {
         sp->sy_ipiv = strip_upload(sp, ip); sp->sy_off = strip_upload(sp, of);
         ok = ok && sp->sy_ipiv && sp->sy_off;
     }
-    sp->smem_bytes = sizeof(double) * ((size_t)STRIP_CMAX * std::max(qx, 1) + (size_t)sp->cmax * nx);
+    sv.sepv_n = (sp->cmax * (qx | 1) + 1) & ~1;                     // even: the strip starts 16-byte aligned
+    sp->smem_bytes = sizeof(double) * ((size_t)sv.sepv_n + (size_t)sp->cmax * sv.sp);
     p->strip = sp;
     if (!ok) { strip_plan_destroy(p); return SPUQ_OK; }       // not fatal: the plain path still works
 #ifndef SPUQ_EMU
@@ -455,7 +473,7 @@ int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx) {
         const int32_t h = p->half;
         const size_t need = sizeof(double) * (size_t)sv.q * 2 * (size_t)((h + 1) & ~1);
         const char* e = std::getenv("SPUQ_SCHUR_PLAIN");                   // A/B switch (development)
-        if (h > 0 && nx == 2 * h && nx <= SCHUR_THREADS && sv.q >= 1 && sv.q <= SCHUR_RMAX && need <= 200 * 1024 &&
+        if (h > 0 && nx == 2 * h && nx <= 512 && sv.q >= 1 && sv.q <= SCHUR_RMAX && need <= 200 * 1024 &&
             !(e && e[0] == '1')) {
             sp->schur_smem = need;
 #ifndef SPUQ_EMU
@@ -514,14 +532,12 @@ static const double* strip_schur(spuq_sg_precond* p, const StripPlan* sp, const 
                                  cudaStream_t stream, const double* gate, const double* R = nullptr,
                                  const double* Gf = nullptr, const double* Gl = nullptr) {
     if (sp->schur_smem > 0) {
-        const dim3 grid((unsigned)L), block(SCHUR_THREADS);
-        const int rt = (sv.q + 3) / 4 * 4;
-#define SPUQ_SCHUR_L(r)                                                                                           \
-    case r: SPUQ_LAUNCH(k_schur_fused<r>, grid, block, sp->schur_smem, stream, sv, L, p->half, R != nullptr ? 1 : 0, \
-                        R, Gf, Gl, Z, p->qsplit_dev, sp->sy_ipiv, sp->sy_off, gate); break;
-        switch (rt) {
-            SPUQ_SCHUR_L(4) SPUQ_SCHUR_L(8) SPUQ_SCHUR_L(12) SPUQ_SCHUR_L(16) SPUQ_SCHUR_L(20) SPUQ_SCHUR_L(24)
-            SPUQ_SCHUR_L(28) SPUQ_SCHUR_L(32)
+        const dim3 grid((unsigned)L);
+#define SPUQ_SCHUR_L(r, c)                                                                                        \
+    case r: SPUQ_LAUNCH((k_schur_fused<r, c>), grid, dim3(SchurShape<c>::threads), sp->schur_smem, stream, sv, L, p->half, \
+                        R != nullptr ? 1 : 0, R, Gf, Gl, Z, p->qsplit_dev, sp->sy_ipiv, sp->sy_off, gate); break;
+        switch (schur_rows_for(sv.q)) {
+            SPUQ_SCHUR_FOR_EACH(SPUQ_SCHUR_L)
         }
 #undef SPUQ_SCHUR_L
         return Z;

@@ -42,11 +42,14 @@ namespace spuq {
 constexpr int STRIP_THREADS = 256;
 constexpr int STRIP_CMAX = 32;        // strip height limit (registers of the y-transform)
 constexpr int STRIP_HP = 16;          // ceil(CMAX / 2)
-constexpr int STRIP_CX = 32;          // longest x-chunk (registers of the chunk sweeps); the plan uses 30 / <= 31
+constexpr int STRIP_CX = 32;          // longest x-chunk (registers of the chunk sweeps)
+constexpr int STRIP_QXMAX = 64;       // most x-separators
 
 // Device view of the strip plan (passed by value).
 struct StripView {
     int32_t nx, ny, P, q;             // P strips, q = P - 1 separator rows
+    int32_t sp;                       // row pitch of the strip in shared memory (>= nx)
+    int32_t sepv_n;                   // doubles reserved in front of the strip for the x-separator values [c][qx | 1]
     int64_t ld;                       // column stride of R and S in doubles (nx * ny, or more: a band inside a halo-padded slab)
     int32_t PX, qx;                   // x-chunks per row, x-separators (= PX - 1)
     int32_t cxmax;                    // longest chunk
@@ -89,22 +92,21 @@ struct StripQ {
 #define STRIP_SYNC() __syncthreads()
 #endif
 
-// y-transform of grid column x of the strip: out[j] = sum_i Q[j][i] strip[i][x] with the mirror symmetry
+// y-transform of grid column x of the strip (row i of the column comes from `load(i)`): out[j] = sum_i Q[j][i] strip[i][x] with the mirror symmetry
 // Q[j][c-1-i] = (-1)^j Q[j][i] folded: qc[j*HP + i] = Q[j][i] for i < ceil(c/2), 0 beyond.  All inputs
 // are read (mirror sums p, differences m) before `emit(j, value)` is called for the first row, so the
 // transform may overwrite its own column.
-template <typename Emit>
-__device__ __forceinline__ void strip_ytransform(const double* __restrict__ qc, const double* __restrict__ colx,
-                                                 int nx, int c, Emit emit) {
+template <typename Load, typename Emit>
+__device__ __forceinline__ void strip_ytransform(const double* __restrict__ qc, Load load, int c, Emit emit) {
     double p[STRIP_HP], m[STRIP_HP];
     const int half = c >> 1;
 #pragma unroll
     for (int s = 0; s < STRIP_HP; ++s) {
         if (s < half) {
-            const double a = colx[(size_t)s * nx], b = colx[(size_t)(c - 1 - s) * nx];
+            const double a = load(s), b = load(c - 1 - s);
             p[s] = a + b; m[s] = a - b;
         } else if (s == half && (c & 1)) {
-            p[s] = colx[(size_t)s * nx]; m[s] = 0.0;
+            p[s] = load(s); m[s] = 0.0;
         } else {
             p[s] = 0.0; m[s] = 0.0;
         }
@@ -139,16 +141,16 @@ __device__ __forceinline__ void strip_ytransform(const double* __restrict__ qc, 
 // The same transform for a strip height known at compile time (the main strips of a plan): both loops are
 // fully unrolled, so every matrix entry is an IMMEDIATE constant-bank operand of its DFMA -- no load
 // instruction at all -- and the chains of different modes interleave freely.
-template <int CT, typename Emit>
-__device__ __forceinline__ void strip_ytransform_ct(const StripQ& Q, const double* __restrict__ colx, int nx, Emit emit) {
+template <int CT, typename Load, typename Emit>
+__device__ __forceinline__ void strip_ytransform_ct(const StripQ& Q, Load load, Emit emit) {
     constexpr int half = CT / 2, hp = (CT + 1) / 2;
     double p[hp], m[hp];
 #pragma unroll
     for (int s = 0; s < half; ++s) {
-        const double a = colx[(size_t)s * nx], b = colx[(size_t)(CT - 1 - s) * nx];
+        const double a = load(s), b = load(CT - 1 - s);
         p[s] = a + b; m[s] = a - b;
     }
-    if (CT & 1) { p[half] = colx[(size_t)half * nx]; m[half] = 0.0; }
+    if (CT & 1) { p[half] = load(half); m[half] = 0.0; }
 #pragma unroll
     for (int j0 = 0; j0 < CT; j0 += 8) {         // groups of four modes per parity: bounded register use
         double e[4], o[4];
@@ -239,12 +241,12 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
 #ifdef SPUQ_EMU
     if (threadIdx.x != 0) return;
-    std::vector<double> smem_store((size_t)STRIP_CMAX * sv.nx + STRIP_CMAX * (sv.qx + 1));
+    std::vector<double> smem_store((size_t)STRIP_CMAX * sv.sp + sv.sepv_n);
     double* smem = smem_store.data();
 #else
     extern __shared__ __align__(16) double smem[];
 #endif
-    const int nx = sv.nx;
+    const int nx = sv.nx, sp = sv.sp;                   // row length in the slab, row pitch in shared memory
     const int p = p_off + (int)(blockIdx.x % (unsigned)p_cnt);
     const int64_t col = blockIdx.x / (unsigned)p_cnt;
     if (col >= L) return;
@@ -256,27 +258,37 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
     const int c = ct_path ? CT : sv.ch[cls];
     const int y0 = (p < sv.n_tall) ? p * (sv.ch[0] + 1) : sv.n_tall * (sv.ch[0] + 1) + (p - sv.n_tall) * (sv.ch[1] + 1);
     const double* qc = Q.q[cls];                        // [c][HP], constant bank
-    double* sepv = smem;                                // [c][qx]
-    double* strip = sepv + STRIP_CMAX * (sv.qx > 0 ? sv.qx : 1);   // [c][nx]
+    const int PX = sv.PX, qx = sv.qx, cxmax = sv.cxmax;
+    const int qp = qx | 1;                              // odd pitch of the x-separator values
+    double* sepv = smem;                                // [c][qp]
+    double* strip = sepv + sv.sepv_n;                   // [c][sp]
     const int64_t N = sv.ld;
     const double* src = R + col * N + (int64_t)y0 * nx;
     double dsep = 0.0;                                  // <R, S> on the separator row below the strip (FINAL, dot)
 
-    // ---- phase 0: strip and transform matrix into shared memory ------------------------------------
+    // ---- phase 0: strip into shared memory -------------------------------------------------------------
 #ifndef SPUQ_EMU
-    // the strip is c*nx contiguous doubles: one bulk copy (TMA) issued by one thread, no registers and no
-    // load instructions spent on it; the rest of the block waits on the mbarrier
+    // bulk copies (TMA) issued by one thread, no registers and no load instructions spent on the strip; the
+    // rest of the block waits on the mbarrier.  sp == nx: the strip is c*nx contiguous doubles, ONE copy;
+    // padded rows (sp > nx, bank layout of phase 2): one copy per row.
     __shared__ __align__(8) unsigned long long strip_bar;
-    const uint32_t bytes = (uint32_t)(c * nx) * 8u;
-    const bool bulk = (bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const uint32_t row_bytes = (uint32_t)nx * 8u;
+    const bool bulk = (row_bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     if (bulk) {
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&strip_bar);
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"((uint32_t)__cvta_generic_to_shared(strip)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (uint32_t)c) : "memory");
+            if (sp == nx) {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"((uint32_t)__cvta_generic_to_shared(strip)), "l"(src), "r"(row_bytes * (uint32_t)c), "r"(bar) : "memory");
+            } else {
+                for (int i = 0; i < c; ++i)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((uint32_t)__cvta_generic_to_shared(strip + (size_t)i * sp)), "l"(src + (size_t)i * nx),
+                                   "r"(row_bytes), "r"(bar) : "memory");
+            }
         }
         __syncthreads();                                     // barrier initialised before anyone waits on it
         asm volatile(
@@ -284,7 +296,7 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
             ::"r"(bar) : "memory");
     } else
 #endif
-    for (int i = STRIP_T0; i < c * nx; i += STRIP_TS) strip[i] = src[i];
+    for (int i = STRIP_T0; i < c * nx; i += STRIP_TS) strip[(size_t)(i / nx) * sp + i % nx] = src[i];
     if (FINAL) {
         STRIP_SYNC();
         const double oy = sv.oy;
@@ -294,7 +306,7 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
         const double* ub = U + (int64_t)(ja + 1) * sv.u_js + col * sv.u_cs;
         for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
             if (has_a) strip[x] -= oy * ua[x];
-            if (has_b) strip[(size_t)(c - 1) * nx + x] -= oy * ub[x];
+            if (has_b) strip[(size_t)(c - 1) * sp + x] -= oy * ub[x];
         }
         // separator row below this strip
         if (has_b) {
@@ -312,24 +324,28 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
 
     // ---- phase 1: sine transform along y, one thread per grid column -------------------------------
     for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
-        auto put = [&](int j, double a) { strip[(size_t)j * nx + x] = a; };
-        if (ct_path) strip_ytransform_ct<(CT > 0 ? CT : 1)>(Q, strip + x, nx, put);
-        else strip_ytransform(qc, strip + x, nx, c, put);
+        auto get = [&](int i) { return strip[(size_t)i * sp + x]; };
+        auto put = [&](int j, double a) { strip[(size_t)j * sp + x] = a; };
+        if (ct_path) strip_ytransform_ct<(CT > 0 ? CT : 1)>(Q, get, put);
+        else strip_ytransform(qc, get, c, put);
     }
     STRIP_SYNC();
 
     // ---- phase 2a: chunk-local Thomas sweeps along x, one thread per (mode, chunk) --------------------
-    const int PX = sv.PX, qx = sv.qx, cxmax = sv.cxmax;
+    // Lanes of a warp take consecutive chunks.  With the plan's preferred layout (16 chunks per row at pitch 33,
+    // rows at a pitch that is a multiple of 16 doubles) the 16 lanes of a half-warp always sit on 16 different
+    // bank pairs, whether they share a row or not; other grid widths keep an odd chunk pitch (no conflicts inside
+    // a row, two-way where a half-warp straddles two rows).
     const double ox = sv.ox;
     const double* ipx = sv.ipivx[cls];
     for (int task = STRIP_T0; task < c * PX; task += STRIP_TS) {
         const int j = task / PX, ch = task - j * PX;
         const int x0 = sv.xstart[ch], len = sv.xlen[ch];
-        double* r = strip + (size_t)j * nx + x0;
+        double* r = strip + (size_t)j * sp + x0;
         const double* ip = ipx + (size_t)j * cxmax;
-        // The chunk lives in registers for both sweeps (static indices, guards on the chunk length): the loads
-        // of the values and of the pivot table are independent of the recurrence and issue ahead of it, so a
-        // step costs its one dependent DFMA instead of a shared-memory + table round trip (~70 clk measured).
+        // The chunk lives in registers for both sweeps (static indices, guards on the chunk length); a step costs
+        // its one dependent DFMA.  The entry after the chunk's last one is zero, so the first step of the
+        // backward sweep needs no special case: fma(-ox pv, 0, rr pv) = rr pv.
         double rr[STRIP_CX];
 #pragma unroll
         for (int t = 0; t < STRIP_CX; ++t) rr[t] = (t < len) ? r[t] : 0.0;
@@ -340,8 +356,7 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
         for (int t = STRIP_CX - 1; t >= 0; --t) {
             if (t < len) {
                 const double pv = __ldg(ip + t);
-                const double nxt = (t + 1 < STRIP_CX) ? rr[(t + 1 < STRIP_CX) ? t + 1 : t] : 0.0;
-                rr[t] = (t == len - 1) ? rr[t] * pv : fma(-ox * pv, nxt, rr[t] * pv);
+                rr[t] = fma(-ox * pv, (t + 1 < STRIP_CX) ? rr[(t + 1 < STRIP_CX) ? t + 1 : t] : 0.0, rr[t] * pv);
             }
         }
 #pragma unroll
@@ -350,17 +365,24 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
     }
     STRIP_SYNC();
 
-    // ---- phase 2b: x-separator system of every mode (tridiagonal, qx unknowns) -------------------------
     if (qx > 0) {
+        // ---- phase 2b: x-separator system of every mode (tridiagonal, qx unknowns) ---------------------
+        // right-hand sides by all threads, one per (mode, separator): lanes along the separators of a row
+        for (int task = STRIP_T0; task < c * qx; task += STRIP_TS) {
+            const int j = task / qx, i = task - j * qx;
+            const double* row = strip + (size_t)j * sp;
+            const int xs = sv.xstart[i] + sv.xlen[i];              // separator between chunk i and i+1
+            sepv[(size_t)j * qp + i] = row[xs] - ox * (row[xs - 1] + row[xs + 1]);
+        }
+        STRIP_SYNC();
+        // the recurrences, one thread per mode, on the separator values alone (odd pitch: no bank conflicts)
         for (int j = STRIP_T0; j < c; j += STRIP_TS) {
-            double* row = strip + (size_t)j * nx;
             const double* sip = sv.sx_ipiv[cls] + (size_t)j * qx;
             const double* sof = sv.sx_off[cls] + (size_t)j * qx;
-            double* sv_j = sepv + (size_t)j * qx;
+            double* sv_j = sepv + (size_t)j * qp;
             double z = 0.0;
             for (int i = 0; i < qx; ++i) {
-                const int xs = sv.xstart[i] + sv.xlen[i];          // separator between chunk i and i+1
-                double rhs = row[xs] - ox * (row[xs - 1] + row[xs + 1]);
+                double rhs = sv_j[i];
                 if (i > 0) rhs -= __ldg(sof + i - 1) * __ldg(sip + i - 1) * z;
                 z = rhs;
                 sv_j[i] = z;
@@ -370,22 +392,23 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
                 const double e = (i + 1 < qx) ? __ldg(sof + i) * u : 0.0;
                 u = (sv_j[i] - e) * __ldg(sip + i);
                 sv_j[i] = u;
-                row[sv.xstart[i] + sv.xlen[i]] = u;
             }
         }
         STRIP_SYNC();
-        // ---- phase 2c: chunks corrected with their spikes ------------------------------------------
+        // ---- phase 2c: chunks corrected with their spikes; the thread of chunk ch also stores the separator
+        // value to its right ------------------------------------------------------------------------------
         for (int task = STRIP_T0; task < c * PX; task += STRIP_TS) {
             const int j = task / PX, ch = task - j * PX;
             const int x0 = sv.xstart[ch], len = sv.xlen[ch];
             const int lc = (len == sv.xlen_cls_len[0]) ? 0 : 1;
-            const double* sp = sv.spike[cls] + ((size_t)lc * c + j) * cxmax;
-            const double sl = (ch > 0) ? sepv[(size_t)j * qx + ch - 1] : 0.0;
-            const double sr = (ch < qx) ? sepv[(size_t)j * qx + ch] : 0.0;
-            double* r = strip + (size_t)j * nx + x0;
+            const double* spk = sv.spike[cls] + ((size_t)lc * c + j) * cxmax;
+            const double sl = (ch > 0) ? sepv[(size_t)j * qp + ch - 1] : 0.0;
+            const double sr = (ch < qx) ? sepv[(size_t)j * qp + ch] : 0.0;
+            double* r = strip + (size_t)j * sp + x0;
             const double a = ox * sl, b = ox * sr;
 #pragma unroll 8
-            for (int t = 0; t < len; ++t) r[t] -= a * __ldg(sp + t) + b * __ldg(sp + len - 1 - t);
+            for (int t = 0; t < len; ++t) r[t] -= a * __ldg(spk + t) + b * __ldg(spk + len - 1 - t);
+            if (ch < qx) r[len] = sr;
         }
         STRIP_SYNC();
     }
@@ -396,12 +419,13 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
         const bool with_dot = dot.partials != nullptr;
         double dsum = 0.0;
         for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
+            auto get = [&](int i) { return strip[(size_t)i * sp + x]; };
             auto put = [&](int j, double a) {
                 if (with_dot) dsum = fma(a, src[(size_t)j * nx + x], dsum);      // before the store: R and S may alias
                 dst[(size_t)j * nx + x] = a;
             };
-            if (ct_path) strip_ytransform_ct<(CT > 0 ? CT : 1)>(Q, strip + x, nx, put);
-            else strip_ytransform(qc, strip + x, nx, c, put);
+            if (ct_path) strip_ytransform_ct<(CT > 0 ? CT : 1)>(Q, get, put);
+            else strip_ytransform(qc, get, c, put);
         }
         if (with_dot) strip_dot_finish(dot, dsum + dsep);
     } else {
@@ -412,7 +436,7 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
             double se = 0.0, so = 0.0;
             for (int j = 0; j < c; ++j) {
                 // Q[0][j] = Q[j][0] (symmetric) = qc[j*HP + 0]
-                const double t = qc[j * STRIP_HP] * strip[(size_t)j * nx + x];
+                const double t = qc[j * STRIP_HP] * strip[(size_t)j * sp + x];
                 if (j & 1) so += t; else se += t;
             }
             gf[x] = se + so;
@@ -469,46 +493,60 @@ k_thomas_sep(int32_t nx, int32_t q, int32_t L, int64_t js, int64_t cs, const dou
 // ---- separator system in ONE kernel --------------------------------------------------------------------------
 // One CTA per slab column keeps the q separator rows of that column (q * nx doubles, 72 KB on configuration 4)
 // in shared memory from the right-hand side to the solution: mirror split, transform to the sine modes of
-// length nx, the q x q tridiagonal solve of every mode, transform back, mirror merge.  Thread t owns transform
-// column t (even modes first, then odd: the order of the sy_ipiv / sy_off tables) with its q accumulators in
-// registers, so the tridiagonal solve along the separators never leaves the register file; the only traffic
+// length nx, the q x q tridiagonal solve of every mode, transform back, mirror merge.  A thread owns CPT
+// transform columns of ONE parity (even modes use the mirror sums, odd modes the differences) with their q
+// accumulators in registers, so the tridiagonal solve along the separators never leaves the register file and,
+// with CPT = 2, every shared-memory operand (a 16-byte broadcast load) feeds four DFMAs.  The only traffic
 // besides the q rows is the transform matrix (4 * (nx/2)^2 doubles per column, streamed from L2, coalesced
 // across the threads).  Replaces eight launches (assembly, split, four GEMMs, Thomas, merge) and the
-// Z <-> Z2 round trips; conditions: nx even, nx <= SCHUR_THREADS, q <= 32, q rows fit shared memory.
-constexpr int SCHUR_THREADS = 512;
+// Z <-> Z2 round trips; conditions: nx even, nx <= 512, q <= 32, q rows fit shared memory.
 constexpr int SCHUR_RMAX = 32;
+constexpr int SCHUR_R2MAX = 24;       // two columns per thread up to this many separators (registers)
+template <int CPT> struct SchurShape { static constexpr int threads = CPT == 2 ? 256 : 512; };
 
-// acc[r] = sum_i F[r][i] * Qm[i][c] for the rows r < q (F: shared memory, row pitch ps, 16-byte aligned rows)
-template <int RT>
+// acc[k * RT + r] = sum_i F[r][i] * Qm[i][c[k]] for the rows r < q and the thread's columns k < CPT
+// (F: shared memory, row pitch ps, 16-byte aligned rows)
+template <int RT, int CPT>
 __device__ __forceinline__ void schur_half_product(const double* __restrict__ F, int ps, int h, int q,
-                                                   const double* __restrict__ Qm, int c, double* acc) {
+                                                   const double* __restrict__ Qm, const int (&c)[2], double* acc) {
 #pragma unroll
-    for (int r = 0; r < RT; ++r) acc[r] = 0.0;
+    for (int r = 0; r < CPT * RT; ++r) acc[r] = 0.0;
     int i = 0;
-#pragma unroll 4
+#pragma unroll 2
     for (; i + 1 < h; i += 2) {
-        const double q0 = __ldg(Qm + (size_t)i * h + c), q1 = __ldg(Qm + (size_t)(i + 1) * h + c);
+        double q0[CPT], q1[CPT];
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            q0[k] = __ldg(Qm + (size_t)i * h + c[k]);
+            q1[k] = __ldg(Qm + (size_t)(i + 1) * h + c[k]);
+        }
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             if (r < q) {
                 const double2 f = *reinterpret_cast<const double2*>(F + (size_t)r * ps + i);
-                acc[r] = fma(f.x, q0, acc[r]);
-                acc[r] = fma(f.y, q1, acc[r]);
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    acc[k * RT + r] = fma(f.x, q0[k], acc[k * RT + r]);
+                    acc[k * RT + r] = fma(f.y, q1[k], acc[k * RT + r]);
+                }
             }
         }
     }
     if (i < h) {
-        const double q0 = __ldg(Qm + (size_t)i * h + c);
 #pragma unroll
-        for (int r = 0; r < RT; ++r)
-            if (r < q) acc[r] = fma(F[(size_t)r * ps + i], q0, acc[r]);
+        for (int k = 0; k < CPT; ++k) {
+            const double q0 = __ldg(Qm + (size_t)i * h + c[k]);
+#pragma unroll
+            for (int r = 0; r < RT; ++r)
+                if (r < q) acc[k * RT + r] = fma(F[(size_t)r * ps + i], q0, acc[k * RT + r]);
+        }
     }
 }
 
 // assemble != 0: the right-hand side is formed here from R, Gf, Gl (what k_sep_assemble writes; one-GPU layout of
 // the strips, u_above0 = -1); else it is read from Z.  The solution is written to Z (layout sv.u_js / sv.u_cs).
-template <int RT>
-__global__ void __launch_bounds__(SCHUR_THREADS, 1)
+template <int RT, int CPT>
+__global__ void __launch_bounds__(SchurShape<CPT>::threads, (CPT == 2 && RT <= 20) ? 2 : 1)
 k_schur_fused(StripView sv, int32_t L, int32_t h, int32_t assemble, const double* __restrict__ R,
               const double* __restrict__ Gf, const double* __restrict__ Gl, double* __restrict__ Z,
               const double* __restrict__ qsplit, const double* __restrict__ ipiv, const double* __restrict__ off,
@@ -516,18 +554,20 @@ k_schur_fused(StripView sv, int32_t L, int32_t h, int32_t assemble, const double
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
     const int nx = sv.nx, q = sv.q;
     const int hp2 = (h + 1) & ~1, ps = 2 * hp2;       // sums in [0, h), differences in [hp2, hp2 + h) of a row
+    const int per = CPT == 2 ? (h + 1) / 2 : h;       // threads per parity
+    const int n_thr = 2 * per;                        // active threads
 #ifdef SPUQ_EMU
     if (threadIdx.x != 0) return;
-    std::vector<double> smem_store((size_t)q * ps), hold((size_t)(nx + 1) * RT);
+    std::vector<double> smem_store((size_t)q * ps), hold((size_t)(n_thr + 1) * CPT * RT);
     double* buf = smem_store.data();
     double* acc = nullptr;
-#define SCHUR_FOR_T for (int t = 0; (acc = &hold[(size_t)t * RT], t < nx); ++t)     // acc: the "registers" of emulated thread t
+#define SCHUR_FOR_T for (int t = 0; (acc = &hold[(size_t)t * CPT * RT], t < n_thr); ++t)   // acc: the "registers" of emulated thread t
 #else
     extern __shared__ __align__(16) double smem[];
     double* buf = smem;
-    double acc[RT];
-    const int t = (int)threadIdx.x;                       // nx <= blockDim.x: one transform column per thread
-#define SCHUR_FOR_T if (t < nx)
+    double acc[CPT * RT];
+    const int t = (int)threadIdx.x;
+#define SCHUR_FOR_T if (t < n_thr)
 #endif
     const int64_t col = blockIdx.x;
     if (col >= L) return;
@@ -553,41 +593,63 @@ k_schur_fused(StripView sv, int32_t L, int32_t h, int32_t assemble, const double
         buf[(size_t)j * ps + hp2 + i] = a - b;
     }
     STRIP_SYNC();
+    // the thread's columns: parity par, modes c[0] (and c[1] = c[0] + per; a thread whose second column does not
+    // exist computes its first one twice and stores it once)
+#define SCHUR_COLUMNS                                                            \
+        const int par = t >= per ? 1 : 0;                                        \
+        const int c[2] = {t - par * per, (CPT == 2 && t - par * per + per < h) ? t - par * per + per : t - par * per}; \
+        const int nvalid = (CPT == 2 && c[1] != c[0]) ? 2 : 1;
     // ---- to the modes, tridiagonal solve along the separators in registers -----------------------------------
     SCHUR_FOR_T {
-        const int par = t >= h ? 1 : 0, c0 = t - par * h;
-        schur_half_product<RT>(buf + par * hp2, ps, h, q, qsplit + par * hh, c0, acc);
-        // the arithmetic of k_thomas_sep
-        double z = acc[0];
+        SCHUR_COLUMNS
+        (void)nvalid;
+        schur_half_product<RT, CPT>(buf + par * hp2, ps, h, q, qsplit + par * hh, c, acc);
 #pragma unroll
-        for (int j = 1; j < RT; ++j)
-            if (j < q) { z = acc[j] - __ldg(off + (size_t)(j - 1) * nx + t) * __ldg(ipiv + (size_t)(j - 1) * nx + t) * z; acc[j] = z; }
-        double u = 0.0;
+        for (int k = 0; k < CPT; ++k) {
+            const int tc = par * h + c[k];                                     // position in the tables
+            double* a = acc + k * RT;
+            // the arithmetic of k_thomas_sep
+            double z = a[0];
 #pragma unroll
-        for (int j = RT - 1; j >= 0; --j) {
-            if (j == q - 1) { u = acc[j] * __ldg(ipiv + (size_t)j * nx + t); acc[j] = u; }
-            else if (j < q - 1) { u = (acc[j] - __ldg(off + (size_t)j * nx + t) * u) * __ldg(ipiv + (size_t)j * nx + t); acc[j] = u; }
+            for (int j = 1; j < RT; ++j)
+                if (j < q) { z = a[j] - __ldg(off + (size_t)(j - 1) * nx + tc) * __ldg(ipiv + (size_t)(j - 1) * nx + tc) * z; a[j] = z; }
+            // backward: the last separator starts from u = 0 (its off-diagonal entry multiplies zero); written
+            // without a test for j == q - 1, which the compiler turns into a dynamically indexed -- local-memory --
+            // accumulator array
+            double u = 0.0;
+#pragma unroll
+            for (int j = RT - 1; j >= 0; --j)
+                if (j < q) { u = (a[j] - __ldg(off + (size_t)j * nx + tc) * u) * __ldg(ipiv + (size_t)j * nx + tc); a[j] = u; }
         }
     }
     STRIP_SYNC();
     SCHUR_FOR_T {
-        const int par = t >= h ? 1 : 0, c0 = t - par * h;
+        SCHUR_COLUMNS
 #pragma unroll
-        for (int r = 0; r < RT; ++r)
-            if (r < q) buf[(size_t)r * ps + par * hp2 + c0] = acc[r];
+        for (int k = 0; k < CPT; ++k)
+            if (k < nvalid) {
+#pragma unroll
+                for (int r = 0; r < RT; ++r)
+                    if (r < q) buf[(size_t)r * ps + par * hp2 + c[k]] = acc[k * RT + r];
+            }
     }
     STRIP_SYNC();
     // ---- back to the grid -------------------------------------------------------------------------------------
     SCHUR_FOR_T {
-        const int par = t >= h ? 1 : 0, c0 = t - par * h;
-        schur_half_product<RT>(buf + par * hp2, ps, h, q, qsplit + (2 + par) * hh, c0, acc);
+        SCHUR_COLUMNS
+        (void)nvalid;
+        schur_half_product<RT, CPT>(buf + par * hp2, ps, h, q, qsplit + (2 + par) * hh, c, acc);
     }
     STRIP_SYNC();
     SCHUR_FOR_T {
-        const int par = t >= h ? 1 : 0, c0 = t - par * h;
+        SCHUR_COLUMNS
 #pragma unroll
-        for (int r = 0; r < RT; ++r)
-            if (r < q) buf[(size_t)r * ps + par * hp2 + c0] = acc[r];
+        for (int k = 0; k < CPT; ++k)
+            if (k < nvalid) {
+#pragma unroll
+                for (int r = 0; r < RT; ++r)
+                    if (r < q) buf[(size_t)r * ps + par * hp2 + c[k]] = acc[k * RT + r];
+            }
     }
     STRIP_SYNC();
     for (int e = STRIP_T0; e < q * h; e += STRIP_TS) {
@@ -598,6 +660,7 @@ k_schur_fused(StripView sv, int32_t L, int32_t h, int32_t assemble, const double
         z[nx - 1 - i] = pp - mm;
     }
 #undef SCHUR_FOR_T
+#undef SCHUR_COLUMNS
 }
 
 }  // namespace spuq

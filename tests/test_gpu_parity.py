@@ -68,6 +68,35 @@ def test_apply_tmem_variants(n, M, p, kind, mu):
         assert relerr(Y, c.Y) <= ps.TOL, (tune, plan.kernel_name, relerr(Y, c.Y))
 
 
+def test_tmem_window_release_stress():
+    """The W-ring windows of k_apply_tmem are released by lane 0's mbarrier arrive after the warp's loads were
+    ISSUED (no __syncwarp, kernels_tmem.cuh `window_reads_issued`).  If the producer's TMA fill could overtake
+    outstanding loads, the result would differ from run to run: 200 applications of a problem with many
+    windows per tile (K = 2 and K = 1 register sets, ring lengths 2 and 3) must all be bit-identical, and equal
+    the one-column-at-a-time cross-check kernel to the parity tolerance."""
+    import torch
+    import spuq_b200 as sp
+    from spuq_b200 import _abi, synthetic
+    from tests.cases import fd_case, relerr
+    idx = synthetic.complete_order_indices(8, 3)                    # 165 columns
+    c = fd_case(192, 8, idx, "hermite", 0.5, with_oracle=False)
+    Yref, plan = ps.product_apply(c, _abi.PATH_ELL, (1, 0, 0, 0))
+    A = sp.MultiOperator.from_blocks(ps.device_blocks(c), c.rvs, path=_abi.PATH_STENCIL)
+    w = sp.SlabMultiVector.from_array(c.idx, c.W)
+    plan = A.plan_for(w)
+    Y0 = torch.empty_like(w.slab)
+    Y = torch.empty_like(w.slab)
+    for tune in [(4, 2, 2, 0), (4, 1, 2, 0), (4, 2, 3, 0)]:
+        plan.tune(*tune)
+        plan.apply(w.slab, Y0)
+        assert "tmem" in plan.kernel_name
+        assert relerr(Y0.cpu().numpy().T, Yref) <= ps.TOL
+        for _ in range(200):
+            Y.fill_(float("nan"))
+            plan.apply(w.slab, Y)
+            assert torch.equal(Y, Y0), tune
+
+
 def test_apply_tmem_nine_point():
     from spuq_b200 import _abi, synthetic
     from tests.cases import relerr

@@ -12,9 +12,12 @@ def main():
     ap.add_argument("--ny", type=int, default=500)
     ap.add_argument("--L", type=int, default=5000)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--lib", default=None, help="another build of libspuq_sg.so (A/B runs of compile-time switches)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     from spuq_b200 import _abi
+    if a.lib:
+        _abi.use_library(os.path.abspath(a.lib), "cuda:0")
     from spuq_b200.multi_operator import MeanSolveSlabOperator
     dev = _abi.device()
     N = a.nx * a.ny
@@ -34,7 +37,7 @@ def main():
     As = 4.0 * s
     As[:, 1:] -= s[:, :-1]; As[:, :-1] -= s[:, 1:]; As[1:, :] -= s[:-1, :]; As[:-1, :] -= s[1:, :]
     res = float((As - r).abs().max() / r.abs().max())
-    print(json.dumps({"nx": a.nx, "ny": a.ny, "L": a.L, "ms": ms, "GB_per_s_24NL": 24.0 * N * a.L / ms / 1e6,
+    print(json.dumps({"lib": os.path.basename(a.lib) if a.lib else "default", "nx": a.nx, "ny": a.ny, "L": a.L, "ms": ms, "GB_per_s_24NL": 24.0 * N * a.L / ms / 1e6,
                       "residual": res}))
 
 
