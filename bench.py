@@ -570,7 +570,11 @@ def pcg_block(args, peak_gbs):
             "max_abs_error_vs_manufactured": err, "ms_apply": t_apply, "ms_precond": t_prec,
             "bytes_model_per_pass": model, "bytes_model_frac": model / (dt / passes) / 1e9 / peak_gbs,
             "preconditioner": "exact A_0^{-1} (strip partition, csrc/precond_strip.cuh)",
-            "gpu_launches": solve_launches, "launches_per_pass": round((solve_launches - 20) / passes, 1)}
+            # spuq_sg_pcg enqueues passes in groups of poll_every = 8 (the ones after convergence are no-ops but still
+            # launches); 9 launches precede the loop: first apply, f - A w, strips forward / separator system / strips
+            # final, copy, first dot, first convergence test (+ the apply's own count)
+            "gpu_launches": solve_launches,
+            "launches_per_pass": round((solve_launches - 9) / (-(-passes // 8) * 8), 1)}
 
 
 def pcg_block_rows(args, world, rank, dev):

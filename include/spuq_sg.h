@@ -305,17 +305,17 @@ SPUQ_API int spuq_sg_pcg_accept(double* state_dev, int32_t src, int32_t dst, voi
  *   copy2d_async     cudaMemcpy2DAsync with cudaMemcpyDefault (either side may be peer memory)
  *   flag_wait_geq    the stream waits until *flag_dev >= value (one polling thread, ahead of the kernel)
  *   enable_peer_access  cudaDeviceEnablePeerAccess, idempotent */
-/* The exchange itself: halo_push waits until the neighbours have consumed the previous halo rows, stores this
- * rank's boundary rows into their slabs (peer pointers, NULL = no neighbour on that side) and publishes
- * `seq` in their flag words; halo_wait holds the stream until both neighbours have published `seq` here;
- * halo_done (after the kernel that read the halo rows) tells them the rows may be overwritten.
- * flags: 4 x int64 per rank, [0] top halo written, [1] bottom halo written, [2] rank above consumed,
- * [3] rank below consumed; ticket_dev: one zeroed uint32. */
+/* The exchange itself: halo_push first publishes "ready to receive exchange `seq`" in the neighbours' flag words
+ * (everything enqueued before it on this rank's stream -- the kernel that read the previous halo rows, any
+ * update that swept over the slab since -- is complete), waits for the same word from them, stores this rank's
+ * boundary rows into their slabs (peer pointers, NULL = no neighbour on that side) and publishes `seq` as
+ * "written"; halo_wait holds the stream until both neighbours have published `seq` here.
+ * flags: 4 x int64 per rank, [0] top halo written, [1] bottom halo written, [2] rank above ready to receive,
+ * [3] rank below ready to receive; ticket_dev: one zeroed uint32. */
 SPUQ_API int spuq_sg_halo_push(const double* W_dev, int32_t L, int32_t nyl, int32_t nx, double* up_slab, int32_t up_nyl,
                       double* dn_slab, int32_t dn_nyl, const int64_t* my_flags, int64_t* up_flags, int64_t* dn_flags,
                       int64_t seq, void* ticket_dev, void* stream);
 SPUQ_API int spuq_sg_halo_wait(const int64_t* my_flags, int has_up, int has_dn, int64_t seq, void* stream);
-SPUQ_API int spuq_sg_halo_done(int64_t* up_flags, int64_t* dn_flags, int64_t seq, void* stream);
 SPUQ_API int spuq_sg_copy2d_async(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width_bytes,
                          int64_t height, void* stream);
 SPUQ_API int spuq_sg_flag_wait_geq(const int64_t* flag_dev, int64_t value, void* stream);

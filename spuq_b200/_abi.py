@@ -94,7 +94,6 @@ SIGNATURES = {
     "spuq_sg_halo_push": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp,
                                      C.c_int64, _vp, _vp]),
     "spuq_sg_halo_wait": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _vp]),
-    "spuq_sg_halo_done": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "spuq_sg_copy2d_async": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, _vp]),
     "spuq_sg_flag_wait_geq": (C.c_int, [_vp, C.c_int64, _vp]),
     "spuq_sg_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),

@@ -101,13 +101,6 @@ void k_dot(int64_t n, const double* x, const double* y, double* out, double*, un
 }
 #endif
 
-__device__ __forceinline__ double ratio_of(double alpha, const double* num, const double* den) {
-    double a = alpha;
-    if (num) a *= __ldg(num);
-    if (den) a /= __ldg(den);
-    return a;
-}
-
 // out[s][i] = sum_mu coef[s][mu] * W[i + ldw*mu], SC samples per pass (coefficients staged in shared
 // memory in chunks of COMBINE_LCHUNK columns).  One thread owns two consecutive rows; a warp reads 512
 // contiguous bytes of a column per step: a pure streaming kernel, 8 n L bytes per SC samples.
@@ -255,6 +248,28 @@ k_xpay(int64_t n, const double* num, const double* den, const double* __restrict
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = tid; i < n; i += nthr) v[i] = s[i] + b * v[i];
+}
+
+// The direction update of a PCG pass together with the solution update of the SAME pass (pcg.py:51 and :47; the
+// latter moved behind the preconditioner, where v is read anyway):  w += a v ; v = s + b v.  a = alpha of this
+// pass (st[7], stored by the <z,v> epilogue before zeta rotates), b = zeta_new / zeta (st[3]).  The solution
+// update also runs in the pass whose convergence test has just succeeded (status CONVERGED with numit = pass + 1):
+// the reference updates w before it tests.
+__global__ void __launch_bounds__(256)
+k_xpay_w(int64_t n, const double* __restrict__ st, int32_t pass, const double* __restrict__ s,
+         double* __restrict__ v, double* __restrict__ w) {
+    const double status = __ldg(st + 4);
+    const bool running = status == (double)SPUQ_PCG_RUNNING;
+    const bool last = status == (double)SPUQ_PCG_CONVERGED && __ldg(st + 5) == (double)(pass + 1);
+    if (!running && !last) return;
+    const double a = __ldg(st + 7), b = __ldg(st + 3);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n; i += nthr) {
+        const double vi = v[i];
+        w[i] += a * vi;
+        if (running) v[i] = s[i] + b * vi;
+    }
 }
 
 __global__ void __launch_bounds__(256)

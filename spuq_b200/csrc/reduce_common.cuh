@@ -20,9 +20,18 @@ struct DotEpilogue {
     int32_t hist_cap;
 };
 
+// alpha * (*num) / (*den) with device scalars (null: factor 1)
+__device__ __forceinline__ double ratio_of(double alpha, const double* num, const double* den) {
+    double a = alpha;
+    if (num) a *= __ldg(num);
+    if (den) a /= __ldg(den);
+    return a;
+}
+
 __device__ __forceinline__ void dot_epilogue(const DotEpilogue& e, double a) {
     if (e.kind == DOT_EPI_ALPHA) {
         e.st[1] = a;
+        e.st[7] = e.st[0] / a;         // alpha of this pass, for the solution update that follows the preconditioner
         if (a == 0.0) e.st[4] = (double)SPUQ_PCG_SINGULAR;
         else if (a < 0.0) e.st[4] = (double)SPUQ_PCG_NOT_PD;
     } else if (e.kind == DOT_EPI_ZETA) {

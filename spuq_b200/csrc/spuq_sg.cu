@@ -818,11 +818,13 @@ __global__ void k_flag_wait_geq(const volatile long long* flag, long long value)
 void k_flag_wait_geq(const volatile long long*, long long) {}
 #endif
 
-// One launch per exchange: wait until both neighbours are done with the halo rows of the previous exchange,
-// store this rank's first / last owned grid row of every column straight into the neighbours' halo rows
-// (coalesced 16-byte stores over NVLink), and -- last CTA to finish, after a system-wide fence -- publish
-// the sequence number in the neighbours' flag words.
-//   my_flags: [0] top halo written, [1] bottom halo written, [2] rank above consumed, [3] rank below consumed
+// One launch per exchange.  The kernel first tells both neighbours that THIS rank's slab is ready to receive
+// exchange number `seq` -- everything enqueued before it on the stream is complete: the kernel that read the
+// halo rows of the previous exchange AND whatever wrote the slab since (a vector update that sweeps over the
+// halo rows, the fill of a new buffer) -- then waits for the same word from them, stores its first / last owned
+// grid row of every column straight into the neighbours' halo rows (coalesced 16-byte stores over NVLink) and
+// -- last CTA to finish, after a system-wide fence -- publishes the sequence number in their flag words.
+//   my_flags: [0] top halo written, [1] bottom halo written, [2] rank above ready to receive, [3] rank below ready
 #ifndef SPUQ_EMU
 __global__ void __launch_bounds__(256)
 k_halo_push(const double* __restrict__ W, int32_t L, int32_t nyl, int32_t nx,
@@ -830,8 +832,11 @@ k_halo_push(const double* __restrict__ W, int32_t L, int32_t nyl, int32_t nx,
             const volatile long long* my_flags, volatile long long* up_flags, volatile long long* dn_flags,
             long long seq, unsigned int* ticket) {
     if (threadIdx.x == 0) {
-        if (up_slab) while (my_flags[2] < seq - 1) __nanosleep(100);
-        if (dn_slab) while (my_flags[3] < seq - 1) __nanosleep(100);
+        __threadfence_system();
+        if (up_flags) up_flags[3] = seq;               // seen from above I am the rank below (every CTA writes the same value)
+        if (dn_flags) dn_flags[2] = seq;
+        if (up_slab) while (my_flags[2] < seq) __nanosleep(100);
+        if (dn_slab) while (my_flags[3] < seq) __nanosleep(100);
     }
     __syncthreads();
     const int64_t row2 = nx / 2;                       // double2 per grid row (nx even)
@@ -859,11 +864,6 @@ k_halo_push(const double* __restrict__ W, int32_t L, int32_t nyl, int32_t nx,
 __global__ void k_halo_wait(const volatile long long* my_flags, int has_up, int has_dn, long long seq) {
     if (has_up) while (my_flags[0] < seq) __nanosleep(100);
     if (has_dn) while (my_flags[1] < seq) __nanosleep(100);
-}
-__global__ void k_halo_done(volatile long long* up_flags, volatile long long* dn_flags, long long seq) {
-    __threadfence_system();
-    if (up_flags) up_flags[3] = seq;                   // seen from above I am the rank below
-    if (dn_flags) dn_flags[2] = seq;
 }
 #endif
 
@@ -894,15 +894,6 @@ extern "C" int spuq_sg_halo_wait(const int64_t* my_flags, int has_up, int has_dn
 #endif
     return SPUQ_OK;
 }
-extern "C" int spuq_sg_halo_done(int64_t* up_flags, int64_t* dn_flags, int64_t seq, void* stream) {
-#ifndef SPUQ_EMU
-    k_halo_done<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<volatile long long*>(up_flags),
-                                                               reinterpret_cast<volatile long long*>(dn_flags), (long long)seq);
-    SPUQ_CUDA_TRY(cudaGetLastError());
-#endif
-    return SPUQ_OK;
-}
-
 extern "C" int spuq_sg_copy2d_async(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width_bytes,
                                     int64_t height, void* stream) {
     SPUQ_REQUIRE(dst && src && width_bytes >= 0 && height >= 0 && dpitch >= width_bytes && spitch >= width_bytes,

@@ -6,6 +6,7 @@ owning the r-th contiguous block of output columns.
 The reference has no multi-process code at all; the split is the sum over m
 of application/egsz/multi_operator2.py:59-82, which is independent per m.
 """
+import collections
 import ctypes as C
 import math
 
@@ -106,20 +107,26 @@ class PeerHaloExchange:
     enqueues on its own stream ONE small kernel that stores its first / last owned grid row of all columns
     into the neighbours' halo rows (coalesced stores over NVLink, no staging buffer) and then publishes a
     sequence number in the neighbours' flag words, followed by a one-thread wait for the two numbers the
-    neighbours publish in its own flags.  A second pair of flags tells a writer that the reader's kernel is
-    done with the previous contents of the halo row.  No NCCL call, no host synchronisation: three tiny
-    launches instead of six staging copies and a send/receive kernel.  (A first version used two
-    cudaMemcpy2DAsync per exchange: ~1000 rows of 8 KB at a 4 MB pitch cost the copy engine 1 ms.)
+    neighbours publish in its own flags.  A second pair of flags is the READY-TO-RECEIVE handshake: the push
+    kernel first tells both neighbours that everything enqueued before it on this rank's stream is complete
+    (the kernel that read the previous halo rows, and any update that swept over the slab since), and stores
+    nothing until it has the same word from them -- a writer can neither overtake the reader of the previous
+    exchange nor be overwritten by the owner's own later sweep over the slab.  No NCCL call, no host
+    synchronisation: two tiny launches instead of six staging copies and a send/receive kernel.  (A first
+    version used two cudaMemcpy2DAsync per exchange: ~1000 rows of 8 KB at a 4 MB pitch cost the copy engine
+    1 ms.)
 
     flags (int64, per rank): [0] top halo written by the rank above, [1] bottom halo written by the rank
-    below, [2] the rank above has consumed what I wrote into its bottom halo, [3] same for the rank below."""
+    below, [2] the rank above is ready to receive exchange k, [3] same for the rank below."""
+
+    MAX_SLABS = 8
 
     def __init__(self, rank, world, device, group=None):
         self.rank, self.world, self.group, self.device = rank, world, group, device
         self.flags = torch.zeros(4, dtype=torch.int64, device=device)
         self.ticket = torch.zeros(2, dtype=torch.int32, device=device)
         self.step = 0
-        self._slabs = {}
+        self._slabs = collections.OrderedDict()
         self._mapped = {}                      # exported handle -> base address in this device's context
         handles = [None] * world
         dist.all_gather_object(handles, (device.index, self._try_export(self.flags)), group=group)
@@ -172,7 +179,9 @@ class PeerHaloExchange:
     def _peers_of(self, W, nyl, nx):
         """Neighbours' addresses of the slab that corresponds to W (registered collectively on first use)."""
         key = (W.data_ptr(), tuple(W.shape))
-        if key not in self._slabs:
+        if key in self._slabs:
+            self._slabs.move_to_end(key)
+        else:
             info = [None] * self.world
             dist.all_gather_object(info, (self._try_export(W), W.shape[0], nyl), group=self.group)
             if any(e is None for e, _, _ in info):
@@ -187,8 +196,13 @@ class PeerHaloExchange:
             except _abi.SpuqError as e:
                 err = e
             self._agree(err is None, "a rank could not map a neighbour's slab (%r)" % (err,))
-            self._slabs[key] = peers
-        return self._slabs[key]
+            # the entry keeps the tensor ALIVE: as long as an address is in the table it cannot be handed to
+            # another tensor, here or (same registration, same order of calls) on the neighbours, so a hit never
+            # names memory that has moved.  Bounded: the oldest registration goes when a ninth arrives.
+            self._slabs[key] = (peers, W)
+            while len(self._slabs) > self.MAX_SLABS:
+                self._slabs.popitem(last=False)
+        return self._slabs[key][0]
 
     def exchange(self, W, nyl, nx, stream):
         """Enqueue the exchange of the halo rows of W (L x nyl*nx) on `stream`; returns after enqueueing."""
@@ -204,14 +218,6 @@ class PeerHaloExchange:
         _abi.check(lib.spuq_sg_halo_push(_abi.ptr(W), W.shape[0], nyl, nx, up_slab, up_nyl, dn_slab, dn_nyl,
                                          _abi.ptr(self.flags), up_fl, dn_fl, k, _abi.ptr(self.ticket), stream), "halo_push")
         _abi.check(lib.spuq_sg_halo_wait(_abi.ptr(self.flags), int(up in peers), int(dn in peers), k, stream), "halo_wait")
-
-    def consumed(self, stream):
-        """After the kernel that read the halo rows: tell both neighbours they may overwrite them."""
-        up, dn = self.rank - 1, self.rank + 1
-        _abi.check(_abi.lib().spuq_sg_halo_done(C.c_void_p(self.peer_flags[up]) if up in self.peer_flags else None,
-                                                C.c_void_p(self.peer_flags[dn]) if dn in self.peer_flags else None,
-                                                self.step, stream), "halo_done")
-
 
 class RowShardedApply:
     """The SG operator with the SPATIAL rows sharded over the ranks (axis 3).
@@ -296,8 +302,7 @@ class RowShardedApply:
                 self._peer_error, self.halo = repr(e), "nccl"
             else:
                 plan.apply(W, Y)
-                self._peer.consumed(st)
-                self.last_launches = plan.last_launches + 3        # + push, wait, done (one small kernel each)
+                self.last_launches = plan.last_launches + 2        # + push, wait (one small kernel each)
                 return Y
         if self.world == 1 or not overlap or W.device.type != "cuda":
             self.exchange_halos(W)

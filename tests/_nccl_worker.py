@@ -42,8 +42,12 @@ def main():
     plan = sh.plan_for(w)
     errs = []
     results = []
-    for halo, overlap in (("peer", False), ("nccl", False), ("nccl", True), ("peer", False)):
+    for k, (halo, overlap) in enumerate((("peer", False), ("nccl", False), ("nccl", True), ("peer", False), ("peer", False))):
         sh.halo = halo
+        # the owner fills a new slab (halo rows included) LATE on one rank: the neighbour's rows must not arrive
+        # before that fill and be overwritten by it (the ready-to-receive handshake of k_halo_push)
+        if k >= 3 and rank == k % world:
+            torch.cuda._sleep(40_000_000)
         Wc = W.clone()
         Y = torch.full_like(Wc, float("nan"))
         sh.apply(plan, Wc, Y, overlap=overlap)
