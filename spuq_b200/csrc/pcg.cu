@@ -209,7 +209,7 @@ extern "C" int64_t spuq_sg_precond_work_bytes(const spuq_sg_precond* p, int64_t 
 
 namespace spuq {
 int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S,
-                       void* work, cudaStream_t stream, const double* gate, FusedDot* fd, PreUpdate* pu) {
+                       void* work, cudaStream_t stream, const double* gate, FusedDot* fd) {
     SPUQ_REQUIRE(p && R && S, "precond_apply: null argument");
     const int64_t n = N * (int64_t)L;
     struct Count {                       // kernels of this call, whatever path returns
@@ -230,7 +230,7 @@ int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
         SPUQ_REQUIRE(p->plan->n_rows == N && p->plan->L == L, "precond_apply: plan shape mismatch");
         return apply_impl(p->plan, R, N, S, N, stream, gate);
     case spuq_sg_precond::MEAN_FD:
-        return mean_fd_apply(p, N, L, R, S, work, stream, gate, fd, pu);
+        return mean_fd_apply(p, N, L, R, S, work, stream, gate, fd);
     case spuq_sg_precond::SPARSE_LU:
         return lu_apply(p, N, L, R, S, work, stream, gate);
     }
@@ -306,11 +306,13 @@ extern "C" int spuq_sg_pcg(spuq_sg_plan* A, spuq_sg_precond* P, const double* F,
     // A pass: apply, <z,v> (+ the singular / not-PD test and alpha), the residual update, P rho, <rho,s> (+ zeta
     // rotation, the factor of the direction update and the convergence test of the next pass), and ONE kernel for
     // the solution update and the direction update (w += alpha v is moved behind the preconditioner, where v is
-    // read anyway).  With the strip preconditioner the residual update happens where its forward pass reads rho
-    // and <rho,s> where its final pass writes s: six launches.  The first convergence test stands alone.
+    // read anyway: 50 GB instead of 60 + 30 on configuration 4).  With the strip preconditioner <rho,s> comes from
+    // its final pass: seven launches.  The first convergence test stands alone.
+    // (Tried on a B200 and removed: the residual update inside the strip solver's forward pass.  It saves the
+    // 30 GB update kernel, but the z loads in that latency-bound kernel cost more than they save: 1.17 s against
+    // 1.04 s for the configuration-4 solve.)
     SPUQ_LAUNCH(k_pcg_check_zeta, dim3(1), dim3(1), 0, stream, st, 1, hist);                 // :33-38, pass 1
     launches += 1;
-    const bool pre_fused = precond_takes_preupdate(P);
     int32_t pass = 1;
     int status = SPUQ_PCG_RUNNING;
     while (pass < maxiter && status == SPUQ_PCG_RUNNING) {
@@ -319,24 +321,19 @@ extern "C" int spuq_sg_pcg(spuq_sg_plan* A, spuq_sg_precond* P, const double* F,
             if ((rc = apply_impl(A, v, N, z, N, stream, gate))) return rc;                   // :40
             const DotEpilogue ea{DOT_EPI_ALPHA, st, pass, nullptr, 0};
             if ((rc = dot_impl(1, n, z, v, st + 8, scratch, stream, gate, &ea))) return rc;  // :41-45
-            PreUpdate pu{z, st + 0, st + 1, false};
-            if (!pre_fused) {
-                SPUQ_LAUNCH(k_axpy, dim3(blas_grid(n, nsm, 256)), dim3(256), 0, stream, n, -1.0, st + 0, st + 1,
-                            z, rho, gate);                                                   // :48
-                launches += 1;
-            }
+            SPUQ_LAUNCH(k_axpy, dim3(blas_grid(n, nsm, 256)), dim3(256), 0, stream, n, -1.0, st + 0, st + 1,
+                        z, rho, gate);                                                       // :48
             // the last pass the loop may run (maxiter - 1) has no successor to test: the reference raises
             // "did not converge" without looking at its zeta
             const DotEpilogue ez{pass + 1 < maxiter ? DOT_EPI_ZETA : DOT_EPI_NONE, st, pass, hist, hist_cap};
             FusedDot fd{&ez, st + 9, false};
-            if ((rc = precond_apply_impl(P, N, L, rho, s, pwork, stream, gate, &fd, pre_fused ? &pu : nullptr))) return rc;  // :49
-            SPUQ_REQUIRE(!pre_fused || pu.done, "pcg: the preconditioner did not take the residual update it announced");
+            if ((rc = precond_apply_impl(P, N, L, rho, s, pwork, stream, gate, &fd))) return rc;  // :49
             if (!fd.done) {
                 if ((rc = dot_impl(1, n, rho, s, st + 9, scratch, stream, gate, &ez))) return rc;  // :50, :33-38
                 launches += 1;
             }
             SPUQ_LAUNCH(k_xpay_w, dim3(blas_grid(n, nsm, 256)), dim3(256), 0, stream, n, st, pass, s, v, Wv);  // :47, :51
-            launches += 3 + A->last_launches - 1 + P->last_launches;
+            launches += 3 + A->last_launches + P->last_launches;
         }
         SPUQ_CUDA_TRY(cudaGetLastError());
         SPUQ_CUDA_TRY(cudaMemcpyAsync(h_state, st, sizeof(h_state), cudaMemcpyDeviceToHost, stream));

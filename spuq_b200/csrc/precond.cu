@@ -492,17 +492,17 @@ int strip_plan_build(spuq_sg_precond* p, const StripRowsCtx* ctx) {
 template <bool FINAL>
 static void strip_launch(int ct, const StripPlan* sp, const StripView& view, int32_t L, int32_t p_off, int32_t p_cnt,
                          const double* R, double* S, double* Gf, double* Gl, const double* U, cudaStream_t stream,
-                         const double* gate, const StripDot& dot, const StripPre& pre) {
+                         const double* gate, const StripDot& dot) {
     if (p_cnt <= 0) return;
     const dim3 grid((unsigned)((int64_t)L * p_cnt)), block(STRIP_THREADS);
 #define SPUQ_STRIP_L(c)                                                                                          \
     case c: SPUQ_LAUNCH((k_strip<FINAL, c>), grid, block, sp->smem_bytes, stream, sp->Q, view, L, p_off, p_cnt, \
-                        R, S, Gf, Gl, U, gate, dot, pre); break;
+                        R, S, Gf, Gl, U, gate, dot); break;
     switch (ct) {
         SPUQ_STRIP_L(8) SPUQ_STRIP_L(12) SPUQ_STRIP_L(16) SPUQ_STRIP_L(20) SPUQ_STRIP_L(24) SPUQ_STRIP_L(26)
         SPUQ_STRIP_L(28) SPUQ_STRIP_L(32)
         default: SPUQ_LAUNCH((k_strip<FINAL, 0>), grid, block, sp->smem_bytes, stream, sp->Q, view, L, p_off, p_cnt,
-                             R, S, Gf, Gl, U, gate, dot, pre);
+                             R, S, Gf, Gl, U, gate, dot);
     }
 #undef SPUQ_STRIP_L
 }
@@ -511,15 +511,13 @@ static void strip_launch(int ct, const StripPlan* sp, const StripView& view, int
 // remainder strip through its generic branch)
 template <bool FINAL>
 static void strip_pass(const StripPlan* sp, const StripView& sv, int32_t L, const double* R, double* S, double* Gf, double* Gl,
-                       const double* U, cudaStream_t stream, const double* gate, const StripDot& dot = StripDot{},
-                       const StripPre& pre = StripPre{}) {
-    strip_launch<FINAL>(sv.n_tall > 0 ? sp->main_ct : 0, sp, sv, L, 0, sv.P, R, S, Gf, Gl, U, stream, gate, dot, pre);
+                       const double* U, cudaStream_t stream, const double* gate, const StripDot& dot = StripDot{}) {
+    strip_launch<FINAL>(sv.n_tall > 0 ? sp->main_ct : 0, sp, sv, L, 0, sv.P, R, S, Gf, Gl, U, stream, gate, dot);
 }
 template <bool FINAL>
 static void strip_pass(const StripPlan* sp, int32_t L, const double* R, double* S, double* Gf, double* Gl, const double* U,
-                       cudaStream_t stream, const double* gate, const StripDot& dot = StripDot{},
-                       const StripPre& pre = StripPre{}) {
-    strip_pass<FINAL>(sp, sp->sv, L, R, S, Gf, Gl, U, stream, gate, dot, pre);
+                       cudaStream_t stream, const double* gate, const StripDot& dot = StripDot{}) {
+    strip_pass<FINAL>(sp, sp->sv, L, R, S, Gf, Gl, U, stream, gate, dot);
 }
 
 static int64_t strip_work_doubles(const StripPlan* sp, int32_t L) {
@@ -532,12 +530,12 @@ static int64_t strip_work_doubles(const StripPlan* sp, int32_t L) {
 // holds the solution.
 static const double* strip_schur(spuq_sg_precond* p, const StripPlan* sp, const StripView& sv, int32_t L, double* Z, double* Z2,
                                  cudaStream_t stream, const double* gate, const double* R = nullptr,
-                                 const double* Gf = nullptr, const double* Gl = nullptr, const StripPre& pre = StripPre{}) {
+                                 const double* Gf = nullptr, const double* Gl = nullptr) {
     if (sp->schur_smem > 0) {
         const dim3 grid((unsigned)L);
 #define SPUQ_SCHUR_L(r, c)                                                                                        \
     case r: SPUQ_LAUNCH((k_schur_fused<r, c>), grid, dim3(SchurShape<c>::threads), sp->schur_smem, stream, sv, L, p->half, \
-                        R != nullptr ? 1 : 0, R, Gf, Gl, Z, p->qsplit_dev, sp->sy_ipiv, sp->sy_off, gate, pre); break;
+                        R != nullptr ? 1 : 0, R, Gf, Gl, Z, p->qsplit_dev, sp->sy_ipiv, sp->sy_off, gate); break;
         switch (schur_rows_for(sv.q)) {
             SPUQ_SCHUR_FOR_EACH(SPUQ_SCHUR_L)
         }
@@ -576,7 +574,7 @@ static const double* strip_schur(spuq_sg_precond* p, const StripPlan* sp, const 
 }
 
 static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
-                       cudaStream_t stream, const double* gate, FusedDot* fd, PreUpdate* pu) {
+                       cudaStream_t stream, const double* gate, FusedDot* fd) {
     StripPlan* sp = static_cast<StripPlan*>(p->strip);
     const StripView& sv = sp->sv;
     const int32_t nx = sv.nx, q = sv.q;
@@ -589,15 +587,9 @@ static int strip_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R
     double* Z = Gl + (int64_t)L * sv.P * nx;
     double* Z2 = Z + (int64_t)L * q * nx;
     const double* U = nullptr;
-    StripPre pre{};
-    if (pu != nullptr) {
-        SPUQ_REQUIRE(precond_takes_preupdate(p), "precond_mean_fd: this plan takes no residual update");
-        pre.z = pu->z; pre.num = pu->num; pre.den = pu->den;
-        pu->done = true;
-    }
     if (q > 0) {
-        strip_pass<false>(sp, L, R, S, Gf, Gl, nullptr, stream, gate, StripDot{}, pre);
-        U = strip_schur(p, sp, sv, L, Z, Z2, stream, gate, R, Gf, Gl, pre);
+        strip_pass<false>(sp, L, R, S, Gf, Gl, nullptr, stream, gate);
+        U = strip_schur(p, sp, sv, L, Z, Z2, stream, gate, R, Gf, Gl);
     }
     StripDot dot{};
     if (fd != nullptr && sp->ticket != nullptr && work != nullptr) {
@@ -631,18 +623,10 @@ int64_t mean_fd_work_bytes(const spuq_sg_precond* p, int64_t N, int32_t L) {
     return need;
 }
 
-bool precond_takes_preupdate(const spuq_sg_precond* p) {
-    if (!p || p->kind != spuq_sg_precond::MEAN_FD || !p->strip) return false;
-    const StripPlan* sp = static_cast<const StripPlan*>(p->strip);
-    // the forward strip pass and the fused separator kernel between them read every entry of R exactly once
-    return sp->sv.q > 0 && sp->schur_smem > 0 && !sp->sv.has_bottom && sp->sv.u_above0 == -1;
-}
-
 int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
-                  cudaStream_t stream, const double* gate, FusedDot* fd, PreUpdate* pu) {
+                  cudaStream_t stream, const double* gate, FusedDot* fd) {
     SPUQ_REQUIRE(N == (int64_t)p->nx * p->ny, "precond_mean_fd: slab rows %lld != nx*ny", (long long)N);
-    if (p->strip) return strip_apply(p, N, L, R, S, work, stream, gate, fd, pu);
-    SPUQ_REQUIRE(pu == nullptr, "precond_mean_fd: this path takes no residual update");
+    if (p->strip) return strip_apply(p, N, L, R, S, work, stream, gate, fd);
     SPUQ_REQUIRE(work != nullptr, "precond_mean_fd: workspace missing");
     double* T = static_cast<double*>(work);
     const int64_t Mrows = (int64_t)L * p->ny;

@@ -49,22 +49,10 @@ struct FusedDot {
     double* out;
     bool done;
 };
-// ... and the residual update that precedes the preconditioner (pcg.py:48, rho -= (num/den) z): a path that can
-// apply it where it first reads rho -- and write the new rho back -- sets `done`; the caller then skips its own
-// update kernel.  R is written in that case.
-struct PreUpdate {
-    const double* z;
-    const double* num;
-    const double* den;
-    bool done;
-};
 int mean_fd_apply(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S, void* work,
-                  cudaStream_t stream, const double* gate, FusedDot* fd = nullptr, PreUpdate* pu = nullptr);
+                  cudaStream_t stream, const double* gate, FusedDot* fd = nullptr);
 int precond_apply_impl(spuq_sg_precond* p, int64_t N, int32_t L, const double* R, double* S,
-                       void* work, cudaStream_t stream, const double* gate, FusedDot* fd = nullptr,
-                       PreUpdate* pu = nullptr);
-// true when precond_apply_impl on this handle will take a PreUpdate (decided before the caller enqueues anything)
-bool precond_takes_preupdate(const spuq_sg_precond* p);
+                       void* work, cudaStream_t stream, const double* gate, FusedDot* fd = nullptr);
 int dot_impl(int nout, int64_t n, const double* x, const double* y, double* out, void* scratch,
              cudaStream_t stream, const double* gate, const DotEpilogue* epi = nullptr);
 }

@@ -182,14 +182,6 @@ __device__ __forceinline__ void strip_ytransform_ct(const StripQ& Q, Load load, 
 // dot.partials != null (FINAL only): the kernel also leaves <R, S> in dot.out -- every CTA one partial (the
 // strip's right-hand side is read a second time, from L2 as a rule: it was loaded by this CTA a few microseconds
 // earlier), the last CTA to finish adds them in index order and runs the PCG epilogue of k_dot.
-// R <- R - (num/den) z where the forward pass (and the separator kernel, for the separator rows) first reads R;
-// z = null: R is only read
-struct StripPre {
-    const double* z;
-    const double* num;
-    const double* den;
-};
-
 struct StripDot {
     double* partials;          // one per CTA of the launch; null: no dot
     unsigned int* ticket;      // zero before the launch, reset by the last CTA
@@ -245,7 +237,7 @@ __global__ void __launch_bounds__(STRIP_THREADS, 2)
 k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off, int32_t p_cnt,
         const double* __restrict__ R, double* __restrict__ S,
         double* __restrict__ Gf, double* __restrict__ Gl, const double* __restrict__ U, const double* gate,
-        StripDot dot, StripPre pre) {
+        StripDot dot) {
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
 #ifdef SPUQ_EMU
     if (threadIdx.x != 0) return;
@@ -305,19 +297,6 @@ k_strip(const __grid_constant__ StripQ Q, StripView sv, int32_t L, int32_t p_off
     } else
 #endif
     for (int i = STRIP_T0; i < c * nx; i += STRIP_TS) strip[(size_t)(i / nx) * sp + i % nx] = src[i];
-    if (!FINAL && pre.z != nullptr) {
-        // the residual update of the PCG pass (pcg.py:48) on this strip, written back for the final pass
-        STRIP_SYNC();
-        const double a = ratio_of(1.0, pre.num, pre.den);
-        const double* zs = pre.z + col * N + (int64_t)y0 * nx;
-        double* rw = const_cast<double*>(src);
-        for (int i = 0; i < c; ++i)
-            for (int x = STRIP_T0; x < nx; x += STRIP_TS) {
-                const double v = fma(-a, zs[(size_t)i * nx + x], strip[(size_t)i * sp + x]);
-                strip[(size_t)i * sp + x] = v;
-                rw[(size_t)i * nx + x] = v;
-            }
-    }
     if (FINAL) {
         STRIP_SYNC();
         const double oy = sv.oy;
@@ -571,7 +550,7 @@ __global__ void __launch_bounds__(SchurShape<CPT>::threads, (CPT == 2 && RT <= 2
 k_schur_fused(StripView sv, int32_t L, int32_t h, int32_t assemble, const double* __restrict__ R,
               const double* __restrict__ Gf, const double* __restrict__ Gl, double* __restrict__ Z,
               const double* __restrict__ qsplit, const double* __restrict__ ipiv, const double* __restrict__ off,
-              const double* gate, StripPre pre) {
+              const double* gate) {
     if (gate != nullptr && __ldg(gate) != (double)SPUQ_PCG_RUNNING) return;
     const int nx = sv.nx, q = sv.q;
     const int hp2 = (h + 1) & ~1, ps = 2 * hp2;       // sums in [0, h), differences in [hp2, hp2 + h) of a row
@@ -604,16 +583,8 @@ k_schur_fused(StripView sv, int32_t L, int32_t h, int32_t assemble, const double
             const double* rr = R + col * N + (int64_t)ys * nx;
             const double* gl = Gl + (col * sv.gf_ld + j) * nx;
             const double* gf = Gf + (col * sv.gf_ld + j + 1) * nx;
-            double ra = rr[i], rb = rr[i2];
-            if (pre.z != nullptr) {                    // the PCG residual update on the separator rows (see k_strip)
-                const double al = ratio_of(1.0, pre.num, pre.den);
-                const double* zz = pre.z + col * N + (int64_t)ys * nx;
-                double* rw = const_cast<double*>(rr);
-                ra = fma(-al, zz[i], ra); rb = fma(-al, zz[i2], rb);
-                rw[i] = ra; rw[i2] = rb;
-            }
-            a = ra - sv.oy * (gl[i] + gf[i]);
-            b = rb - sv.oy * (gl[i2] + gf[i2]);
+            a = rr[i] - sv.oy * (gl[i] + gf[i]);
+            b = rr[i2] - sv.oy * (gl[i2] + gf[i2]);
         } else {
             const double* z = Z + (int64_t)j * sv.u_js + col * sv.u_cs;
             a = z[i]; b = z[i2];

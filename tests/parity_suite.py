@@ -957,11 +957,11 @@ def check_pcg_sg_mean(n=12, M=3, p=2, eps=1e-10):
     assert np.max(np.abs(x.to_array() - x_o.to_slab())) <= 1e-8
     assert np.max(np.abs(x.to_array() - c.W)) <= 1e-7
     assert it <= 30                                       # mean-based preconditioning: few iterations
-    # a pass: apply, <z,v>, strips forward (+ the residual update), separator system, strips final (+ <rho,s>),
-    # the solution / direction update -- six launches (five when the grid is a single strip: separate residual
-    # update, no forward pass, no separator system); the solve's count includes ~9 for the start-up
+    # a pass: apply, <z,v>, the residual update, strips forward, separator system, strips final (+ <rho,s>), the
+    # solution / direction update -- seven launches (five when the grid is a single strip); the solve's count
+    # includes ~9 for the start-up
     launches = A.plan_for(f).last_launches
-    assert launches <= 10 + 6 * it, (launches, it)
+    assert launches <= 10 + 7 * it, (launches, it)
     # the preconditioner as a stand-alone operator: P * f, host containers too
     s = P * f
     lu_ref = (P_o * f_o).to_slab()
