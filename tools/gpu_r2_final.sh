@@ -32,7 +32,10 @@ PY
 # full captures: the apply kernel on c3, the strip kernels, the general sparse kernel
 ncu --set full --clock-control none --import-source on -k regex:k_apply_tmem -s 3 -c 1 -f -o $O/r2_c3_apply_tmem python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-pcg > $O/r2_ncu_full_c3.log 2>&1
 python tools/ncu_to_json.py $O/r2_c3_apply_tmem.ncu-rep $O/r2_c3_apply_tmem_ncu_full.json $O/r2_traffic.json "c3|k_apply_tmem<K=2,G=2,5pt>" "profiles/r2_c3_apply_tmem_ncu_full.json (ncu --set full --clock-control none, one launch of bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-pcg)" > /dev/null
-ncu --set full --clock-control none --import-source on -k regex:k_strip -c 4 -f -o $O/r2_strip python tools/precond_bench.py --nx 500 --ny 500 --L 600 --reps 1 > $O/r2_ncu_full_strip.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_strip|k_schur" -s 3 -c 3 -f -o $O/r2_strip python tools/precond_bench.py --nx 500 --ny 500 --L 5000 --reps 1 > $O/r2_ncu_full_strip.log 2>&1
+python tools/ncu_lines.py $O/r2_strip.ncu-rep k_strip 0 22 > $O/r2_precond_strip_lines.txt; python tools/ncu_lines.py $O/r2_strip.ncu-rep k_schur 0 12 >> $O/r2_precond_strip_lines.txt; python tools/ncu_lines.py $O/r2_strip.ncu-rep k_strip 1 22 >> $O/r2_precond_strip_lines.txt
+python tools/ncu_launches_json.py $O/r2_strip.ncu-rep $O/r2_precond_strip_ncu_full.json "ncu --set full --clock-control none --import-source on -k regex:k_strip|k_schur -s 3 -c 3 python tools/precond_bench.py --nx 500 --ny 500 --L 5000 --reps 1"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 30 --csv --log-file $O/r2_precond_strip_launches.csv python tools/precond_bench.py --nx 500 --ny 500 --L 5000 --reps 2 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_apply_ellblk -s 3 -c 1 -f -o $O/r2_c3n_ellblk python bench.py --config c3n --steps 1 --warmup 3 --no-e2e --no-cpu --no-pcg > $O/r2_ncu_full_c3n.log 2>&1
 python tools/ncu_to_json.py $O/r2_c3n_ellblk.ncu-rep $O/r2_c3n_ellblk_ncu_full.json $O/r2_traffic.json "c3n|k_apply_ellblk<5>" "profiles/r2_c3n_ellblk_ncu_full.json (ncu --set full, one launch of bench.py --config c3n)" > /dev/null
 for s in "500 500 5000" "512 512 1771" "1000 1000 988"; do set -- $s; python tools/precond_bench.py --nx $1 --ny $2 --L $3; done > $O/r2_precond_bench.json 2>/dev/null; cat $O/r2_precond_bench.json
