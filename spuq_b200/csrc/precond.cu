@@ -251,7 +251,12 @@ static void partition_chunks(int n, int len, std::vector<int32_t>* start, std::v
         start->push_back(pos); lens->push_back(len);
         pos += len + 1;
     }
-    start->push_back(pos); lens->push_back(n - pos);     // last chunk: 1 .. len + 1 points
+    if (n - pos == len + 1 && len + 1 > STRIP_CX) {      // one point too many for the sweeps' registers: two halves and a separator
+        const int half = len / 2;
+        start->push_back(pos); lens->push_back(half);
+        pos += half + 1;
+    }
+    start->push_back(pos); lens->push_back(n - pos);     // last chunk: 1 .. min(len + 1, STRIP_CX) points
 }
 
 template <typename T>

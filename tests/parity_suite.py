@@ -831,7 +831,7 @@ def check_mean_preconditioner():
     for nx, ny, L in [(12, 12, 5), (70, 9, 3), (9, 33, 4), (130, 2, 2), (17, 1, 3), (4, 3, 2), (6, 7, 3),
                       (70, 75, 3), (33, 67, 2), (95, 64, 2), (31, 100, 2), (64, 34, 2), (100, 133, 1),
                       # 16 x-chunks at pitch 33 with padded shared-memory rows (the layout of configurations 2 and 4)
-                      (500, 40, 1), (512, 30, 2), (498, 29, 1)]:
+                      (500, 40, 1), (512, 30, 2), (498, 29, 1), (66, 40, 1)]:
         T = lambda n, o, dd: sps.diags([o, dd, o], [-1, 0, 1], shape=(n, n))      # noqa: E731
         if ny > 1:
             A0 = sps.kron(sps.identity(ny), T(nx, -1.0, 2.0)) + sps.kron(T(ny, -1.0, 2.0), sps.identity(nx))
