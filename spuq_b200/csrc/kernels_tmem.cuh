@@ -396,7 +396,8 @@ k_apply_tmem(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
                 if (P.c >= P.c1) P.active = false;      // (window groups end with the block: pad commands)
                 if (npre > 0) progress = true;
             }
-            if (!progress && !all_done) __nanosleep(100);
+            // back-off of the idle producer: 100 ns << (bits 4-6 of SPUQ_KDEBUG); development switch for the polling cost
+            if (!progress && !all_done) __nanosleep(100u << ((debug_flags >> 4) & 7));
         }
         return;
     }
