@@ -18,6 +18,7 @@ import numpy as np
 import scipy.sparse as sps
 import torch
 
+from . import _abi
 from .multi_operator import CsrSlabOperator, PreconditioningOperator, _block_to_csr
 from .multi_vector import MultiVector, SlabMultiVector
 from .multiindex import Multiindex
@@ -109,7 +110,10 @@ class _EnergyNorm:
 
 def pcg_solve(A, w, coeff_field, pde, stats, pcg_eps, pcg_maxiter):
     """adaptive_solver2.py:71-85.  Returns ``(w, zeta)`` and fills ``stats`` with RESIDUAL-L2,
-    RESIDUAL-H1A, DOFS and CELLS."""
+    RESIDUAL-H1A, DOFS and CELLS; also TIME-PCG, the wall time of the call with the device drained (the
+    reference's adaptive loop stores it around this call, adaptive_solver2.py:150)."""
+    import time
+    t0 = time.perf_counter()
     w = _as_slab(w)
     b = prepare_rhs(A, w, coeff_field, pde)
     P = PreconditioningOperator(coeff_field.mean_func, pde.assemble_solve_operator)
@@ -124,4 +128,7 @@ def pcg_solve(A, w, coeff_field, pde, stats, pcg_eps, pcg_maxiter):
     stats["RESIDUAL-H1A"] = error_norm(b, b2, energy, pde)
     stats["DOFS"] = len(b) * b.spatial_basis.dim
     stats["CELLS"] = len(b) * int(pde.num_cells(b.spatial_basis))
+    if torch.cuda.is_available() and not _abi.is_emulated():
+        torch.cuda.synchronize()
+    stats["TIME-PCG"] = time.perf_counter() - t0
     return w, zeta

@@ -8,9 +8,12 @@ as plain ``Exception`` (:33-36, :42-45, :53), same type check (Operator, Vector,
 The loop itself runs in libspuq_sg (``spuq_sg_pcg``): operator application, fused dot products and
 vector updates read and write zeta / alpha in device memory, the reference's branch conditions are
 evaluated by one-thread kernels, and the host only polls a status word every ``poll_every`` passes.
-The extra ``<rho, rho>`` the reference computes every pass for its log line (:32) is not computed.
+The extra ``<rho, rho>`` the reference computes every pass for its log line (:32) is not computed; the
+line itself ("pcg iter: i -> zeta=...") is written after the solve from the device-side zeta history when the
+module's logger is enabled for INFO.
 """
 import ctypes as C
+import logging
 
 import numpy as np
 import torch
@@ -24,6 +27,8 @@ from .multi_vector import MultiVector, SlabMultiVector
 from .multiindex import Multiindex
 
 __all__ = ["pcg", "PCG_MESSAGES"]
+
+logger = logging.getLogger(__name__)
 
 PCG_MESSAGES = {
     _abi.PCG_PRECOND_NOT_PD: "Preconditioner for PCG is not positive definite (%s)",
@@ -95,6 +100,9 @@ def _solve_on_device(plan, precond, F, W0, eps, maxiter, poll_every, history):
                                _abi.ptr(hist), _abi.stream_ptr()), "pcg")
     if history is not None:
         history.extend(hist[:numit.value].tolist())
+    if logger.isEnabledFor(logging.INFO):
+        for i, z in enumerate(hist[:numit.value].tolist(), 1):          # pcg.py:32 (without the rho^2 it adds)
+            logger.info("pcg iter: %s -> zeta=%s", i, z)
     return W, zeta.value, numit.value, status.value
 
 

@@ -512,6 +512,7 @@ def check_pcg_solve(n=10, M=3, p=2, kind="hermite", mu=0.5):
     assert np.max(np.abs(x.to_array() - x_o.to_slab())) <= 1e-8 * np.max(np.abs(x_o.to_slab()))
     assert stats["DOFS"] == stats_o["DOFS"] == c.N * idx.shape[0]
     assert stats["CELLS"] == stats_o["CELLS"] == (n + 1) ** 2 * idx.shape[0]
+    assert stats["TIME-PCG"] > 0.0 and stats["PCG-ITERATIONS"] >= 2
     for key in ("RESIDUAL-L2", "RESIDUAL-H1A"):
         # residuals of two converged runs: same size, both tiny against the right-hand side
         assert stats[key] <= 1e-6 and stats_o[key] <= 1e-6, (key, stats[key], stats_o[key])
